@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 path tracer (BASELINE.json metric:
+Mpaths*bounces/s = path SEGMENTS per second, one segment = one closest-hit query + its shading).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): bundled Scene1 (67 spheres), 1920x1080, 1024 spp, depth 8,
+default camera. One step = one rt_render_spp(1024) over the whole frame (2.12 G paths). At N > 1
+every rank renders its own 1024 samples of the full frame (global spp = 1024*N, weak scaling) and
+the float4 accumulation buffers are summed with one NCCL all-reduce inside the timed step.
+
+`value`  : segments/s with the scene resident on the device (CUDA events around the kernels).
+`e2e`    : the same metric through the C-ABI with HOST buffers each step: rt_set_scene (H2D) +
+           rt_set_camera + rt_reset_accumulation + rt_render_spp + rt_resolve_rgba8 (D2H ARGB8).
+`--impl reference`: the reference's own CPU code (oracle/_ref, else the validated C port) on the
+           host cores, same metric, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "software-raytracer_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "Mpaths*bounces/s (path segments per second), bundled Scene1 @1920x1080"
+UNIT = "Msegments/s"
+W, H, SPP, DEPTH = 1920, 1080, 1024, 8
+
+
+def load_scene():
+    return np.load(os.path.join(ROOT, "tests", "golden", "bundled_scenes.npz"))["Scene1"]
+
+
+def flops_per_segment(objs):
+    """23 per sphere test + 30 per cube test + 110 shading/scatter."""
+    return 23 * int((objs["type"] == 1).sum()) + 30 * int((objs["type"] == 2).sum()) + 110
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 4 + i and r[4 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_run(objs, frames, want_ref=True):
+    """Time the reference's CPU implementation of the path on all host cores: `frames` 1-spp frames at
+    WxH. Returns (segments/s, info). oracle/_ref (the reference's own code, 16 strip threads, per-thread
+    MSVC rand) when its .so is present, else the bit-for-bit validated C port."""
+    from oracle_py import Oracle, Reference, OrcCamera, REF_SO
+    cores = os.cpu_count() or 1
+    tmp_scene = "/tmp/_bench_scene1.json"
+    if want_ref and os.path.exists(REF_SO):
+        import rtb200
+        rtb200.scene_file_write(tmp_scene, objs, None, "")        # host-only writer: the _ref loader needs a JSON file
+        ref = Reference()
+        assert ref.load_scene(tmp_scene) == len(objs)
+        ref.setup(W, H, 55, DEPTH, False, None)
+        sec, segs = ref.render_frames(frames, rng_mode=0, count_segments=True)
+        return segs / sec, {"kind": "reference", "cores": cores, "threads": 16, "seconds": sec, "segments": int(segs),
+                            "sample": "%d frames of 1 spp at %dx%d, depth %d, Scene1; reference's own renderArea loop, 16 threads, per-thread MSVC rand()" % (frames, W, H, DEPTH)}
+    orc = Oracle()
+    cam = OrcCamera(); cam.right[0] = 1; cam.up[1] = 1; cam.forward[2] = 1; cam.fov_deg = 55
+    p = orc.default_params(width=W, height=H, max_bounces=DEPTH, mode=0)
+    sec, segs = orc.time_render(objs, cam, p, frames, rng_mode=0, threads=cores)
+    return segs / sec, {"kind": "port", "cores": cores, "threads": cores, "seconds": sec, "segments": int(segs),
+                        "sample": "%d spp at %dx%d, depth %d, Scene1; validated C port, %d threads" % (frames, W, H, DEPTH, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    objs = load_scene()
+    frames_per_step = 2
+    for _ in range(args.warmup):
+        cpu_reference_run(objs, 1)
+    times, segs = [], 0
+    info = None
+    for _ in range(args.steps):
+        rate, info = cpu_reference_run(objs, frames_per_step)
+        times.append(info["seconds"]); segs += info["segments"]
+    total = sum(times)
+    value = segs / total / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic: bundled Scene1 fixture, default camera",
+            "config": {"workload": "Scene1 (67 spheres) %dx%d depth %d; each step = %d frames of 1 spp on the host CPU" % (W, H, DEPTH, frames_per_step)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "paths_per_s_M": (W * H * frames_per_step * args.steps) / total / 1e6}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import rtb200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    objs = load_scene()
+    spp = args.spp
+    stream = torch.cuda.Stream()
+    tr = rtb200.PathTracer(local)
+    tr.set_stream(stream.cuda_stream)
+    tr.set_scene(objs)
+    tr.set_camera(rtb200.default_camera())
+    tr.set_params(rtb200.default_params(width=W, height=H, mode=rtb200.RT_MODE_PATH, max_bounces=DEPTH,
+                                        seed_lo=2026, seed_hi=rank))       # every rank: its own sample streams
+    tr.reset_accumulation()
+
+    class DevBuf:                                   # wrap the library's accumulation buffer for NCCL
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    accum = torch.as_tensor(DevBuf(tr.accum_device_ptr(), W * H * 4), device=torch.device("cuda", local))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        """device-resident step: samples into the accumulation buffer (+ the one exchange at N > 1)."""
+        tr.render_spp(spp)
+        if world > 1:
+            dist.all_reduce(accum)
+
+    # ---- device-timed: value ---------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            tr.reset_accumulation(); step_resident()
+        barrier()
+        seg0 = tr.stats().segments
+        sampler = ClockSampler(local); sampler.start()
+        evs = []
+        tr.reset_accumulation()
+        barrier()
+        for _ in range(args.steps):
+            flush.fill_(1)                                                  # L2 flush between timed steps
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); step_resident(); e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        clocks = sampler.summary()
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        segs_rank = tr.stats().segments - seg0
+        paths_rank = W * H * spp * args.steps
+
+        # ---- end to end through the C-ABI with host buffers: e2e ------------------------------
+        out = np.zeros((H, W), np.uint32)
+        cam = rtb200.default_camera()
+
+        def step_e2e():
+            tr.set_scene(objs)                       # host rt_object[] -> device SoA (H2D)
+            tr.set_camera(cam)
+            tr.reset_accumulation()
+            tr.render_spp(spp)
+            if world > 1:
+                dist.all_reduce(accum)
+                tr.set_sample_count(spp * world)
+            tr.resolve_rgba8(True, out)              # Reinhard + pack, D2H into the host surface; synchronises
+        for _ in range(max(1, args.warmup - 1)):
+            step_e2e()
+        barrier()
+        seg1 = tr.stats().segments
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record(stream)
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        e2e_dev_ms = e0.elapsed_time(e1)
+        e2e_segs = tr.stats().segments - seg1
+
+    total_ms = sum(step_ms)
+    t = torch.tensor([total_ms, e2e_wall * 1e3, float(segs_rank), float(e2e_segs)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = tmax[0].item(), tmax[1].item()
+        segs_all, e2e_segs_all = tsum[2].item(), tsum[3].item()
+    else:
+        e2e_ms, segs_all, e2e_segs_all = e2e_wall * 1e3, float(segs_rank), float(e2e_segs)
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        st = tr.stats()
+        fps = flops_per_segment(objs)
+        value = segs_all / (total_ms * 1e-3) / 1e6
+        # dominant kernel = k_render_regen, one launch per step; its duration = the step (N=1)
+        kern_s = statistics.mean(step_ms) * 1e-3
+        achieved_tf = (segs_rank / args.steps) * fps / kern_s / 1e12
+        sm_mhz = peaks.get("sm_max_mhz", 1965.0)
+        peak_tf = st.sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic: bundled Scene1 fixture (tests/golden/bundled_scenes.npz), default camera, Philox seeds",
+            "config": {"workload": "Scene1 (67 spheres) %dx%d, %d spp per GPU per step, depth %d, path mode" % (W, H, spp, DEPTH),
+                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": "spp-sharded x%d, one all-reduce per step" % world,
+                       "build": "strict IEEE, -fmad=false (bit-exact geometry vs the reference)"},
+            "paths_per_s_M": paths_rank * world / (total_ms * 1e-3) / 1e6,
+            "ms_per_1spp_frame": total_ms / args.steps / spp,
+            "segments_per_path": segs_rank / paths_rank,
+            "e2e": {"value": e2e_segs_all / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
+                    "h2d_bytes_per_step": int(objs.nbytes + 52), "d2h_bytes_per_step": int(W * H * 4),
+                    "ms_per_step": e2e_ms / args.steps, "device_ms_per_step": e2e_dev_ms / args.steps,
+                    "api": "rt_set_scene + rt_set_camera + rt_reset_accumulation + rt_render_spp + rt_resolve_rgba8(host)"},
+            "gpu_launches": int(args.steps * 1 + args.steps * 2),
+            "gpu_launches_detail": "timed value region: 1 k_render_regen per step; e2e region: k_render_regen + k_resolve per step",
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         "traffic": None, "kernel": "k_render_regen", "kernel_ms": kern_s * 1e3,
+                         "flop_per_segment": fps,
+                         "peak_source": "%d SMs x 128 lanes x 2 (FMA) x %.0f MHz (%s MEASURED_PEAKS.json sm_max_mhz)" % (st.sm_count, sm_mhz, peaks_src),
+                         "note": "path is FP32-CUDA-core bound, not HBM or tensor (SURVEY.md 8d); the strict build issues no FMA, "
+                                 "so the attainable ceiling is peak/2: frac_of_no_fma_peak below",
+                         "frac_of_no_fma_peak": achieved_tf / (peak_tf / 2),
+                         "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_algorithmic_gbs": (W * H * 32 / kern_s) / 1e9},
+        }
+        if world == 1 and not args.no_cpu:
+            rate, info = cpu_reference_run(objs, args.cpu_frames)
+            line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                                    "sample": info["sample"], "threads": info["threads"]}
+        print(json.dumps(line), flush=True)
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spp", type=int, default=SPP, help="samples per pixel per GPU per step (default: the config's 1024)")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="1-spp frames of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

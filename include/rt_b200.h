@@ -1,0 +1,198 @@
+/* rt_b200.h - C-ABI of the B200-native path tracer (librt_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of JoshuaLim007/Software-Raytracer:
+ * per-pixel ray generation -> closest hit over the Scene's object list -> scatter / shade ->
+ * bounce loop -> progressive accumulation -> Reinhard resolve to ARGB8.
+ *
+ * The reference has no FFI; its seam is the set of free functions and globals that main()
+ * and the 16 worker threads share. Every entry point below names the reference
+ * code it replaces as file:line under Raytracer/ of the reference tree. Plain pointers and
+ * sizes only; no C++/torch types. All functions return 0 on success and a negative rt_status
+ * on failure (the reference reports no errors at all: Scene.hpp:30-32,75-77 fail silently);
+ * rt_last_error() gives the message. A context is used by one host thread at a time - the
+ * reference's own rule ("thread safe after this point", Raytracer.cpp:373-385).
+ *
+ * There is NO CPU fallback: every compute entry point runs CUDA kernels on an sm_100a
+ * device or fails with RT_ERR_CUDA.
+ *
+ * Conventions kept from the reference: image space is y-UP, row-major, pixel index
+ * x + y*width (Raytracer.cpp:67); object id == index in the scene's object list == JSON
+ * order (Raytracer.cpp:127-137); colours are linear float; the resolved surface is
+ * 0xAARRGGBB with alpha byte 0 and rows flipped to y-down (Raytracer.cpp:64, Common.hpp:205).
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+typedef struct rt_ctx rt_ctx;
+
+typedef enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,   /* bad argument / call order */
+    RT_ERR_CUDA = -2,      /* no usable device, launch or copy failure */
+    RT_ERR_IO = -3,        /* file missing / unreadable */
+    RT_ERR_PARSE = -4,     /* malformed scene JSON or missing required key */
+    RT_ERR_NOMEM = -5
+} rt_status;
+
+/* Object types: Scene.hpp:43-55 ("Sphere", "Cube", anything else -> never-hit Object). */
+enum { RT_OBJ_NONE = 0, RT_OBJ_SPHERE = 1, RT_OBJ_CUBE = 2 };
+
+/* One scene object: Object.transform.position + Sphere::radius | Box::size (half extents) +
+ * Material (Common.hpp:293-319). 76 bytes, no padding. */
+typedef struct {
+    int32_t type;
+    float pos[3];
+    float radius;          /* spheres */
+    float half[3];         /* cubes: half extents, axis aligned (Object.hpp:173-200,203) */
+    float base[3];         /* Material.BaseColor      JSON "Color" */
+    float emissive[3];     /* Material.EmissiveColor  JSON "Emissive" */
+    float spec_color[3];   /* Material.SpecularColor  JSON "SpecularColor" */
+    float smoothness;      /* Material.Smoothness */
+    float spec_amount;     /* Material.SpecularAmount */
+} rt_object;
+
+/* Transform camera + FOV (Raytracer.cpp:295-297, :31). The basis is NOT re-orthonormalised,
+ * exactly like the reference. fov_deg is the vertical field of view, an int like the reference's. */
+typedef struct {
+    float pos[3], right[3], up[3], forward[3];
+    int32_t fov_deg;
+} rt_camera;
+
+enum { RT_MODE_PATH = 0, RT_MODE_PREVIEW = 1 };   /* SIMPLEDRAW false / true (Raytracer.cpp:35,147) */
+
+/* Render parameters: the reference's compile-time #defines and mutable globals
+ * (Raytracer.cpp:26-35, 55-59, 166, 177). rt_default_params() fills the reference's values. */
+typedef struct {
+    int32_t width, height;         /* SCREEN_WIDTH / SCREEN_HEIGHT */
+    int32_t max_bounces;           /* MAXBOUNCES */
+    int32_t mode;                  /* RT_MODE_* */
+    int32_t selected_id;           /* selectedObject as an object id, -1 = none (preview highlight) */
+    float sun_dir[3];              /* SunDirection after Normalized() (:55,:264) */
+    float sky[3], horizon[3], ground[3], sun[3];   /* :56-59 */
+    float dissipation;             /* lightEnergyDissipation 0.8 (:166) */
+    float eps;                     /* secondary-origin offset 1e-5 (:177) */
+    uint32_t seed_lo, seed_hi;     /* Philox key; the reference's srand(0) (:263) has no equivalent */
+} rt_params;
+
+typedef struct {
+    uint64_t paths;                /* primary rays started since rt_reset_accumulation */
+    uint64_t segments;             /* closest-hit queries traced (the metric's "path*bounces") */
+    uint32_t samples;              /* samples per pixel accumulated so far (ACCUMULATIONFRAMES analogue) */
+    uint32_t n_objects;
+    float last_render_ms;          /* device time of the last rt_render_spp, CUDA events */
+    float last_resolve_ms;
+    int32_t pipeline;              /* RT_PIPELINE_* actually used by the last render */
+    int32_t accel;                 /* RT_ACCEL_* actually used */
+    int32_t sm_count;
+    int32_t reserved;
+} rt_stats;
+
+/* Tuning knobs that have no counterpart in the reference (they never change results). */
+enum {
+    RT_OPT_PIPELINE = 1,           /* RT_PIPELINE_* */
+    RT_OPT_ACCEL = 2,              /* RT_ACCEL_* */
+    RT_OPT_BVH_THRESHOLD = 3       /* object count at which RT_ACCEL_AUTO switches to the BVH */
+};
+enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
+enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2 };
+
+/* ---- lifetime: replaces the worker spawn/join (Raytracer.cpp:331-342, 598-607) -------- */
+int rt_create(int cuda_device, rt_ctx** out);
+int rt_destroy(rt_ctx* ctx);
+const char* rt_last_error(const rt_ctx* ctx);   /* ctx may be NULL: last rt_create failure */
+int rt_abi_version(void);
+
+/* ---- scene: replaces Scene::Load/SaveAs + `ObjectsToRender = GetObjects()`
+ *      (Scene.hpp:27-104, Raytracer.cpp:291-293,418-421) ------------------------------ */
+int rt_load_scene(rt_ctx* ctx, const char* json_path);              /* returns object count (>= 0) */
+int rt_save_scene(rt_ctx* ctx, const char* json_path);              /* Scene::SaveAs */
+int rt_set_scene(rt_ctx* ctx, const rt_object* objects, int n);     /* host array -> device SoA */
+int rt_get_scene(rt_ctx* ctx, rt_object* out, int max_objects);     /* returns count */
+
+/* Host-only helpers over the same reader/writer (no device, no context): parse a scene file
+ * into a caller array / write one with dump(4) formatting. *n_total receives the number of
+ * objects parsed (also on RT_ERR_PARSE: the partial-load count). names may be NULL. */
+int rt_scene_file_read(const char* json_path, rt_object* out, int max_objects, int* n_total,
+                       char* err_buf, int err_buf_len);
+int rt_scene_file_write(const char* json_path, const char* scene_name, const rt_object* objects,
+                        const char* const* names, int n);
+/* Object / scene names travel with the scene (Object::name, Scene::sceneName). */
+const char* rt_object_name(rt_ctx* ctx, int index);
+int rt_set_object_name(rt_ctx* ctx, int index, const char* name);
+const char* rt_scene_name(rt_ctx* ctx);
+
+/* ---- camera and parameters ----------------------------------------------------------- */
+void rt_default_params(rt_params* p);                               /* Raytracer.cpp:26-35,55-59 */
+void rt_default_camera(rt_camera* c);                               /* Raytracer.cpp:295-297 */
+void rt_rotate_camera(rt_camera* c, float angle, const float axis[3]);  /* Transform::RotateAboutAxis, Common.hpp:287-291 */
+int rt_set_camera(rt_ctx* ctx, const rt_camera* cam);
+int rt_set_params(rt_ctx* ctx, const rt_params* p);
+int rt_set_option(rt_ctx* ctx, int option, int value);
+
+/* Multi-GPU sharding by samples-per-pixel: rank r of `world` renders its slice of the global
+ * sample indices of every rt_render_spp call, so the reduced image does not depend on the
+ * GPU count (up to float summation order). Default (0, 1). */
+int rt_set_shard(rt_ctx* ctx, int rank, int world);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* `setFrame = true; ACCUMULATIONFRAMES = 1` (Raytracer.cpp:576-581). */
+int rt_reset_accumulation(rt_ctx* ctx);
+
+/* Adds `spp` samples per pixel (global count; this rank traces its shard) to the device float4
+ * SUM buffer and advances the sample counter: renderArea frames (Raytracer.cpp:231-252) +
+ * RaytraceScene (:141-213) + the accumulate half of SetScreenPixel (:65-71). The reference
+ * keeps a running mean; sum/count is the same value up to rounding. Asynchronous
+ * on the context's stream. */
+int rt_render_spp(rt_ctx* ctx, int spp);
+
+/* Reinhard c/(1+c), truncating 8-bit pack to 0xAARRGGBB (alpha 0), optional row flip to y-down:
+ * the resolve half of SetScreenPixel (Raytracer.cpp:73-75, Common.hpp:189-206).
+ * host_out: height rows of pitch_bytes. Synchronises. */
+int rt_resolve_rgba8(rt_ctx* ctx, uint32_t* host_out, int pitch_bytes, int flip_y);
+
+/* Mouse picking: GetClosestObject(camera.position, GetRayDirection(camera, x, H - y))
+ * (Raytracer.cpp:530-541). x, y in window space (y-down). id = -1 on miss. */
+int rt_pick(rt_ctx* ctx, int x, int y_window, int* id);
+
+/* ---- test / inspection hooks ----------------------------------------------------------- */
+/* Accumulated SUM image, width*height float4 (r,g,b,0), y-up; *samples = sample count. */
+int rt_read_accum(rt_ctx* ctx, float* host_rgba, uint32_t* samples);
+/* Checkpoint/resume of a long accumulation: upload a SUM image holding `samples` samples. */
+int rt_write_accum(rt_ctx* ctx, const float* host_rgba, uint32_t samples);
+/* Primary visibility AOVs (any pointer may be NULL): id int32 (-1 miss), t, normal[3], point[3]. */
+int rt_read_aov(rt_ctx* ctx, int32_t* id, float* t, float* normal, float* point);
+/* GetRayDirection for every pixel (Raytracer.cpp:106-122): width*height*3 floats. */
+int rt_read_ray_dirs(rt_ctx* ctx, float* dirs);
+/* GetClosestObject on arbitrary rays (Raytracer.cpp:123-140). */
+int rt_trace_rays(rt_ctx* ctx, const float* origins, const float* dirs, int n,
+                  int32_t* id, float* t, float* normal, float* point);
+/* GetEnvironmentColor (Raytracer.cpp:77-89). */
+int rt_env_color(rt_ctx* ctx, const float* dirs, int n, float* rgb);
+/* Philox4x32-10 block as the device computes it (known-answer tests). */
+int rt_philox_block(rt_ctx* ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+int rt_get_stats(rt_ctx* ctx, rt_stats* out);
+
+/* ---- device-side interop (multi-GPU reduce, benchmarks) -------------------------------- */
+void* rt_accum_device_ptr(rt_ctx* ctx);          /* float4[width*height] sum buffer, device memory */
+int rt_set_stream(rt_ctx* ctx, void* cuda_stream);   /* cudaStream_t to launch on (default: own stream) */
+int rt_sync(rt_ctx* ctx);
+/* Tells the context that the accumulation buffer now holds `samples` samples per pixel
+ * (after an external reduce added other ranks' sums). */
+int rt_set_sample_count(rt_ctx* ctx, uint32_t samples);
+/* Resolve any device float4 sum buffer (n_pixels of it, starting at first_pixel of the image)
+ * into a device ARGB8 buffer - the per-rank slice step of reduce-scatter + resolve + gather. */
+int rt_resolve_device(rt_ctx* ctx, const void* dev_accum_rgba, uint32_t samples,
+                      int first_pixel, int n_pixels, void* dev_out_argb, int flip_y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

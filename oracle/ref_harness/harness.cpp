@@ -49,12 +49,13 @@ SDL_Surface g_surface;
 SDL_PixelFormat g_format;
 bool g_sun_normalized = false;
 std::atomic<long long> g_segment_calls{0};
+thread_local long long t_segment_calls = 0;    // per-thread, folded into the global when a worker exits
 
 // a never-hit Object appended last; calls / 1 = closest-hit queries.
 class CountingObject : public Object {
 public:
     Rayhit Raytrace(const float3&, const float3&) const override {
-        g_segment_calls.fetch_add(1, std::memory_order_relaxed);
+        ++t_segment_calls;                     // no shared atomic on the hot path: do not slow the baseline
         return Rayhit();
     }
 };
@@ -267,15 +268,17 @@ void ref_count_segments(int enable) {
         ObjectsToRender.pop_back();
         delete g_counter; g_counter = nullptr;
     }
-    g_segment_calls = 0;
+    g_segment_calls = 0; t_segment_calls = 0;
 }
-long long ref_segments() { return g_segment_calls.load(); }
+long long ref_segments() { long long v = g_segment_calls.load() + t_segment_calls; return v; }
 
 // The reference's own frame loop: THREADS persistent workers over column strips
 // (Raytracer.cpp:330-342), released and gated per frame the way main() does (:374-384,
 // :572-595). rng_mode 0 = per-thread MSVC LCG (what the shipped Windows binary does),
 // 2 = glibc's global locked rand(). first frame overwrites (setFrame), the rest accumulate.
 // Returns wall seconds over the frame loop only.
+static uint32_t g_thread_seed = 1u;   // MSVC: every new thread's rand() state starts at 1
+void ref_set_thread_seed(uint32_t s) { g_thread_seed = s; }
 double ref_render_frames(int frames, int rng_mode, int start_frame) {
     ref_rng_mode(rng_mode);
     suspendAllThreads = false;
@@ -290,8 +293,10 @@ double ref_render_frames(int frames, int rng_mode, int start_frame) {
         if (initialX > SCREEN_WIDTH) initialX = SCREEN_WIDTH;
         workers[i] = new std::thread([=]() {
             ref_rng_mode(rng_mode);
-            ref_rng_seed_lcg(1u);                          // MSVC: every new thread starts at seed 1
+            ref_rng_seed_lcg(g_thread_seed == 1u ? 1u : g_thread_seed + 7919u * (uint32_t)i);
+            t_segment_calls = 0;
             renderArea(i, initialX, nextX, 0, SCREEN_HEIGHT, &g_camera);
+            g_segment_calls.fetch_add(t_segment_calls, std::memory_order_relaxed);
         });
     }
     auto t0 = std::chrono::steady_clock::now();

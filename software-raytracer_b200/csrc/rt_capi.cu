@@ -1,0 +1,630 @@
+// rt_capi.cu - the C-ABI (include/rt_b200.h) over the CUDA kernels: context, scene upload as
+// SoA, camera/parameter state, launch orchestration, accumulation bookkeeping.
+//
+// No CPU fallback lives here: every compute entry point launches kernels or fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rt_device.cuh"
+#include "rt_kernels.h"
+#include "scene_json.h"
+
+using namespace rtb;
+
+struct rt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    HostScene scene;
+    rt_camera cam;
+    rt_params par;
+    FrameView frame;
+    SceneView view;
+    bool frame_dirty = true;
+
+    // device scene
+    float4* d_sph = nullptr; int* d_sph_id = nullptr;
+    float4* d_box = nullptr; int* d_box_id = nullptr;
+    float4* d_mat = nullptr;
+    size_t cap_sph = 0, cap_sph_id = 0, cap_box = 0, cap_box_id = 0, cap_mat = 0;
+
+    // frame buffers
+    float4* d_accum = nullptr;
+    uint32_t* d_argb = nullptr;
+    size_t cap_pixels = 0;
+    unsigned long long* d_counters = nullptr;     // [0] segments
+    uint32_t* d_scratch = nullptr;                // small device scratch (philox / pick)
+
+    // accumulation state
+    uint32_t samples = 0;          // samples per pixel in the buffer (global, after any external reduce)
+    uint32_t next_sample = 0;      // next global sample index
+    uint64_t paths = 0;
+    int rank = 0, world = 1;
+    int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
+    int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;
+    float last_render_ms = 0.f, last_resolve_ms = 0.f;
+    bool render_timed = false, resolve_timed = false;
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+int fail(rt_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(rt_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, RT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define RT_CUDA(ctx, call)                                              \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);      \
+    } while (0)
+
+template <typename T>
+cudaError_t ensure_capacity(T*& ptr, size_t& cap, size_t need) {
+    if (need <= cap && ptr) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    size_t n = need < 16 ? 16 : need;
+    cudaError_t e = cudaMalloc((void**)&ptr, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+}
+
+inline float3 h3(const float* v) { return make_float3(v[0], v[1], v[2]); }
+
+// Host half of GetRayDirection (Raytracer.cpp:107-117): everything that does not depend on the
+// pixel, in the reference's expression order, so device code never calls tanf.
+void build_frame(rt_ctx* c) {
+    const rt_params& p = c->par;
+    const rt_camera& cam = c->cam;
+    FrameView& f = c->frame;
+    const float clip = .01f;
+    float aspect = (float)p.width / (float)p.height;
+    float hFov = cam.fov_deg * M_PI / 180.0f;
+    float rd = (clip * tanf(hFov / 2.0f)) * aspect;
+    float ld = (clip * tanf(hFov / 2.0f));
+    f.cam_pos = h3(cam.pos);
+    f.u_axis = make_float3(cam.right[0] * rd, cam.right[1] * rd, cam.right[2] * rd);
+    f.v_axis = make_float3(cam.up[0] * ld, cam.up[1] * ld, cam.up[2] * ld);
+    f.fwd = make_float3(cam.forward[0] * clip, cam.forward[1] * clip, cam.forward[2] * clip);
+    f.sun_neg = make_float3(p.sun_dir[0] * -1, p.sun_dir[1] * -1, p.sun_dir[2] * -1);
+    float thr = (float)0.99;                                  // (double)dot > 0.99  <=>  dot >= thr
+    if (!((double)thr > 0.99)) thr = nextafterf(thr, INFINITY);
+    f.sun_thr = thr;
+    auto clamp0 = [](float v) { return v < 0 ? 0.f : v; };
+    f.sky = h3(p.sky); f.horizon = h3(p.horizon); f.ground = h3(p.ground); f.sun = h3(p.sun);
+    f.sky10 = make_float3(clamp0(p.sky[0] * 0.1f), clamp0(p.sky[1] * 0.1f), clamp0(p.sky[2] * 0.1f));
+    f.dissipation = p.dissipation; f.eps = p.eps;
+    f.width = p.width; f.height = p.height; f.max_bounces = p.max_bounces; f.mode = p.mode; f.selected_id = p.selected_id;
+    f.seed_lo = p.seed_lo; f.seed_hi = p.seed_hi;
+    c->frame_dirty = false;
+}
+
+int ensure_buffers(rt_ctx* c) {
+    size_t px = (size_t)c->par.width * c->par.height;
+    if (px > c->cap_pixels || !c->d_accum) {
+        if (c->d_accum) cudaFree(c->d_accum);
+        if (c->d_argb) cudaFree(c->d_argb);
+        c->d_accum = nullptr; c->d_argb = nullptr; c->cap_pixels = 0;
+        RT_CUDA(c, cudaMalloc((void**)&c->d_accum, px * sizeof(float4)));
+        RT_CUDA(c, cudaMalloc((void**)&c->d_argb, px * sizeof(uint32_t)));
+        c->cap_pixels = px;
+        RT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, px * sizeof(float4), c->stream));
+        c->samples = 0; c->next_sample = 0; c->paths = 0;
+    }
+    return RT_OK;
+}
+
+int upload_scene(rt_ctx* c) {
+    const std::vector<rt_object>& objs = c->scene.objects;
+    std::vector<float4> sph, box, mat;
+    std::vector<int> sph_id, box_id;
+    mat.reserve(objs.size() * 3);
+    for (size_t i = 0; i < objs.size(); ++i) {
+        const rt_object& o = objs[i];
+        if (o.type == RT_OBJ_SPHERE) {
+            sph.push_back(make_float4(o.pos[0], o.pos[1], o.pos[2], o.radius * o.radius));   // squaredRadius Object.hpp:122
+            sph_id.push_back((int)i);
+        } else if (o.type == RT_OBJ_CUBE) {
+            box.push_back(make_float4(o.pos[0], o.pos[1], o.pos[2], 0.f));
+            box.push_back(make_float4(o.half[0], o.half[1], o.half[2], 0.f));
+            box_id.push_back((int)i);
+        }
+        mat.push_back(make_float4(o.base[0], o.base[1], o.base[2], o.smoothness));
+        mat.push_back(make_float4(o.emissive[0], o.emissive[1], o.emissive[2], o.spec_amount));
+        mat.push_back(make_float4(o.spec_color[0], o.spec_color[1], o.spec_color[2], 0.f));
+    }
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));             // nothing in flight may still read the old arrays
+    RT_CUDA(c, ensure_capacity(c->d_sph, c->cap_sph, sph.size()));
+    RT_CUDA(c, ensure_capacity(c->d_sph_id, c->cap_sph_id, sph_id.size()));
+    RT_CUDA(c, ensure_capacity(c->d_box, c->cap_box, box.size()));
+    RT_CUDA(c, ensure_capacity(c->d_box_id, c->cap_box_id, box_id.size()));
+    RT_CUDA(c, ensure_capacity(c->d_mat, c->cap_mat, mat.size()));
+    if (!sph.empty()) {
+        RT_CUDA(c, cudaMemcpyAsync(c->d_sph, sph.data(), sph.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(c, cudaMemcpyAsync(c->d_sph_id, sph_id.data(), sph_id.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (!box.empty()) {
+        RT_CUDA(c, cudaMemcpyAsync(c->d_box, box.data(), box.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(c, cudaMemcpyAsync(c->d_box_id, box_id.data(), box_id.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (!mat.empty())
+        RT_CUDA(c, cudaMemcpyAsync(c->d_mat, mat.data(), mat.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));             // host vectors die at return
+    c->view.sph = c->d_sph; c->view.sph_id = c->d_sph_id;
+    c->view.box = c->d_box; c->view.box_id = c->d_box_id;
+    c->view.mat = c->d_mat;
+    c->view.n_sph = (int)sph_id.size(); c->view.n_box = (int)box_id.size(); c->view.n_obj = (int)objs.size();
+    return RT_OK;
+}
+
+int prepare(rt_ctx* c) {
+    if (!c) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    if (c->frame_dirty) build_frame(c);
+    return ensure_buffers(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void rt_default_params(rt_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->width = 1280; p->height = 720;                          // Raytracer.cpp:26-27
+    p->max_bounces = 2;                                        // :32
+    p->mode = RT_MODE_PREVIEW;                                 // SIMPLEDRAW = true :35
+    p->selected_id = -1;                                       // selectedObject = NULL :53
+    // SunDirection = float3(1,-1,-1).Normalized() (:55,:264): three divisions by sqrtf(3)
+    float len = sqrtf(1.f * 1.f + -1.f * -1.f + -1.f * -1.f);
+    p->sun_dir[0] = 1.f / len; p->sun_dir[1] = -1.f / len; p->sun_dir[2] = -1.f / len;
+    const float sky[3] = {(float).2, (float).35, 1.0f}, hor[3] = {(float)1.0, 0.9f, 0.5f};
+    for (int i = 0; i < 3; ++i) { p->sky[i] = sky[i] * 10.0f; p->horizon[i] = hor[i] * 5.0f; }   // :56-57
+    p->ground[0] = .08f; p->ground[1] = .06f; p->ground[2] = .03f;                                // :58
+    p->sun[0] = p->sun[1] = p->sun[2] = 500.f;                                                    // :59
+    p->dissipation = 0.8f;                                     // :166
+    p->eps = .00001f;                                          // :177
+    p->seed_lo = 0; p->seed_hi = 0;
+}
+
+void rt_default_camera(rt_camera* c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->right[0] = 1.f; c->up[1] = 1.f; c->forward[2] = 1.f;    // Transform defaults Common.hpp:282-285
+    c->fov_deg = 55;                                           // Raytracer.cpp:31
+}
+
+// Transform::RotateAboutAxis (Common.hpp:287-291): Rodrigues per basis vector, in the
+// reference's expression order (host libm cosf/sinf, like the reference).
+void rt_rotate_camera(rt_camera* c, float angle, const float axis[3]) {
+    if (!c || !axis) return;
+    auto rot = [&](float* b) {
+        float ax = axis[0], ay = axis[1], az = axis[2];
+        float cx = ay * b[2] - b[1] * az, cy = b[0] * az - ax * b[2], cz = ax * b[1] - b[0] * ay;   // Cross(axis, b) Common.hpp:94-96
+        float dt = ax * b[0] + ay * b[1] + az * b[2];
+        float co = cosf(angle), si = sinf(angle);
+        float r0 = (b[0] * co + cx * si) + (ax * dt) * (1 - co);
+        float r1 = (b[1] * co + cy * si) + (ay * dt) * (1 - co);
+        float r2 = (b[2] * co + cz * si) + (az * dt) * (1 - co);
+        b[0] = r0; b[1] = r1; b[2] = r2;
+    };
+    rot(c->forward); rot(c->up); rot(c->right);
+}
+
+int rt_create(int cuda_device, rt_ctx** out) {
+    if (!out) return fail(nullptr, RT_ERR_INVALID, "rt_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RT_ERR_CUDA, std::string("rt_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    if (cuda_device < 0 || cuda_device >= count) return fail(nullptr, RT_ERR_INVALID, "rt_create: device index out of range");
+    if ((e = cudaSetDevice(cuda_device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cuda_device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "rt_create: device %d is sm_%d%d; this library carries sm_100a code only", cuda_device, prop.major, prop.minor);
+        return fail(nullptr, RT_ERR_CUDA, buf);
+    }
+    rt_ctx* c = new (std::nothrow) rt_ctx();
+    if (!c) return fail(nullptr, RT_ERR_NOMEM, "rt_create: out of host memory");
+    c->device = cuda_device;
+    c->sm_count = prop.multiProcessorCount;
+    rt_default_params(&c->par);
+    rt_default_camera(&c->cam);
+    memset(&c->view, 0, sizeof c->view);
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&c->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&c->d_scratch, 4096)) != cudaSuccess ||
+        (e = cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long))) != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "rt_create");
+        rt_destroy(c);
+        return rc;
+    }
+    c->stream = c->own_stream;
+    // an empty scene is valid (everything is sky), like a failed Scene::Load in the reference
+    int rc = upload_scene(c);
+    if (rc != RT_OK) { g_create_error = c->err; rt_destroy(c); return rc; }
+    *out = c;
+    return RT_OK;
+}
+
+int rt_destroy(rt_ctx* c) {
+    if (!c) return RT_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
+    cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return RT_OK;
+}
+
+int rt_load_scene(rt_ctx* c, const char* json_path) {
+    if (!c || !json_path) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    std::string err;
+    int rc = c->scene.Load(json_path, err);
+    int up = upload_scene(c);                                  // also after a partial load, like the reference
+    rt_reset_accumulation(c);
+    if (rc != RT_OK) return fail(c, rc, err);
+    if (up != RT_OK) return up;
+    return (int)c->scene.objects.size();
+}
+
+int rt_save_scene(rt_ctx* c, const char* json_path) {
+    if (!c || !json_path) return RT_ERR_INVALID;
+    std::string err;
+    int rc = c->scene.SaveAs(json_path, err);
+    return rc == RT_OK ? RT_OK : fail(c, rc, err);
+}
+
+int rt_set_scene(rt_ctx* c, const rt_object* objects, int n) {
+    if (!c || n < 0 || (n > 0 && !objects)) return fail(c, RT_ERR_INVALID, "rt_set_scene: bad arguments");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    c->scene.objects.assign(objects, objects + n);
+    c->scene.names.resize((size_t)n);
+    for (rt_object& o : c->scene.objects) {                    // Color ctor clamp (Common.hpp:253-262)
+        for (int k = 0; k < 3; ++k) {
+            if (o.base[k] < 0) o.base[k] = 0;
+            if (o.emissive[k] < 0) o.emissive[k] = 0;
+            if (o.spec_color[k] < 0) o.spec_color[k] = 0;
+        }
+    }
+    int rc = upload_scene(c);
+    if (rc != RT_OK) return rc;
+    return rt_reset_accumulation(c);
+}
+
+int rt_get_scene(rt_ctx* c, rt_object* out, int max_objects) {
+    if (!c) return RT_ERR_INVALID;
+    int n = (int)c->scene.objects.size();
+    if (out) for (int i = 0; i < n && i < max_objects; ++i) out[i] = c->scene.objects[(size_t)i];
+    return n;
+}
+
+int rt_scene_file_read(const char* json_path, rt_object* out, int max_objects, int* n_total, char* err_buf, int err_buf_len) {
+    if (!json_path) return RT_ERR_INVALID;
+    HostScene sc;
+    std::string err;
+    int rc = sc.Load(json_path, err);
+    if (n_total) *n_total = (int)sc.objects.size();
+    if (out) for (int i = 0; i < (int)sc.objects.size() && i < max_objects; ++i) out[i] = sc.objects[(size_t)i];
+    if (err_buf && err_buf_len > 0) { strncpy(err_buf, err.c_str(), (size_t)err_buf_len - 1); err_buf[err_buf_len - 1] = 0; }
+    return rc;
+}
+
+int rt_scene_file_write(const char* json_path, const char* scene_name, const rt_object* objects, const char* const* names, int n) {
+    if (!json_path || n < 0 || (n > 0 && !objects)) return RT_ERR_INVALID;
+    HostScene sc;
+    sc.scene_name = scene_name ? scene_name : "";
+    for (int i = 0; i < n; ++i) sc.AddObject(objects[i], names && names[i] ? names[i] : "");
+    std::string err;
+    return sc.SaveAs(json_path, err);
+}
+
+const char* rt_object_name(rt_ctx* c, int index) {
+    if (!c || index < 0 || (size_t)index >= c->scene.names.size()) return nullptr;
+    return c->scene.names[(size_t)index].c_str();
+}
+int rt_set_object_name(rt_ctx* c, int index, const char* name) {
+    if (!c || !name || index < 0 || (size_t)index >= c->scene.names.size()) return RT_ERR_INVALID;
+    c->scene.names[(size_t)index] = name;
+    return RT_OK;
+}
+const char* rt_scene_name(rt_ctx* c) { return c ? c->scene.scene_name.c_str() : nullptr; }
+
+int rt_set_camera(rt_ctx* c, const rt_camera* cam) {
+    if (!c || !cam) return RT_ERR_INVALID;
+    c->cam = *cam;
+    c->frame_dirty = true;
+    return RT_OK;
+}
+
+int rt_set_params(rt_ctx* c, const rt_params* p) {
+    if (!c || !p) return RT_ERR_INVALID;
+    if (p->width <= 0 || p->height <= 0 || (long long)p->width * p->height > (1ll << 28))
+        return fail(c, RT_ERR_INVALID, "rt_set_params: bad resolution");
+    if (p->mode != RT_MODE_PATH && p->mode != RT_MODE_PREVIEW) return fail(c, RT_ERR_INVALID, "rt_set_params: bad mode");
+    bool resized = p->width != c->par.width || p->height != c->par.height;
+    c->par = *p;
+    if (c->par.max_bounces < 0) c->par.max_bounces = 0;        // MAXBOUNCES = max(MAXBOUNCES, 0) Raytracer.cpp:475
+    c->frame_dirty = true;
+    if (resized) {
+        RT_CUDA(c, cudaSetDevice(c->device));
+        RT_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->d_accum) { cudaFree(c->d_accum); c->d_accum = nullptr; }
+        if (c->d_argb) { cudaFree(c->d_argb); c->d_argb = nullptr; }
+        c->cap_pixels = 0;
+    }
+    return RT_OK;
+}
+
+int rt_set_option(rt_ctx* c, int option, int value) {
+    if (!c) return RT_ERR_INVALID;
+    switch (option) {
+        case RT_OPT_PIPELINE: c->opt_pipeline = value; return RT_OK;
+        case RT_OPT_ACCEL: c->opt_accel = value; return RT_OK;
+        case RT_OPT_BVH_THRESHOLD: c->opt_bvh_threshold = value; return RT_OK;
+    }
+    return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
+}
+
+int rt_set_shard(rt_ctx* c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return fail(c, RT_ERR_INVALID, "rt_set_shard: bad rank/world");
+    c->rank = rank; c->world = world;
+    return RT_OK;
+}
+
+int rt_reset_accumulation(rt_ctx* c) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    RT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)c->par.width * c->par.height * sizeof(float4), c->stream));
+    RT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    c->samples = 0; c->next_sample = 0; c->paths = 0;
+    return RT_OK;
+}
+
+int rt_render_spp(rt_ctx* c, int spp) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (spp < 0) return fail(c, RT_ERR_INVALID, "rt_render_spp: negative spp");
+    if (spp == 0) return RT_OK;
+    const size_t px = (size_t)c->par.width * c->par.height;
+    RT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    if (c->par.mode == RT_MODE_PREVIEW) {
+        // SIMPLEDRAW: ACCUMULATIONFRAMES stays 1, every frame overwrites (Raytracer.cpp:66-67,589)
+        RT_CUDA(c, launch_render_preview(c->view, c->frame, c->d_accum, c->d_counters, c->stream));
+        c->samples = 1; c->next_sample = 0; c->paths += px;
+    } else {
+        // this rank's slice of the global sample indices [next, next+spp)
+        const int base = spp / c->world, rem = spp % c->world;
+        const int mine = base + (c->rank < rem ? 1 : 0);
+        const uint32_t first = c->next_sample + (uint32_t)(c->rank * base + (c->rank < rem ? c->rank : rem));
+        RT_CUDA(c, launch_render_regen(c->view, c->frame, c->d_accum, first, mine, c->d_counters, c->stream));
+        c->used_pipeline = RT_PIPELINE_REGEN; c->used_accel = RT_ACCEL_BRUTE;
+        c->next_sample += (uint32_t)spp;
+        c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce
+        c->paths += (uint64_t)mine * px;
+    }
+    RT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->render_timed = true;
+    return RT_OK;
+}
+
+int rt_resolve_device(rt_ctx* c, const void* dev_accum, uint32_t samples, int first_pixel, int n_pixels, void* dev_out, int flip_y) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (!dev_accum || !dev_out || first_pixel < 0 || n_pixels < 0 ||
+        (long long)first_pixel + n_pixels > (long long)c->par.width * c->par.height)
+        return fail(c, RT_ERR_INVALID, "rt_resolve_device: bad arguments");
+    RT_CUDA(c, launch_resolve((const float4*)dev_accum, samples, c->par.width, c->par.height, first_pixel, n_pixels, flip_y,
+                              (uint32_t*)dev_out, 1, c->stream));
+    return RT_OK;
+}
+
+int rt_resolve_rgba8(rt_ctx* c, uint32_t* host_out, int pitch_bytes, int flip_y) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    const int w = c->par.width, h = c->par.height;
+    if (!host_out || pitch_bytes < w * 4) return fail(c, RT_ERR_INVALID, "rt_resolve_rgba8: bad output buffer");
+    cudaEvent_t r0, r1;
+    RT_CUDA(c, cudaEventCreate(&r0)); RT_CUDA(c, cudaEventCreate(&r1));
+    cudaEventRecord(r0, c->stream);
+    cudaError_t e = launch_resolve(c->d_accum, c->samples, w, h, 0, w * h, flip_y, c->d_argb, 0, c->stream);
+    cudaEventRecord(r1, c->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(host_out, (size_t)pitch_bytes, c->d_argb, (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) cudaEventElapsedTime(&c->last_resolve_ms, r0, r1);
+    cudaEventDestroy(r0); cudaEventDestroy(r1);
+    if (e != cudaSuccess) return cuda_fail(c, e, "rt_resolve_rgba8");
+    return RT_OK;
+}
+
+int rt_read_accum(rt_ctx* c, float* host_rgba, uint32_t* samples) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (host_rgba)
+        RT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_accum, (size_t)c->par.width * c->par.height * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (samples) *samples = c->samples;
+    return RT_OK;
+}
+
+int rt_write_accum(rt_ctx* c, const float* host_rgba, uint32_t samples) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (!host_rgba) return fail(c, RT_ERR_INVALID, "rt_write_accum: NULL input");
+    RT_CUDA(c, cudaMemcpyAsync(c->d_accum, host_rgba, (size_t)c->par.width * c->par.height * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->samples = samples; c->next_sample = samples;
+    return RT_OK;
+}
+
+int rt_read_aov(rt_ctx* c, int32_t* id, float* t, float* normal, float* point) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    const size_t px = (size_t)c->par.width * c->par.height;
+    int* d_id = nullptr; float *d_t = nullptr, *d_n = nullptr, *d_p = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (id) e = cudaMalloc((void**)&d_id, px * 4);
+    if (e == cudaSuccess && t) e = cudaMalloc((void**)&d_t, px * 4);
+    if (e == cudaSuccess && normal) e = cudaMalloc((void**)&d_n, px * 12);
+    if (e == cudaSuccess && point) e = cudaMalloc((void**)&d_p, px * 12);
+    if (e == cudaSuccess) e = launch_primary_aov(c->view, c->frame, d_id, d_t, d_n, d_p, c->stream);
+    if (e == cudaSuccess && id) e = cudaMemcpyAsync(id, d_id, px * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, d_t, px * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && normal) e = cudaMemcpyAsync(normal, d_n, px * 12, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && point) e = cudaMemcpyAsync(point, d_p, px * 12, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_id); cudaFree(d_t); cudaFree(d_n); cudaFree(d_p);
+    if (e != cudaSuccess) return cuda_fail(c, e, "rt_read_aov");
+    return RT_OK;
+}
+
+int rt_read_ray_dirs(rt_ctx* c, float* dirs) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (!dirs) return fail(c, RT_ERR_INVALID, "rt_read_ray_dirs: NULL output");
+    const size_t px = (size_t)c->par.width * c->par.height;
+    float* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, px * 12);
+    if (e == cudaSuccess) e = launch_ray_dirs(c->frame, d, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dirs, d, px * 12, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(c, e, "rt_read_ray_dirs");
+    return RT_OK;
+}
+
+int rt_trace_rays(rt_ctx* c, const float* origins, const float* dirs, int n, int32_t* id, float* t, float* normal, float* point) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (n < 0 || (n > 0 && (!origins || !dirs || !id || !t || !normal || !point)))
+        return fail(c, RT_ERR_INVALID, "rt_trace_rays: bad arguments");
+    if (n == 0) return RT_OK;
+    const size_t N = (size_t)n;
+    float* buf = nullptr;                                      // org3 dir3 n3 p3 t1 id1 = 14 words per ray
+    cudaError_t e = cudaMalloc((void**)&buf, N * 14 * 4);
+    float *d_o = buf, *d_d = buf + 3 * N, *d_n = buf + 6 * N, *d_p = buf + 9 * N, *d_t = buf + 12 * N;
+    int* d_id = (int*)(buf + 13 * N);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, origins, N * 12, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, N * 12, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_trace_rays(c->view, d_o, d_d, n, d_id, d_t, d_n, d_p, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(id, d_id, N * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t, d_t, N * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(normal, d_n, N * 12, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(point, d_p, N * 12, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(buf);
+    if (e != cudaSuccess) return cuda_fail(c, e, "rt_trace_rays");
+    return RT_OK;
+}
+
+int rt_pick(rt_ctx* c, int x, int y_window, int* id) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (!id) return fail(c, RT_ERR_INVALID, "rt_pick: NULL id");
+    // y = SCREEN_HEIGHT - y (Raytracer.cpp:532); no bounds check, like the reference: the ray
+    // through any (x, y) is well defined. One-thread launch through the same device raygen
+    // and closest-hit code as the render path.
+    const int y = c->par.height - y_window;
+    int* d_id = (int*)c->d_scratch;
+    RT_CUDA(c, launch_pick(c->view, c->frame, x, y, d_id, c->stream));
+    RT_CUDA(c, cudaMemcpyAsync(id, d_id, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+int rt_env_color(rt_ctx* c, const float* dirs, int n, float* rgb) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (n < 0 || (n > 0 && (!dirs || !rgb))) return fail(c, RT_ERR_INVALID, "rt_env_color: bad arguments");
+    if (n == 0) return RT_OK;
+    float* buf = nullptr;
+    const size_t N = (size_t)n;
+    cudaError_t e = cudaMalloc((void**)&buf, N * 24);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(buf, dirs, N * 12, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_env_color(c->frame, buf, n, buf + 3 * N, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb, buf + 3 * N, N * 12, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(buf);
+    if (e != cudaSuccess) return cuda_fail(c, e, "rt_env_color");
+    return RT_OK;
+}
+
+int rt_philox_block(rt_ctx* c, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    if (!c || !ctr || !key || !out) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, launch_philox(ctr, key, c->d_scratch, c->stream));
+    RT_CUDA(c, cudaMemcpyAsync(out, c->d_scratch, 16, cudaMemcpyDeviceToHost, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+int rt_get_stats(rt_ctx* c, rt_stats* out) {
+    if (!c || !out) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    RT_CUDA(c, cudaMemcpy(counters, c->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
+    if (c->render_timed) { cudaEventElapsedTime(&c->last_render_ms, c->ev0, c->ev1); }
+    memset(out, 0, sizeof *out);
+    out->paths = c->paths; out->segments = counters[0];
+    out->samples = c->samples; out->n_objects = (uint32_t)c->scene.objects.size();
+    out->last_render_ms = c->last_render_ms; out->last_resolve_ms = c->last_resolve_ms;
+    out->pipeline = c->used_pipeline; out->accel = c->used_accel; out->sm_count = c->sm_count;
+    return RT_OK;
+}
+
+void* rt_accum_device_ptr(rt_ctx* c) {
+    if (!c || prepare(c) != RT_OK) return nullptr;
+    return c->d_accum;
+}
+
+int rt_set_stream(rt_ctx* c, void* cuda_stream) {
+    if (!c) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return RT_OK;
+}
+
+int rt_sync(rt_ctx* c) {
+    if (!c) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+int rt_set_sample_count(rt_ctx* c, uint32_t samples) {
+    if (!c) return RT_ERR_INVALID;
+    c->samples = samples;
+    return RT_OK;
+}
+
+}  // extern "C"

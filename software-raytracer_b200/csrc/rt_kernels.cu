@@ -1,0 +1,315 @@
+// rt_kernels.cu - hand-written CUDA kernels for sm_100a: primary visibility, the path-tracing
+// render kernel (persistent-lane megakernel with in-register sample regeneration), preview
+// shading, resolve, and the small test-hook kernels.
+//
+// Compiled with -fmad=false (see rt_device.cuh for the parity rules).
+#include "rt_kernels.h"
+
+#include "rt_device.cuh"
+
+namespace rtb {
+
+namespace {
+
+constexpr int kTileW = 16, kTileH = 8;          // CTA tile: 4 warps, each an 8x4 pixel block
+constexpr int kThreads = 128;
+
+// Copy the geometry lists into shared memory (spheres then cubes). Everything the
+// closest-hit loop touches per object is 16 B per sphere / 32 B per cube, read by all 32 lanes
+// at the same address (LDS.128 broadcast, no bank conflicts).
+__device__ __forceinline__ void stage_geometry(const SceneView& sc, float4* smem) {
+    const int n4 = sc.n_sph + 2 * sc.n_box;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        smem[i] = i < sc.n_sph ? __ldg(sc.sph + i) : __ldg(sc.box + (i - sc.n_sph));
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool tile_pixel(const FrameView& fr, int& px, int& py) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    px = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
+    py = blockIdx.y * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    return px < fr.width && py < fr.height;
+}
+
+// ---- primary visibility AOVs ----------------------------------------------------------------
+template <bool STAGED>
+__global__ void __launch_bounds__(kThreads) k_primary_aov(SceneView sc, FrameView fr, int* __restrict__ out_id,
+                                                           float* __restrict__ out_t, float* __restrict__ out_n,
+                                                           float* __restrict__ out_p) {
+    extern __shared__ float4 smem[];
+    const float4* sph = sc.sph; const float4* box = sc.box;
+    if (STAGED) { stage_geometry(sc, smem); sph = smem; box = smem + sc.n_sph; }
+    int px, py;
+    if (!tile_pixel(fr, px, py)) return;
+    const size_t p = (size_t)px + (size_t)py * fr.width;
+    Hit h = closest_hit(sc, sph, box, fr.cam_pos, ray_dir(fr, px, py));
+    if (out_id) out_id[p] = h.id;
+    if (out_t) out_t[p] = h.t;
+    if (out_n) { out_n[3 * p] = h.n.x; out_n[3 * p + 1] = h.n.y; out_n[3 * p + 2] = h.n.z; }
+    if (out_p) { out_p[3 * p] = h.p.x; out_p[3 * p + 1] = h.p.y; out_p[3 * p + 2] = h.p.z; }
+}
+
+__global__ void k_ray_dirs(FrameView fr, float* __restrict__ out) {
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+    if (px >= fr.width) return;
+    float3 d = ray_dir(fr, px, py);
+    size_t p = (size_t)px + (size_t)py * fr.width;
+    out[3 * p] = d.x; out[3 * p + 1] = d.y; out[3 * p + 2] = d.z;
+}
+
+__global__ void k_trace_rays(SceneView sc, const float* __restrict__ org, const float* __restrict__ dir, int n,
+                             int* __restrict__ out_id, float* __restrict__ out_t, float* __restrict__ out_n,
+                             float* __restrict__ out_p) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Hit h = closest_hit(sc, sc.sph, sc.box, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
+                        f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+    out_id[i] = h.id; out_t[i] = h.t;
+    out_n[3 * i] = h.n.x; out_n[3 * i + 1] = h.n.y; out_n[3 * i + 2] = h.n.z;
+    out_p[3 * i] = h.p.x; out_p[3 * i + 1] = h.p.y; out_p[3 * i + 2] = h.p.z;
+}
+
+__global__ void k_env_color(FrameView fr, const float* __restrict__ dir, int n, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 c = env_color(fr, f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+    out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+
+__global__ void k_pick(SceneView sc, FrameView fr, int px, int py, int* out_id) {
+    *out_id = closest_hit(sc, sc.sph, sc.box, fr.cam_pos, ray_dir(fr, px, py)).id;
+}
+
+__global__ void k_philox(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32_10(ctr.x, ctr.y, ctr.z, ctr.w, key.x, key.y); }
+
+// ---- the render kernel -----------------------------------------------------------------------
+// One lane owns one pixel for the whole launch and walks its samples [s_begin, s_begin+n) in
+// order. The loop is flat over path SEGMENTS: every iteration does one closest-hit query over
+// the staged object list (the ~90 % part, identical control flow for all 32 lanes) and a short
+// divergent shading tail. A lane whose path ends starts its next sample in the same iteration
+// slot ("regeneration"), so the warp stays full until a lane runs out of samples; with many
+// samples per launch the per-lane totals converge (law of large numbers) and neighbouring
+// pixels finish together. Per-pixel sums are kept in registers in sample order and added to
+// the float4 accumulation buffer once - no atomics, bit-reproducible for a given
+// (seed, sample range), independent of the launch shape.
+template <bool STAGED>
+__global__ void __launch_bounds__(kThreads) k_render_regen(SceneView sc, FrameView fr, float4* __restrict__ accum,
+                                                            uint32_t s_begin, int n_samples,
+                                                            unsigned long long* __restrict__ seg_counter) {
+    extern __shared__ float4 smem[];
+    const float4* sph = sc.sph; const float4* box = sc.box;
+    if (STAGED) { stage_geometry(sc, smem); sph = smem; box = smem + sc.n_sph; }
+    int px, py;
+    const bool inside = tile_pixel(fr, px, py);              // no early return: the warp reduce below needs every lane
+    const uint32_t pixel = inside ? (uint32_t)px + (uint32_t)py * (uint32_t)fr.width : 0u;
+    if (!inside) n_samples = 0;
+
+    const float3 d0 = ray_dir(fr, px, py);
+    float3 acc = f3(0.f, 0.f, 0.f);
+    float3 o = fr.cam_pos, d = d0;
+    float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);     // hitColor, incomingLight (Raytracer.cpp:162-163)
+    uint32_t pending_coin = 0;                               // word3 of the block that made the current ray
+    int s = 0, depth = 0;
+    unsigned int segs = 0;
+
+    while (s < n_samples) {
+        const Hit h = closest_hit(sc, sph, box, o, d);
+        ++segs;
+        bool done;
+        float3 c;
+        if (h.id < 0) {
+            const float3 e = env_color(fr, d);
+            c = depth == 0 ? e : cadd(L, cmul(e, T));                        // :144 / :179
+            done = true;
+        } else {
+            const float4 m0 = __ldg(sc.mat + 3 * h.id), m1 = __ldg(sc.mat + 3 * h.id + 1), m2 = __ldg(sc.mat + 3 * h.id + 2);
+            const float3 base = f3(m0.x, m0.y, m0.z), emis = f3(m1.x, m1.y, m1.z), spec = f3(m2.x, m2.y, m2.z);
+            const float smooth = m0.w, amount = m1.w;
+            uint32_t coin_word;
+            if (depth == 0) coin_word = philox4x32_10(pixel, s_begin + (uint32_t)s, 0u, 0u, fr.seed_lo, fr.seed_hi).x;
+            else coin_word = pending_coin;
+            const float coin = amount >= unit_from_word(coin_word) ? 1.f : 0.f;   // :165 / :182
+            if (depth == 0) { L = emis; T = base; }                               // :162-163
+            else {
+                L = cadd(L, cmul(emis, T));                                       // :183
+                T = cmul(T, clerp(base, spec, coin));                             // :184
+            }
+            if (depth == fr.max_bounces) { c = L; done = true; }
+            else {
+                if (depth != 0) T = cscale(T, fr.dissipation);                    // :169-171
+                const float3 refl = reflect3(d, h.n);                             // :172
+                const uint4 w = philox4x32_10(pixel, s_begin + (uint32_t)s, (uint32_t)depth + 1u, 0u, fr.seed_lo, fr.seed_hi);
+                pending_coin = w.w;
+                float3 sr = hemisphere_dir(w, h.n);                               // :174
+                sr = normalized3(lerp3(sr, refl, smooth * coin));                 // :175-176
+                o = add3(h.p, scale3(h.n, fr.eps));                               // :177
+                d = sr;
+                ++depth;
+                done = false;
+            }
+        }
+        if (done) {
+            acc.x += c.x; acc.y += c.y; acc.z += c.z;
+            ++s; depth = 0; o = fr.cam_pos; d = d0;
+        }
+    }
+
+    if (inside) {
+        float4 a = accum[pixel];
+        a.x += acc.x; a.y += acc.y; a.z += acc.z;
+        accum[pixel] = a;
+    }
+
+    // segment count: warp reduce, one atomic per warp
+    unsigned int total = segs;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(0xffffffffu, total, off);
+    if ((threadIdx.x & 31) == 0 && total) atomicAdd(seg_counter, (unsigned long long)total);
+}
+
+// ---- preview mode (SIMPLEDRAW, Raytracer.cpp:147-160): one primary ray, overwrite ----------
+template <bool STAGED>
+__global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, FrameView fr, float4* __restrict__ accum,
+                                                              unsigned long long* __restrict__ seg_counter) {
+    extern __shared__ float4 smem[];
+    const float4* sph = sc.sph; const float4* box = sc.box;
+    if (STAGED) { stage_geometry(sc, smem); sph = smem; box = smem + sc.n_sph; }
+    int px, py;
+    if (!tile_pixel(fr, px, py)) return;
+    const size_t pixel = (size_t)px + (size_t)py * fr.width;
+    const float3 d = ray_dir(fr, px, py);
+    const Hit h = closest_hit(sc, sph, box, fr.cam_pos, d);
+    float3 c;
+    if (h.id < 0) c = env_color(fr, d);
+    else {
+        const float4 m0 = __ldg(sc.mat + 3 * h.id), m1 = __ldg(sc.mat + 3 * h.id + 1);
+        const float3 base = f3(m0.x, m0.y, m0.z), emis = f3(m1.x, m1.y, m1.z);
+        const float k = m1.w, sm = m0.w;
+        const float3 refl = env_color(fr, reflect3(d, h.n));                       // :148
+        float fres = 0.f;
+        if (h.id == fr.selected_id) {                                              // :153-157
+            fres = 1.f - dot3(scale3(h.n, -1.f), d);
+            fres = maxsel(fres, 0.f);
+            fres = smoothstep1(0.f, 0.5f, fres);
+        }
+        const float3 a = cadd(cadd(cscale(base, 1.f - k), cscale(cscale(refl, k), sm)), emis);
+        c = clerp(a, col(3.f, 3.f, 0.f), fres);                                    // :159
+    }
+    accum[pixel] = make_float4(c.x, c.y, c.z, 0.f);
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        atomicAdd(seg_counter, (unsigned long long)fr.width * fr.height);
+}
+
+// ---- resolve: sum/count -> Reinhard -> truncating ARGB8 pack (Raytracer.cpp:73-75) -----------
+__device__ __forceinline__ uint32_t pack_lane(float v) {
+    const float s = v * 255.f;                              // Common.hpp:190-193 (int)(c*255)
+    int i;
+    // out-of-range and NaN conversions give INT_MIN on the reference's x86 targets (cvttss2si)
+    if (!(s > -2147483904.0f && s < 2147483648.0f)) i = (int)0x80000000;
+    else i = __float2int_rz(s);
+    if (i > 255) i = 255;                                   // :195-198
+    return (uint32_t)(i & 0xff);                            // (Uint8) :200-203
+}
+__device__ __forceinline__ uint32_t resolve_pixel(float4 a, float count) {
+    float r = a.x, g = a.y, b = a.z;
+    if (count > 0.f) { r = r / count; g = g / count; b = b / count; }      // sum -> mean; count 0: already a mean
+    const float R = c0(r / c0(1.f + r)), G = c0(g / c0(1.f + g)), B = c0(b / c0(1.f + b));   // :74
+    return (pack_lane(R) << 16) | (pack_lane(G) << 8) | pack_lane(B);                        // alpha byte 0
+}
+// Generic slice resolve: pixels [first, first+n) of a width x height image; `accum` points at
+// the slice. Output row = flip ? (H-1-y) : y (Raytracer.cpp:64), tightly packed width*4 pitch,
+// `out` points at the start of the WHOLE image when whole_image_out, else at the slice.
+__global__ void k_resolve(const float4* __restrict__ accum, float count, int width, int height, int first, int n,
+                          int flip_y, uint32_t* __restrict__ out, int out_is_slice) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = first + i;
+    const int x = p % width, y = p / width;
+    const uint32_t v = resolve_pixel(accum[i], count);
+    const size_t dst = (size_t)x + (size_t)(flip_y ? height - 1 - y : y) * width;
+    out[out_is_slice ? (size_t)i : dst] = v;
+}
+
+}  // namespace
+
+// ---- launchers --------------------------------------------------------------------------------
+static inline dim3 tile_grid(int w, int h) { return dim3((w + kTileW - 1) / kTileW, (h + kTileH - 1) / kTileH); }
+
+size_t staged_bytes(const SceneView& sc) { return (size_t)(sc.n_sph + 2 * sc.n_box) * sizeof(float4); }
+
+static cudaError_t ensure_smem_optin() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_render_regen<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_render_preview<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_primary_aov<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes)) != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
+}
+
+cudaError_t launch_primary_aov(const SceneView& sc, const FrameView& fr, int* id, float* t, float* n, float* p, cudaStream_t st) {
+    cudaError_t e = ensure_smem_optin();
+    if (e != cudaSuccess) return e;
+    const size_t sb = staged_bytes(sc);
+    if (sb <= kMaxStagedBytes) k_primary_aov<true><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, fr, id, t, n, p);
+    else k_primary_aov<false><<<tile_grid(fr.width, fr.height), kThreads, 0, st>>>(sc, fr, id, t, n, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ray_dirs(const FrameView& fr, float* out, cudaStream_t st) {
+    k_ray_dirs<<<dim3((fr.width + 127) / 128, fr.height), 128, 0, st>>>(fr, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_rays(const SceneView& sc, const float* org, const float* dir, int n, int* id, float* t,
+                              float* nrm, float* pt, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_trace_rays<<<(n + 127) / 128, 128, 0, st>>>(sc, org, dir, n, id, t, nrm, pt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_env_color(const FrameView& fr, const float* dir, int n, float* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_env_color<<<(n + 127) / 128, 128, 0, st>>>(fr, dir, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t* dev_out4, cudaStream_t st) {
+    k_philox<<<1, 1, 0, st>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), (uint4*)dev_out4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pick(const SceneView& sc, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st) {
+    k_pick<<<1, 1, 0, st>>>(sc, fr, px, py, dev_id);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_regen(const SceneView& sc, const FrameView& fr, float4* accum, uint32_t s_begin, int n_samples,
+                                unsigned long long* seg_counter, cudaStream_t st) {
+    if (n_samples <= 0) return cudaSuccess;
+    cudaError_t e = ensure_smem_optin();
+    if (e != cudaSuccess) return e;
+    const size_t sb = staged_bytes(sc);
+    if (sb <= kMaxStagedBytes) k_render_regen<true><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, fr, accum, s_begin, n_samples, seg_counter);
+    else k_render_regen<false><<<tile_grid(fr.width, fr.height), kThreads, 0, st>>>(sc, fr, accum, s_begin, n_samples, seg_counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_preview(const SceneView& sc, const FrameView& fr, float4* accum, unsigned long long* seg_counter, cudaStream_t st) {
+    cudaError_t e = ensure_smem_optin();
+    if (e != cudaSuccess) return e;
+    const size_t sb = staged_bytes(sc);
+    if (sb <= kMaxStagedBytes) k_render_preview<true><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, fr, accum, seg_counter);
+    else k_render_preview<false><<<tile_grid(fr.width, fr.height), kThreads, 0, st>>>(sc, fr, accum, seg_counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int height, int first, int n, int flip_y,
+                           uint32_t* out, int out_is_slice, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(accum, (float)samples, width, height, first, n, flip_y, out, out_is_slice);
+    return cudaGetLastError();
+}
+
+}  // namespace rtb

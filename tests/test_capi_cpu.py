@@ -1,0 +1,142 @@
+"""CPU: the C-ABI library loads, exports every symbol include/rt_b200.h declares, refuses to
+run without a GPU (no fallback), and its host-only scene reader/writer matches the reference."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rtb200
+from conftest import ROOT, SCENES
+
+
+def header_functions():
+    with open(os.path.join(ROOT, "include", "rt_b200.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = rtb200.load_library()
+    names = header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(rtb200.EXPORTS) == names
+    assert lib.rt_abi_version() == 1
+
+
+def test_struct_layouts():
+    assert C.sizeof(rtb200.RtObject) == 76 and C.sizeof(rtb200.RtCamera) == 52
+    assert C.sizeof(rtb200.RtParams) == 96 and C.sizeof(rtb200.RtStats) == 48
+
+
+def test_defaults_equal_reference(oracle):
+    p, q = rtb200.default_params(), oracle.default_params()
+    assert bytes(p) == bytes(q)
+    assert bytes(rtb200.default_camera()) == bytes(oracle.default_camera())
+
+
+def test_rotate_camera_matches_reference(meta):
+    cam = rtb200.default_camera(70)
+    rtb200.rotate_camera(cam, 0.35, [0, 1, 0])
+    rtb200.rotate_camera(cam, -0.2, list(cam.right))
+    r = meta["rotated_camera_by_reference"]
+    for k in ("right", "up", "forward"):
+        assert np.array_equal(np.array(list(getattr(cam, k)), np.float32), np.array(r[k], np.float32)), k
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rtb200.RtError) as e:
+        rtb200.PathTracer(0)
+    assert e.value.code == rtb200.RT_ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def _write_json(path, objs, names=None, scene_name=""):
+    out = []
+    for i, o in enumerate(objs):
+        r = {"Type": "None"}
+        if o["type"] == 1:
+            r = {"Type": "Sphere", "Radius": float(o["radius"])}
+        elif o["type"] == 2:
+            r = {"Type": "Cube", "Size": [float(v) for v in o["half"]]}
+        out.append({"Name": names[i] if names else "", "Position": [float(v) for v in o["pos"]], "Renderer": r,
+                    "Material": {"Color": [float(v) for v in o["base"]], "Emissive": [float(v) for v in o["emissive"]],
+                                 "SpecularColor": [float(v) for v in o["spec_color"]], "Smoothness": float(o["smoothness"]),
+                                 "SpecularAmount": float(o["spec_amount"]), "Metalness": float(o["spec_amount"])}})
+    with open(path, "w") as f:
+        json.dump({"SceneName": scene_name, "SceneObjects": out}, f)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_scene_reader_and_writer(tmp_path, scenes, meta, scene):
+    src = tmp_path / "in.json"
+    names, scene_name = meta["scenes"][scene]["names"], meta["scenes"][scene]["scene_name"]
+    _write_json(src, scenes[scene], names, scene_name)
+    rc, objs, err = rtb200.scene_file_read(src)
+    assert rc == 0, err
+    assert objs.tobytes() == scenes[scene].tobytes()
+    # the writer reproduces the reference's own Scene::Save output byte for byte (dump(4))
+    dst = tmp_path / "out.json"
+    assert rtb200.scene_file_write(dst, objs, names, scene_name) == 0
+    data = dst.read_bytes()
+    assert len(data) == meta["scenes"][scene]["save_bytes"]
+    assert hashlib.sha256(data).hexdigest() == meta["scenes"][scene]["save_sha256"]
+    rc, again, _ = rtb200.scene_file_read(dst)        # load -> save -> load round trip
+    assert rc == 0 and again.tobytes() == objs.tobytes()
+
+
+def test_scene_reader_defaults_and_failures(tmp_path):
+    p = tmp_path / "s.json"
+    # Material key defaults (Scene.hpp:61-68), whole-Material default (Common.hpp:313-318), unknown type,
+    # negative colours clamped by the Color ctor, integer literals
+    p.write_text(json.dumps({"SceneName": "n", "SceneObjects": [
+        {"Name": "a", "Position": [1, 2, 3], "Renderer": {"Type": "Sphere", "Radius": 2}, "Material": {}},
+        {"Name": "b", "Position": [0, 0, 0], "Renderer": {"Type": "Cube", "Size": [1, 2, 3]}},
+        {"Name": "c", "Position": [0, 0, 0], "Renderer": {"Type": "Torus"},
+         "Material": {"Color": [-1, 0.5, 2], "Smoothness": 0.25}},
+        {"Name": "d", "Position": [0, 0, 0]}]}))
+    rc, o, err = rtb200.scene_file_read(p)
+    assert rc == 0, err
+    assert o["type"].tolist() == [1, 2, 0, 0]
+    assert o[0]["radius"] == 2 and o[0]["smoothness"] == 0.5 and o[0]["spec_amount"] == np.float32(0.1)
+    assert o[1]["spec_amount"] == 0 and o[1]["smoothness"] == 0.5 and o[1]["half"].tolist() == [1, 2, 3]
+    assert o[2]["base"].tolist() == [0, 0.5, 2] and o[2]["smoothness"] == 0.25 and o[2]["spec_amount"] == np.float32(0.1)
+    # missing file: RT_ERR_IO, empty scene (Scene.hpp:30-32)
+    rc, o, err = rtb200.scene_file_read(tmp_path / "nope.json")
+    assert rc == rtb200.RT_ERR_IO and len(o) == 0
+    # a bad entry ends the load but keeps what came before (Scene.hpp:75-77)
+    p.write_text(json.dumps({"SceneName": "", "SceneObjects": [
+        {"Name": "ok", "Position": [0, 0, 0], "Renderer": {"Type": "Sphere", "Radius": 1}},
+        {"Position": [0, 0, 0], "Renderer": {"Type": "Sphere", "Radius": 1}},
+        {"Name": "never", "Position": [0, 0, 0], "Renderer": {"Type": "Sphere", "Radius": 1}}]}))
+    rc, o, err = rtb200.scene_file_read(p)
+    assert rc == rtb200.RT_ERR_PARSE and len(o) == 1 and "Name" in err
+    p.write_text('{"SceneObjects": []}')                   # SceneName is required (Scene.hpp:35)
+    assert rtb200.scene_file_read(p)[0] == rtb200.RT_ERR_PARSE
+    p.write_text('{"SceneName": "x", "SceneObjects": [')   # malformed JSON
+    assert rtb200.scene_file_read(p)[0] == rtb200.RT_ERR_PARSE
+    p.write_text('{"SceneName": "x", "SceneObjects": []}')
+    rc, o, _ = rtb200.scene_file_read(p)
+    assert rc == 0 and len(o) == 0
+
+
+def test_writer_number_and_string_formatting(tmp_path):
+    o = np.zeros(1, rtb200.OBJECT_DTYPE)
+    o["type"] = 1; o["radius"] = 1e-7; o["pos"] = [1e20, -0.0, 123456.5]
+    o["base"] = [0.1, 1.0, 1e-5]; o["smoothness"] = 3.0
+    dst = tmp_path / "o.json"
+    rtb200.scene_file_write(dst, o, ['q"\\\n\x01é'], "name")
+    text = dst.read_text(encoding="utf-8")
+    assert '"Radius": 1.0000000116860974e-07' in text
+    assert "1.0000000200408773e+20" in text and "-0.0" in text and "123456.5" in text
+    assert "0.10000000149011612" in text and "9.999999747378752e-06" in text and '"Smoothness": 3.0' in text
+    assert '"Name": "q\\"\\\\\\n\\u0001é"' in text
+    assert json.loads(text)["SceneObjects"][0]["Name"] == 'q"\\\n\x01é'
