@@ -180,7 +180,7 @@ def run_b200(args):
         for _ in range(args.warmup):
             tr.reset_accumulation(); step_resident()
         barrier()
-        seg0 = tr.stats().segments
+        seg0 = tr.stats().total_segments
         sampler = ClockSampler(local); sampler.start()
         evs = []
         tr.reset_accumulation()
@@ -193,7 +193,7 @@ def run_b200(args):
         barrier()
         clocks = sampler.summary()
         step_ms = [a.elapsed_time(b) for a, b in evs]
-        segs_rank = tr.stats().segments - seg0
+        segs_rank = tr.stats().total_segments - seg0
         paths_rank = W * H * spp * args.steps
 
         # ---- end to end through the C-ABI with host buffers: e2e ------------------------------
@@ -212,7 +212,7 @@ def run_b200(args):
         for _ in range(max(1, args.warmup - 1)):
             step_e2e()
         barrier()
-        seg1 = tr.stats().segments
+        seg1 = tr.stats().total_segments
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -222,7 +222,7 @@ def run_b200(args):
         barrier()
         e2e_wall = time.perf_counter() - t0
         e2e_dev_ms = e0.elapsed_time(e1)
-        e2e_segs = tr.stats().segments - seg1
+        e2e_segs = tr.stats().total_segments - seg1
 
     total_ms = sum(step_ms)
     t = torch.tensor([total_ms, e2e_wall * 1e3, float(segs_rank), float(e2e_segs)], dtype=torch.float64, device="cuda")

@@ -93,6 +93,8 @@ typedef struct {
     int32_t accel;                 /* RT_ACCEL_* actually used */
     int32_t sm_count;
     int32_t reserved;
+    uint64_t total_paths;          /* since rt_create: never reset (benchmarks) */
+    uint64_t total_segments;
 } rt_stats;
 
 /* Tuning knobs that have no counterpart in the reference (they never change results). */

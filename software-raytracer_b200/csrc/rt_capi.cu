@@ -48,7 +48,7 @@ struct rt_ctx {
     // accumulation state
     uint32_t samples = 0;          // samples per pixel in the buffer (global, after any external reduce)
     uint32_t next_sample = 0;      // next global sample index
-    uint64_t paths = 0;
+    uint64_t paths = 0, total_paths = 0, total_segments_base = 0;
     int rank = 0, world = 1;
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
     int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;
@@ -403,7 +403,8 @@ int rt_reset_accumulation(rt_ctx* c) {
     int rc = prepare(c);
     if (rc != RT_OK) return rc;
     RT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)c->par.width * c->par.height * sizeof(float4), c->stream));
-    RT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    // counters: [0] segments since the last reset, [1] segments since rt_create (never cleared)
+    RT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long), c->stream));
     c->samples = 0; c->next_sample = 0; c->paths = 0;
     return RT_OK;
 }
@@ -418,7 +419,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
     if (c->par.mode == RT_MODE_PREVIEW) {
         // SIMPLEDRAW: ACCUMULATIONFRAMES stays 1, every frame overwrites (Raytracer.cpp:66-67,589)
         RT_CUDA(c, launch_render_preview(c->view, c->frame, c->d_accum, c->d_counters, c->stream));
-        c->samples = 1; c->next_sample = 0; c->paths += px;
+        c->samples = 1; c->next_sample = 0; c->paths += px; c->total_paths += px;
     } else {
         // this rank's slice of the global sample indices [next, next+spp)
         const int base = spp / c->world, rem = spp % c->world;
@@ -428,7 +429,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
         c->used_pipeline = RT_PIPELINE_REGEN; c->used_accel = RT_ACCEL_BRUTE;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce
-        c->paths += (uint64_t)mine * px;
+        c->paths += (uint64_t)mine * px; c->total_paths += (uint64_t)mine * px;
     }
     RT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->render_timed = true;
@@ -597,6 +598,7 @@ int rt_get_stats(rt_ctx* c, rt_stats* out) {
     out->paths = c->paths; out->segments = counters[0];
     out->samples = c->samples; out->n_objects = (uint32_t)c->scene.objects.size();
     out->last_render_ms = c->last_render_ms; out->last_resolve_ms = c->last_resolve_ms;
+    out->total_paths = c->total_paths; out->total_segments = counters[1];
     out->pipeline = c->used_pipeline; out->accel = c->used_accel; out->sm_count = c->sm_count;
     return RT_OK;
 }

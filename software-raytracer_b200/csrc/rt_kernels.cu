@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kThreads) k_render_regen(SceneView sc, FrameVi
     unsigned int total = segs;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(0xffffffffu, total, off);
-    if ((threadIdx.x & 31) == 0 && total) atomicAdd(seg_counter, (unsigned long long)total);
+    if ((threadIdx.x & 31) == 0 && total) { atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total); }
 }
 
 // ---- preview mode (SIMPLEDRAW, Raytracer.cpp:147-160): one primary ray, overwrite ----------
@@ -196,8 +196,10 @@ __global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, Frame
         c = clerp(a, col(3.f, 3.f, 0.f), fres);                                    // :159
     }
     accum[pixel] = make_float4(c.x, c.y, c.z, 0.f);
-    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
         atomicAdd(seg_counter, (unsigned long long)fr.width * fr.height);
+        atomicAdd(seg_counter + 1, (unsigned long long)fr.width * fr.height);
+    }
 }
 
 // ---- resolve: sum/count -> Reinhard -> truncating ARGB8 pack (Raytracer.cpp:73-75) -----------

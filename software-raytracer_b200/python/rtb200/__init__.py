@@ -43,7 +43,8 @@ class RtParams(C.Structure):
 class RtStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("samples", C.c_uint32), ("n_objects", C.c_uint32),
                 ("last_render_ms", C.c_float), ("last_resolve_ms", C.c_float), ("pipeline", C.c_int32),
-                ("accel", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32)]
+                ("accel", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32),
+                ("total_paths", C.c_uint64), ("total_segments", C.c_uint64)]
 
 
 OBJECT_DTYPE = np.dtype([("type", "<i4"), ("pos", "<f4", 3), ("radius", "<f4"), ("half", "<f4", 3),

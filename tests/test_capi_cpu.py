@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts():
     assert C.sizeof(rtb200.RtObject) == 76 and C.sizeof(rtb200.RtCamera) == 52
-    assert C.sizeof(rtb200.RtParams) == 96 and C.sizeof(rtb200.RtStats) == 48
+    assert C.sizeof(rtb200.RtParams) == 96 and C.sizeof(rtb200.RtStats) == 64
 
 
 def test_defaults_equal_reference(oracle):
