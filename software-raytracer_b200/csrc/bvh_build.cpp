@@ -1,0 +1,190 @@
+// bvh_build.cpp - binned-SAH BVH2 builder (host). See bvh_build.h for the exactness contract.
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace rtb {
+namespace {
+
+struct Box3 {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    void grow(const Box3& b) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+    void grow_pt(const float* p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+    bool valid() const { return lo[0] <= hi[0]; }
+};
+
+struct Prim {
+    Box3 box;
+    float centroid[3];
+    int32_t ref;          // >= 0 sphere slot, < 0 ~cube slot
+};
+
+struct Builder {
+    std::vector<Prim> prims;
+    HostBvh* out;
+    float eps;
+
+    static constexpr int kBins = 16;
+    static constexpr int kMaxLeaf = 4;
+    static constexpr float kTravCost = 1.0f, kPrimCost = 0.7f;
+
+    int32_t make_leaf(int first, int count) {
+        int start = (int)out->refs.size();
+        for (int i = 0; i < count; ++i) out->refs.push_back(prims[(size_t)first + i].ref);
+        return ~(int32_t)((uint32_t)start | ((uint32_t)count << 24));
+    }
+
+    Box3 bounds(int first, int count) const {
+        Box3 b;
+        for (int i = 0; i < count; ++i) b.grow(prims[(size_t)first + i].box);
+        return b;
+    }
+
+    void store_child(BvhNode& n, int which, const Box3& b) const {
+        float* f = n.f + 6 * which;
+        if (!b.valid()) {                       // empty child: NaN planes fail every slab comparison
+            for (int k = 0; k < 6; ++k) f[k] = std::nanf("");
+            return;
+        }
+        for (int k = 0; k < 3; ++k) { f[2 * k] = b.lo[k] - eps; f[2 * k + 1] = b.hi[k] + eps; }
+    }
+
+    // splits prims[first, first+count) and returns the split position (first < mid < first+count), or -1 for "make a leaf"
+    int split(int first, int count, const Box3& nb, bool force) {
+        Box3 cb;
+        for (int i = 0; i < count; ++i) cb.grow_pt(prims[(size_t)first + i].centroid);
+        float best_cost = FLT_MAX; int best_axis = -1, best_bin = -1;
+        for (int axis = 0; axis < 3; ++axis) {
+            float lo = cb.lo[axis], ext = cb.hi[axis] - cb.lo[axis];
+            if (!(ext > 0)) continue;
+            Box3 bb[kBins]; int bc[kBins] = {0};
+            float scale = kBins / ext;
+            for (int i = 0; i < count; ++i) {
+                const Prim& p = prims[(size_t)first + i];
+                int b = std::min(kBins - 1, std::max(0, (int)((p.centroid[axis] - lo) * scale)));
+                bb[b].grow(p.box); bc[b]++;
+            }
+            float right_area[kBins]; int right_cnt[kBins];
+            Box3 acc; int cnt = 0;
+            for (int b = kBins - 1; b > 0; --b) { acc.grow(bb[b]); cnt += bc[b]; right_area[b] = acc.area(); right_cnt[b] = cnt; }
+            acc = Box3(); cnt = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                acc.grow(bb[b]); cnt += bc[b];
+                if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+                float cost = acc.area() * cnt + right_area[b + 1] * right_cnt[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            }
+        }
+        if (best_axis < 0) {                    // all centroids coincide: median split by index if forced
+            return (force || count > kMaxLeaf) ? first + count / 2 : -1;
+        }
+        float leaf_cost = kPrimCost * count;
+        float split_cost = kTravCost + kPrimCost * best_cost / std::max(nb.area(), 1e-30f);
+        if (!force && count <= kMaxLeaf && leaf_cost <= split_cost) return -1;
+        float lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+        auto mid_it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim& p) {
+            int b = std::min(kBins - 1, std::max(0, (int)((p.centroid[best_axis] - lo) * scale)));
+            return b <= best_bin;
+        });
+        int mid = (int)(mid_it - prims.begin());
+        if (mid == first || mid == first + count) mid = first + count / 2;
+        return mid;
+    }
+
+    // Builds the subtree over prims[first, first+count) and returns its link (inner index or encoded leaf).
+    int32_t build(int first, int count, int depth) {
+        out->max_depth = std::max(out->max_depth, depth);
+        if (count <= 0) return make_leaf(first, 0);
+        const bool depth_left = depth < kMaxBvhDepth - 2;
+        if (count == 1 || !depth_left) {
+            // depth cap: emit (possibly several) leaves of <= 127 prims chained is not needed in practice;
+            // a leaf holds up to 127 refs
+            if (count <= 127) return make_leaf(first, count);
+        }
+        Box3 nb = bounds(first, count);
+        int mid = split(first, count, nb, count > 127);
+        if (mid < 0) return make_leaf(first, count);
+        int32_t idx = (int32_t)out->nodes.size();
+        out->nodes.emplace_back();
+        Box3 lb = bounds(first, mid - first), rb = bounds(mid, first + count - mid);
+        int32_t l = build(first, mid - first, depth + 1);
+        int32_t r = build(mid, first + count - mid, depth + 1);
+        BvhNode& n = out->nodes[(size_t)idx];
+        memset(&n, 0, sizeof n);
+        store_child(n, 0, lb); store_child(n, 1, rb);
+        n.c[0] = l; n.c[1] = r;
+        return idx;
+    }
+};
+
+}  // namespace
+
+void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out) {
+    out = HostBvh();
+    Builder b; b.out = &out;
+    int sph_slot = 0, box_slot = 0;
+    Box3 scene;
+    for (const rt_object& o : objects) {
+        Prim p;
+        if (o.type == RT_OBJ_SPHERE) {
+            float r = std::fabs(o.radius);
+            if (!(r == r)) r = 0.f;
+            for (int k = 0; k < 3; ++k) { p.box.lo[k] = o.pos[k] - r; p.box.hi[k] = o.pos[k] + r; p.centroid[k] = o.pos[k]; }
+            p.ref = sph_slot++;
+        } else if (o.type == RT_OBJ_CUBE) {
+            for (int k = 0; k < 3; ++k) {
+                float h = std::fabs(o.half[k]);
+                p.box.lo[k] = o.pos[k] - h; p.box.hi[k] = o.pos[k] + h; p.centroid[k] = o.pos[k];
+            }
+            p.ref = ~(box_slot++);
+        } else continue;
+        bool finite = true;
+        for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(p.box.lo[k]) && std::isfinite(p.box.hi[k]);
+        if (!finite) {                          // non-finite geometry: keep it a candidate for every ray
+            for (int k = 0; k < 3; ++k) { p.box.lo[k] = -1e30f; p.box.hi[k] = 1e30f; p.centroid[k] = 0.f; }
+        }
+        scene.grow(p.box);
+        b.prims.push_back(p);
+    }
+    out.n_prims = (int)b.prims.size();
+    float extent = std::fabs(origin_extent);
+    if (scene.valid())
+        for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(scene.lo[k]), std::fabs(scene.hi[k])));
+    if (extent > 1e29f) extent = 1e29f;
+    out.extent = extent;
+    out.inflate_abs = kInflate * std::max(extent, 1e-3f);
+    b.eps = out.inflate_abs;
+
+    // the root is always an inner node so the traversal loop has a single entry shape
+    out.nodes.emplace_back();
+    int n = (int)b.prims.size();
+    if (n == 0) {
+        BvhNode& r = out.nodes[0];
+        memset(&r, 0, sizeof r);
+        b.store_child(r, 0, Box3()); b.store_child(r, 1, Box3());
+        r.c[0] = b.make_leaf(0, 0); r.c[1] = r.c[0];
+        return;
+    }
+    Box3 nb = b.bounds(0, n);
+    int mid = n >= 2 ? b.split(0, n, nb, true) : -1;
+    int32_t l, rgt; Box3 lb, rb;
+    if (mid < 0) { lb = nb; l = b.build(0, n, 1); rgt = b.make_leaf(0, 0); }
+    else {
+        lb = b.bounds(0, mid); rb = b.bounds(mid, n - mid);
+        l = b.build(0, mid, 1); rgt = b.build(mid, n - mid, 1);
+    }
+    BvhNode& r = out.nodes[0];
+    memset(&r, 0, sizeof r);
+    b.store_child(r, 0, lb); b.store_child(r, 1, rb);
+    r.c[0] = l; r.c[1] = rgt;
+}
+
+}  // namespace rtb

@@ -13,6 +13,7 @@
 #include "../../include/rt_b200.h"
 #include "rt_device.cuh"
 #include "rt_kernels.h"
+#include "bvh_build.h"
 #include "scene_json.h"
 
 using namespace rtb;
@@ -37,6 +38,13 @@ struct rt_ctx {
     float4* d_box = nullptr; int* d_box_id = nullptr;
     float4* d_mat = nullptr;
     size_t cap_sph = 0, cap_sph_id = 0, cap_box = 0, cap_box_id = 0, cap_mat = 0;
+
+    // BVH (built lazily; see bvh_build.h)
+    HostBvh bvh;
+    BvhView bview;
+    float4* d_bvh_nodes = nullptr; int* d_bvh_refs = nullptr;
+    size_t cap_bvh_nodes = 0, cap_bvh_refs = 0;
+    bool bvh_valid = false;
 
     // frame buffers
     float4* d_accum = nullptr;
@@ -169,7 +177,40 @@ int upload_scene(rt_ctx* c) {
     c->view.box = c->d_box; c->view.box_id = c->d_box_id;
     c->view.mat = c->d_mat;
     c->view.n_sph = (int)sph_id.size(); c->view.n_box = (int)box_id.size(); c->view.n_obj = (int)objs.size();
+    c->bvh_valid = false;
     return RT_OK;
+}
+
+// (Re)builds and uploads the BVH when the scene changed or a ray origin lies outside the extent its
+// box inflation was derived from.
+int ensure_bvh(rt_ctx* c, float origin_extent) {
+    if (c->bvh_valid && origin_extent <= c->bvh.extent) return RT_OK;
+    build_bvh(c->scene.objects, origin_extent, c->bvh);
+    if (c->bvh.max_depth + 2 > 62) return fail(c, RT_ERR_INVALID, "BVH too deep for the traversal stack");
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    RT_CUDA(c, ensure_capacity(c->d_bvh_nodes, c->cap_bvh_nodes, c->bvh.nodes.size() * 4));
+    RT_CUDA(c, ensure_capacity(c->d_bvh_refs, c->cap_bvh_refs, c->bvh.refs.size()));
+    RT_CUDA(c, cudaMemcpyAsync(c->d_bvh_nodes, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, c->stream));
+    if (!c->bvh.refs.empty())
+        RT_CUDA(c, cudaMemcpyAsync(c->d_bvh_refs, c->bvh.refs.data(), c->bvh.refs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->bview.nodes = c->d_bvh_nodes; c->bview.refs = c->d_bvh_refs;
+    c->bview.n_nodes = (int)c->bvh.nodes.size(); c->bview.n_refs = (int)c->bvh.refs.size();
+    c->bview.stack_entries = c->bvh.max_depth + 2;
+    c->bvh_valid = true;
+    return RT_OK;
+}
+
+bool want_bvh(const rt_ctx* c) {
+    if (c->opt_accel == RT_ACCEL_BVH) return true;
+    if (c->opt_accel == RT_ACCEL_BRUTE) return false;
+    return c->view.n_sph + c->view.n_box >= c->opt_bvh_threshold;
+}
+
+float camera_extent(const rt_ctx* c) {
+    float e = 0.f;
+    for (int k = 0; k < 3; ++k) e = fmaxf(e, fabsf(c->cam.pos[k]));
+    return e;
 }
 
 int prepare(rt_ctx* c) {
@@ -253,6 +294,7 @@ int rt_create(int cuda_device, rt_ctx** out) {
     rt_default_params(&c->par);
     rt_default_camera(&c->cam);
     memset(&c->view, 0, sizeof c->view);
+    memset(&c->bview, 0, sizeof c->bview);
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
         (e = cudaMalloc((void**)&c->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess ||
@@ -276,6 +318,7 @@ int rt_destroy(rt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
+    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -415,18 +458,21 @@ int rt_render_spp(rt_ctx* c, int spp) {
     if (spp < 0) return fail(c, RT_ERR_INVALID, "rt_render_spp: negative spp");
     if (spp == 0) return RT_OK;
     const size_t px = (size_t)c->par.width * c->par.height;
+    const bool bvh = want_bvh(c);
+    if (bvh && (rc = ensure_bvh(c, camera_extent(c))) != RT_OK) return rc;
+    c->used_accel = bvh ? RT_ACCEL_BVH : RT_ACCEL_BRUTE;
     RT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if (c->par.mode == RT_MODE_PREVIEW) {
         // SIMPLEDRAW: ACCUMULATIONFRAMES stays 1, every frame overwrites (Raytracer.cpp:66-67,589)
-        RT_CUDA(c, launch_render_preview(c->view, c->frame, c->d_accum, c->d_counters, c->stream));
+        RT_CUDA(c, launch_render_preview(c->view, c->bview, bvh, c->frame, c->d_accum, c->d_counters, c->stream));
         c->samples = 1; c->next_sample = 0; c->paths += px; c->total_paths += px;
     } else {
         // this rank's slice of the global sample indices [next, next+spp)
         const int base = spp / c->world, rem = spp % c->world;
         const int mine = base + (c->rank < rem ? 1 : 0);
         const uint32_t first = c->next_sample + (uint32_t)(c->rank * base + (c->rank < rem ? c->rank : rem));
-        RT_CUDA(c, launch_render_regen(c->view, c->frame, c->d_accum, first, mine, c->d_counters, c->stream));
-        c->used_pipeline = RT_PIPELINE_REGEN; c->used_accel = RT_ACCEL_BRUTE;
+        RT_CUDA(c, launch_render_regen(c->view, c->bview, bvh, c->frame, c->d_accum, first, mine, c->d_counters, c->stream));
+        c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce
         c->paths += (uint64_t)mine * px; c->total_paths += (uint64_t)mine * px;
@@ -490,13 +536,15 @@ int rt_read_aov(rt_ctx* c, int32_t* id, float* t, float* normal, float* point) {
     int rc = prepare(c);
     if (rc != RT_OK) return rc;
     const size_t px = (size_t)c->par.width * c->par.height;
+    const bool bvh = want_bvh(c);
+    if (bvh && (rc = ensure_bvh(c, camera_extent(c))) != RT_OK) return rc;
     int* d_id = nullptr; float *d_t = nullptr, *d_n = nullptr, *d_p = nullptr;
     cudaError_t e = cudaSuccess;
     if (id) e = cudaMalloc((void**)&d_id, px * 4);
     if (e == cudaSuccess && t) e = cudaMalloc((void**)&d_t, px * 4);
     if (e == cudaSuccess && normal) e = cudaMalloc((void**)&d_n, px * 12);
     if (e == cudaSuccess && point) e = cudaMalloc((void**)&d_p, px * 12);
-    if (e == cudaSuccess) e = launch_primary_aov(c->view, c->frame, d_id, d_t, d_n, d_p, c->stream);
+    if (e == cudaSuccess) e = launch_primary_aov(c->view, c->bview, bvh, c->frame, d_id, d_t, d_n, d_p, c->stream);
     if (e == cudaSuccess && id) e = cudaMemcpyAsync(id, d_id, px * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, d_t, px * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess && normal) e = cudaMemcpyAsync(normal, d_n, px * 12, cudaMemcpyDeviceToHost, c->stream);
@@ -529,13 +577,26 @@ int rt_trace_rays(rt_ctx* c, const float* origins, const float* dirs, int n, int
         return fail(c, RT_ERR_INVALID, "rt_trace_rays: bad arguments");
     if (n == 0) return RT_OK;
     const size_t N = (size_t)n;
+    // The BVH's conservativeness argument needs unit-length directions and origins inside the inflation
+    // extent; anything else goes through the brute-force loop.
+    bool bvh = want_bvh(c);
+    if (bvh) {
+        float ext = 0.f;
+        for (size_t i = 0; i < N && bvh; ++i) {
+            const float* d = dirs + 3 * i; const float* o = origins + 3 * i;
+            float l2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            if (!(fabsf(l2 - 1.f) <= 1e-3f)) bvh = false;
+            for (int k = 0; k < 3; ++k) { if (!(fabsf(o[k]) < 1e29f)) bvh = false; ext = fmaxf(ext, fabsf(o[k])); }
+        }
+        if (bvh && (rc = ensure_bvh(c, ext)) != RT_OK) return rc;
+    }
     float* buf = nullptr;                                      // org3 dir3 n3 p3 t1 id1 = 14 words per ray
     cudaError_t e = cudaMalloc((void**)&buf, N * 14 * 4);
     float *d_o = buf, *d_d = buf + 3 * N, *d_n = buf + 6 * N, *d_p = buf + 9 * N, *d_t = buf + 12 * N;
     int* d_id = (int*)(buf + 13 * N);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, origins, N * 12, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, N * 12, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = launch_trace_rays(c->view, d_o, d_d, n, d_id, d_t, d_n, d_p, c->stream);
+    if (e == cudaSuccess) e = launch_trace_rays(c->view, c->bview, bvh, d_o, d_d, n, d_id, d_t, d_n, d_p, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(id, d_id, N * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(t, d_t, N * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(normal, d_n, N * 12, cudaMemcpyDeviceToHost, c->stream);

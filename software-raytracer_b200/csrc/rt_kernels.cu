@@ -13,15 +13,51 @@ namespace {
 
 constexpr int kTileW = 16, kTileH = 8;          // CTA tile: 4 warps, each an 8x4 pixel block
 constexpr int kThreads = 128;
+#ifndef RTB_REGEN_MIN_BLOCKS
+#define RTB_REGEN_MIN_BLOCKS 6      // register budget of the render kernel: 65536 / (128 * 6) -> 80 registers
+#endif
 
-// Copy the geometry lists into shared memory (spheres then cubes). Everything the
-// closest-hit loop touches per object is 16 B per sphere / 32 B per cube, read by all 32 lanes
-// at the same address (LDS.128 broadcast, no bank conflicts).
-__device__ __forceinline__ void stage_geometry(const SceneView& sc, float4* smem) {
-    const int n4 = sc.n_sph + 2 * sc.n_box;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x)
-        smem[i] = i < sc.n_sph ? __ldg(sc.sph + i) : __ldg(sc.box + (i - sc.n_sph));
-    __syncthreads();
+// ---- closest-hit back ends -------------------------------------------------------------------
+// MODE 0: brute force, geometry staged in shared memory      MODE 1: brute force from global (L1)
+// MODE 2: BVH, nodes + refs + geometry staged in shared mem  MODE 3: BVH from global (L1/L2)
+// Shared memory layout: [BVH stack: stack_entries x blockDim ints][spheres][cubes][nodes][refs]
+struct TraceCtx {
+    const float4* sph; const float4* box; const float4* nodes; const int* refs;
+    int* stack; int stride;
+};
+
+template <int MODE>
+__device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhView& bv, float4* smem) {
+    TraceCtx t;
+    t.sph = sc.sph; t.box = sc.box; t.nodes = bv.nodes; t.refs = bv.refs; t.stack = nullptr; t.stride = blockDim.x;
+    float4* p = smem;
+    if (MODE >= 2) {
+        t.stack = reinterpret_cast<int*>(p) + threadIdx.x;
+        p += (bv.stack_entries * blockDim.x + 3) / 4;
+    }
+    if (MODE == 0 || MODE == 2) {
+        const int ng = sc.n_sph + 2 * sc.n_box;
+        for (int i = threadIdx.x; i < ng; i += blockDim.x)
+            p[i] = i < sc.n_sph ? __ldg(sc.sph + i) : __ldg(sc.box + (i - sc.n_sph));
+        t.sph = p; t.box = p + sc.n_sph;
+        p += ng;
+        if (MODE == 2) {
+            for (int i = threadIdx.x; i < 4 * bv.n_nodes; i += blockDim.x) p[i] = __ldg(bv.nodes + i);
+            t.nodes = p;
+            p += 4 * bv.n_nodes;
+            int* r = reinterpret_cast<int*>(p);
+            for (int i = threadIdx.x; i < bv.n_refs; i += blockDim.x) r[i] = __ldg(bv.refs + i);
+            t.refs = r;
+        }
+        __syncthreads();
+    }
+    return t;
+}
+
+template <int MODE>
+__device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d) {
+    if (MODE >= 2) return closest_hit_bvh(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d);
+    return closest_hit(sc, t.sph, t.box, o, d);
 }
 
 __device__ __forceinline__ bool tile_pixel(const FrameView& fr, int& px, int& py) {
@@ -32,17 +68,16 @@ __device__ __forceinline__ bool tile_pixel(const FrameView& fr, int& px, int& py
 }
 
 // ---- primary visibility AOVs ----------------------------------------------------------------
-template <bool STAGED>
-__global__ void __launch_bounds__(kThreads) k_primary_aov(SceneView sc, FrameView fr, int* __restrict__ out_id,
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_primary_aov(SceneView sc, BvhView bv, FrameView fr, int* __restrict__ out_id,
                                                            float* __restrict__ out_t, float* __restrict__ out_n,
                                                            float* __restrict__ out_p) {
     extern __shared__ float4 smem[];
-    const float4* sph = sc.sph; const float4* box = sc.box;
-    if (STAGED) { stage_geometry(sc, smem); sph = smem; box = smem + sc.n_sph; }
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
     int px, py;
     if (!tile_pixel(fr, px, py)) return;
     const size_t p = (size_t)px + (size_t)py * fr.width;
-    Hit h = closest_hit(sc, sph, box, fr.cam_pos, ray_dir(fr, px, py));
+    Hit h = trace<MODE>(sc, tc, fr.cam_pos, ray_dir(fr, px, py));
     if (out_id) out_id[p] = h.id;
     if (out_t) out_t[p] = h.t;
     if (out_n) { out_n[3 * p] = h.n.x; out_n[3 * p + 1] = h.n.y; out_n[3 * p + 2] = h.n.z; }
@@ -57,12 +92,16 @@ __global__ void k_ray_dirs(FrameView fr, float* __restrict__ out) {
     out[3 * p] = d.x; out[3 * p + 1] = d.y; out[3 * p + 2] = d.z;
 }
 
-__global__ void k_trace_rays(SceneView sc, const float* __restrict__ org, const float* __restrict__ dir, int n,
-                             int* __restrict__ out_id, float* __restrict__ out_t, float* __restrict__ out_n,
-                             float* __restrict__ out_p) {
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_trace_rays(SceneView sc, BvhView bv, const float* __restrict__ org,
+                                                          const float* __restrict__ dir, int n,
+                                                          int* __restrict__ out_id, float* __restrict__ out_t,
+                                                          float* __restrict__ out_n, float* __restrict__ out_p) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Hit h = closest_hit(sc, sc.sph, sc.box, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
+    Hit h = trace<MODE>(sc, tc, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
                         f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
     out_id[i] = h.id; out_t[i] = h.t;
     out_n[3 * i] = h.n.x; out_n[3 * i + 1] = h.n.y; out_n[3 * i + 2] = h.n.z;
@@ -92,13 +131,12 @@ __global__ void k_philox(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32_1
 // pixels finish together. Per-pixel sums are kept in registers in sample order and added to
 // the float4 accumulation buffer once - no atomics, bit-reproducible for a given
 // (seed, sample range), independent of the launch shape.
-template <bool STAGED>
-__global__ void __launch_bounds__(kThreads) k_render_regen(SceneView sc, FrameView fr, float4* __restrict__ accum,
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen(SceneView sc, BvhView bv, FrameView fr, float4* __restrict__ accum,
                                                             uint32_t s_begin, int n_samples,
                                                             unsigned long long* __restrict__ seg_counter) {
     extern __shared__ float4 smem[];
-    const float4* sph = sc.sph; const float4* box = sc.box;
-    if (STAGED) { stage_geometry(sc, smem); sph = smem; box = smem + sc.n_sph; }
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
     int px, py;
     const bool inside = tile_pixel(fr, px, py);              // no early return: the warp reduce below needs every lane
     const uint32_t pixel = inside ? (uint32_t)px + (uint32_t)py * (uint32_t)fr.width : 0u;
@@ -113,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) k_render_regen(SceneView sc, FrameVi
     unsigned int segs = 0;
 
     while (s < n_samples) {
-        const Hit h = closest_hit(sc, sph, box, o, d);
+        const Hit h = trace<MODE>(sc, tc, o, d);
         ++segs;
         bool done;
         float3 c;
@@ -168,17 +206,16 @@ __global__ void __launch_bounds__(kThreads) k_render_regen(SceneView sc, FrameVi
 }
 
 // ---- preview mode (SIMPLEDRAW, Raytracer.cpp:147-160): one primary ray, overwrite ----------
-template <bool STAGED>
-__global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, FrameView fr, float4* __restrict__ accum,
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, BvhView bv, FrameView fr, float4* __restrict__ accum,
                                                               unsigned long long* __restrict__ seg_counter) {
     extern __shared__ float4 smem[];
-    const float4* sph = sc.sph; const float4* box = sc.box;
-    if (STAGED) { stage_geometry(sc, smem); sph = smem; box = smem + sc.n_sph; }
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
     int px, py;
     if (!tile_pixel(fr, px, py)) return;
     const size_t pixel = (size_t)px + (size_t)py * fr.width;
     const float3 d = ray_dir(fr, px, py);
-    const Hit h = closest_hit(sc, sph, box, fr.cam_pos, d);
+    const Hit h = trace<MODE>(sc, tc, fr.cam_pos, d);
     float3 c;
     if (h.id < 0) c = env_color(fr, d);
     else {
@@ -239,23 +276,51 @@ static inline dim3 tile_grid(int w, int h) { return dim3((w + kTileW - 1) / kTil
 
 size_t staged_bytes(const SceneView& sc) { return (size_t)(sc.n_sph + 2 * sc.n_box) * sizeof(float4); }
 
+// Picks the back end and its dynamic shared memory size. use_bvh: caller's decision (accel option).
+static int pick_mode(const SceneView& sc, const BvhView& bv, bool use_bvh, size_t& smem) {
+    const size_t geo = staged_bytes(sc);
+    if (!use_bvh) {
+        if (geo <= kMaxStagedBytes) { smem = geo; return 0; }
+        smem = 0; return 1;
+    }
+    const size_t stack = ((size_t)bv.stack_entries * kThreads * sizeof(int) + 15) / 16 * 16;
+    const size_t all = stack + geo + (size_t)bv.n_nodes * 64 + (size_t)bv.n_refs * 4 + 16;
+    if (all <= kMaxBvhStagedBytes) { smem = all; return 2; }
+    smem = stack; return 3;
+}
+
+template <typename K>
+static cudaError_t optin(K kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes); }
+
 static cudaError_t ensure_smem_optin() {
     static bool done = false;
     if (done) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_render_regen<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_render_preview<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_primary_aov<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes)) != cudaSuccess) return e;
+#define RTB_OPTIN(K) \
+    if ((e = optin(K<0>)) != cudaSuccess) return e; \
+    if ((e = optin(K<1>)) != cudaSuccess) return e; \
+    if ((e = optin(K<2>)) != cudaSuccess) return e; \
+    if ((e = optin(K<3>)) != cudaSuccess) return e;
+    RTB_OPTIN(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays)
+#undef RTB_OPTIN
     done = true;
     return cudaSuccess;
 }
 
-cudaError_t launch_primary_aov(const SceneView& sc, const FrameView& fr, int* id, float* t, float* n, float* p, cudaStream_t st) {
+#define RTB_DISPATCH(MODE, K, GRID, SMEM, ST, ...)                                     \
+    switch (MODE) {                                                                    \
+        case 0: K<0><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;                \
+        case 1: K<1><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;                \
+        case 2: K<2><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;                \
+        default: K<3><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;               \
+    }
+
+cudaError_t launch_primary_aov(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, int* id, float* t,
+                               float* n, float* p, cudaStream_t st) {
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    const size_t sb = staged_bytes(sc);
-    if (sb <= kMaxStagedBytes) k_primary_aov<true><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, fr, id, t, n, p);
-    else k_primary_aov<false><<<tile_grid(fr.width, fr.height), kThreads, 0, st>>>(sc, fr, id, t, n, p);
+    size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
+    RTB_DISPATCH(mode, k_primary_aov, tile_grid(fr.width, fr.height), sb, st, sc, bv, fr, id, t, n, p)
     return cudaGetLastError();
 }
 
@@ -264,10 +329,13 @@ cudaError_t launch_ray_dirs(const FrameView& fr, float* out, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace_rays(const SceneView& sc, const float* org, const float* dir, int n, int* id, float* t,
-                              float* nrm, float* pt, cudaStream_t st) {
+cudaError_t launch_trace_rays(const SceneView& sc, const BvhView& bv, bool use_bvh, const float* org, const float* dir, int n,
+                              int* id, float* t, float* nrm, float* pt, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    k_trace_rays<<<(n + 127) / 128, 128, 0, st>>>(sc, org, dir, n, id, t, nrm, pt);
+    cudaError_t e = ensure_smem_optin();
+    if (e != cudaSuccess) return e;
+    size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
+    RTB_DISPATCH(mode, k_trace_rays, dim3((n + kThreads - 1) / kThreads), sb, st, sc, bv, org, dir, n, id, t, nrm, pt)
     return cudaGetLastError();
 }
 
@@ -287,23 +355,22 @@ cudaError_t launch_pick(const SceneView& sc, const FrameView& fr, int px, int py
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_regen(const SceneView& sc, const FrameView& fr, float4* accum, uint32_t s_begin, int n_samples,
-                                unsigned long long* seg_counter, cudaStream_t st) {
+cudaError_t launch_render_regen(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, float4* accum,
+                                uint32_t s_begin, int n_samples, unsigned long long* seg_counter, cudaStream_t st) {
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    const size_t sb = staged_bytes(sc);
-    if (sb <= kMaxStagedBytes) k_render_regen<true><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, fr, accum, s_begin, n_samples, seg_counter);
-    else k_render_regen<false><<<tile_grid(fr.width, fr.height), kThreads, 0, st>>>(sc, fr, accum, s_begin, n_samples, seg_counter);
+    size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
+    RTB_DISPATCH(mode, k_render_regen, tile_grid(fr.width, fr.height), sb, st, sc, bv, fr, accum, s_begin, n_samples, seg_counter)
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_preview(const SceneView& sc, const FrameView& fr, float4* accum, unsigned long long* seg_counter, cudaStream_t st) {
+cudaError_t launch_render_preview(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, float4* accum,
+                                  unsigned long long* seg_counter, cudaStream_t st) {
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    const size_t sb = staged_bytes(sc);
-    if (sb <= kMaxStagedBytes) k_render_preview<true><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, fr, accum, seg_counter);
-    else k_render_preview<false><<<tile_grid(fr.width, fr.height), kThreads, 0, st>>>(sc, fr, accum, seg_counter);
+    size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
+    RTB_DISPATCH(mode, k_render_preview, tile_grid(fr.width, fr.height), sb, st, sc, bv, fr, accum, seg_counter)
     return cudaGetLastError();
 }
 

