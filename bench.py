@@ -35,8 +35,8 @@ UNIT = "Msegments/s"
 W, H, SPP, DEPTH = 1920, 1080, 1024, 8
 
 
-def load_scene():
-    return np.load(os.path.join(ROOT, "tests", "golden", "bundled_scenes.npz"))["Scene1"]
+def load_scene(name="Scene1"):
+    return np.load(os.path.join(ROOT, "tests", "golden", "bundled_scenes.npz"))[name]
 
 
 def flops_per_segment(objs):
@@ -147,11 +147,12 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    objs = load_scene()
+    objs = load_scene(args.scene)
     spp = args.spp
     stream = torch.cuda.Stream()
     tr = rtb200.PathTracer(local)
     tr.set_stream(stream.cuda_stream)
+    tr.set_option(rtb200.RT_OPT_ACCEL, {"auto": rtb200.RT_ACCEL_AUTO, "brute": rtb200.RT_ACCEL_BRUTE, "bvh": rtb200.RT_ACCEL_BVH}[args.accel])
     tr.set_scene(objs)
     tr.set_camera(rtb200.default_camera())
     tr.set_params(rtb200.default_params(width=W, height=H, mode=rtb200.RT_MODE_PATH, max_bounces=DEPTH,
@@ -250,7 +251,9 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic: bundled Scene1 fixture (tests/golden/bundled_scenes.npz), default camera, Philox seeds",
             "config": {"workload": "Scene1 (67 spheres) %dx%d, %d spp per GPU per step, depth %d, path mode" % (W, H, spp, DEPTH),
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": "spp-sharded x%d, one all-reduce per step" % world,
-                       "build": "strict IEEE, -fmad=false (bit-exact geometry vs the reference)"},
+                       "build": "strict IEEE, -fmad=false (bit-exact geometry vs the reference)",
+                       "accel": {rtb200.RT_ACCEL_BRUTE: "brute-force object loop", rtb200.RT_ACCEL_BVH: "host-built BVH candidates + strict tests"}[st.accel],
+                       "scene": args.scene},
             "paths_per_s_M": paths_rank * world / (total_ms * 1e-3) / 1e6,
             "ms_per_1spp_frame": total_ms / args.steps / spp,
             "segments_per_path": segs_rank / paths_rank,
@@ -289,6 +292,8 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP, help="samples per pixel per GPU per step (default: the config's 1024)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="1-spp frames of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh"], help="closest-hit back end (results are identical)")
+    ap.add_argument("--scene", default="Scene1", help="bundled scene fixture (the headline config is Scene1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

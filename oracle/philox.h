@@ -4,11 +4,13 @@
  * The product has its own device implementation (csrc/rt_rng.cuh); tests pin the two
  * against each other and against the Random123 known-answer vectors.
  *
- * Stream layout (one 128-bit block per scatter event, so a path never shares words):
- *   counter = (pixel = x + y*W [y-up], sample index, block, 0), key = (seed_lo, seed_hi)
- *   block 0      : word0 -> specular coin drawn at the primary hit   (Raytracer.cpp:165)
- *   block i+1    : word0..2 -> direction x,y,z of bounce i            (Raytracer.cpp:93-95)
- *                  word3    -> specular coin at the hit of bounce i   (Raytracer.cpp:182)
+ * Stream layout: the reference's rand() calls of ONE path, in call order, read consecutive words
+ * of one Philox stream: counter = (pixel = x + y*W [y-up], sample index, block, 0), key =
+ * (seed_lo, seed_hi), draw j = word (j & 3) of block (j >> 2). With the reference's call order
+ * (Raytracer.cpp:165, then per bounce :93-95 and :182) that is, for the hit at depth k:
+ *   block k: word0 -> specular coin drawn at that hit, word1..3 -> direction x,y,z of the
+ *            scatter that leaves it.
+ * So one 128-bit block serves one hit; a path never shares words with another path.
  * A word becomes the reference's `rand()` value as word >> 17, i.e. 15 bits in
  * [0, RAND_MAX=32767] - the MSVC C runtime the reference ships on. */
 #ifndef ORACLE_PHILOX_H

@@ -225,7 +225,7 @@ static int rng_next(rng_t* r) {                                      /* the valu
         r->have = 1;
     }
     uint32_t w = r->buf[r->widx];
-    if (r->block == 0 || r->widx == 3) { r->block++; r->widx = 0; r->have = 0; }
+    if (r->widx == 3) { r->block++; r->widx = 0; r->have = 0; }      /* consecutive words, 4 per block */
     else r->widx++;
     return (int)(w >> 17);
 }

@@ -37,7 +37,7 @@ int ref_rand(void) {
         r.have = true;
     }
     uint32_t w = r.buf[r.widx];
-    if (r.block == 0 || r.widx == 3) { r.block++; r.widx = 0; r.have = false; }   // block 0 holds one draw
+    if (r.widx == 3) { r.block++; r.widx = 0; r.have = false; }   // consecutive words, 4 per block
     else r.widx++;
     return (int)(w >> 17);
 }

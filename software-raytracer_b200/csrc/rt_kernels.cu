@@ -119,6 +119,12 @@ __global__ void k_pick(SceneView sc, FrameView fr, int px, int py, int* out_id) 
     *out_id = closest_hit(sc, sc.sph, sc.box, fr.cam_pos, ray_dir(fr, px, py)).id;
 }
 
+__global__ void k_selftest_uniform(int* failures) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;       // 32768 threads
+    const uint32_t w = k << 17;
+    if (__float_as_uint(unit_from_word(w)) != __float_as_uint(unit_from_word_div(w))) atomicAdd(failures, 1);
+}
+
 __global__ void k_philox(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32_10(ctr.x, ctr.y, ctr.z, ctr.w, key.x, key.y); }
 
 // ---- the render kernel -----------------------------------------------------------------------
@@ -146,7 +152,6 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     float3 acc = f3(0.f, 0.f, 0.f);
     float3 o = fr.cam_pos, d = d0;
     float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);     // hitColor, incomingLight (Raytracer.cpp:162-163)
-    uint32_t pending_coin = 0;                               // word3 of the block that made the current ray
     int s = 0, depth = 0;
     unsigned int segs = 0;
 
@@ -163,21 +168,22 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
             const float4 m0 = __ldg(sc.mat + 3 * h.id), m1 = __ldg(sc.mat + 3 * h.id + 1), m2 = __ldg(sc.mat + 3 * h.id + 2);
             const float3 base = f3(m0.x, m0.y, m0.z), emis = f3(m1.x, m1.y, m1.z), spec = f3(m2.x, m2.y, m2.z);
             const float smooth = m0.w, amount = m1.w;
-            uint32_t coin_word;
-            if (depth == 0) coin_word = philox4x32_10(pixel, s_begin + (uint32_t)s, 0u, 0u, fr.seed_lo, fr.seed_hi).x;
-            else coin_word = pending_coin;
-            const float coin = amount >= unit_from_word(coin_word) ? 1.f : 0.f;   // :165 / :182
+            // one Philox block per hit: word0 = the coin drawn at this hit (:165 / :182), words 1..3 = the
+            // direction of the scatter that leaves it (:93-95). At the last depth nothing downstream
+            // reads the coin, so the block is not generated at all.
+            const bool last = depth == fr.max_bounces;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (!last) w = philox4x32_10(pixel, s_begin + (uint32_t)s, (uint32_t)depth, 0u, fr.seed_lo, fr.seed_hi);
+            const float coin = amount >= unit_from_word(w.x) ? 1.f : 0.f;
             if (depth == 0) { L = emis; T = base; }                               // :162-163
             else {
                 L = cadd(L, cmul(emis, T));                                       // :183
-                T = cmul(T, clerp(base, spec, coin));                             // :184
+                T = cmul(T, clerp(base, spec, coin));                             // :184 (dead at the last depth)
             }
-            if (depth == fr.max_bounces) { c = L; done = true; }
+            if (last) { c = L; done = true; }
             else {
                 if (depth != 0) T = cscale(T, fr.dissipation);                    // :169-171
                 const float3 refl = reflect3(d, h.n);                             // :172
-                const uint4 w = philox4x32_10(pixel, s_begin + (uint32_t)s, (uint32_t)depth + 1u, 0u, fr.seed_lo, fr.seed_hi);
-                pending_coin = w.w;
                 float3 sr = hemisphere_dir(w, h.n);                               // :174
                 sr = normalized3(lerp3(sr, refl, smooth * coin));                 // :175-176
                 o = add3(h.p, scale3(h.n, fr.eps));                               // :177
@@ -347,6 +353,13 @@ cudaError_t launch_env_color(const FrameView& fr, const float* dir, int n, float
 
 cudaError_t launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t* dev_out4, cudaStream_t st) {
     k_philox<<<1, 1, 0, st>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), (uint4*)dev_out4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(dev_failures, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_selftest_uniform<<<32768 / 256, 256, 0, st>>>(dev_failures);
     return cudaGetLastError();
 }
 

@@ -59,7 +59,7 @@ EXPORTS = [
     "rt_set_option", "rt_set_shard", "rt_reset_accumulation", "rt_render_spp", "rt_resolve_rgba8", "rt_pick",
     "rt_read_accum", "rt_read_aov", "rt_read_ray_dirs", "rt_trace_rays", "rt_env_color", "rt_philox_block",
     "rt_scene_file_read", "rt_scene_file_write", "rt_object_name", "rt_set_object_name", "rt_scene_name",
-    "rt_write_accum", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
+    "rt_write_accum", "rt_selftest", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
 ]
 
 
@@ -284,6 +284,11 @@ class PathTracer:
         ctr = np.asarray(ctr, np.uint32); key = np.asarray(key, np.uint32); out = np.zeros(4, np.uint32)
         self._chk(self.lib.rt_philox_block(self.h, _p(ctr), _p(key), _p(out)))
         return out
+
+    def selftest(self, which=0):
+        n = C.c_int(-1)
+        self._chk(self.lib.rt_selftest(self.h, which, C.byref(n)))
+        return n.value
 
     def stats(self):
         s = RtStats()

@@ -140,3 +140,12 @@ def test_writer_number_and_string_formatting(tmp_path):
     assert "0.10000000149011612" in text and "9.999999747378752e-06" in text and '"Smoothness": 3.0' in text
     assert '"Name": "q\\"\\\\\\n\\u0001é"' in text
     assert json.loads(text)["SceneObjects"][0]["Name"] == 'q"\\\n\x01é'
+
+
+def test_uniform_shortcut_is_exact_on_the_host():
+    """(float)rand()/RAND_MAX with RAND_MAX 32767: the device computes it as a double multiply + round.
+    Exhaustive over all 32768 rand() values (the GPU repeats this check in rt_selftest)."""
+    k = np.arange(32768, dtype=np.float32)
+    want = k / np.float32(32767)
+    got = (k.astype(np.float64) * (1.0 / 32767.0)).astype(np.float32)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))

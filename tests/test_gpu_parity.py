@@ -44,6 +44,10 @@ def test_native_library_is_loaded(tracer):
         assert "librt_b200.so" in f.read()
 
 
+def test_uniform_shortcut_is_exact_on_device(tracer):
+    assert tracer.selftest(0) == 0
+
+
 def test_philox_device_matches_known_answers(tracer, oracle):
     assert tracer.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert tracer.philox([0xffffffff] * 4, [0xffffffff] * 2).tolist() == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
