@@ -153,6 +153,10 @@ def run_b200(args):
     tr = rtb200.PathTracer(local)
     tr.set_stream(stream.cuda_stream)
     tr.set_option(rtb200.RT_OPT_ACCEL, {"auto": rtb200.RT_ACCEL_AUTO, "brute": rtb200.RT_ACCEL_BRUTE, "bvh": rtb200.RT_ACCEL_BVH}[args.accel])
+    if args.bvh_sched >= 0:
+        tr.set_option(rtb200.RT_OPT_BVH_SCHED, args.bvh_sched)
+    if args.wait_k >= 0:
+        tr.set_option(rtb200.RT_OPT_BVH_WAIT_K, args.wait_k)
     tr.set_scene(objs)
     tr.set_camera(rtb200.default_camera())
     tr.set_params(rtb200.default_params(width=W, height=H, mode=rtb200.RT_MODE_PATH, max_bounces=DEPTH,
@@ -293,6 +297,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=24, help="1-spp frames of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh"], help="closest-hit back end (results are identical)")
+    ap.add_argument("--bvh-sched", type=int, default=-1, help="RT_OPT_BVH_SCHED override")
+    ap.add_argument("--wait-k", type=int, default=-1, help="RT_OPT_BVH_WAIT_K override")
     ap.add_argument("--scene", default="Scene1", help="bundled scene fixture (the headline config is Scene1)")
     args = ap.parse_args()
     if args.impl == "reference":

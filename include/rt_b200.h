@@ -101,7 +101,9 @@ typedef struct {
 enum {
     RT_OPT_PIPELINE = 1,           /* RT_PIPELINE_* */
     RT_OPT_ACCEL = 2,              /* RT_ACCEL_* */
-    RT_OPT_BVH_THRESHOLD = 3       /* object count at which RT_ACCEL_AUTO switches to the BVH */
+    RT_OPT_BVH_THRESHOLD = 3,      /* object count at which RT_ACCEL_AUTO switches to the BVH */
+    RT_OPT_BVH_SCHED = 4,          /* 1 (default): warp-scheduled BVH kernel, 0: per-ray traversal loop */
+    RT_OPT_BVH_WAIT_K = 5          /* lanes waiting for shading that trigger a shading pass (default 8) */
 };
 enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
 enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2 };

@@ -12,6 +12,7 @@
 
 #include "../../include/rt_b200.h"
 #include "rt_device.cuh"
+#include "rt_host_pack.h"
 #include "rt_kernels.h"
 #include "bvh_build.h"
 #include "scene_json.h"
@@ -59,6 +60,7 @@ struct rt_ctx {
     uint64_t paths = 0, total_paths = 0, total_segments_base = 0;
     int rank = 0, world = 1;
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
+    int opt_bvh_sched = 1, opt_bvh_wait_k = 8;
     int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;
     float last_render_ms = 0.f, last_resolve_ms = 0.f;
     bool render_timed = false, resolve_timed = false;
@@ -92,33 +94,8 @@ cudaError_t ensure_capacity(T*& ptr, size_t& cap, size_t need) {
     return e;
 }
 
-inline float3 h3(const float* v) { return make_float3(v[0], v[1], v[2]); }
-
-// Host half of GetRayDirection (Raytracer.cpp:107-117): everything that does not depend on the
-// pixel, in the reference's expression order, so device code never calls tanf.
 void build_frame(rt_ctx* c) {
-    const rt_params& p = c->par;
-    const rt_camera& cam = c->cam;
-    FrameView& f = c->frame;
-    const float clip = .01f;
-    float aspect = (float)p.width / (float)p.height;
-    float hFov = cam.fov_deg * M_PI / 180.0f;
-    float rd = (clip * tanf(hFov / 2.0f)) * aspect;
-    float ld = (clip * tanf(hFov / 2.0f));
-    f.cam_pos = h3(cam.pos);
-    f.u_axis = make_float3(cam.right[0] * rd, cam.right[1] * rd, cam.right[2] * rd);
-    f.v_axis = make_float3(cam.up[0] * ld, cam.up[1] * ld, cam.up[2] * ld);
-    f.fwd = make_float3(cam.forward[0] * clip, cam.forward[1] * clip, cam.forward[2] * clip);
-    f.sun_neg = make_float3(p.sun_dir[0] * -1, p.sun_dir[1] * -1, p.sun_dir[2] * -1);
-    float thr = (float)0.99;                                  // (double)dot > 0.99  <=>  dot >= thr
-    if (!((double)thr > 0.99)) thr = nextafterf(thr, INFINITY);
-    f.sun_thr = thr;
-    auto clamp0 = [](float v) { return v < 0 ? 0.f : v; };
-    f.sky = h3(p.sky); f.horizon = h3(p.horizon); f.ground = h3(p.ground); f.sun = h3(p.sun);
-    f.sky10 = make_float3(clamp0(p.sky[0] * 0.1f), clamp0(p.sky[1] * 0.1f), clamp0(p.sky[2] * 0.1f));
-    f.dissipation = p.dissipation; f.eps = p.eps;
-    f.width = p.width; f.height = p.height; f.max_bounces = p.max_bounces; f.mode = p.mode; f.selected_id = p.selected_id;
-    f.seed_lo = p.seed_lo; f.seed_hi = p.seed_hi;
+    fill_frame_view(c->cam, c->par, c->frame);
     c->frame_dirty = false;
 }
 
@@ -141,21 +118,7 @@ int upload_scene(rt_ctx* c) {
     const std::vector<rt_object>& objs = c->scene.objects;
     std::vector<float4> sph, box, mat;
     std::vector<int> sph_id, box_id;
-    mat.reserve(objs.size() * 3);
-    for (size_t i = 0; i < objs.size(); ++i) {
-        const rt_object& o = objs[i];
-        if (o.type == RT_OBJ_SPHERE) {
-            sph.push_back(make_float4(o.pos[0], o.pos[1], o.pos[2], o.radius * o.radius));   // squaredRadius Object.hpp:122
-            sph_id.push_back((int)i);
-        } else if (o.type == RT_OBJ_CUBE) {
-            box.push_back(make_float4(o.pos[0], o.pos[1], o.pos[2], 0.f));
-            box.push_back(make_float4(o.half[0], o.half[1], o.half[2], 0.f));
-            box_id.push_back((int)i);
-        }
-        mat.push_back(make_float4(o.base[0], o.base[1], o.base[2], o.smoothness));
-        mat.push_back(make_float4(o.emissive[0], o.emissive[1], o.emissive[2], o.spec_amount));
-        mat.push_back(make_float4(o.spec_color[0], o.spec_color[1], o.spec_color[2], 0.f));
-    }
+    pack_scene(objs, sph, sph_id, box, box_id, mat);
     RT_CUDA(c, cudaStreamSynchronize(c->stream));             // nothing in flight may still read the old arrays
     RT_CUDA(c, ensure_capacity(c->d_sph, c->cap_sph, sph.size()));
     RT_CUDA(c, ensure_capacity(c->d_sph_id, c->cap_sph_id, sph_id.size()));
@@ -432,6 +395,8 @@ int rt_set_option(rt_ctx* c, int option, int value) {
         case RT_OPT_PIPELINE: c->opt_pipeline = value; return RT_OK;
         case RT_OPT_ACCEL: c->opt_accel = value; return RT_OK;
         case RT_OPT_BVH_THRESHOLD: c->opt_bvh_threshold = value; return RT_OK;
+        case RT_OPT_BVH_SCHED: c->opt_bvh_sched = value; return RT_OK;
+        case RT_OPT_BVH_WAIT_K: c->opt_bvh_wait_k = value < 1 ? 1 : value; return RT_OK;
     }
     return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
 }
@@ -471,7 +436,10 @@ int rt_render_spp(rt_ctx* c, int spp) {
         const int base = spp / c->world, rem = spp % c->world;
         const int mine = base + (c->rank < rem ? 1 : 0);
         const uint32_t first = c->next_sample + (uint32_t)(c->rank * base + (c->rank < rem ? c->rank : rem));
-        RT_CUDA(c, launch_render_regen(c->view, c->bview, bvh, c->frame, c->d_accum, first, mine, c->d_counters, c->stream));
+        if (bvh && c->opt_bvh_sched)
+            RT_CUDA(c, launch_render_bvh(c->view, c->bview, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
+        else
+            RT_CUDA(c, launch_render_regen(c->view, c->bview, bvh, c->frame, c->d_accum, first, mine, c->d_counters, c->stream));
         c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce

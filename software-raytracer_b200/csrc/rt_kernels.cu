@@ -33,7 +33,7 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
     float4* p = smem;
     if (MODE >= 2) {
         t.stack = reinterpret_cast<int*>(p) + threadIdx.x;
-        p += (bv.stack_entries * blockDim.x + 3) / 4;
+        p += (2 * bv.stack_entries * blockDim.x + 3) / 4;      // links + entry distances
     }
     if (MODE == 0 || MODE == 2) {
         const int ng = sc.n_sph + 2 * sc.n_box;
@@ -151,48 +151,15 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     const float3 d0 = ray_dir(fr, px, py);
     float3 acc = f3(0.f, 0.f, 0.f);
     float3 o = fr.cam_pos, d = d0;
-    float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);     // hitColor, incomingLight (Raytracer.cpp:162-163)
+    float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
     int s = 0, depth = 0;
     unsigned int segs = 0;
 
     while (s < n_samples) {
         const Hit h = trace<MODE>(sc, tc, o, d);
         ++segs;
-        bool done;
         float3 c;
-        if (h.id < 0) {
-            const float3 e = env_color(fr, d);
-            c = depth == 0 ? e : cadd(L, cmul(e, T));                        // :144 / :179
-            done = true;
-        } else {
-            const float4 m0 = __ldg(sc.mat + 3 * h.id), m1 = __ldg(sc.mat + 3 * h.id + 1), m2 = __ldg(sc.mat + 3 * h.id + 2);
-            const float3 base = f3(m0.x, m0.y, m0.z), emis = f3(m1.x, m1.y, m1.z), spec = f3(m2.x, m2.y, m2.z);
-            const float smooth = m0.w, amount = m1.w;
-            // one Philox block per hit: word0 = the coin drawn at this hit (:165 / :182), words 1..3 = the
-            // direction of the scatter that leaves it (:93-95). At the last depth nothing downstream
-            // reads the coin, so the block is not generated at all.
-            const bool last = depth == fr.max_bounces;
-            uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (!last) w = philox4x32_10(pixel, s_begin + (uint32_t)s, (uint32_t)depth, 0u, fr.seed_lo, fr.seed_hi);
-            const float coin = amount >= unit_from_word(w.x) ? 1.f : 0.f;
-            if (depth == 0) { L = emis; T = base; }                               // :162-163
-            else {
-                L = cadd(L, cmul(emis, T));                                       // :183
-                T = cmul(T, clerp(base, spec, coin));                             // :184 (dead at the last depth)
-            }
-            if (last) { c = L; done = true; }
-            else {
-                if (depth != 0) T = cscale(T, fr.dissipation);                    // :169-171
-                const float3 refl = reflect3(d, h.n);                             // :172
-                float3 sr = hemisphere_dir(w, h.n);                               // :174
-                sr = normalized3(lerp3(sr, refl, smooth * coin));                 // :175-176
-                o = add3(h.p, scale3(h.n, fr.eps));                               // :177
-                d = sr;
-                ++depth;
-                done = false;
-            }
-        }
-        if (done) {
+        if (shade_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth, c)) {
             acc.x += c.x; acc.y += c.y; acc.z += c.z;
             ++s; depth = 0; o = fr.cam_pos; d = d0;
         }
@@ -208,6 +175,180 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     unsigned int total = segs;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(0xffffffffu, total, off);
+    if ((threadIdx.x & 31) == 0 && total) { atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total); }
+}
+
+// ---- BVH render kernel with warp-level phase scheduling ---------------------------------------
+// Same lane-owns-a-pixel / regeneration scheme as k_render_regen, but the BVH traversal is an
+// explicit per-lane state machine and the WARP decides what runs next, so no lane waits for the
+// slowest ray of its warp:
+//   NODE  one inner-node visit (two slab tests, push far child with its entry distance)
+//   LEAF  one primitive test with the strict reference arithmetic
+//   WAIT  traversal finished: the hit is pending shading
+//   DEAD  the lane's pixel has all its samples
+// Each warp iteration ballots the states and runs exactly ONE of: the shading block (when nothing is
+// traversing any more, or at least `wait_k` lanes are waiting), the NODE block or the LEAF block
+// (whichever has more lanes). Shaded lanes immediately get their next ray (scatter or next sample), so
+// traversal runs with most lanes busy instead of the mean/max trip-count ratio of a per-ray loop.
+// Results are bit-identical to the other back ends (same candidate semantics, same strict tests).
+#ifndef RTB_BVH_MIN_BLOCKS
+#define RTB_BVH_MIN_BLOCKS 5
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, RTB_BVH_MIN_BLOCKS) k_render_bvh(SceneView sc, BvhView bv, FrameView fr,
+                                                                           float4* __restrict__ accum, uint32_t s_begin,
+                                                                           int n_samples, unsigned long long* __restrict__ seg_counter,
+                                                                           int wait_k) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
+    const float4* __restrict__ nodes = tc.nodes;
+    const int* __restrict__ refs = tc.refs;
+    int* const stk = tc.stack;                                   // [entry][thread] links
+    float* const stk_t = reinterpret_cast<float*>(tc.stack + bv.stack_entries * tc.stride);   // entry distances
+    const int stride = tc.stride;
+    constexpr unsigned FULL = 0xffffffffu;
+    enum { NODE = 0, LEAF = 1, WAIT = 2, DEAD = 3 };
+
+    int px, py;
+    const bool inside = tile_pixel(fr, px, py);
+    const uint32_t pixel = inside ? (uint32_t)px + (uint32_t)py * (uint32_t)fr.width : 0u;
+    const float3 d0 = ray_dir(fr, px, py);
+    float3 acc = f3(0.f, 0.f, 0.f);
+    float3 o = fr.cam_pos, d = d0;
+    float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
+    int s = 0, depth = 0;
+    unsigned int segs = 0;
+
+    // traversal state
+    float ix, iy, iz, ox, oy, oz;
+    float best_t; int best_id, best_ref;
+    int cur = 0, li = 0, lend = 0, sp = 0;
+    int st = (inside && n_samples > 0) ? NODE : DEAD;
+
+    auto begin_ray = [&]() {
+        const float big = 1e30f;
+        ix = fabsf(d.x) > 1e-30f ? 1.f / d.x : copysignf(big, d.x);
+        iy = fabsf(d.y) > 1e-30f ? 1.f / d.y : copysignf(big, d.y);
+        iz = fabsf(d.z) > 1e-30f ? 1.f / d.z : copysignf(big, d.z);
+        ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
+        best_t = __int_as_float(0x7f800000); best_id = 0x7fffffff; best_ref = 0;
+        cur = 0; sp = 0; st = NODE;
+    };
+    auto enter = [&](int link) -> bool {                     // false: empty leaf, keep popping
+        if (link >= 0) { cur = link; st = NODE; return true; }
+        const unsigned v = (unsigned)(~link);
+        const int cnt = (int)(v >> 24);
+        if (cnt == 0) return false;
+        li = (int)(v & 0xffffffu); lend = li + cnt; st = LEAF;
+        return true;
+    };
+    auto pop = [&]() {
+        for (;;) {
+            if (sp == 0) { st = WAIT; return; }
+            --sp;
+            const int link = stk[sp * stride];
+            const float tn = stk_t[sp * stride];
+            if (tn > best_t) continue;                           // entered after the best hit found since the push
+            if (enter(link)) return;
+        }
+    };
+    if (st == NODE) begin_ray();
+
+    int alive_cnt = __popc(__ballot_sync(FULL, st != DEAD));
+    int k_eff = max(1, min(wait_k, (alive_cnt * 3) >> 2));
+    for (;;) {
+        const unsigned m_node = __ballot_sync(FULL, st == NODE);
+        const unsigned m_leaf = __ballot_sync(FULL, st == LEAF);
+        const unsigned m_wait = __ballot_sync(FULL, st == WAIT);
+        if ((m_node | m_leaf) == 0u || __popc(m_wait) >= k_eff) {
+            if (m_wait == 0u) break;                             // nothing traversing, nothing pending: all lanes done
+            if (st == WAIT) {
+                Hit h;
+                h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f); h.p = f3(0.f, 0.f, 0.f);
+                if (best_id != 0x7fffffff) {
+                    h.id = best_id; h.t = best_t;
+                    h.p = f3(o.x + d.x * best_t, o.y + d.y * best_t, o.z + d.z * best_t);
+                    if (best_ref >= 0) {
+                        const float4 sp4 = tc.sph[best_ref];
+                        h.n = normalized3(f3(h.p.x - sp4.x, h.p.y - sp4.y, h.p.z - sp4.z));
+                    } else {                                     // cube: the normal comes out of the same test again
+                        float dist; float3 nrm = f3(0.f, 0.f, 0.f);
+                        box_hit(tc.box[2 * (~best_ref)], tc.box[2 * (~best_ref) + 1], o, d, dist, nrm);
+                        h.n = nrm;
+                    }
+                }
+                ++segs;
+                float3 c;
+                if (shade_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth, c)) {
+                    acc.x += c.x; acc.y += c.y; acc.z += c.z;
+                    ++s; depth = 0; o = fr.cam_pos; d = d0;
+                }
+                if (s < n_samples) begin_ray(); else st = DEAD;
+            }
+            alive_cnt = __popc(__ballot_sync(FULL, st != DEAD));
+            k_eff = max(1, min(wait_k, (alive_cnt * 3) >> 2));
+            continue;
+        }
+        if (__popc(m_node) >= __popc(m_leaf)) {
+            if (st == NODE) {
+                const float4 n0 = nodes[4 * cur], n1 = nodes[4 * cur + 1], n2 = nodes[4 * cur + 2];
+                const int2 ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
+                float a, b;
+                a = fmaf(n0.x, ix, ox); b = fmaf(n0.y, ix, ox);
+                float lo0 = fminf(a, b), hi0 = fmaxf(a, b);
+                a = fmaf(n0.z, iy, oy); b = fmaf(n0.w, iy, oy);
+                lo0 = fmaxf(lo0, fminf(a, b)); hi0 = fminf(hi0, fmaxf(a, b));
+                a = fmaf(n1.x, iz, oz); b = fmaf(n1.y, iz, oz);
+                lo0 = fmaxf(lo0, fminf(a, b)); hi0 = fminf(hi0, fmaxf(a, b));
+                a = fmaf(n1.z, ix, ox); b = fmaf(n1.w, ix, ox);
+                float lo1 = fminf(a, b), hi1 = fmaxf(a, b);
+                a = fmaf(n2.x, iy, oy); b = fmaf(n2.y, iy, oy);
+                lo1 = fmaxf(lo1, fminf(a, b)); hi1 = fminf(hi1, fmaxf(a, b));
+                a = fmaf(n2.z, iz, oz); b = fmaf(n2.w, iz, oz);
+                lo1 = fmaxf(lo1, fminf(a, b)); hi1 = fminf(hi1, fmaxf(a, b));
+                const bool h0 = lo0 <= hi0 && hi0 >= 0.f && lo0 <= best_t;
+                const bool h1 = lo1 <= hi1 && hi1 >= 0.f && lo1 <= best_t;
+                if (h0 && h1) {
+                    const bool swap = lo1 < lo0;
+                    stk[sp * stride] = swap ? ch.x : ch.y;
+                    stk_t[sp * stride] = swap ? lo0 : lo1;
+                    ++sp;
+                    if (!enter(swap ? ch.y : ch.x)) pop();
+                } else if (h0) { if (!enter(ch.x)) pop(); }
+                else if (h1) { if (!enter(ch.y)) pop(); }
+                else pop();
+            }
+        } else {
+            if (st == LEAF) {
+                const int r = refs[li];
+                ++li;
+                if (r >= 0) {
+                    float t;
+                    if (sphere_t(tc.sph[r], o, d, t)) {
+                        const int oid = sc.sph_id[r];
+                        if (t < best_t || (t == best_t && oid < best_id)) { best_t = t; best_id = oid; best_ref = r; }
+                    }
+                } else {
+                    const int j = ~r;
+                    float dist; float3 nrm;
+                    if (box_hit(tc.box[2 * j], tc.box[2 * j + 1], o, d, dist, nrm)) {
+                        const int oid = sc.box_id[j];
+                        if (dist < best_t || (dist == best_t && oid < best_id)) { best_t = dist; best_id = oid; best_ref = r; }
+                    }
+                }
+                if (li == lend) pop();
+            }
+        }
+    }
+
+    if (inside) {
+        float4 a4 = accum[pixel];
+        a4.x += acc.x; a4.y += acc.y; a4.z += acc.z;
+        accum[pixel] = a4;
+    }
+    unsigned int total = segs;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(FULL, total, off);
     if ((threadIdx.x & 31) == 0 && total) { atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total); }
 }
 
@@ -289,7 +430,7 @@ static int pick_mode(const SceneView& sc, const BvhView& bv, bool use_bvh, size_
         if (geo <= kMaxStagedBytes) { smem = geo; return 0; }
         smem = 0; return 1;
     }
-    const size_t stack = ((size_t)bv.stack_entries * kThreads * sizeof(int) + 15) / 16 * 16;
+    const size_t stack = ((size_t)2 * bv.stack_entries * kThreads * sizeof(int) + 15) / 16 * 16;
     const size_t all = stack + geo + (size_t)bv.n_nodes * 64 + (size_t)bv.n_refs * 4 + 16;
     if (all <= kMaxBvhStagedBytes) { smem = all; return 2; }
     smem = stack; return 3;
@@ -308,6 +449,8 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(K<2>)) != cudaSuccess) return e; \
     if ((e = optin(K<3>)) != cudaSuccess) return e;
     RTB_OPTIN(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays)
+    if ((e = optin(k_render_bvh<2>)) != cudaSuccess) return e;
+    if ((e = optin(k_render_bvh<3>)) != cudaSuccess) return e;
 #undef RTB_OPTIN
     done = true;
     return cudaSuccess;
@@ -375,6 +518,17 @@ cudaError_t launch_render_regen(const SceneView& sc, const BvhView& bv, bool use
     if (e != cudaSuccess) return e;
     size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
     RTB_DISPATCH(mode, k_render_regen, tile_grid(fr.width, fr.height), sb, st, sc, bv, fr, accum, s_begin, n_samples, seg_counter)
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_bvh(const SceneView& sc, const BvhView& bv, const FrameView& fr, float4* accum, uint32_t s_begin,
+                              int n_samples, unsigned long long* seg_counter, int wait_k, cudaStream_t st) {
+    if (n_samples <= 0) return cudaSuccess;
+    cudaError_t e = ensure_smem_optin();
+    if (e != cudaSuccess) return e;
+    size_t sb; const int mode = pick_mode(sc, bv, true, sb);
+    if (mode == 2) k_render_bvh<2><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, bv, fr, accum, s_begin, n_samples, seg_counter, wait_k);
+    else k_render_bvh<3><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, bv, fr, accum, s_begin, n_samples, seg_counter, wait_k);
     return cudaGetLastError();
 }
 

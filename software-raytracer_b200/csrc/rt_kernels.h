@@ -28,6 +28,8 @@ cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st);
 cudaError_t launch_pick(const SceneView& sc, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st);
 cudaError_t launch_render_regen(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, float4* accum,
                                 uint32_t s_begin, int n_samples, unsigned long long* seg_counter, cudaStream_t st);
+cudaError_t launch_render_bvh(const SceneView& sc, const BvhView& bv, const FrameView& fr, float4* accum, uint32_t s_begin,
+                              int n_samples, unsigned long long* seg_counter, int wait_k, cudaStream_t st);
 cudaError_t launch_render_preview(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, float4* accum,
                                   unsigned long long* seg_counter, cudaStream_t st);
 cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int height, int first, int n, int flip_y,

@@ -1,0 +1,21 @@
+// Host shim so tests can compile csrc/rt_device.cuh with g++ and run the DEVICE functions'
+// logic on the CPU (test infrastructure only - the product never runs this).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+struct float3 { float x, y, z; };
+struct float4 { float x, y, z, w; };
+struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+struct int2 { int x, y; };
+static inline float3 make_float3(float x, float y, float z) { float3 r = {x, y, z}; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+template <typename T> static inline T __ldg(const T* p) { return *p; }

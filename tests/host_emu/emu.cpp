@@ -1,0 +1,64 @@
+// CPU emulation of the render kernel's per-lane loop using the PRODUCT'S OWN device functions
+// (csrc/rt_device.cuh compiled for the host through cuda_shim.h, -ffp-contract=off) and host
+// code (scene packing, frame constants, BVH builder). TEST INFRASTRUCTURE: lets the CPU-only
+// test run check the device-side logic against the oracle without a GPU. Never shipped, never
+// loaded by the product.
+#include "cuda_shim.h"
+#define RTB_HOST_EMULATION 1
+#include "../../software-raytracer_b200/csrc/rt_device.cuh"
+#include "../../software-raytracer_b200/csrc/rt_host_pack.h"
+#include "../../software-raytracer_b200/csrc/bvh_build.h"
+
+using namespace rtb;
+
+extern "C" {
+// Sum over samples [s0, s0+n) for every pixel (float3 per pixel, y-up); accel 0 = brute force,
+// 1 = BVH candidates. Also returns primary AOVs when the pointers are given. Returns segments traced.
+long long emu_render(const rt_object* objects, int n_obj, const rt_camera* cam, const rt_params* par, int accel,
+                     uint32_t s0, int n, float* out_rgb, int32_t* aov_id, float* aov_t, float* aov_n, float* aov_p) {
+    std::vector<rt_object> objs(objects, objects + n_obj);
+    std::vector<float4> sph, box, mat; std::vector<int> sph_id, box_id;
+    pack_scene(objs, sph, sph_id, box, box_id, mat);
+    SceneView sc;
+    sc.sph = sph.data(); sc.sph_id = sph_id.data(); sc.box = box.data(); sc.box_id = box_id.data(); sc.mat = mat.data();
+    sc.n_sph = (int)sph_id.size(); sc.n_box = (int)box_id.size(); sc.n_obj = n_obj;
+    FrameView fr;
+    fill_frame_view(*cam, *par, fr);
+    HostBvh bvh;
+    float ext = 0.f;
+    for (int k = 0; k < 3; ++k) ext = fmaxf(ext, fabsf(cam->pos[k]));
+    build_bvh(objs, ext, bvh);
+    const float4* nodes = reinterpret_cast<const float4*>(bvh.nodes.data());
+    std::vector<int> stack((size_t)bvh.max_depth + 8);
+    long long segs = 0;
+    for (int py = 0; py < fr.height; ++py)
+        for (int px = 0; px < fr.width; ++px) {
+            const uint32_t pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
+            const float3 d0 = ray_dir(fr, px, py);
+            auto trace = [&](float3 o, float3 d) {
+                return accel ? closest_hit_bvh(sc, sc.sph, sc.box, nodes, bvh.refs.data(), stack.data(), 1, o, d)
+                             : closest_hit(sc, sc.sph, sc.box, o, d);
+            };
+            if (aov_id) {
+                Hit h = trace(fr.cam_pos, d0);
+                aov_id[pixel] = h.id; aov_t[pixel] = h.t;
+                aov_n[3 * pixel] = h.n.x; aov_n[3 * pixel + 1] = h.n.y; aov_n[3 * pixel + 2] = h.n.z;
+                aov_p[3 * pixel] = h.p.x; aov_p[3 * pixel + 1] = h.p.y; aov_p[3 * pixel + 2] = h.p.z;
+            }
+            float3 acc = f3(0.f, 0.f, 0.f);
+            float3 o = fr.cam_pos, d = d0, T = f3(0, 0, 0), L = f3(0, 0, 0);
+            int s = 0, depth = 0;
+            while (s < n) {
+                Hit h = trace(o, d);
+                ++segs;
+                float3 c;
+                if (shade_segment(sc, fr, h, pixel, s0 + (uint32_t)s, o, d, T, L, depth, c)) {
+                    acc.x += c.x; acc.y += c.y; acc.z += c.z;
+                    ++s; depth = 0; o = fr.cam_pos; d = d0;
+                }
+            }
+            if (out_rgb) { out_rgb[3 * pixel] = acc.x; out_rgb[3 * pixel + 1] = acc.y; out_rgb[3 * pixel + 2] = acc.z; }
+        }
+    return segs;
+}
+}
