@@ -102,8 +102,8 @@ enum {
     RT_OPT_PIPELINE = 1,           /* RT_PIPELINE_* */
     RT_OPT_ACCEL = 2,              /* RT_ACCEL_* */
     RT_OPT_BVH_THRESHOLD = 3,      /* object count at which RT_ACCEL_AUTO switches to the BVH */
-    RT_OPT_BVH_SCHED = 4,          /* 1 (default): warp-scheduled BVH kernel, 0: per-ray traversal loop */
-    RT_OPT_BVH_WAIT_K = 5          /* lanes waiting for shading that trigger a shading pass (default 8) */
+    RT_OPT_BVH_SCHED = 4,          /* 0 (default): per-ray traversal loop, 1: experimental warp-scheduled BVH kernel */
+    RT_OPT_BVH_WAIT_K = 5          /* scheduled kernel: waiting lanes that trigger a shading pass (default 20) */
 };
 enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
 enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2 };
@@ -145,6 +145,9 @@ int rt_set_option(rt_ctx* ctx, int option, int value);
  * sample indices of every rt_render_spp call, so the reduced image does not depend on the
  * GPU count (up to float summation order). Default (0, 1). */
 int rt_set_shard(rt_ctx* ctx, int rank, int world);
+/* The shard arithmetic itself (host only, no context): for a call adding `spp` global samples starting
+ * at global index `next_sample`, rank r of `world` traces samples [*first, *first + *count). */
+int rt_shard_range(int spp, int rank, int world, uint32_t next_sample, uint32_t* first, int* count);
 
 /* ---- the hot path --------------------------------------------------------------------- */
 /* `setFrame = true; ACCUMULATIONFRAMES = 1` (Raytracer.cpp:576-581). */

@@ -60,7 +60,10 @@ struct rt_ctx {
     uint64_t paths = 0, total_paths = 0, total_segments_base = 0;
     int rank = 0, world = 1;
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
-    int opt_bvh_sched = 1, opt_bvh_wait_k = 8;
+    int opt_bvh_sched = 0, opt_bvh_wait_k = 20;
+    int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
+    float4* d_tune = nullptr; size_t cap_tune = 0;
+    float tune_ms[2] = {0.f, 0.f};
     int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;
     float last_render_ms = 0.f, last_resolve_ms = 0.f;
     bool render_timed = false, resolve_timed = false;
@@ -140,7 +143,7 @@ int upload_scene(rt_ctx* c) {
     c->view.box = c->d_box; c->view.box_id = c->d_box_id;
     c->view.mat = c->d_mat;
     c->view.n_sph = (int)sph_id.size(); c->view.n_box = (int)box_id.size(); c->view.n_obj = (int)objs.size();
-    c->bvh_valid = false;
+    c->bvh_valid = false; c->tuned_accel = -1;
     return RT_OK;
 }
 
@@ -167,7 +170,43 @@ int ensure_bvh(rt_ctx* c, float origin_extent) {
 bool want_bvh(const rt_ctx* c) {
     if (c->opt_accel == RT_ACCEL_BVH) return true;
     if (c->opt_accel == RT_ACCEL_BRUTE) return false;
+    if (c->tuned_accel >= 0) return c->tuned_accel == RT_ACCEL_BVH;
     return c->view.n_sph + c->view.n_box >= c->opt_bvh_threshold;
+}
+
+float camera_extent(const rt_ctx* c);
+int ensure_bvh(rt_ctx* c, float origin_extent);
+
+// RT_ACCEL_AUTO between 8 and `bvh_threshold` primitives: both back ends give identical results and
+// which one is faster depends on the scene (open scenes favour the BVH, closed rooms the brute-force
+// loop), so the first path-mode render after a scene/camera/parameter change times 4 spp of each into
+// a scratch buffer and keeps the faster. Below 8 primitives brute force, above the threshold the BVH.
+int autotune_accel(rt_ctx* c) {
+    if (c->opt_accel != RT_ACCEL_AUTO || c->tuned_accel >= 0) return RT_OK;
+    const int n = c->view.n_sph + c->view.n_box;
+    if (n < 8) { c->tuned_accel = RT_ACCEL_BRUTE; return RT_OK; }
+    if (n >= c->opt_bvh_threshold) { c->tuned_accel = RT_ACCEL_BVH; return RT_OK; }
+    int rc = ensure_bvh(c, camera_extent(c));
+    if (rc != RT_OK) return rc;
+    const size_t px = (size_t)c->par.width * c->par.height;
+    RT_CUDA(c, ensure_capacity(c->d_tune, c->cap_tune, px));
+    cudaEvent_t e[3];
+    for (auto& ev : e) RT_CUDA(c, cudaEventCreate(&ev));
+    unsigned long long* dummy = c->d_counters + 2;            // not part of the reported statistics
+    cudaError_t err = cudaSuccess;
+    for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 warms the instruction cache
+        cudaEventRecord(e[0], c->stream);
+        err = launch_render_regen(c->view, c->bview, false, c->frame, c->d_tune, 0u, 4, dummy, c->stream);
+        cudaEventRecord(e[1], c->stream);
+        if (err == cudaSuccess) err = launch_render_regen(c->view, c->bview, true, c->frame, c->d_tune, 0u, 4, dummy, c->stream);
+        cudaEventRecord(e[2], c->stream);
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+    if (err == cudaSuccess) { cudaEventElapsedTime(&c->tune_ms[0], e[0], e[1]); cudaEventElapsedTime(&c->tune_ms[1], e[1], e[2]); }
+    for (auto& ev : e) cudaEventDestroy(ev);
+    if (err != cudaSuccess) return cuda_fail(c, err, "autotune_accel");
+    c->tuned_accel = c->tune_ms[1] < c->tune_ms[0] ? RT_ACCEL_BVH : RT_ACCEL_BRUTE;
+    return RT_OK;
 }
 
 float camera_extent(const rt_ctx* c) {
@@ -281,7 +320,7 @@ int rt_destroy(rt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
-    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs);
+    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_tune);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -311,6 +350,10 @@ int rt_save_scene(rt_ctx* c, const char* json_path) {
 int rt_set_scene(rt_ctx* c, const rt_object* objects, int n) {
     if (!c || n < 0 || (n > 0 && !objects)) return fail(c, RT_ERR_INVALID, "rt_set_scene: bad arguments");
     RT_CUDA(c, cudaSetDevice(c->device));
+    // identical content (a host that re-submits its object array every frame): the device copy is still
+    // refreshed, but the BVH and the back-end choice stay valid
+    const bool same = (size_t)n == c->scene.objects.size() && c->bvh_valid &&
+                      (n == 0 || memcmp(objects, c->scene.objects.data(), (size_t)n * sizeof(rt_object)) == 0);
     c->scene.objects.assign(objects, objects + n);
     c->scene.names.resize((size_t)n);
     for (rt_object& o : c->scene.objects) {                    // Color ctor clamp (Common.hpp:253-262)
@@ -320,8 +363,11 @@ int rt_set_scene(rt_ctx* c, const rt_object* objects, int n) {
             if (o.spec_color[k] < 0) o.spec_color[k] = 0;
         }
     }
+    const int keep_tuned = same ? c->tuned_accel : -1;
     int rc = upload_scene(c);
     if (rc != RT_OK) return rc;
+    if (same) c->bvh_valid = true;
+    c->tuned_accel = keep_tuned;
     return rt_reset_accumulation(c);
 }
 
@@ -365,6 +411,7 @@ const char* rt_scene_name(rt_ctx* c) { return c ? c->scene.scene_name.c_str() : 
 
 int rt_set_camera(rt_ctx* c, const rt_camera* cam) {
     if (!c || !cam) return RT_ERR_INVALID;
+    if (memcmp(&c->cam, cam, sizeof *cam) != 0) c->tuned_accel = -1;
     c->cam = *cam;
     c->frame_dirty = true;
     return RT_OK;
@@ -376,6 +423,7 @@ int rt_set_params(rt_ctx* c, const rt_params* p) {
         return fail(c, RT_ERR_INVALID, "rt_set_params: bad resolution");
     if (p->mode != RT_MODE_PATH && p->mode != RT_MODE_PREVIEW) return fail(c, RT_ERR_INVALID, "rt_set_params: bad mode");
     bool resized = p->width != c->par.width || p->height != c->par.height;
+    if (resized || p->max_bounces != c->par.max_bounces || p->mode != c->par.mode) c->tuned_accel = -1;
     c->par = *p;
     if (c->par.max_bounces < 0) c->par.max_bounces = 0;        // MAXBOUNCES = max(MAXBOUNCES, 0) Raytracer.cpp:475
     c->frame_dirty = true;
@@ -407,6 +455,14 @@ int rt_set_shard(rt_ctx* c, int rank, int world) {
     return RT_OK;
 }
 
+int rt_shard_range(int spp, int rank, int world, uint32_t next_sample, uint32_t* first, int* count) {
+    if (spp < 0 || world < 1 || rank < 0 || rank >= world || !first || !count) return RT_ERR_INVALID;
+    const int base = spp / world, rem = spp % world;          // the first `rem` ranks take one extra sample
+    *count = base + (rank < rem ? 1 : 0);
+    *first = next_sample + (uint32_t)(rank * base + (rank < rem ? rank : rem));
+    return RT_OK;
+}
+
 int rt_reset_accumulation(rt_ctx* c) {
     int rc = prepare(c);
     if (rc != RT_OK) return rc;
@@ -423,6 +479,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
     if (spp < 0) return fail(c, RT_ERR_INVALID, "rt_render_spp: negative spp");
     if (spp == 0) return RT_OK;
     const size_t px = (size_t)c->par.width * c->par.height;
+    if (c->par.mode == RT_MODE_PATH && (rc = autotune_accel(c)) != RT_OK) return rc;
     const bool bvh = want_bvh(c);
     if (bvh && (rc = ensure_bvh(c, camera_extent(c))) != RT_OK) return rc;
     c->used_accel = bvh ? RT_ACCEL_BVH : RT_ACCEL_BRUTE;
@@ -433,9 +490,8 @@ int rt_render_spp(rt_ctx* c, int spp) {
         c->samples = 1; c->next_sample = 0; c->paths += px; c->total_paths += px;
     } else {
         // this rank's slice of the global sample indices [next, next+spp)
-        const int base = spp / c->world, rem = spp % c->world;
-        const int mine = base + (c->rank < rem ? 1 : 0);
-        const uint32_t first = c->next_sample + (uint32_t)(c->rank * base + (c->rank < rem ? c->rank : rem));
+        int mine = 0; uint32_t first = 0;
+        rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
         if (bvh && c->opt_bvh_sched)
             RT_CUDA(c, launch_render_bvh(c->view, c->bview, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else

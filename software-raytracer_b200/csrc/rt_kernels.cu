@@ -13,6 +13,9 @@ namespace {
 
 constexpr int kTileW = 16, kTileH = 8;          // CTA tile: 4 warps, each an 8x4 pixel block
 constexpr int kThreads = 128;
+#ifndef RTB_BVH_POP_CULL
+#define RTB_BVH_POP_CULL 1             // big (global-memory) BVHs: keep the far child's entry distance on the stack, skip stale pops
+#endif
 #ifndef RTB_REGEN_MIN_BLOCKS
 #define RTB_REGEN_MIN_BLOCKS 6      // register budget of the render kernel: 65536 / (128 * 6) -> 80 registers
 #endif
@@ -23,16 +26,17 @@ constexpr int kThreads = 128;
 // Shared memory layout: [BVH stack: stack_entries x blockDim ints][spheres][cubes][nodes][refs]
 struct TraceCtx {
     const float4* sph; const float4* box; const float4* nodes; const int* refs;
-    int* stack; int stride;
+    int* stack; float* stack_t; int stride;
 };
 
 template <int MODE>
 __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhView& bv, float4* smem) {
     TraceCtx t;
-    t.sph = sc.sph; t.box = sc.box; t.nodes = bv.nodes; t.refs = bv.refs; t.stack = nullptr; t.stride = blockDim.x;
+    t.sph = sc.sph; t.box = sc.box; t.nodes = bv.nodes; t.refs = bv.refs; t.stack = nullptr; t.stack_t = nullptr; t.stride = blockDim.x;
     float4* p = smem;
     if (MODE >= 2) {
         t.stack = reinterpret_cast<int*>(p) + threadIdx.x;
+        t.stack_t = reinterpret_cast<float*>(t.stack + bv.stack_entries * blockDim.x);
         p += (2 * bv.stack_entries * blockDim.x + 3) / 4;      // links + entry distances
     }
     if (MODE == 0 || MODE == 2) {
@@ -56,7 +60,7 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
 
 template <int MODE>
 __device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d) {
-    if (MODE >= 2) return closest_hit_bvh(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d);
+    if (MODE >= 2) return closest_hit_bvh(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr);
     return closest_hit(sc, t.sph, t.box, o, d);
 }
 
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, RTB_BVH_MIN_BLOCKS) k_render_bvh(Sce
     const float4* __restrict__ nodes = tc.nodes;
     const int* __restrict__ refs = tc.refs;
     int* const stk = tc.stack;                                   // [entry][thread] links
-    float* const stk_t = reinterpret_cast<float*>(tc.stack + bv.stack_entries * tc.stride);   // entry distances
+    float* const stk_t = tc.stack_t;                             // entry distances
     const int stride = tc.stride;
     constexpr unsigned FULL = 0xffffffffu;
     enum { NODE = 0, LEAF = 1, WAIT = 2, DEAD = 3 };

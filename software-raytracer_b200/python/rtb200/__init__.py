@@ -56,7 +56,7 @@ assert OBJECT_DTYPE.itemsize == C.sizeof(RtObject) == 76
 EXPORTS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_load_scene", "rt_save_scene", "rt_set_scene",
     "rt_get_scene", "rt_default_params", "rt_default_camera", "rt_rotate_camera", "rt_set_camera", "rt_set_params",
-    "rt_set_option", "rt_set_shard", "rt_reset_accumulation", "rt_render_spp", "rt_resolve_rgba8", "rt_pick",
+    "rt_set_option", "rt_set_shard", "rt_shard_range", "rt_reset_accumulation", "rt_render_spp", "rt_resolve_rgba8", "rt_pick",
     "rt_read_accum", "rt_read_aov", "rt_read_ray_dirs", "rt_trace_rays", "rt_env_color", "rt_philox_block",
     "rt_scene_file_read", "rt_scene_file_write", "rt_object_name", "rt_set_object_name", "rt_scene_name",
     "rt_write_accum", "rt_selftest", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
@@ -147,6 +147,14 @@ def scene_file_write(path, objs, names=None, scene_name=""):
     if names is not None:
         arr = (C.c_char_p * len(objs))(*[n.encode() for n in names])
     return lib.rt_scene_file_write(str(path).encode(), scene_name.encode(), _p(objs), arr, len(objs))
+
+
+def shard_range(spp, rank, world, next_sample=0):
+    first, count = C.c_uint32(0), C.c_int(0)
+    rc = load_library().rt_shard_range(spp, rank, world, C.c_uint32(next_sample), C.byref(first), C.byref(count))
+    if rc != RT_OK:
+        raise RtError(rc, "rt_shard_range: bad arguments")
+    return first.value, count.value
 
 
 class PathTracer:

@@ -358,7 +358,7 @@ def test_bvh_hit_for_hit_bundled(tracer, scenes, golden, meta, scene):
         assert np.array_equal(bits(a), bits(b)) and sa.segments == sb.segments
         # the per-ray traversal loop (RT_OPT_BVH_SCHED 0) and other scheduling thresholds give the same bits
         tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_BVH)
-        for sched, k in ((0, 8), (1, 1), (1, 31)):
+        for sched, k in ((1, 20), (1, 1), (1, 31)):
             tracer.set_option(rtb200.RT_OPT_BVH_SCHED, sched); tracer.set_option(rtb200.RT_OPT_BVH_WAIT_K, k)
             tracer.reset_accumulation()
             tracer.render_spp(16)
@@ -366,7 +366,7 @@ def test_bvh_hit_for_hit_bundled(tracer, scenes, golden, meta, scene):
             assert np.array_equal(bits(a), bits(c2)) and tracer.stats().segments == sa.segments, (sched, k)
     finally:
         tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
-        tracer.set_option(rtb200.RT_OPT_BVH_SCHED, 1); tracer.set_option(rtb200.RT_OPT_BVH_WAIT_K, 8)
+        tracer.set_option(rtb200.RT_OPT_BVH_SCHED, 0); tracer.set_option(rtb200.RT_OPT_BVH_WAIT_K, 20)
 
 
 @pytest.mark.parametrize("scene", ["Scene1", "Scene2", "Scene3", "Scene_indirect"])
