@@ -126,6 +126,10 @@ int rt_get_scene(rt_ctx* ctx, rt_object* out, int max_objects);     /* returns c
  * objects parsed (also on RT_ERR_PARSE: the partial-load count). names may be NULL. */
 int rt_scene_file_read(const char* json_path, rt_object* out, int max_objects, int* n_total,
                        char* err_buf, int err_buf_len);
+/* Names of the same file: object names as consecutive NUL-terminated strings in names_buf (in object
+ * order; returns the number of bytes needed), the scene's "SceneName" in scene_name. */
+int rt_scene_file_read_names(const char* json_path, char* names_buf, int names_buf_len,
+                             char* scene_name, int scene_name_len);
 int rt_scene_file_write(const char* json_path, const char* scene_name, const rt_object* objects,
                         const char* const* names, int n);
 /* Object / scene names travel with the scene (Object::name, Scene::sceneName). */

@@ -389,6 +389,25 @@ int rt_scene_file_read(const char* json_path, rt_object* out, int max_objects, i
     return rc;
 }
 
+int rt_scene_file_read_names(const char* json_path, char* names_buf, int names_buf_len, char* scene_name, int scene_name_len) {
+    if (!json_path) return RT_ERR_INVALID;
+    HostScene sc;
+    std::string err;
+    sc.Load(json_path, err);
+    size_t need = 0;
+    for (const std::string& n : sc.names) need += n.size() + 1;
+    if (names_buf && names_buf_len > 0) {
+        size_t off = 0;
+        for (const std::string& n : sc.names) {
+            if (off + n.size() + 1 > (size_t)names_buf_len) break;
+            memcpy(names_buf + off, n.c_str(), n.size() + 1);
+            off += n.size() + 1;
+        }
+    }
+    if (scene_name && scene_name_len > 0) { strncpy(scene_name, sc.scene_name.c_str(), (size_t)scene_name_len - 1); scene_name[scene_name_len - 1] = 0; }
+    return (int)need;
+}
+
 int rt_scene_file_write(const char* json_path, const char* scene_name, const rt_object* objects, const char* const* names, int n) {
     if (!json_path || n < 0 || (n > 0 && !objects)) return RT_ERR_INVALID;
     HostScene sc;

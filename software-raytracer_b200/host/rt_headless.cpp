@@ -1,0 +1,74 @@
+// rt_headless - headless driver over the C-ABI: the reference's main loop without SDL/ImGui.
+//   rt_headless --scene Scenes/Scene1.json [--width 1280 --height 720 --spp 64 --bounces 8]
+//               [--preview] [--out frame.ppm] [--interactive N]
+// --interactive N: N frames of 1 spp + resolve + download each (the viewer's per-frame work,
+// BASELINE config 5) and prints p50/p99 frame latency.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+#include "rt_host.hpp"
+
+int main(int argc, char** argv) {
+    std::string scene_path, out_path;
+    int w = 1280, h = 720, spp = 64, bounces = 8, interactive = 0;
+    bool preview = false;
+    for (int i = 1; i < argc; ++i) {
+        auto arg = [&](const char* n) { return !strcmp(argv[i], n) && i + 1 < argc; };
+        if (arg("--scene")) scene_path = argv[++i];
+        else if (arg("--width")) w = atoi(argv[++i]);
+        else if (arg("--height")) h = atoi(argv[++i]);
+        else if (arg("--spp")) spp = atoi(argv[++i]);
+        else if (arg("--bounces")) bounces = atoi(argv[++i]);
+        else if (arg("--out")) out_path = argv[++i];
+        else if (arg("--interactive")) interactive = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--preview")) preview = true;
+        else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
+    }
+    if (scene_path.empty()) { fprintf(stderr, "usage: rt_headless --scene file.json [options]\n"); return 2; }
+    try {
+        rtb200::Scene scene1(scene_path);
+        scene1.Load();
+        if (scene1.lastStatus != RT_OK) fprintf(stderr, "scene load: %s (continuing with %zu objects, like the reference)\n",
+                                                scene1.lastError.c_str(), scene1.GetObjects().size());
+        rtb200::Raytracer rt(w, h);
+        rt.SetObjectsToRender(scene1.GetObjects());
+        rt.SIMPLEDRAW = preview; rt.MAXBOUNCES = bounces; rt.TARGETFRAMES = 1 << 30;
+        std::vector<uint32_t> surface((size_t)w * h);
+        using clk = std::chrono::steady_clock;
+        if (interactive > 0) {
+            std::vector<double> ms;
+            for (int f = 0; f < interactive + 10; ++f) {
+                auto t0 = clk::now();
+                rt.RenderFrame();
+                rt.Present(surface.data(), w * 4);
+                double d = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+                if (f >= 10) ms.push_back(d);
+            }
+            std::sort(ms.begin(), ms.end());
+            printf("{\"frames\": %d, \"width\": %d, \"height\": %d, \"p50_ms\": %.4f, \"p99_ms\": %.4f, \"mean_ms\": %.4f}\n", interactive, w, h,
+                   ms[ms.size() / 2], ms[(size_t)(ms.size() * 0.99)], [&] { double s = 0; for (double v : ms) s += v; return s / ms.size(); }());
+        } else {
+            auto t0 = clk::now();
+            rt.RenderFrame();                                        // first frame: overwrite
+            if (!preview && spp > 1) {                               // the rest of the accumulation in one call
+                if (rt_render_spp(rt.Context(), spp - 1) < 0) throw std::runtime_error(rt_last_error(rt.Context()));
+                rt.ACCUMULATIONFRAMES = spp;
+            }
+            rt.Present(surface.data(), w * 4);
+            double ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+            rt_stats st; rt_get_stats(rt.Context(), &st);
+            printf("{\"objects\": %u, \"spp\": %u, \"paths\": %llu, \"segments\": %llu, \"wall_ms\": %.3f, \"render_ms\": %.3f}\n", st.n_objects,
+                   st.samples, (unsigned long long)st.paths, (unsigned long long)st.segments, ms, st.last_render_ms);
+        }
+        if (!out_path.empty()) {                                     // binary PPM of the ARGB surface
+            std::ofstream f(out_path, std::ios::binary);
+            f << "P6\n" << w << " " << h << "\n255\n";
+            for (uint32_t p : surface) { char rgb[3] = {(char)(p >> 16), (char)(p >> 8), (char)p}; f.write(rgb, 3); }
+        }
+    } catch (const std::exception& e) { fprintf(stderr, "rt_headless: %s\n", e.what()); return 1; }
+    return 0;
+}

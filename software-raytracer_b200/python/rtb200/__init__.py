@@ -58,7 +58,7 @@ EXPORTS = [
     "rt_get_scene", "rt_default_params", "rt_default_camera", "rt_rotate_camera", "rt_set_camera", "rt_set_params",
     "rt_set_option", "rt_set_shard", "rt_shard_range", "rt_reset_accumulation", "rt_render_spp", "rt_resolve_rgba8", "rt_pick",
     "rt_read_accum", "rt_read_aov", "rt_read_ray_dirs", "rt_trace_rays", "rt_env_color", "rt_philox_block",
-    "rt_scene_file_read", "rt_scene_file_write", "rt_object_name", "rt_set_object_name", "rt_scene_name",
+    "rt_scene_file_read", "rt_scene_file_read_names", "rt_scene_file_write", "rt_object_name", "rt_set_object_name", "rt_scene_name",
     "rt_write_accum", "rt_selftest", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
 ]
 
@@ -138,6 +138,15 @@ def scene_file_read(path):
     if n.value:
         lib.rt_scene_file_read(str(path).encode(), _p(out), n.value, C.byref(n), err, 512)
     return rc, out, err.value.decode()
+
+
+def scene_file_names(path):
+    lib = load_library()
+    need = lib.rt_scene_file_read_names(str(path).encode(), None, 0, None, 0)
+    buf = C.create_string_buffer(max(need, 1)); sn = C.create_string_buffer(1024)
+    lib.rt_scene_file_read_names(str(path).encode(), buf, need, sn, 1024)
+    names = buf.raw[:need].split(b"\0")[:-1] if need else []
+    return [n.decode() for n in names], sn.value.decode()
 
 
 def scene_file_write(path, objs, names=None, scene_name=""):

@@ -91,6 +91,7 @@ def test_scene_reader_and_writer(tmp_path, scenes, meta, scene):
     assert hashlib.sha256(data).hexdigest() == meta["scenes"][scene]["save_sha256"]
     rc, again, _ = rtb200.scene_file_read(dst)        # load -> save -> load round trip
     assert rc == 0 and again.tobytes() == objs.tobytes()
+    assert rtb200.scene_file_names(dst) == (names, scene_name)
 
 
 def test_scene_reader_defaults_and_failures(tmp_path):
@@ -149,3 +150,32 @@ def test_uniform_shortcut_is_exact_on_the_host():
     want = k / np.float32(32767)
     got = (k.astype(np.float64) * (1.0 / 32767.0)).astype(np.float32)
     assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+
+
+def test_cpp_host_mirror_round_trips_a_scene_without_a_gpu(tmp_path, scenes, meta):
+    """host/rt_host.hpp (the C++ mirror of Scene/Object/Transform) compiles against the C-ABI and its
+    Scene::Load -> SaveAs reproduces the reference's file byte for byte."""
+    import subprocess
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "rt_host.hpp"
+#include <cstdio>
+int main(int argc, char** argv) {
+    rtb200::Scene s(argv[1]); s.Load();
+    if (s.lastStatus != RT_OK) return 3;
+    rtb200::Transform cam; cam.RotateAboutAxis(0.35f, rtb200::float3(0, 1, 0)); cam.RotateAboutAxis(-0.2f, cam.right);
+    printf("%zu %s %.9g %.9g %.9g\n", s.GetObjects().size(), s.GetObjects()[64].name.c_str(), cam.forward.x, cam.forward.y, cam.forward.z);
+    s.SaveAs(argv[2]);
+    return s.lastStatus;
+}''')
+    exe = tmp_path / "t"
+    prod = os.path.join(ROOT, "software-raytracer_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(prod, "host"), str(src), "-o", str(exe), "-L" + os.path.join(prod, "lib"),
+                           "-lrt_b200", "-Wl,-rpath," + os.path.join(prod, "lib")])
+    inp = tmp_path / "in.json"
+    _write_json(inp, scenes["Scene1"], meta["scenes"]["Scene1"]["names"], meta["scenes"]["Scene1"]["scene_name"])
+    out = subprocess.check_output([str(exe), str(inp), str(tmp_path / "out.json")]).decode().split()
+    assert out[0] == "67" and out[1] == "big"
+    r = meta["rotated_camera_by_reference"]["forward"]
+    assert [np.float32(v) for v in out[3:6]] == [np.float32(v) for v in r]
+    assert hashlib.sha256((tmp_path / "out.json").read_bytes()).hexdigest() == meta["scenes"]["Scene1"]["save_sha256"]

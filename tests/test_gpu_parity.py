@@ -310,28 +310,7 @@ def test_full_size_properties_1080p(tracer, scenes):
 
 
 # ---- BVH: hit-for-hit against the brute-force object loop ---------------------------------------
-def synthetic_spheres(n, seed=12345, cubes_every=0):
-    """BASELINE config 3 shape (SURVEY.md 8d): random spheres over a ground sphere with emissive lights;
-    materials by thirds: diffuse / metal / 'dielectric-like'."""
-    rng = np.random.default_rng(seed)
-    o = np.zeros(n + 9, rtb200.OBJECT_DTYPE)
-    o["type"] = 1
-    o["pos"][:n] = rng.uniform([-50, 0.2, 5], [50, 20, 105], (n, 3)).astype(np.float32)
-    o["radius"][:n] = rng.uniform(0.2, 1.0, n).astype(np.float32)
-    o["base"][:n] = rng.uniform(0.1, 0.95, (n, 3)).astype(np.float32)
-    o["spec_color"] = 1
-    third = n // 3
-    o["spec_amount"][third:2 * third] = 1; o["smoothness"][third:2 * third] = rng.uniform(0.6, 1, third).astype(np.float32)
-    o["spec_color"][third:2 * third] = o["base"][third:2 * third]
-    o["spec_amount"][2 * third:n] = 0.1; o["smoothness"][2 * third:n] = 1
-    o["pos"][n] = [0, -1000, 50]; o["radius"][n] = 1000; o["base"][n] = 0.8                     # ground
-    for k in range(8):                                                                            # lights
-        o["pos"][n + 1 + k] = [-45 + 12.5 * k, 30, 20 + 10 * k]; o["radius"][n + 1 + k] = 3
-        o["emissive"][n + 1 + k] = 30; o["base"][n + 1 + k] = 1
-    if cubes_every:
-        idx = np.arange(0, n, cubes_every)
-        o["type"][idx] = 2; o["half"][idx] = rng.uniform(0.2, 0.8, (len(idx), 3)).astype(np.float32)
-    return o
+from rtb200.scenes import synthetic_spheres  # noqa: E402
 
 
 @pytest.mark.parametrize("scene", SCENES)
