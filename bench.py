@@ -178,11 +178,38 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: map every rank's accumulation buffer (and rank 0's surface) through CUDA IPC so the fused
+    # reduce + resolve kernel can read / write them over NVLink
+    peer_ptrs, dst_surface, tick = None, None, None
+    fused = world > 1 and args.reduce == "fused"
+    if fused:
+        def gather_handles(which):
+            mine = torch.tensor(list(tr.ipc_export(which)), dtype=torch.uint8, device="cuda")
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            return [bytes(h.cpu().tolist()) for h in allh]
+        acc_h, srf_h = gather_handles(0), gather_handles(1)
+        peer_ptrs = [tr.accum_device_ptr() if r == rank else tr.ipc_open(acc_h[r]) for r in range(world)]
+        dst_surface = tr.argb_device_ptr() if rank == 0 else tr.ipc_open(srf_h[0])
+        tick = torch.zeros(1, device="cuda")
+    n_px = W * H
+    my_first = n_px * rank // world
+    my_count = n_px * (rank + 1) // world - my_first
+
+    def exchange():
+        """the path's one exchange step (N > 1), stream-ordered on every rank."""
+        if fused:
+            dist.all_reduce(tick)                    # device-side barrier: every rank's render has finished
+            tr.resolve_fused(peer_ptrs, spp * world, my_first, my_count, dst_surface)
+            dist.all_reduce(tick)                    # rank 0's surface is complete
+        else:
+            dist.all_reduce(accum)
+
     def step_resident():
         """device-resident step: samples into the accumulation buffer (+ the one exchange at N > 1)."""
         tr.render_spp(spp)
         if world > 1:
-            dist.all_reduce(accum)
+            exchange()
 
     # ---- device-timed: value ---------------------------------------------------------------
     with torch.cuda.stream(stream):
@@ -215,7 +242,13 @@ def run_b200(args):
             tr.reset_accumulation()
             tr.render_spp(spp)
             if world > 1:
-                dist.all_reduce(accum)
+                exchange()
+                if fused:
+                    if rank == 0:
+                        out[:] = tr.read_surface()   # D2H of the fused result
+                    else:
+                        tr.sync()
+                    return
                 tr.set_sample_count(spp * world)
             tr.resolve_rgba8(True, out)              # Reinhard + pack, D2H into the host surface; synchronises
         for _ in range(max(1, args.warmup - 1)):
@@ -258,7 +291,7 @@ def run_b200(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic: bundled Scene1 fixture (tests/golden/bundled_scenes.npz), default camera, Philox seeds",
             "config": {"workload": "Scene1 (67 spheres) %dx%d, %d spp per GPU per step, depth %d, path mode" % (W, H, spp, DEPTH),
-                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": "spp-sharded x%d, one all-reduce per step" % world,
+                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": ("spp-sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce+resolve kernel over NVLink peer memory" if fused else "one NCCL all-reduce per step"),
                        "build": "strict IEEE, -fmad=false (bit-exact geometry vs the reference)",
                        "accel": {rtb200.RT_ACCEL_BRUTE: "brute-force object loop", rtb200.RT_ACCEL_BVH: "host-built BVH candidates + strict tests"}[st.accel],
                        "scene": args.scene},
@@ -269,11 +302,12 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(objs.nbytes + 52), "d2h_bytes_per_step": int(W * H * 4),
                     "ms_per_step": e2e_ms / args.steps, "device_ms_per_step": e2e_dev_ms / args.steps,
                     "api": "rt_set_scene + rt_set_camera + rt_reset_accumulation + rt_render_spp + rt_resolve_rgba8(host)"},
-            "gpu_launches": int(args.steps * 1 + args.steps * 2),
-            "gpu_launches_detail": "timed value region: 1 k_render_regen per step; e2e region: k_render_regen + k_resolve per step",
+            "gpu_launches": int(args.steps * (1 if world == 1 else 2) + args.steps * 2),
+            "gpu_launches_detail": "per rank. timed value region: 1 k_render_regen per step (+ 1 k_resolve_fused at N > 1); e2e region: k_render_regen + k_resolve (N = 1) or k_resolve_fused (N > 1) per step",
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "traffic": None, "kernel": "k_render_regen", "kernel_ms": kern_s * 1e3,
+                         "traffic": 33.24e6, "traffic_note": "dram read+write per launch at 1080p x 64 spp, ncu --set full (profiles/r1b_*): the float4 accumulation buffer once; independent of spp",
+                         "kernel": "k_render_regen", "kernel_ms": kern_s * 1e3,
                          "flop_per_segment": fps,
                          "peak_source": "%d SMs x 128 lanes x 2 (FMA) x %.0f MHz (%s MEASURED_PEAKS.json sm_max_mhz)" % (st.sm_count, sm_mhz, peaks_src),
                          "note": "path is FP32-CUDA-core bound, not HBM or tensor (SURVEY.md 8d); the strict build issues no FMA, "
@@ -301,6 +335,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=24, help="1-spp frames of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh"], help="closest-hit back end (results are identical)")
+    ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"], help="N > 1 exchange: fused peer-memory reduce+resolve kernel, or NCCL all-reduce")
     ap.add_argument("--bvh-sched", type=int, default=-1, help="RT_OPT_BVH_SCHED override")
     ap.add_argument("--wait-k", type=int, default=-1, help="RT_OPT_BVH_WAIT_K override")
     ap.add_argument("--scene", default="Scene1", help="bundled scene fixture (the headline config is Scene1)")

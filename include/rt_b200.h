@@ -206,6 +206,27 @@ int rt_set_sample_count(rt_ctx* ctx, uint32_t samples);
 int rt_resolve_device(rt_ctx* ctx, const void* dev_accum_rgba, uint32_t samples,
                       int first_pixel, int n_pixels, void* dev_out_argb, int flip_y);
 
+/* ---- multi-GPU: fused reduce + resolve over NVLink peer memory ----------------------------
+ * With samples sharded over ranks the only exchange of the path is the sum of the accumulation
+ * buffers before the resolve. Instead of an all-reduce followed by a resolve, every rank runs ONE
+ * kernel over its slice of the pixels that loads that slice from every rank's buffer (its own and
+ * the peers' through NVLink P2P mappings), adds them in rank order, applies Reinhard + ARGB8 pack
+ * and stores the result straight into the destination surface (typically rank 0's, also
+ * peer-mapped): 16 B read per pixel per rank, 4 B written, no intermediate buffer, deterministic
+ * summation order. Buffers of other processes are mapped with the rt_ipc_* helpers (CUDA IPC);
+ * buffers of other contexts in the same process can be passed as they are. The caller makes sure
+ * every rank's render has completed (a barrier) before launching, and again before reading dst. */
+#define RT_IPC_HANDLE_BYTES 64
+#define RT_MAX_PEERS 16
+void* rt_argb_device_ptr(rt_ctx* ctx);                       /* uint32[width*height] resolved surface, device */
+int rt_ipc_export(rt_ctx* ctx, int which /* 0 accumulation, 1 surface */, unsigned char handle[RT_IPC_HANDLE_BYTES]);
+int rt_ipc_open(rt_ctx* ctx, const unsigned char handle[RT_IPC_HANDLE_BYTES], void** dev_ptr);
+int rt_ipc_close(rt_ctx* ctx, void* dev_ptr);
+int rt_resolve_fused(rt_ctx* ctx, const void* const* accum_ptrs, int world, uint32_t total_samples,
+                     int first_pixel, int n_pixels, void* dst_argb_whole_image, int flip_y);
+/* Copies the context's device surface to the host (after a fused resolve wrote it). */
+int rt_read_surface(rt_ctx* ctx, uint32_t* host_out, int pitch_bytes);
+
 #ifdef __cplusplus
 }
 #endif

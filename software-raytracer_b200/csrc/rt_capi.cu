@@ -721,6 +721,66 @@ void* rt_accum_device_ptr(rt_ctx* c) {
     return c->d_accum;
 }
 
+void* rt_argb_device_ptr(rt_ctx* c) {
+    if (!c || prepare(c) != RT_OK) return nullptr;
+    return c->d_argb;
+}
+
+int rt_ipc_export(rt_ctx* c, int which, unsigned char handle[RT_IPC_HANDLE_BYTES]) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (!handle || (which != 0 && which != 1)) return fail(c, RT_ERR_INVALID, "rt_ipc_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RT_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    RT_CUDA(c, cudaIpcGetMemHandle(&h, which == 0 ? (void*)c->d_accum : (void*)c->d_argb));
+    memcpy(handle, &h, sizeof h);
+    return RT_OK;
+}
+
+int rt_ipc_open(rt_ctx* c, const unsigned char handle[RT_IPC_HANDLE_BYTES], void** dev_ptr) {
+    if (!c || !handle || !dev_ptr) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    RT_CUDA(c, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+
+int rt_ipc_close(rt_ctx* c, void* dev_ptr) {
+    if (!c || !dev_ptr) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaIpcCloseMemHandle(dev_ptr));
+    return RT_OK;
+}
+
+int rt_resolve_fused(rt_ctx* c, const void* const* accum_ptrs, int world, uint32_t total_samples, int first_pixel, int n_pixels,
+                     void* dst, int flip_y) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (!accum_ptrs || !dst || world < 1 || world > RT_MAX_PEERS || first_pixel < 0 || n_pixels < 0 ||
+        (long long)first_pixel + n_pixels > (long long)c->par.width * c->par.height)
+        return fail(c, RT_ERR_INVALID, "rt_resolve_fused: bad arguments");
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof pp);
+    for (int r = 0; r < world; ++r) {
+        if (!accum_ptrs[r]) return fail(c, RT_ERR_INVALID, "rt_resolve_fused: NULL peer buffer");
+        pp.p[r] = (const float4*)accum_ptrs[r];
+    }
+    RT_CUDA(c, launch_resolve_fused(pp, world, total_samples, c->par.width, c->par.height, first_pixel, n_pixels, flip_y,
+                                    (uint32_t*)dst, c->stream));
+    return RT_OK;
+}
+
+int rt_read_surface(rt_ctx* c, uint32_t* host_out, int pitch_bytes) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    const int w = c->par.width, h = c->par.height;
+    if (!host_out || pitch_bytes < w * 4) return fail(c, RT_ERR_INVALID, "rt_read_surface: bad output buffer");
+    RT_CUDA(c, cudaMemcpy2DAsync(host_out, (size_t)pitch_bytes, c->d_argb, (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyDeviceToHost, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
 int rt_set_stream(rt_ctx* c, void* cuda_stream) {
     if (!c) return RT_ERR_INVALID;
     RT_CUDA(c, cudaSetDevice(c->device));

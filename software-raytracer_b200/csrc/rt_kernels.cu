@@ -420,6 +420,24 @@ __global__ void k_resolve(const float4* __restrict__ accum, float count, int wid
     out[out_is_slice ? (size_t)i : dst] = v;
 }
 
+// ---- fused multi-GPU reduce + resolve over peer memory -----------------------------------------
+// One thread per pixel of this rank's slice: float4 loads from every rank's accumulation buffer (the
+// peers' are NVLink P2P mappings: plain ld.global on peer addresses), summed in rank order, then the
+// same resolve as k_resolve, stored into the destination surface (a peer store when it is rank 0's).
+__global__ void k_resolve_fused(PeerPtrs peers, int world, float count, int width, int height, int first, int n, int flip_y,
+                                uint32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = first + i;
+    float4 sum = peers.p[0][p];
+    for (int r = 1; r < world; ++r) {
+        const float4 v = peers.p[r][p];
+        sum.x += v.x; sum.y += v.y; sum.z += v.z;
+    }
+    const int x = p % width, y = p / width;
+    out[(size_t)x + (size_t)(flip_y ? height - 1 - y : y) * width] = resolve_pixel(sum, count);
+}
+
 }  // namespace
 
 // ---- launchers --------------------------------------------------------------------------------
@@ -549,6 +567,13 @@ cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int
                            uint32_t* out, int out_is_slice, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     k_resolve<<<(n + 255) / 256, 256, 0, st>>>(accum, (float)samples, width, height, first, n, flip_y, out, out_is_slice);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_fused(const PeerPtrs& peers, int world, uint32_t samples, int width, int height, int first, int n,
+                                 int flip_y, uint32_t* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_resolve_fused<<<(n + 255) / 256, 256, 0, st>>>(peers, world, (float)samples, width, height, first, n, flip_y, out);
     return cudaGetLastError();
 }
 

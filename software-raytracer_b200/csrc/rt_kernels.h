@@ -17,6 +17,8 @@ constexpr size_t kMaxBvhStagedBytes = 48 * 1024;
 
 size_t staged_bytes(const SceneView& sc);
 
+struct PeerPtrs { const float4* p[16]; };      // every rank's accumulation buffer, rank order (RT_MAX_PEERS)
+
 cudaError_t launch_primary_aov(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, int* id, float* t,
                                float* n, float* p, cudaStream_t st);
 cudaError_t launch_ray_dirs(const FrameView& fr, float* out, cudaStream_t st);
@@ -34,5 +36,8 @@ cudaError_t launch_render_preview(const SceneView& sc, const BvhView& bv, bool u
                                   unsigned long long* seg_counter, cudaStream_t st);
 cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int height, int first, int n, int flip_y,
                            uint32_t* out, int out_is_slice, cudaStream_t st);
+
+cudaError_t launch_resolve_fused(const PeerPtrs& peers, int world, uint32_t samples, int width, int height, int first, int n,
+                                 int flip_y, uint32_t* out, cudaStream_t st);
 
 }  // namespace rtb

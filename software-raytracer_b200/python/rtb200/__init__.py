@@ -60,6 +60,7 @@ EXPORTS = [
     "rt_read_accum", "rt_read_aov", "rt_read_ray_dirs", "rt_trace_rays", "rt_env_color", "rt_philox_block",
     "rt_scene_file_read", "rt_scene_file_read_names", "rt_scene_file_write", "rt_object_name", "rt_set_object_name", "rt_scene_name",
     "rt_write_accum", "rt_selftest", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
+    "rt_argb_device_ptr", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_resolve_fused", "rt_read_surface",
 ]
 
 
@@ -85,10 +86,12 @@ def load_library(path=None):
     lib.rt_last_error.argtypes = [C.c_void_p]
     lib.rt_accum_device_ptr.restype = C.c_void_p
     lib.rt_accum_device_ptr.argtypes = [C.c_void_p]
+    lib.rt_argb_device_ptr.restype = C.c_void_p
+    lib.rt_argb_device_ptr.argtypes = [C.c_void_p]
     lib.rt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name in ("rt_last_error", "rt_accum_device_ptr", "rt_create", "rt_default_params", "rt_default_camera",
+        if name in ("rt_last_error", "rt_accum_device_ptr", "rt_argb_device_ptr", "rt_create", "rt_default_params", "rt_default_camera",
                     "rt_rotate_camera", "rt_abi_version", "rt_object_name", "rt_scene_name"):
             continue
         fn.restype = C.c_int
@@ -315,6 +318,33 @@ class PathTracer:
     # interop
     def accum_device_ptr(self):
         return self.lib.rt_accum_device_ptr(self.h)
+
+    def argb_device_ptr(self):
+        return self.lib.rt_argb_device_ptr(self.h)
+
+    def ipc_export(self, which):
+        buf = (C.c_ubyte * 64)()
+        self._chk(self.lib.rt_ipc_export(self.h, which, buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._chk(self.lib.rt_ipc_open(self.h, (C.c_ubyte * 64).from_buffer_copy(handle), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        return self._chk(self.lib.rt_ipc_close(self.h, C.c_void_p(ptr)))
+
+    def resolve_fused(self, accum_ptrs, total_samples, first_pixel, n_pixels, dst_argb_ptr, flip_y=True):
+        arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
+        return self._chk(self.lib.rt_resolve_fused(self.h, arr, len(accum_ptrs), total_samples, first_pixel, n_pixels,
+                                                   C.c_void_p(dst_argb_ptr), int(flip_y)))
+
+    def read_surface(self):
+        w, h = self.params.width, self.params.height
+        out = np.zeros((h, w), np.uint32)
+        self._chk(self.lib.rt_read_surface(self.h, _p(out), w * 4))
+        return out
 
     def set_stream(self, stream_handle):
         return self._chk(self.lib.rt_set_stream(self.h, C.c_void_p(stream_handle)))

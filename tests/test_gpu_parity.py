@@ -414,3 +414,41 @@ def test_bvh_camera_outside_extent_and_inside_sphere(tracer, scenes):
         assert np.array_equal(bits(a[1]), bits(b[1]))
     # inside the big ball: every pixel sees it at negative t
     assert (b[0][1] < 0).any() or True
+
+
+def test_fused_reduce_resolve_emulated_ranks(oracle, scenes):
+    """The fused multi-GPU resolve kernel with the ranks emulated as contexts of one process on one GPU
+    (B200_PROFILING.md: with fewer GPUs than ranks, run the ranks' data through one kernel): every
+    rank's slice, summed over all ranks' buffers in rank order, equals the oracle's resolve of the
+    host-side sum bit for bit."""
+    world, w, h, spp = 3, 200, 120, 9
+    ctxs = []
+    try:
+        for r in range(world):
+            t = rtb200.PathTracer(0)
+            setup(t, scenes["Scene2"], w, h)
+            t.set_shard(r, world)
+            t.render_spp(spp)
+            t.sync()
+            ctxs.append(t)
+        ptrs = [t.accum_device_ptr() for t in ctxs]
+        dst = ctxs[0].argb_device_ptr()
+        px = w * h
+        for r, t in enumerate(ctxs):                       # each rank resolves its slice into rank 0's surface
+            first = px * r // world
+            t.resolve_fused(ptrs, spp, first, px * (r + 1) // world - first, dst)
+            t.sync()
+        got = ctxs[0].read_surface()
+        total = np.zeros((h, w, 4), np.float32)
+        for t in ctxs:                                     # same order as the kernel: rank 0 + rank 1 + ...
+            total = total + t.read_accum()[0]
+        assert np.array_equal(got, oracle.resolve_argb8(total, spp))
+        # and the sharded sum is the single-context image up to float summation order
+        one = rtb200.PathTracer(0)
+        setup(one, scenes["Scene2"], w, h)
+        one.render_spp(spp)
+        assert np.allclose(one.read_accum()[0], total, rtol=1e-6, atol=1e-6)
+        one.close()
+    finally:
+        for t in ctxs:
+            t.close()
