@@ -6,6 +6,8 @@ relative (this implementation is in fact bit-exact: asserted); radiance per samp
 relative of the reference fed the same Philox stream (only powf differs, by ULPs); converged
 radiance vs the reference's own rand() within its Monte Carlo noise floor; ARGB8 resolve exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -452,3 +454,15 @@ def test_fused_reduce_resolve_emulated_ranks(oracle, scenes):
     finally:
         for t in ctxs:
             t.close()
+
+
+def test_fused_reduce_resolve_across_real_gpus():
+    """2 (or more) real GPUs, one process each, buffers mapped through CUDA IPC over NVLink."""
+    import subprocess, sys, torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multigpu_fused_check.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
+    assert "FUSED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
