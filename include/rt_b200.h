@@ -103,7 +103,8 @@ enum {
     RT_OPT_ACCEL = 2,              /* RT_ACCEL_* */
     RT_OPT_BVH_THRESHOLD = 3,      /* object count at which RT_ACCEL_AUTO switches to the BVH */
     RT_OPT_BVH_SCHED = 4,          /* 0 (default): per-ray traversal loop, 1: experimental warp-scheduled BVH kernel */
-    RT_OPT_BVH_WAIT_K = 5          /* scheduled kernel: waiting lanes that trigger a shading pass (default 20) */
+    RT_OPT_BVH_WAIT_K = 5,         /* scheduled kernel: waiting lanes that trigger a shading pass (default 20) */
+    RT_OPT_BVH_LEAF = 6            /* BVH builder: maximum primitives per leaf (default 4) */
 };
 enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
 enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2 };

@@ -33,7 +33,7 @@ struct Builder {
     float eps;
 
     static constexpr int kBins = 16;
-    static constexpr int kMaxLeaf = 4;
+    int kMaxLeaf = 4;
     static constexpr float kTravCost = 1.0f, kPrimCost = 0.7f;
 
     int32_t make_leaf(int first, int count) {
@@ -127,9 +127,10 @@ struct Builder {
 
 }  // namespace
 
-void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out) {
+void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf) {
     out = HostBvh();
     Builder b; b.out = &out;
+    b.kMaxLeaf = max_leaf < 1 ? 1 : (max_leaf > 64 ? 64 : max_leaf);
     int sph_slot = 0, box_slot = 0;
     Box3 scene;
     for (const rt_object& o : objects) {

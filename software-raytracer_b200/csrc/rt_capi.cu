@@ -60,7 +60,7 @@ struct rt_ctx {
     uint64_t paths = 0, total_paths = 0, total_segments_base = 0;
     int rank = 0, world = 1;
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
-    int opt_bvh_sched = 0, opt_bvh_wait_k = 20;
+    int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
     float4* d_tune = nullptr; size_t cap_tune = 0;
     float tune_ms[2] = {0.f, 0.f};
@@ -151,7 +151,7 @@ int upload_scene(rt_ctx* c) {
 // box inflation was derived from.
 int ensure_bvh(rt_ctx* c, float origin_extent) {
     if (c->bvh_valid && origin_extent <= c->bvh.extent) return RT_OK;
-    build_bvh(c->scene.objects, origin_extent, c->bvh);
+    build_bvh(c->scene.objects, origin_extent, c->bvh, c->opt_bvh_leaf);
     if (c->bvh.max_depth + 2 > 62) return fail(c, RT_ERR_INVALID, "BVH too deep for the traversal stack");
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     RT_CUDA(c, ensure_capacity(c->d_bvh_nodes, c->cap_bvh_nodes, c->bvh.nodes.size() * 4));
@@ -463,6 +463,7 @@ int rt_set_option(rt_ctx* c, int option, int value) {
         case RT_OPT_ACCEL: c->opt_accel = value; return RT_OK;
         case RT_OPT_BVH_THRESHOLD: c->opt_bvh_threshold = value; return RT_OK;
         case RT_OPT_BVH_SCHED: c->opt_bvh_sched = value; return RT_OK;
+        case RT_OPT_BVH_LEAF: c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = -1; return RT_OK;
         case RT_OPT_BVH_WAIT_K: c->opt_bvh_wait_k = value < 1 ? 1 : value; return RT_OK;
     }
     return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
