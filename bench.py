@@ -156,7 +156,9 @@ def run_b200(args):
     stream = torch.cuda.Stream()
     tr = rtb200.PathTracer(local)
     tr.set_stream(stream.cuda_stream)
-    tr.set_option(rtb200.RT_OPT_ACCEL, {"auto": rtb200.RT_ACCEL_AUTO, "brute": rtb200.RT_ACCEL_BRUTE, "bvh": rtb200.RT_ACCEL_BVH}[args.accel])
+    tr.set_option(rtb200.RT_OPT_ACCEL, {"auto": rtb200.RT_ACCEL_AUTO, "brute": rtb200.RT_ACCEL_BRUTE, "bvh": rtb200.RT_ACCEL_BVH,
+                                        "flat": rtb200.RT_ACCEL_FLAT}[args.accel])
+    tr.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 0 if args.no_primary_reuse else 1)
     if args.bvh_sched >= 0:
         tr.set_option(rtb200.RT_OPT_BVH_SCHED, args.bvh_sched)
     if args.wait_k >= 0:
@@ -217,6 +219,7 @@ def run_b200(args):
             tr.reset_accumulation(); step_resident()
         barrier()
         seg0 = tr.stats().total_segments
+        trc0 = tr.stats().total_traced_segments
         sampler = ClockSampler(local); sampler.start()
         evs = []
         tr.reset_accumulation()
@@ -230,6 +233,7 @@ def run_b200(args):
         clocks = sampler.summary()
         step_ms = [a.elapsed_time(b) for a, b in evs]
         segs_rank = tr.stats().total_segments - seg0
+        traced_rank = tr.stats().total_traced_segments - trc0
         paths_rank = W * H * spp * args.steps
 
         # ---- end to end through the C-ABI with host buffers: e2e ------------------------------
@@ -293,11 +297,18 @@ def run_b200(args):
             "config": {"workload": "Scene1 (67 spheres) %dx%d, %d spp per GPU per step, depth %d, path mode" % (W, H, spp, DEPTH),
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": ("spp-sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce+resolve kernel over NVLink peer memory" if fused else "one NCCL all-reduce per step"),
                        "build": "strict IEEE, -fmad=false (bit-exact geometry vs the reference)",
-                       "accel": {rtb200.RT_ACCEL_BRUTE: "brute-force object loop", rtb200.RT_ACCEL_BVH: "host-built BVH candidates + strict tests"}[st.accel],
+                       "accel": {rtb200.RT_ACCEL_BRUTE: "brute-force object loop", rtb200.RT_ACCEL_BVH: "host-built BVH candidates + strict tests",
+                                 rtb200.RT_ACCEL_FLAT: "flat two-level accelerator (conservative FMA culls, warp-uniform) + strict tests"}[st.accel],
+                       "primary_reuse": ("off: every sample re-traces its primary ray" if args.no_primary_reuse else
+                                         "on: the reference has no pixel jitter, so the primary closest-hit query of a pixel is identical for "
+                                         "all samples; it runs once per pixel per launch and every sample shades/scatters from it "
+                                         "(bit-identical radiance; `value` counts path segments delivered, traced_segments_per_s_M the queries executed)"),
                        "scene": args.scene},
             "paths_per_s_M": paths_rank * world / (total_ms * 1e-3) / 1e6,
             "ms_per_1spp_frame": total_ms / args.steps / spp,
             "segments_per_path": segs_rank / paths_rank,
+            "traced_segments_per_s_M": traced_rank * world / (total_ms * 1e-3) / 1e6,
+            "traced_segments_per_path": traced_rank / paths_rank,
             "e2e": {"value": e2e_segs_all / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": int(objs.nbytes + 52), "d2h_bytes_per_step": int(W * H * 4),
                     "ms_per_step": e2e_ms / args.steps, "device_ms_per_step": e2e_dev_ms / args.steps,
@@ -334,7 +345,8 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP, help="samples per pixel per GPU per step (default: the config's 1024)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="1-spp frames of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh"], help="closest-hit back end (results are identical)")
+    ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh", "flat"], help="closest-hit back end (results are identical)")
+    ap.add_argument("--no-primary-reuse", action="store_true", help="re-trace the (identical) primary ray for every sample, like the reference")
     ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"], help="N > 1 exchange: fused peer-memory reduce+resolve kernel, or NCCL all-reduce")
     ap.add_argument("--bvh-sched", type=int, default=-1, help="RT_OPT_BVH_SCHED override")
     ap.add_argument("--wait-k", type=int, default=-1, help="RT_OPT_BVH_WAIT_K override")

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef struct rt_ctx rt_ctx;
 
@@ -95,6 +95,11 @@ typedef struct {
     int32_t reserved;
     uint64_t total_paths;          /* since rt_create: never reset (benchmarks) */
     uint64_t total_segments;
+    /* closest-hit queries actually executed. Equal to `segments` unless primary-hit reuse is on
+     * (RT_OPT_PRIMARY_REUSE): the reference has no pixel jitter, so every sample of a pixel starts with the
+     * same primary query; it is then run once per pixel per rt_render_spp call and its result reused. */
+    uint64_t traced_segments;
+    uint64_t total_traced_segments;
 } rt_stats;
 
 /* Tuning knobs that have no counterpart in the reference (they never change results). */
@@ -104,10 +109,16 @@ enum {
     RT_OPT_BVH_THRESHOLD = 3,      /* object count at which RT_ACCEL_AUTO switches to the BVH */
     RT_OPT_BVH_SCHED = 4,          /* 0 (default): per-ray traversal loop, 1: experimental warp-scheduled BVH kernel */
     RT_OPT_BVH_WAIT_K = 5,         /* scheduled kernel: waiting lanes that trigger a shading pass (default 20) */
-    RT_OPT_BVH_LEAF = 6            /* BVH builder: maximum primitives per leaf (default 4) */
+    RT_OPT_BVH_LEAF = 6,           /* BVH builder: maximum primitives per leaf (default 4) */
+    RT_OPT_PRIMARY_REUSE = 7       /* 1 (default): one primary closest-hit query per pixel per rt_render_spp call,
+                                      reused by every sample (identical ray: the reference has no pixel jitter);
+                                      0: re-trace it for every sample like the reference. Results are bit-identical. */
 };
 enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
-enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2 };
+/* BRUTE: the reference's object loop. BVH: host-built BVH2. FLAT: two-level flat accelerator for scenes of up
+ * to 255 objects (conservative culls with warp-uniform control flow, then the strict tests). All three give
+ * bit-identical hits; AUTO measures them on the first render of a scene. */
+enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2, RT_ACCEL_FLAT = 3 };
 
 /* ---- lifetime: replaces the worker spawn/join (Raytracer.cpp:331-342, 598-607) -------- */
 int rt_create(int cuda_device, rt_ctx** out);

@@ -15,6 +15,7 @@
 #include "rt_host_pack.h"
 #include "rt_kernels.h"
 #include "bvh_build.h"
+#include "flat_build.h"
 #include "scene_json.h"
 
 using namespace rtb;
@@ -47,6 +48,13 @@ struct rt_ctx {
     size_t cap_bvh_nodes = 0, cap_bvh_refs = 0;
     bool bvh_valid = false;
 
+    // flat two-level accelerator for small scenes (built lazily; see flat_build.h)
+    HostFlat flat;
+    FlatView fview;
+    float4* d_flat_boxes = nullptr; float4* d_flat_cull = nullptr; unsigned char* d_flat_slots = nullptr; int* d_flat_ids = nullptr;
+    size_t cap_flat_boxes = 0, cap_flat_cull = 0, cap_flat_slots = 0, cap_flat_ids = 0;
+    bool flat_valid = false;
+
     // frame buffers
     float4* d_accum = nullptr;
     uint32_t* d_argb = nullptr;
@@ -60,10 +68,10 @@ struct rt_ctx {
     uint64_t paths = 0, total_paths = 0, total_segments_base = 0;
     int rank = 0, world = 1;
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
-    int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4;
+    int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4, opt_primary_reuse = 1;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
     float4* d_tune = nullptr; size_t cap_tune = 0;
-    float tune_ms[2] = {0.f, 0.f};
+    float tune_ms[3] = {0.f, 0.f, 0.f};
     int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;
     float last_render_ms = 0.f, last_resolve_ms = 0.f;
     bool render_timed = false, resolve_timed = false;
@@ -143,7 +151,7 @@ int upload_scene(rt_ctx* c) {
     c->view.box = c->d_box; c->view.box_id = c->d_box_id;
     c->view.mat = c->d_mat;
     c->view.n_sph = (int)sph_id.size(); c->view.n_box = (int)box_id.size(); c->view.n_obj = (int)objs.size();
-    c->bvh_valid = false; c->tuned_accel = -1;
+    c->bvh_valid = false; c->flat_valid = false; c->tuned_accel = -1;
     return RT_OK;
 }
 
@@ -167,45 +175,26 @@ int ensure_bvh(rt_ctx* c, float origin_extent) {
     return RT_OK;
 }
 
-bool want_bvh(const rt_ctx* c) {
-    if (c->opt_accel == RT_ACCEL_BVH) return true;
-    if (c->opt_accel == RT_ACCEL_BRUTE) return false;
-    if (c->tuned_accel >= 0) return c->tuned_accel == RT_ACCEL_BVH;
-    return c->view.n_sph + c->view.n_box >= c->opt_bvh_threshold;
-}
-
-float camera_extent(const rt_ctx* c);
-int ensure_bvh(rt_ctx* c, float origin_extent);
-
-// RT_ACCEL_AUTO between 8 and `bvh_threshold` primitives: both back ends give identical results and
-// which one is faster depends on the scene (open scenes favour the BVH, closed rooms the brute-force
-// loop), so the first path-mode render after a scene/camera/parameter change times 4 spp of each into
-// a scratch buffer and keeps the faster. Below 8 primitives brute force, above the threshold the BVH.
-int autotune_accel(rt_ctx* c) {
-    if (c->opt_accel != RT_ACCEL_AUTO || c->tuned_accel >= 0) return RT_OK;
-    const int n = c->view.n_sph + c->view.n_box;
-    if (n < 8) { c->tuned_accel = RT_ACCEL_BRUTE; return RT_OK; }
-    if (n >= c->opt_bvh_threshold) { c->tuned_accel = RT_ACCEL_BVH; return RT_OK; }
-    int rc = ensure_bvh(c, camera_extent(c));
-    if (rc != RT_OK) return rc;
-    const size_t px = (size_t)c->par.width * c->par.height;
-    RT_CUDA(c, ensure_capacity(c->d_tune, c->cap_tune, px));
-    cudaEvent_t e[3];
-    for (auto& ev : e) RT_CUDA(c, cudaEventCreate(&ev));
-    unsigned long long* dummy = c->d_counters + 2;            // not part of the reported statistics
-    cudaError_t err = cudaSuccess;
-    for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 warms the instruction cache
-        cudaEventRecord(e[0], c->stream);
-        err = launch_render_regen(c->view, c->bview, false, c->frame, c->d_tune, 0u, 4, dummy, c->stream);
-        cudaEventRecord(e[1], c->stream);
-        if (err == cudaSuccess) err = launch_render_regen(c->view, c->bview, true, c->frame, c->d_tune, 0u, 4, dummy, c->stream);
-        cudaEventRecord(e[2], c->stream);
-    }
-    if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
-    if (err == cudaSuccess) { cudaEventElapsedTime(&c->tune_ms[0], e[0], e[1]); cudaEventElapsedTime(&c->tune_ms[1], e[1], e[2]); }
-    for (auto& ev : e) cudaEventDestroy(ev);
-    if (err != cudaSuccess) return cuda_fail(c, err, "autotune_accel");
-    c->tuned_accel = c->tune_ms[1] < c->tune_ms[0] ? RT_ACCEL_BVH : RT_ACCEL_BRUTE;
+// (Re)builds and uploads the flat accelerator; c->flat.usable tells whether the scene qualifies.
+int ensure_flat(rt_ctx* c, float origin_extent) {
+    if (c->flat_valid && origin_extent <= c->flat.extent) return RT_OK;
+    build_flat(c->scene.objects, origin_extent, c->flat);
+    c->flat_valid = true;
+    memset(&c->fview, 0, sizeof c->fview);
+    if (!c->flat.usable) return RT_OK;
+    const HostFlat& f = c->flat;
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    RT_CUDA(c, ensure_capacity(c->d_flat_boxes, c->cap_flat_boxes, f.boxes.size() / 4));
+    RT_CUDA(c, ensure_capacity(c->d_flat_cull, c->cap_flat_cull, f.cull.size() / 4));
+    RT_CUDA(c, ensure_capacity(c->d_flat_slots, c->cap_flat_slots, f.cull_slot.size()));
+    RT_CUDA(c, ensure_capacity(c->d_flat_ids, c->cap_flat_ids, f.prim_id.size()));
+    if (!f.boxes.empty()) RT_CUDA(c, cudaMemcpyAsync(c->d_flat_boxes, f.boxes.data(), f.boxes.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (!f.cull.empty()) RT_CUDA(c, cudaMemcpyAsync(c->d_flat_cull, f.cull.data(), f.cull.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (!f.cull_slot.empty()) RT_CUDA(c, cudaMemcpyAsync(c->d_flat_slots, f.cull_slot.data(), f.cull_slot.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!f.prim_id.empty()) RT_CUDA(c, cudaMemcpyAsync(c->d_flat_ids, f.prim_id.data(), f.prim_id.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->fview.boxes = c->d_flat_boxes; c->fview.cull = c->d_flat_cull; c->fview.cull_slot = c->d_flat_slots; c->fview.prim_id = c->d_flat_ids;
+    c->fview.n_clusters = f.n_clusters; c->fview.n_cubes = f.n_cubes; c->fview.n_singles = f.n_singles; c->fview.kappa = f.kappa;
     return RT_OK;
 }
 
@@ -213,6 +202,78 @@ float camera_extent(const rt_ctx* c) {
     float e = 0.f;
     for (int k = 0; k < 3; ++k) e = fmaxf(e, fabsf(c->cam.pos[k]));
     return e;
+}
+
+// Makes the requested back end ready for rays whose origins lie within origin_extent of the axes and fills
+// the launch selector. A flat request on a scene that does not qualify degrades to the BVH.
+int make_accel(rt_ctx* c, int rt_accel, float origin_extent, AccelSel& ac) {
+    memset(&ac, 0, sizeof ac);
+    int rc;
+    if (rt_accel == RT_ACCEL_FLAT) {
+        if ((rc = ensure_flat(c, origin_extent)) != RT_OK) return rc;
+        if (c->flat.usable) { ac.kind = kAccelFlat; ac.flat = c->fview; return RT_OK; }
+        rt_accel = RT_ACCEL_BVH;
+    }
+    if (rt_accel == RT_ACCEL_BVH) {
+        if ((rc = ensure_bvh(c, origin_extent)) != RT_OK) return rc;
+        ac.kind = kAccelBvh; ac.bvh = c->bview;
+        return RT_OK;
+    }
+    ac.kind = kAccelBrute;
+    return RT_OK;
+}
+int accel_of(const AccelSel& ac) { return ac.kind == kAccelFlat ? RT_ACCEL_FLAT : ac.kind == kAccelBvh ? RT_ACCEL_BVH : RT_ACCEL_BRUTE; }
+
+// The back end a launch should use. Explicit options win; RT_ACCEL_AUTO uses the measured choice when there
+// is one (autotune_accel), else: flat for scenes that qualify, BVH from `bvh_threshold` primitives, brute force
+// below 8.
+int want_accel(rt_ctx* c) {
+    if (c->opt_accel != RT_ACCEL_AUTO) return c->opt_accel;
+    if (c->tuned_accel >= 0) return c->tuned_accel;
+    const int n = c->view.n_sph + c->view.n_box;
+    if (n >= c->opt_bvh_threshold) return RT_ACCEL_BVH;
+    if (n >= 8 && n <= kFlatMaxPrims) return RT_ACCEL_FLAT;
+    return RT_ACCEL_BRUTE;
+}
+
+// RT_ACCEL_AUTO between 8 and `bvh_threshold` primitives: all back ends give identical results and which
+// one is fastest depends on the scene, so the first path-mode render after a scene/camera/parameter change
+// times 4 spp of each into a scratch buffer and keeps the fastest. Below 8 primitives brute force, above the
+// threshold the BVH.
+int autotune_accel(rt_ctx* c) {
+    if (c->opt_accel != RT_ACCEL_AUTO || c->tuned_accel >= 0) return RT_OK;
+    const int n = c->view.n_sph + c->view.n_box;
+    if (n < 8) { c->tuned_accel = RT_ACCEL_BRUTE; return RT_OK; }
+    if (n >= c->opt_bvh_threshold) { c->tuned_accel = RT_ACCEL_BVH; return RT_OK; }
+    const int kinds[3] = {RT_ACCEL_BRUTE, RT_ACCEL_BVH, RT_ACCEL_FLAT};
+    AccelSel sel[3];
+    int rc;
+    for (int k = 0; k < 3; ++k) if ((rc = make_accel(c, kinds[k], camera_extent(c), sel[k])) != RT_OK) return rc;
+    const size_t px = (size_t)c->par.width * c->par.height;
+    RT_CUDA(c, ensure_capacity(c->d_tune, c->cap_tune, px));
+    cudaEvent_t e[4];
+    for (auto& ev : e) RT_CUDA(c, cudaEventCreate(&ev));
+    unsigned long long* dummy = c->d_counters + 4;            // not part of the reported statistics
+    cudaError_t err = cudaSuccess;
+    const bool reuse = c->opt_primary_reuse != 0;
+    for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 warms the instruction cache
+        cudaEventRecord(e[0], c->stream);
+        for (int k = 0; k < 3 && err == cudaSuccess; ++k) {
+            err = launch_render_regen(c->view, sel[k], c->frame, c->d_tune, 0u, 4, reuse, dummy, c->stream);
+            cudaEventRecord(e[k + 1], c->stream);
+        }
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+    if (err == cudaSuccess) for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&c->tune_ms[k], e[k], e[k + 1]);
+    for (auto& ev : e) cudaEventDestroy(ev);
+    if (err != cudaSuccess) return cuda_fail(c, err, "autotune_accel");
+    int best = 0;
+    for (int k = 1; k < 3; ++k) {
+        if (kinds[k] == RT_ACCEL_FLAT && sel[k].kind != kAccelFlat) continue;   // scene does not qualify
+        if (c->tune_ms[k] < c->tune_ms[best]) best = k;
+    }
+    c->tuned_accel = kinds[best];
+    return RT_OK;
 }
 
 int prepare(rt_ctx* c) {
@@ -299,9 +360,9 @@ int rt_create(int cuda_device, rt_ctx** out) {
     memset(&c->bview, 0, sizeof c->bview);
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&c->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&c->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMalloc((void**)&c->d_scratch, 4096)) != cudaSuccess ||
-        (e = cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "rt_create");
         rt_destroy(c);
         return rc;
@@ -321,6 +382,7 @@ int rt_destroy(rt_ctx* c) {
     cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
     cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_tune);
+    cudaFree(c->d_flat_boxes); cudaFree(c->d_flat_cull); cudaFree(c->d_flat_slots); cudaFree(c->d_flat_ids);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -464,6 +526,7 @@ int rt_set_option(rt_ctx* c, int option, int value) {
         case RT_OPT_BVH_THRESHOLD: c->opt_bvh_threshold = value; return RT_OK;
         case RT_OPT_BVH_SCHED: c->opt_bvh_sched = value; return RT_OK;
         case RT_OPT_BVH_LEAF: c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = -1; return RT_OK;
+        case RT_OPT_PRIMARY_REUSE: c->opt_primary_reuse = value != 0; c->tuned_accel = -1; return RT_OK;
         case RT_OPT_BVH_WAIT_K: c->opt_bvh_wait_k = value < 1 ? 1 : value; return RT_OK;
     }
     return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
@@ -487,8 +550,10 @@ int rt_reset_accumulation(rt_ctx* c) {
     int rc = prepare(c);
     if (rc != RT_OK) return rc;
     RT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)c->par.width * c->par.height * sizeof(float4), c->stream));
-    // counters: [0] segments since the last reset, [1] segments since rt_create (never cleared)
+    // counters: [0] segments since the last reset, [1] since rt_create (never cleared); [2], [3] the same for the
+    // closest-hit queries actually executed (primary-hit reuse); [4..7] scratch for the autotuner
     RT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long), c->stream));
+    RT_CUDA(c, cudaMemsetAsync(c->d_counters + 2, 0, sizeof(unsigned long long), c->stream));
     c->samples = 0; c->next_sample = 0; c->paths = 0;
     return RT_OK;
 }
@@ -500,22 +565,22 @@ int rt_render_spp(rt_ctx* c, int spp) {
     if (spp == 0) return RT_OK;
     const size_t px = (size_t)c->par.width * c->par.height;
     if (c->par.mode == RT_MODE_PATH && (rc = autotune_accel(c)) != RT_OK) return rc;
-    const bool bvh = want_bvh(c);
-    if (bvh && (rc = ensure_bvh(c, camera_extent(c))) != RT_OK) return rc;
-    c->used_accel = bvh ? RT_ACCEL_BVH : RT_ACCEL_BRUTE;
+    AccelSel ac;
+    if ((rc = make_accel(c, want_accel(c), camera_extent(c), ac)) != RT_OK) return rc;
+    c->used_accel = accel_of(ac);
     RT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if (c->par.mode == RT_MODE_PREVIEW) {
         // SIMPLEDRAW: ACCUMULATIONFRAMES stays 1, every frame overwrites (Raytracer.cpp:66-67,589)
-        RT_CUDA(c, launch_render_preview(c->view, c->bview, bvh, c->frame, c->d_accum, c->d_counters, c->stream));
+        RT_CUDA(c, launch_render_preview(c->view, ac, c->frame, c->d_accum, c->d_counters, c->stream));
         c->samples = 1; c->next_sample = 0; c->paths += px; c->total_paths += px;
     } else {
         // this rank's slice of the global sample indices [next, next+spp)
         int mine = 0; uint32_t first = 0;
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
-        if (bvh && c->opt_bvh_sched)
-            RT_CUDA(c, launch_render_bvh(c->view, c->bview, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
+        if (ac.kind == kAccelBvh && c->opt_bvh_sched)
+            RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else
-            RT_CUDA(c, launch_render_regen(c->view, c->bview, bvh, c->frame, c->d_accum, first, mine, c->d_counters, c->stream));
+            RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream));
         c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce
@@ -580,15 +645,15 @@ int rt_read_aov(rt_ctx* c, int32_t* id, float* t, float* normal, float* point) {
     int rc = prepare(c);
     if (rc != RT_OK) return rc;
     const size_t px = (size_t)c->par.width * c->par.height;
-    const bool bvh = want_bvh(c);
-    if (bvh && (rc = ensure_bvh(c, camera_extent(c))) != RT_OK) return rc;
+    AccelSel ac;
+    if ((rc = make_accel(c, want_accel(c), camera_extent(c), ac)) != RT_OK) return rc;
     int* d_id = nullptr; float *d_t = nullptr, *d_n = nullptr, *d_p = nullptr;
     cudaError_t e = cudaSuccess;
     if (id) e = cudaMalloc((void**)&d_id, px * 4);
     if (e == cudaSuccess && t) e = cudaMalloc((void**)&d_t, px * 4);
     if (e == cudaSuccess && normal) e = cudaMalloc((void**)&d_n, px * 12);
     if (e == cudaSuccess && point) e = cudaMalloc((void**)&d_p, px * 12);
-    if (e == cudaSuccess) e = launch_primary_aov(c->view, c->bview, bvh, c->frame, d_id, d_t, d_n, d_p, c->stream);
+    if (e == cudaSuccess) e = launch_primary_aov(c->view, ac, c->frame, d_id, d_t, d_n, d_p, c->stream);
     if (e == cudaSuccess && id) e = cudaMemcpyAsync(id, d_id, px * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, d_t, px * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess && normal) e = cudaMemcpyAsync(normal, d_n, px * 12, cudaMemcpyDeviceToHost, c->stream);
@@ -621,26 +686,28 @@ int rt_trace_rays(rt_ctx* c, const float* origins, const float* dirs, int n, int
         return fail(c, RT_ERR_INVALID, "rt_trace_rays: bad arguments");
     if (n == 0) return RT_OK;
     const size_t N = (size_t)n;
-    // The BVH's conservativeness argument needs unit-length directions and origins inside the inflation
-    // extent; anything else goes through the brute-force loop.
-    bool bvh = want_bvh(c);
-    if (bvh) {
-        float ext = 0.f;
-        for (size_t i = 0; i < N && bvh; ++i) {
+    // The conservativeness arguments of the BVH and the flat accelerator need unit-length directions (to
+    // float rounding) and origins inside the extent their margins were derived for; anything else goes through
+    // the brute-force loop.
+    int kind = want_accel(c);
+    float ext = 0.f;
+    if (kind != RT_ACCEL_BRUTE) {
+        for (size_t i = 0; i < N && kind != RT_ACCEL_BRUTE; ++i) {
             const float* d = dirs + 3 * i; const float* o = origins + 3 * i;
             float l2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-            if (!(fabsf(l2 - 1.f) <= 1e-3f)) bvh = false;
-            for (int k = 0; k < 3; ++k) { if (!(fabsf(o[k]) < 1e29f)) bvh = false; ext = fmaxf(ext, fabsf(o[k])); }
+            if (!(fabsf(l2 - 1.f) <= 2e-6f)) kind = kind == RT_ACCEL_FLAT && fabsf(l2 - 1.f) <= 1e-3f ? RT_ACCEL_BVH : RT_ACCEL_BRUTE;
+            for (int k = 0; k < 3; ++k) { if (!(fabsf(o[k]) < 1e14f)) kind = RT_ACCEL_BRUTE; ext = fmaxf(ext, fabsf(o[k])); }
         }
-        if (bvh && (rc = ensure_bvh(c, ext)) != RT_OK) return rc;
     }
+    AccelSel ac;
+    if ((rc = make_accel(c, kind, ext, ac)) != RT_OK) return rc;
     float* buf = nullptr;                                      // org3 dir3 n3 p3 t1 id1 = 14 words per ray
     cudaError_t e = cudaMalloc((void**)&buf, N * 14 * 4);
     float *d_o = buf, *d_d = buf + 3 * N, *d_n = buf + 6 * N, *d_p = buf + 9 * N, *d_t = buf + 12 * N;
     int* d_id = (int*)(buf + 13 * N);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, origins, N * 12, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, N * 12, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = launch_trace_rays(c->view, c->bview, bvh, d_o, d_d, n, d_id, d_t, d_n, d_p, c->stream);
+    if (e == cudaSuccess) e = launch_trace_rays(c->view, ac, d_o, d_d, n, d_id, d_t, d_n, d_p, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(id, d_id, N * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(t, d_t, N * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(normal, d_n, N * 12, cudaMemcpyDeviceToHost, c->stream);
@@ -705,7 +772,7 @@ int rt_get_stats(rt_ctx* c, rt_stats* out) {
     if (!c || !out) return RT_ERR_INVALID;
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
-    unsigned long long counters[4] = {0, 0, 0, 0};
+    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     RT_CUDA(c, cudaMemcpy(counters, c->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
     if (c->render_timed) { cudaEventElapsedTime(&c->last_render_ms, c->ev0, c->ev1); }
     memset(out, 0, sizeof *out);
@@ -713,6 +780,7 @@ int rt_get_stats(rt_ctx* c, rt_stats* out) {
     out->samples = c->samples; out->n_objects = (uint32_t)c->scene.objects.size();
     out->last_render_ms = c->last_render_ms; out->last_resolve_ms = c->last_resolve_ms;
     out->total_paths = c->total_paths; out->total_segments = counters[1];
+    out->traced_segments = counters[2]; out->total_traced_segments = counters[3];
     out->pipeline = c->used_pipeline; out->accel = c->used_accel; out->sm_count = c->sm_count;
     return RT_OK;
 }

@@ -23,17 +23,42 @@ constexpr int kThreads = 128;
 // ---- closest-hit back ends -------------------------------------------------------------------
 // MODE 0: brute force, geometry staged in shared memory      MODE 1: brute force from global (L1)
 // MODE 2: BVH, nodes + refs + geometry staged in shared mem  MODE 3: BVH from global (L1/L2)
+// MODE 4: flat two-level accelerator (flat_build.h), everything staged in shared memory
 // Shared memory layout: [BVH stack: stack_entries x blockDim ints][spheres][cubes][nodes][refs]
+//                       MODE 4: [candidate queues: kFlatQueue x blockDim bytes][spheres][cubes][level-1 boxes][cull records][prim ids][cull slots]
 struct TraceCtx {
     const float4* sph; const float4* box; const float4* nodes; const int* refs;
     int* stack; float* stack_t; int stride;
+    FlatView fl;
+    unsigned char* q;          // MODE 4: this thread's candidate queue, entries `stride` bytes apart
 };
 
 template <int MODE>
-__device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhView& bv, float4* smem) {
+__device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhView& bv, const FlatView& fl, float4* smem) {
     TraceCtx t;
     t.sph = sc.sph; t.box = sc.box; t.nodes = bv.nodes; t.refs = bv.refs; t.stack = nullptr; t.stack_t = nullptr; t.stride = blockDim.x;
+    t.fl = fl; t.q = nullptr;
     float4* p = smem;
+    if (MODE == 4) {
+        t.q = reinterpret_cast<unsigned char*>(p) + threadIdx.x;
+        p += (kFlatQueue * blockDim.x + 15) / 16;
+        const int ng = sc.n_sph + 2 * sc.n_box, nb = 2 * (fl.n_clusters + fl.n_cubes), ncull = 8 * fl.n_clusters + fl.n_singles;
+        const int np = sc.n_sph + sc.n_box;
+        for (int i = threadIdx.x; i < ng; i += blockDim.x) p[i] = i < sc.n_sph ? __ldg(sc.sph + i) : __ldg(sc.box + (i - sc.n_sph));
+        t.sph = p; t.box = p + sc.n_sph; p += ng;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) p[i] = __ldg(fl.boxes + i);
+        t.fl.boxes = p; p += nb;
+        for (int i = threadIdx.x; i < ncull; i += blockDim.x) p[i] = __ldg(fl.cull + i);
+        t.fl.cull = p; p += ncull;
+        int* ids = reinterpret_cast<int*>(p);
+        for (int i = threadIdx.x; i < np; i += blockDim.x) ids[i] = __ldg(fl.prim_id + i);
+        t.fl.prim_id = ids;
+        unsigned char* slots = reinterpret_cast<unsigned char*>(ids + np);
+        for (int i = threadIdx.x; i < ncull; i += blockDim.x) slots[i] = __ldg(fl.cull_slot + i);
+        t.fl.cull_slot = slots;
+        __syncthreads();
+        return t;
+    }
     if (MODE >= 2) {
         t.stack = reinterpret_cast<int*>(p) + threadIdx.x;
         t.stack_t = reinterpret_cast<float*>(t.stack + bv.stack_entries * blockDim.x);
@@ -60,6 +85,7 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
 
 template <int MODE>
 __device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d) {
+    if (MODE == 4) return closest_hit_flat(sc, t.fl, t.sph, t.box, t.q, t.stride, o, d);
     if (MODE >= 2) return closest_hit_bvh(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr);
     return closest_hit(sc, t.sph, t.box, o, d);
 }
@@ -73,11 +99,11 @@ __device__ __forceinline__ bool tile_pixel(const FrameView& fr, int& px, int& py
 
 // ---- primary visibility AOVs ----------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_primary_aov(SceneView sc, BvhView bv, FrameView fr, int* __restrict__ out_id,
+__global__ void __launch_bounds__(kThreads) k_primary_aov(SceneView sc, BvhView bv, FlatView fl, FrameView fr, int* __restrict__ out_id,
                                                            float* __restrict__ out_t, float* __restrict__ out_n,
                                                            float* __restrict__ out_p) {
     extern __shared__ float4 smem[];
-    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     int px, py;
     if (!tile_pixel(fr, px, py)) return;
     const size_t p = (size_t)px + (size_t)py * fr.width;
@@ -97,12 +123,12 @@ __global__ void k_ray_dirs(FrameView fr, float* __restrict__ out) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_trace_rays(SceneView sc, BvhView bv, const float* __restrict__ org,
+__global__ void __launch_bounds__(kThreads) k_trace_rays(SceneView sc, BvhView bv, FlatView fl, const float* __restrict__ org,
                                                           const float* __restrict__ dir, int n,
                                                           int* __restrict__ out_id, float* __restrict__ out_t,
                                                           float* __restrict__ out_n, float* __restrict__ out_p) {
     extern __shared__ float4 smem[];
-    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Hit h = trace<MODE>(sc, tc, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
@@ -133,20 +159,28 @@ __global__ void k_philox(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32_1
 
 // ---- the render kernel -----------------------------------------------------------------------
 // One lane owns one pixel for the whole launch and walks its samples [s_begin, s_begin+n) in
-// order. The loop is flat over path SEGMENTS: every iteration does one closest-hit query over
-// the staged object list (the ~90 % part, identical control flow for all 32 lanes) and a short
-// divergent shading tail. A lane whose path ends starts its next sample in the same iteration
-// slot ("regeneration"), so the warp stays full until a lane runs out of samples; with many
-// samples per launch the per-lane totals converge (law of large numbers) and neighbouring
-// pixels finish together. Per-pixel sums are kept in registers in sample order and added to
-// the float4 accumulation buffer once - no atomics, bit-reproducible for a given
+// order. The loop is flat over path SEGMENTS: every iteration does one closest-hit query (the
+// ~90 % part) and a short divergent shading tail. A lane whose path ends starts its next sample
+// in the same iteration slot ("regeneration"), so the warp stays full until a lane runs out of
+// samples; with many samples per launch the per-lane totals converge (law of large numbers) and
+// neighbouring pixels finish together. Per-pixel sums are kept in registers in sample order and
+// added to the float4 accumulation buffer once - no atomics, bit-reproducible for a given
 // (seed, sample range), independent of the launch shape.
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen(SceneView sc, BvhView bv, FrameView fr, float4* __restrict__ accum,
+//
+// REUSE (primary-hit reuse): the reference shoots every sample of a pixel through the pixel CORNER
+// (GetRayDirection has no jitter, Raytracer.cpp:106-122), so the primary closest-hit query of a pixel
+// has the same inputs - and the same result - for every sample. With REUSE the query runs once per
+// pixel per launch; each sample still draws its own Philox block at the primary hit and scatters its
+// own secondary ray, so every sample's radiance is bit-identical to the non-reuse loop (asserted by
+// the tests). A pixel whose primary ray misses (or max_bounces == 0) has the same value for every
+// sample: the value is added n times, in order. seg_counter[0..1] count path segments DELIVERED (what
+// the reference traces), seg_counter[2..3] the closest-hit queries actually EXECUTED.
+template <int MODE, bool REUSE>
+__global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
                                                             uint32_t s_begin, int n_samples,
                                                             unsigned long long* __restrict__ seg_counter) {
     extern __shared__ float4 smem[];
-    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     int px, py;
     const bool inside = tile_pixel(fr, px, py);              // no early return: the warp reduce below needs every lane
     const uint32_t pixel = inside ? (uint32_t)px + (uint32_t)py * (uint32_t)fr.width : 0u;
@@ -157,15 +191,30 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     float3 o = fr.cam_pos, d = d0;
     float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
     int s = 0, depth = 0;
-    unsigned int segs = 0;
+    unsigned int segs = 0, traced = 0;
 
+    // One closest-hit site and one shading site (code size matters: instruction fetch was the top stall of
+    // the first version). `primary` marks the query of the pixel's primary ray when REUSE keeps its result.
+    Hit h0;
+    h0.id = -1; h0.t = 0.f; h0.n = f3(0.f, 0.f, 0.f); h0.p = f3(0.f, 0.f, 0.f);
+    bool primary = true;
     while (s < n_samples) {
-        const Hit h = trace<MODE>(sc, tc, o, d);
-        ++segs;
-        float3 c;
-        if (shade_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth, c)) {
+        Hit h = trace<MODE>(sc, tc, o, d);
+        ++segs; ++traced;
+        if (REUSE && primary) { h0 = h; primary = false; }
+        for (;;) {
+            float3 c;
+            if (!shade_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth, c)) break;   // scattered: trace (o, d)
             acc.x += c.x; acc.y += c.y; acc.z += c.z;
             ++s; depth = 0; o = fr.cam_pos; d = d0;
+            if (!REUSE || s >= n_samples) break;
+            if (h0.id < 0 || fr.max_bounces == 0) {
+                // the primary ray misses (or nothing scatters): no random number is consumed and every sample
+                // of this pixel has the value c - add it n times, in order
+                for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; ++segs; }
+                break;
+            }
+            h = h0; ++segs;                                  // next sample starts from the cached primary hit
         }
     }
 
@@ -175,11 +224,17 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
         accum[pixel] = a;
     }
 
-    // segment count: warp reduce, one atomic per warp
-    unsigned int total = segs;
+    // segment counts: warp reduce, one atomic per warp and counter
+    unsigned int total = segs, total_tr = traced;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(0xffffffffu, total, off);
-    if ((threadIdx.x & 31) == 0 && total) { atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total); }
+    for (int off = 16; off > 0; off >>= 1) {
+        total += __shfl_down_sync(0xffffffffu, total, off);
+        total_tr += __shfl_down_sync(0xffffffffu, total_tr, off);
+    }
+    if ((threadIdx.x & 31) == 0 && total) {
+        atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total);
+        atomicAdd(seg_counter + 2, (unsigned long long)total_tr); atomicAdd(seg_counter + 3, (unsigned long long)total_tr);
+    }
 }
 
 // ---- BVH render kernel with warp-level phase scheduling ---------------------------------------
@@ -199,12 +254,12 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
 #define RTB_BVH_MIN_BLOCKS 5
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, RTB_BVH_MIN_BLOCKS) k_render_bvh(SceneView sc, BvhView bv, FrameView fr,
+__global__ void __launch_bounds__(kThreads, RTB_BVH_MIN_BLOCKS) k_render_bvh(SceneView sc, BvhView bv, FlatView fl, FrameView fr,
                                                                            float4* __restrict__ accum, uint32_t s_begin,
                                                                            int n_samples, unsigned long long* __restrict__ seg_counter,
                                                                            int wait_k) {
     extern __shared__ float4 smem[];
-    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     const float4* __restrict__ nodes = tc.nodes;
     const int* __restrict__ refs = tc.refs;
     int* const stk = tc.stack;                                   // [entry][thread] links
@@ -353,15 +408,18 @@ __global__ void __launch_bounds__(kThreads, RTB_BVH_MIN_BLOCKS) k_render_bvh(Sce
     unsigned int total = segs;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(FULL, total, off);
-    if ((threadIdx.x & 31) == 0 && total) { atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total); }
+    if ((threadIdx.x & 31) == 0 && total) {
+        atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total);
+        atomicAdd(seg_counter + 2, (unsigned long long)total); atomicAdd(seg_counter + 3, (unsigned long long)total);
+    }
 }
 
 // ---- preview mode (SIMPLEDRAW, Raytracer.cpp:147-160): one primary ray, overwrite ----------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, BvhView bv, FrameView fr, float4* __restrict__ accum,
+__global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
                                                               unsigned long long* __restrict__ seg_counter) {
     extern __shared__ float4 smem[];
-    const TraceCtx tc = setup_trace<MODE>(sc, bv, smem);
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     int px, py;
     if (!tile_pixel(fr, px, py)) return;
     const size_t pixel = (size_t)px + (size_t)py * fr.width;
@@ -385,8 +443,7 @@ __global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, BvhVi
     }
     accum[pixel] = make_float4(c.x, c.y, c.z, 0.f);
     if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-        atomicAdd(seg_counter, (unsigned long long)fr.width * fr.height);
-        atomicAdd(seg_counter + 1, (unsigned long long)fr.width * fr.height);
+        for (int k = 0; k < 4; ++k) atomicAdd(seg_counter + k, (unsigned long long)fr.width * fr.height);
     }
 }
 
@@ -445,13 +502,20 @@ static inline dim3 tile_grid(int w, int h) { return dim3((w + kTileW - 1) / kTil
 
 size_t staged_bytes(const SceneView& sc) { return (size_t)(sc.n_sph + 2 * sc.n_box) * sizeof(float4); }
 
-// Picks the back end and its dynamic shared memory size. use_bvh: caller's decision (accel option).
-static int pick_mode(const SceneView& sc, const BvhView& bv, bool use_bvh, size_t& smem) {
+size_t flat_staged_bytes(const SceneView& sc, const FlatView& fl) {
+    const size_t ncull = (size_t)8 * fl.n_clusters + fl.n_singles;
+    return (size_t)kFlatQueue * kThreads + staged_bytes(sc) + (size_t)2 * (fl.n_clusters + fl.n_cubes) * 16 + ncull * 16 + (size_t)(sc.n_sph + sc.n_box) * 4 + ncull + 16;
+}
+
+// Picks the kernel variant and its dynamic shared memory size for the caller's back end (AccelSel::kind).
+static int pick_mode(const SceneView& sc, const AccelSel& ac, size_t& smem) {
     const size_t geo = staged_bytes(sc);
-    if (!use_bvh) {
+    if (ac.kind == kAccelFlat) { smem = flat_staged_bytes(sc, ac.flat); return 4; }
+    if (ac.kind == kAccelBrute) {
         if (geo <= kMaxStagedBytes) { smem = geo; return 0; }
         smem = 0; return 1;
     }
+    const BvhView& bv = ac.bvh;
     const size_t stack = ((size_t)2 * bv.stack_entries * kThreads * sizeof(int) + 15) / 16 * 16;
     const size_t all = stack + geo + (size_t)bv.n_nodes * 64 + (size_t)bv.n_refs * 4 + 16;
     if (all <= kMaxBvhStagedBytes) { smem = all; return 2; }
@@ -469,11 +533,19 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(K<0>)) != cudaSuccess) return e; \
     if ((e = optin(K<1>)) != cudaSuccess) return e; \
     if ((e = optin(K<2>)) != cudaSuccess) return e; \
-    if ((e = optin(K<3>)) != cudaSuccess) return e;
-    RTB_OPTIN(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays)
+    if ((e = optin(K<3>)) != cudaSuccess) return e; \
+    if ((e = optin(K<4>)) != cudaSuccess) return e;
+#define RTB_OPTIN2(K) \
+    if ((e = optin(K<0, false>)) != cudaSuccess) return e; if ((e = optin(K<0, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<1, false>)) != cudaSuccess) return e; if ((e = optin(K<1, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<2, false>)) != cudaSuccess) return e; if ((e = optin(K<2, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<3, false>)) != cudaSuccess) return e; if ((e = optin(K<3, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<4, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true>)) != cudaSuccess) return e;
+    RTB_OPTIN2(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays)
     if ((e = optin(k_render_bvh<2>)) != cudaSuccess) return e;
     if ((e = optin(k_render_bvh<3>)) != cudaSuccess) return e;
 #undef RTB_OPTIN
+#undef RTB_OPTIN2
     done = true;
     return cudaSuccess;
 }
@@ -483,15 +555,24 @@ static cudaError_t ensure_smem_optin() {
         case 0: K<0><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;                \
         case 1: K<1><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;                \
         case 2: K<2><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;                \
-        default: K<3><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;               \
+        case 3: K<3><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;                \
+        default: K<4><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break;               \
+    }
+#define RTB_DISPATCH2(MODE, FLAG, K, GRID, SMEM, ST, ...)                                                  \
+    switch (MODE) {                                                                                        \
+        case 0: if (FLAG) K<0, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<0, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
+        case 1: if (FLAG) K<1, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<1, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
+        case 2: if (FLAG) K<2, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<2, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
+        case 3: if (FLAG) K<3, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<3, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
+        default: if (FLAG) K<4, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<4, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
     }
 
-cudaError_t launch_primary_aov(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, int* id, float* t,
+cudaError_t launch_primary_aov(const SceneView& sc, const AccelSel& ac, const FrameView& fr, int* id, float* t,
                                float* n, float* p, cudaStream_t st) {
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
-    RTB_DISPATCH(mode, k_primary_aov, tile_grid(fr.width, fr.height), sb, st, sc, bv, fr, id, t, n, p)
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    RTB_DISPATCH(mode, k_primary_aov, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, id, t, n, p)
     return cudaGetLastError();
 }
 
@@ -500,13 +581,13 @@ cudaError_t launch_ray_dirs(const FrameView& fr, float* out, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace_rays(const SceneView& sc, const BvhView& bv, bool use_bvh, const float* org, const float* dir, int n,
+cudaError_t launch_trace_rays(const SceneView& sc, const AccelSel& ac, const float* org, const float* dir, int n,
                               int* id, float* t, float* nrm, float* pt, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
-    RTB_DISPATCH(mode, k_trace_rays, dim3((n + kThreads - 1) / kThreads), sb, st, sc, bv, org, dir, n, id, t, nrm, pt)
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    RTB_DISPATCH(mode, k_trace_rays, dim3((n + kThreads - 1) / kThreads), sb, st, sc, ac.bvh, ac.flat, org, dir, n, id, t, nrm, pt)
     return cudaGetLastError();
 }
 
@@ -533,33 +614,34 @@ cudaError_t launch_pick(const SceneView& sc, const FrameView& fr, int px, int py
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_regen(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, float4* accum,
-                                uint32_t s_begin, int n_samples, unsigned long long* seg_counter, cudaStream_t st) {
+cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
+                                uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st) {
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
-    RTB_DISPATCH(mode, k_render_regen, tile_grid(fr.width, fr.height), sb, st, sc, bv, fr, accum, s_begin, n_samples, seg_counter)
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    RTB_DISPATCH2(mode, reuse_primary, k_render_regen, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter)
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_bvh(const SceneView& sc, const BvhView& bv, const FrameView& fr, float4* accum, uint32_t s_begin,
+cudaError_t launch_render_bvh(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum, uint32_t s_begin,
                               int n_samples, unsigned long long* seg_counter, int wait_k, cudaStream_t st) {
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    size_t sb; const int mode = pick_mode(sc, bv, true, sb);
-    if (mode == 2) k_render_bvh<2><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, bv, fr, accum, s_begin, n_samples, seg_counter, wait_k);
-    else k_render_bvh<3><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, bv, fr, accum, s_begin, n_samples, seg_counter, wait_k);
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    if (mode == 2) k_render_bvh<2><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter, wait_k);
+    else if (mode == 3) k_render_bvh<3><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter, wait_k);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_preview(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, float4* accum,
+cudaError_t launch_render_preview(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                   unsigned long long* seg_counter, cudaStream_t st) {
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    size_t sb; const int mode = pick_mode(sc, bv, use_bvh, sb);
-    RTB_DISPATCH(mode, k_render_preview, tile_grid(fr.width, fr.height), sb, st, sc, bv, fr, accum, seg_counter)
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    RTB_DISPATCH(mode, k_render_preview, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, accum, seg_counter)
     return cudaGetLastError();
 }
 

@@ -3,11 +3,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "rt_device.cuh"
+
 namespace rtb {
 
-struct SceneView;
-struct BvhView;
-struct FrameView;
+// Which closest-hit back end a launch uses, with the device views it needs.
+enum { kAccelBrute = 0, kAccelBvh = 1, kAccelFlat = 2 };
+struct AccelSel {
+    int kind;
+    BvhView bvh;
+    FlatView flat;
+};
 
 // Geometry lists up to this size are staged into shared memory by every CTA
 // (8192 spheres); larger scenes go through the BVH or read global memory.
@@ -16,23 +22,24 @@ constexpr size_t kMaxStagedBytes = 128 * 1024;
 constexpr size_t kMaxBvhStagedBytes = 48 * 1024;
 
 size_t staged_bytes(const SceneView& sc);
+size_t flat_staged_bytes(const SceneView& sc, const FlatView& fl);
 
 struct PeerPtrs { const float4* p[16]; };      // every rank's accumulation buffer, rank order (RT_MAX_PEERS)
 
-cudaError_t launch_primary_aov(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, int* id, float* t,
+cudaError_t launch_primary_aov(const SceneView& sc, const AccelSel& ac, const FrameView& fr, int* id, float* t,
                                float* n, float* p, cudaStream_t st);
 cudaError_t launch_ray_dirs(const FrameView& fr, float* out, cudaStream_t st);
-cudaError_t launch_trace_rays(const SceneView& sc, const BvhView& bv, bool use_bvh, const float* org, const float* dir, int n,
+cudaError_t launch_trace_rays(const SceneView& sc, const AccelSel& ac, const float* org, const float* dir, int n,
                               int* id, float* t, float* nrm, float* pt, cudaStream_t st);
 cudaError_t launch_env_color(const FrameView& fr, const float* dir, int n, float* out, cudaStream_t st);
 cudaError_t launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t* dev_out4, cudaStream_t st);
 cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st);
 cudaError_t launch_pick(const SceneView& sc, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st);
-cudaError_t launch_render_regen(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, float4* accum,
-                                uint32_t s_begin, int n_samples, unsigned long long* seg_counter, cudaStream_t st);
-cudaError_t launch_render_bvh(const SceneView& sc, const BvhView& bv, const FrameView& fr, float4* accum, uint32_t s_begin,
+cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
+                                uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st);
+cudaError_t launch_render_bvh(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum, uint32_t s_begin,
                               int n_samples, unsigned long long* seg_counter, int wait_k, cudaStream_t st);
-cudaError_t launch_render_preview(const SceneView& sc, const BvhView& bv, bool use_bvh, const FrameView& fr, float4* accum,
+cudaError_t launch_render_preview(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                   unsigned long long* seg_counter, cudaStream_t st);
 cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int height, int first, int n, int flip_y,
                            uint32_t* out, int out_is_slice, cudaStream_t st);

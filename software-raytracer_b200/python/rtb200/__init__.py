@@ -17,9 +17,9 @@ LIB_PATH = os.path.join(PRODUCT_DIR, "lib", "librt_b200.so")
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 RT_OBJ_NONE, RT_OBJ_SPHERE, RT_OBJ_CUBE = 0, 1, 2
 RT_MODE_PATH, RT_MODE_PREVIEW = 0, 1
-RT_OPT_PIPELINE, RT_OPT_ACCEL, RT_OPT_BVH_THRESHOLD, RT_OPT_BVH_SCHED, RT_OPT_BVH_WAIT_K, RT_OPT_BVH_LEAF = 1, 2, 3, 4, 5, 6
+RT_OPT_PIPELINE, RT_OPT_ACCEL, RT_OPT_BVH_THRESHOLD, RT_OPT_BVH_SCHED, RT_OPT_BVH_WAIT_K, RT_OPT_BVH_LEAF, RT_OPT_PRIMARY_REUSE = 1, 2, 3, 4, 5, 6, 7
 RT_PIPELINE_AUTO, RT_PIPELINE_REGEN, RT_PIPELINE_WAVEFRONT = 0, 1, 2
-RT_ACCEL_AUTO, RT_ACCEL_BRUTE, RT_ACCEL_BVH = 0, 1, 2
+RT_ACCEL_AUTO, RT_ACCEL_BRUTE, RT_ACCEL_BVH, RT_ACCEL_FLAT = 0, 1, 2, 3
 
 
 class RtObject(C.Structure):
@@ -44,7 +44,8 @@ class RtStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("samples", C.c_uint32), ("n_objects", C.c_uint32),
                 ("last_render_ms", C.c_float), ("last_resolve_ms", C.c_float), ("pipeline", C.c_int32),
                 ("accel", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32),
-                ("total_paths", C.c_uint64), ("total_segments", C.c_uint64)]
+                ("total_paths", C.c_uint64), ("total_segments", C.c_uint64),
+                ("traced_segments", C.c_uint64), ("total_traced_segments", C.c_uint64)]
 
 
 OBJECT_DTYPE = np.dtype([("type", "<i4"), ("pos", "<f4", 3), ("radius", "<f4"), ("half", "<f4", 3),

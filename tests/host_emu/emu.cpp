@@ -8,12 +8,13 @@
 #include "../../software-raytracer_b200/csrc/rt_device.cuh"
 #include "../../software-raytracer_b200/csrc/rt_host_pack.h"
 #include "../../software-raytracer_b200/csrc/bvh_build.h"
+#include "../../software-raytracer_b200/csrc/flat_build.h"
 
 using namespace rtb;
 
 extern "C" {
 // Sum over samples [s0, s0+n) for every pixel (float3 per pixel, y-up); accel 0 = brute force,
-// 1 = BVH candidates. Also returns primary AOVs when the pointers are given. Returns segments traced.
+// 1 = BVH candidates, 2 = flat two-level accelerator. Also returns primary AOVs when the pointers are given. Returns segments traced.
 long long emu_render(const rt_object* objects, int n_obj, const rt_camera* cam, const rt_params* par, int accel,
                      uint32_t s0, int n, float* out_rgb, int32_t* aov_id, float* aov_t, float* aov_n, float* aov_p) {
     std::vector<rt_object> objs(objects, objects + n_obj);
@@ -30,12 +31,21 @@ long long emu_render(const rt_object* objects, int n_obj, const rt_camera* cam, 
     build_bvh(objs, ext, bvh);
     const float4* nodes = reinterpret_cast<const float4*>(bvh.nodes.data());
     std::vector<int> stack((size_t)bvh.max_depth + 8);
+    unsigned char queue[64];
+    HostFlat flat;
+    build_flat(objs, ext, flat);
+    if (accel == 2 && !flat.usable) return -1;
+    FlatView fv;
+    fv.boxes = reinterpret_cast<const float4*>(flat.boxes.data()); fv.cull = reinterpret_cast<const float4*>(flat.cull.data());
+    fv.cull_slot = flat.cull_slot.data(); fv.prim_id = flat.prim_id.data();
+    fv.n_clusters = flat.n_clusters; fv.n_cubes = flat.n_cubes; fv.n_singles = flat.n_singles; fv.kappa = flat.kappa;
     long long segs = 0;
     for (int py = 0; py < fr.height; ++py)
         for (int px = 0; px < fr.width; ++px) {
             const uint32_t pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
             const float3 d0 = ray_dir(fr, px, py);
             auto trace = [&](float3 o, float3 d) {
+                if (accel == 2) return closest_hit_flat(sc, fv, sc.sph, sc.box, queue, 1, o, d);
                 return accel ? closest_hit_bvh(sc, sc.sph, sc.box, nodes, bvh.refs.data(), stack.data(), 1, o, d)
                              : closest_hit(sc, sc.sph, sc.box, o, d);
             };

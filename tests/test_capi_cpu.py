@@ -27,12 +27,12 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     assert sorted(rtb200.EXPORTS) == names
-    assert lib.rt_abi_version() == 1
+    assert lib.rt_abi_version() == 2
 
 
 def test_struct_layouts():
     assert C.sizeof(rtb200.RtObject) == 76 and C.sizeof(rtb200.RtCamera) == 52
-    assert C.sizeof(rtb200.RtParams) == 96 and C.sizeof(rtb200.RtStats) == 64
+    assert C.sizeof(rtb200.RtParams) == 96 and C.sizeof(rtb200.RtStats) == 80
 
 
 def test_defaults_equal_reference(oracle):

@@ -19,7 +19,8 @@ EMU_SO = os.path.join(EMU_DIR, "libemu.so")
 
 @pytest.fixture(scope="session")
 def emu():
-    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(ROOT, "software-raytracer_b200", "csrc", "bvh_build.cpp")]
+    srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(ROOT, "software-raytracer_b200", "csrc", "bvh_build.cpp"),
+            os.path.join(ROOT, "software-raytracer_b200", "csrc", "flat_build.cpp")]
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
                            "-o", EMU_SO] + srcs)
     lib = C.CDLL(EMU_SO)
@@ -39,7 +40,7 @@ def emu():
 
 
 @pytest.mark.parametrize("scene", SCENES)
-@pytest.mark.parametrize("accel", [0, 1])
+@pytest.mark.parametrize("accel", [0, 1, 2])
 def test_device_logic_matches_reference_goldens(emu, scenes, golden, meta, scene, accel):
     z = golden("radiance_philox")
     for cam_name, mb in (("default", 8), ("default", 2), ("rotated", 8)):
@@ -76,3 +77,29 @@ def test_device_logic_bvh_equals_brute_on_random_scene(emu):
     for x, y in zip(aa, ab):
         assert np.array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32))
     assert (aa[0] >= 0).mean() > 0.5
+
+
+@pytest.mark.parametrize("n,spread,seed", [(250, 12.0, 1), (120, 2.0, 2), (40, 0.6, 3), (9, 5.0, 4), (3, 1.0, 5)])
+def test_device_logic_flat_equals_brute_on_random_scenes(emu, n, spread, seed):
+    """flat two-level accelerator (conservative culls + strict tests) vs the brute-force loop: ids, t, n, p,
+    radiance and segment counts bit-equal. Small `spread` packs overlapping spheres so lanes overflow the
+    8-entry candidate queue (exact fallback) and origins sit inside several spheres (negative t)."""
+    rng = np.random.default_rng(seed)
+    o = np.zeros(n + 1, rtb200.OBJECT_DTYPE)
+    o["type"] = 1
+    o["pos"][:n] = rng.uniform([-spread, 0, 4], [spread, spread, 4 + 2 * spread], (n, 3)).astype(np.float32)
+    o["radius"][:n] = rng.uniform(0.1, 0.8, n).astype(np.float32)
+    o["base"] = rng.uniform(0.1, 0.9, (n + 1, 3)).astype(np.float32); o["spec_color"] = 1
+    o["spec_amount"][::3] = 1; o["smoothness"][::3] = 0.9
+    cubes = np.arange(2, n, 7)
+    o["type"][cubes] = 2; o["half"][cubes] = rng.uniform(0.2, 0.7, (len(cubes), 3)).astype(np.float32)
+    o["emissive"][::10] = 20
+    o["pos"][n] = [0, -500, 20]; o["radius"][n] = 500
+    cam = rtb200.default_camera(60); cam.pos[1] = 0.5 * spread; cam.pos[2] = -2.0
+    par = rtb200.default_params(width=96, height=64, mode=0, max_bounces=6, seed_lo=5, seed_hi=6)
+    a, sa, aa = emu(o, cam, par, 0, 3, 3, aov=True)
+    b, sb, ab = emu(o, cam, par, 2, 3, 3, aov=True)
+    assert sb >= 0, "flat accelerator not usable for this scene"
+    assert sa == sb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for x, y in zip(aa, ab):
+        assert np.array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32))

@@ -466,3 +466,98 @@ def test_fused_reduce_resolve_across_real_gpus():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
                           "--master-addr", "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
     assert "FUSED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- flat two-level accelerator and primary-hit reuse: bit-identical to the reference's loop ------------
+@pytest.mark.parametrize("scene", SCENES)
+def test_flat_accel_hit_for_hit_bundled(tracer, scenes, golden, meta, scene):
+    z = golden("trace_rays")
+    try:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_FLAT)
+        for cam_name in ("default", "rotated"):
+            m = meta["aov"]["%s_640x480_%s" % (scene, cam_name)]
+            setup(tracer, scenes[scene], 640, 480, make_camera(rtb200.RtCamera, meta, cam_name == "rotated"))
+            ids, t, nrm, pt = tracer.read_aov()
+            assert sha(ids) == m["ids_sha256"] and sha(t) == m["t_sha256"]
+            assert sha(nrm) == m["normal_sha256"] and sha(pt) == m["point_sha256"]
+        if scene + "_org" in z.files:                     # the reference's answers on arbitrary rays
+            ids, t, nrm, pt = tracer.trace_rays(z[scene + "_org"], z[scene + "_dir"])
+            assert np.array_equal(ids, z[scene + "_id"].astype(np.int32))
+            hit = ids >= 0
+            for a, b in ((t, z[scene + "_t"]), (nrm, z[scene + "_normal"]), (pt, z[scene + "_point"])):
+                assert np.array_equal(bits(a[hit]), bits(b[hit]))
+        out = {}
+        for accel in (rtb200.RT_ACCEL_FLAT, rtb200.RT_ACCEL_BRUTE):
+            for reuse in (1, 0):
+                tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+                tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, reuse)
+                setup(tracer, scenes[scene], 160, 120)
+                tracer.render_spp(5); tracer.render_spp(11)
+                st = tracer.stats()
+                assert st.accel == accel
+                out[(accel, reuse)] = (tracer.read_accum()[0], st.segments, st.traced_segments)
+        base = out[(rtb200.RT_ACCEL_BRUTE, 0)]
+        assert base[1] == base[2]                                            # no reuse: every segment is traced
+        for k, v in out.items():
+            assert np.array_equal(bits(v[0]), bits(base[0])), k              # same bits
+            assert v[1] == base[1], k                                        # same path segments delivered
+            if k[1]:
+                # reuse: one primary query per pixel per launch (2 launches), plus every secondary segment
+                assert v[2] == base[1] - 160 * 120 * 16 + 2 * 160 * 120, k
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 1)
+
+
+@pytest.mark.parametrize("n,spread,seed", [(250, 12.0, 1), (120, 2.0, 2), (40, 0.6, 3), (9, 5.0, 4)])
+def test_flat_accel_random_scenes(tracer, n, spread, seed):
+    """Dense overlapping spheres + cubes: candidate-queue overflow (exact fallback), origins inside spheres."""
+    rng = np.random.default_rng(seed)
+    o = np.zeros(n + 1, rtb200.OBJECT_DTYPE)
+    o["type"] = 1
+    o["pos"][:n] = rng.uniform([-spread, 0, 4], [spread, spread, 4 + 2 * spread], (n, 3)).astype(np.float32)
+    o["radius"][:n] = rng.uniform(0.1, 0.8, n).astype(np.float32)
+    o["base"] = rng.uniform(0.1, 0.9, (n + 1, 3)).astype(np.float32); o["spec_color"] = 1
+    o["spec_amount"][::3] = 1; o["smoothness"][::3] = 0.9
+    cubes = np.arange(2, n, 7)
+    o["type"][cubes] = 2; o["half"][cubes] = rng.uniform(0.2, 0.7, (len(cubes), 3)).astype(np.float32)
+    o["emissive"][::10] = 20
+    o["pos"][n] = [0, -500, 20]; o["radius"][n] = 500
+    cam = rtb200.default_camera(60); cam.pos[1] = 0.5 * spread; cam.pos[2] = -2.0
+    res = {}
+    try:
+        for accel in (rtb200.RT_ACCEL_FLAT, rtb200.RT_ACCEL_BRUTE):
+            tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+            setup(tracer, o, 256, 144, cam, max_bounces=6)
+            aov = tracer.read_aov()
+            tracer.render_spp(6)
+            st = tracer.stats()
+            assert st.accel == accel
+            res[accel] = (aov, tracer.read_accum()[0], st.segments)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+    a, b = res[rtb200.RT_ACCEL_FLAT], res[rtb200.RT_ACCEL_BRUTE]
+    assert np.array_equal(a[0][0], b[0][0])
+    for x, y in zip(a[0][1:], b[0][1:]):
+        assert np.array_equal(bits(x), bits(y))
+    assert np.array_equal(bits(a[1]), bits(b[1])) and a[2] == b[2]
+
+
+def test_flat_accel_far_camera_and_inside_sphere(tracer, scenes):
+    objs = scenes["Scene1"]
+    for pos in ([0, 0, 5.2], [3000.0, 1500.0, -9000.0], [0.0, -500.0, 5.0]):
+        cam = rtb200.default_camera(40)
+        cam.pos[0], cam.pos[1], cam.pos[2] = pos
+        out = {}
+        try:
+            for accel in (rtb200.RT_ACCEL_FLAT, rtb200.RT_ACCEL_BRUTE):
+                tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+                setup(tracer, objs, 200, 150, cam)
+                aov = tracer.read_aov()
+                tracer.render_spp(3)
+                out[accel] = (aov, tracer.read_accum()[0])
+        finally:
+            tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        a, b = out[rtb200.RT_ACCEL_FLAT], out[rtb200.RT_ACCEL_BRUTE]
+        assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(bits(a[0][1]), bits(b[0][1]))
+        assert np.array_equal(bits(a[1]), bits(b[1]))
