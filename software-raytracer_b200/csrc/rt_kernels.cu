@@ -193,29 +193,36 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     int s = 0, depth = 0;
     unsigned int segs = 0, traced = 0;
 
-    // One closest-hit site and one shading site (code size matters: instruction fetch was the top stall of
-    // the first version). `primary` marks the query of the pixel's primary ray when REUSE keeps its result.
+    // REUSE prologue: the pixel's one primary query. A miss (or max_bounces == 0) consumes no random number, so
+    // every sample of the pixel has the same value: add it n times, in order, and the lane is done.
     Hit h0;
     h0.id = -1; h0.t = 0.f; h0.n = f3(0.f, 0.f, 0.f); h0.p = f3(0.f, 0.f, 0.f);
-    bool primary = true;
+    if (REUSE && n_samples > 0) {
+        h0 = trace<MODE>(sc, tc, o, d);
+        traced = 1;
+        float3 c;
+        if (path_ends(sc, fr, h0, d, T, L, 0, c)) {
+            for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
+            segs = (unsigned int)n_samples;
+        } else {
+            scatter_segment(sc, fr, h0, pixel, s_begin, o, d, T, L, depth);
+            segs = 1;
+        }
+    }
+    // Main loop: one closest-hit query per lane per iteration, then ONE pass through each shading block - the
+    // flag (instead of continue/break) lets the warp reconverge before the scatter block.
     while (s < n_samples) {
         Hit h = trace<MODE>(sc, tc, o, d);
         ++segs; ++traced;
-        if (REUSE && primary) { h0 = h; primary = false; }
-        for (;;) {
-            float3 c;
-            if (!shade_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth, c)) break;   // scattered: trace (o, d)
+        bool scatter = true;
+        float3 c;
+        if (path_ends(sc, fr, h, d, T, L, depth, c)) {
             acc.x += c.x; acc.y += c.y; acc.z += c.z;
             ++s; depth = 0; o = fr.cam_pos; d = d0;
-            if (!REUSE || s >= n_samples) break;
-            if (h0.id < 0 || fr.max_bounces == 0) {
-                // the primary ray misses (or nothing scatters): no random number is consumed and every sample
-                // of this pixel has the value c - add it n times, in order
-                for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; ++segs; }
-                break;
-            }
-            h = h0; ++segs;                                  // next sample starts from the cached primary hit
+            scatter = false;                                 // no reuse: trace the primary ray again
+            if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }   // next sample starts from the cached primary hit
         }
+        if (scatter) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
     }
 
     if (inside) {
