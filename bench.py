@@ -151,8 +151,23 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    global W, H, DEPTH
     objs = load_scene(args.scene)
     spp = args.spp
+    cam0 = rtb200.default_camera()
+    mesh = None
+    workload = "Scene1 (67 spheres)" if args.scene == "Scene1" else args.scene
+    if args.config == "c3":                              # BASELINE.json configs[2]: 10k random spheres at 4K
+        from rtb200.scenes import synthetic_spheres, config3_camera
+        objs = synthetic_spheres(10000); cam0 = config3_camera(rtb200.default_camera); W, H = 3840, 2160
+        workload = "config 3: 10 000 random spheres + ground + 8 lights"
+    elif args.config == "c4":                            # configs[3]: ~1M-triangle mesh through the BVH
+        from rtb200.scenes import heightfield_mesh, mesh_scene
+        objs = mesh_scene(); mesh = heightfield_mesh(1024, 512)
+        cam0.pos[1] = 1.5; cam0.pos[2] = -1.0
+        workload = "config 4: 1 048 576-triangle heightfield mesh + 3 spheres"
+    elif args.config == "c5":                            # configs[4]: interactive 1 spp frames at 720p
+        W, H = 1280, 720
     stream = torch.cuda.Stream()
     tr = rtb200.PathTracer(local)
     tr.set_stream(stream.cuda_stream)
@@ -164,10 +179,14 @@ def run_b200(args):
     if args.wait_k >= 0:
         tr.set_option(rtb200.RT_OPT_BVH_WAIT_K, args.wait_k)
     tr.set_scene(objs)
-    tr.set_camera(rtb200.default_camera())
+    if mesh is not None:
+        tr.set_mesh(0, mesh[0], mesh[1])
+    tr.set_camera(cam0)
     tr.set_params(rtb200.default_params(width=W, height=H, mode=rtb200.RT_MODE_PATH, max_bounces=DEPTH,
                                         seed_lo=2026, seed_hi=rank))       # every rank: its own sample streams
     tr.reset_accumulation()
+    if args.config == "c5":
+        return run_interactive(args, tr, stream, torch)
 
     class DevBuf:                                   # wrap the library's accumulation buffer for NCCL
         def __init__(self, ptr, n):
@@ -238,10 +257,11 @@ def run_b200(args):
 
         # ---- end to end through the C-ABI with host buffers: e2e ------------------------------
         out = np.zeros((H, W), np.uint32)
-        cam = rtb200.default_camera()
+        cam = cam0
 
         def step_e2e():
-            tr.set_scene(objs)                       # host rt_object[] -> device SoA (H2D)
+            if mesh is None:
+                tr.set_scene(objs)                   # host rt_object[] -> device SoA (H2D)
             tr.set_camera(cam)
             tr.reset_accumulation()
             tr.render_spp(spp)
@@ -294,7 +314,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic: bundled Scene1 fixture (tests/golden/bundled_scenes.npz), default camera, Philox seeds",
-            "config": {"workload": "Scene1 (67 spheres) %dx%d, %d spp per GPU per step, depth %d, path mode" % (W, H, spp, DEPTH),
+            "config": {"workload": "%s %dx%d, %d spp per GPU per step, depth %d, path mode" % (workload, W, H, spp, DEPTH),
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": ("spp-sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce+resolve kernel over NVLink peer memory" if fused else "one NCCL all-reduce per step"),
                        "build": "strict IEEE, -fmad=false (bit-exact geometry vs the reference)",
                        "accel": {rtb200.RT_ACCEL_BRUTE: "brute-force object loop", rtb200.RT_ACCEL_BVH: "host-built BVH candidates + strict tests",
@@ -326,7 +346,7 @@ def run_b200(args):
                          "frac_of_no_fma_peak": achieved_tf / (peak_tf / 2),
                          "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_algorithmic_gbs": (W * H * 32 / kern_s) / 1e9},
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == "c2":
             rate, info = cpu_reference_run(objs, args.cpu_frames)
             line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"], "threads": info["threads"]}
@@ -336,8 +356,40 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_interactive(args, tr, stream, torch):
+    """BASELINE.json configs[4]: progressive 1 spp frames at 1280x720, each frame = rt_render_spp(1) +
+    rt_resolve_rgba8 into a HOST surface (D2H 3.7 MB), what a viewer's frame loop does. Frame latency p50/p99."""
+    import rtb200
+    out = np.zeros((H, W), np.uint32)
+    n = max(args.steps, 1) * 200
+    with torch.cuda.stream(stream):
+        for _ in range(20):
+            tr.render_spp(1); tr.resolve_rgba8(True, out)
+        tr.reset_accumulation(); tr.sync()
+        seg0 = tr.stats().total_segments
+        lat = []
+        t_all = time.perf_counter()
+        for _ in range(n):
+            t0 = time.perf_counter()
+            tr.render_spp(1)
+            tr.resolve_rgba8(True, out)              # synchronises: the frame is on the host
+            lat.append((time.perf_counter() - t0) * 1e3)
+        total = time.perf_counter() - t_all
+        segs = tr.stats().total_segments - seg0
+    lat.sort()
+    line = {"metric": "frame latency, progressive 1 spp/frame (BASELINE.json configs[4])", "value": lat[len(lat) // 2], "unit": "ms (p50)",
+            "p99_ms": lat[int(len(lat) * 0.99) - 1], "mean_ms": 1e3 * total / n, "frames": n, "fps": n / total,
+            "n_gpus": 1, "higher_is_better": False, "dtype": "f32", "data": "synthetic: bundled Scene1 fixture",
+            "config": {"workload": "Scene1 %dx%d, 1 spp per frame, depth %d, render + resolve + D2H of %d bytes per frame" % (W, H, DEPTH, W * H * 4)},
+            "Msegments_per_s": segs / total / 1e6}
+    print(json.dumps(line), flush=True)
+    tr.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configs[1..4]; the headline (and default) is c2, the others are report-only lines")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)

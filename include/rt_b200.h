@@ -43,7 +43,8 @@ typedef enum {
 } rt_status;
 
 /* Object types: Scene.hpp:43-55 ("Sphere", "Cube", anything else -> never-hit Object). */
-enum { RT_OBJ_NONE = 0, RT_OBJ_SPHERE = 1, RT_OBJ_CUBE = 2 };
+enum { RT_OBJ_NONE = 0, RT_OBJ_SPHERE = 1, RT_OBJ_CUBE = 2,
+       RT_OBJ_MESH = 3 };   /* triangle mesh: an extension, the reference has no such type (rt_set_mesh below) */
 
 /* One scene object: Object.transform.position + Sphere::radius | Box::size (half extents) +
  * Material (Common.hpp:293-319). 76 bytes, no padding. */
@@ -148,6 +149,18 @@ int rt_scene_file_write(const char* json_path, const char* scene_name, const rt_
 const char* rt_object_name(rt_ctx* ctx, int index);
 int rt_set_object_name(rt_ctx* ctx, int index, const char* name);
 const char* rt_scene_name(rt_ctx* ctx);
+
+/* ---- triangle meshes: EXTENSION (BASELINE.json config 4) ---------------------------------
+ * The reference's Scene holds Sphere and Box objects only (Scene.hpp:43-55); a mesh follows the same
+ * Object contract: one scene object (one id, one Material, Transform.position as a translation) whose
+ * Raytrace() reports the closest of its triangles (Object.hpp:21-23; csrc/mesh.h defines the intersector).
+ * JSON: "Renderer": {"Type": "Mesh", "File": "mesh.obj"} (path relative to the scene file) or inline
+ * "Vertices": [x,y,z,...] / "Triangles": [i,j,k,...]. Geometry is attached to an object of type RT_OBJ_MESH
+ * AFTER rt_set_scene / rt_load_scene (which drop all mesh data); scenes with meshes use the BVH back end. */
+int rt_set_mesh(rt_ctx* ctx, int object_index, const float* vertices_xyz, int n_vertices,
+                const int32_t* indices, int n_triangles);
+int rt_load_mesh_obj(rt_ctx* ctx, int object_index, const char* obj_path);
+int rt_get_mesh_info(rt_ctx* ctx, int object_index, int* n_vertices, int* n_triangles);
 
 /* ---- camera and parameters ----------------------------------------------------------- */
 void rt_default_params(rt_params* p);                               /* Raytracer.cpp:26-35,55-59 */

@@ -134,6 +134,21 @@ class Oracle:
         self.lib.orc_ray_dirs(C.byref(cam), w, h, _p(out))
         return out
 
+    def set_triangles(self, objs, meshes):
+        """mesh extension: meshes = {object_index: (vertices float32 (n,3) object space, triangles int32 (m,3))}.
+        World-space vertex = vertex + pos with one float32 add (what the product does); pass {} to clear."""
+        verts, owner = [], []
+        for oi in sorted(meshes):
+            v, t = meshes[oi]
+            v = (np.ascontiguousarray(v, np.float32).reshape(-1, 3) + np.asarray(objs["pos"][oi], np.float32)).astype(np.float32)
+            t = np.ascontiguousarray(t, np.int32).reshape(-1, 3)
+            verts.append(v[t].reshape(-1, 9)); owner.append(np.full(len(t), oi, np.int32))
+        if verts:
+            v9 = np.ascontiguousarray(np.concatenate(verts), np.float32); ow = np.ascontiguousarray(np.concatenate(owner), np.int32)
+            self.lib.orc_set_triangles(_p(v9), _p(ow), len(ow))
+        else:
+            self.lib.orc_set_triangles(None, None, 0)
+
     def trace_rays(self, objs, origin, direction):
         origin = np.ascontiguousarray(origin, np.float32)
         direction = np.ascontiguousarray(direction, np.float32)

@@ -177,6 +177,71 @@ static hit_t hit_box(const orc_object* b, v3 o, v3 rd) {
     return h;
 }
 
+/* ---- triangle meshes: EXTENSION, not in the reference ("parity unpinned") -----------
+ * A mesh is one Object (type 3) whose Raytrace() reports the closest of its triangles, tested in index order
+ * with a strict '<' - the Object contract of Object.hpp:21-23 / Raytracer.cpp:127-137. The plane-first
+ * intersector and its 12 precomputed floats per triangle are an independent restatement of the product's
+ * definition (software-raytracer_b200/csrc/mesh.h); nothing here is derived from reference behaviour. */
+typedef struct { float n[3], dn, m1[3], k1, m2[3], k2; } tri_rec;
+static tri_rec* g_tri = NULL;
+static int32_t* g_tri_obj = NULL;
+static int g_ntri = 0;
+
+/* verts9: 3 world-space float vertices per triangle; tri_obj: owning object index, ascending */
+void orc_set_triangles(const float* verts9, const int32_t* tri_obj, int n) {
+    free(g_tri); free(g_tri_obj); g_tri = NULL; g_tri_obj = NULL; g_ntri = 0;
+    if (n <= 0) return;
+    g_tri = (tri_rec*)calloc((size_t)n, sizeof(tri_rec));
+    g_tri_obj = (int32_t*)malloc((size_t)n * sizeof(int32_t));
+    g_ntri = n;
+    for (int t = 0; t < n; ++t) {
+        const float* v = verts9 + (size_t)9 * t;
+        g_tri_obj[t] = tri_obj[t];
+        double e1[3], e2[3], N[3];
+        for (int k = 0; k < 3; ++k) { e1[k] = (double)v[3 + k] - (double)v[k]; e2[k] = (double)v[6 + k] - (double)v[k]; }
+        N[0] = e1[1] * e2[2] - e1[2] * e2[1]; N[1] = e1[2] * e2[0] - e1[0] * e2[2]; N[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+        if (!(nn > 0.0) || !isfinite(nn)) continue;                  /* degenerate: all zeros, never hit */
+        double len = sqrt(nn);
+        tri_rec* r = &g_tri[t];
+        double nx = N[0] / len, ny = N[1] / len, nz = N[2] / len;
+        r->n[0] = (float)nx; r->n[1] = (float)ny; r->n[2] = (float)nz;
+        r->dn = (float)(nx * v[0] + ny * v[1] + nz * v[2]);
+        double m1[3] = {(e2[1] * N[2] - e2[2] * N[1]) / nn, (e2[2] * N[0] - e2[0] * N[2]) / nn, (e2[0] * N[1] - e2[1] * N[0]) / nn};
+        double m2[3] = {(N[1] * e1[2] - N[2] * e1[1]) / nn, (N[2] * e1[0] - N[0] * e1[2]) / nn, (N[0] * e1[1] - N[1] * e1[0]) / nn};
+        for (int k = 0; k < 3; ++k) { r->m1[k] = (float)m1[k]; r->m2[k] = (float)m2[k]; }
+        r->k1 = (float)-(m1[0] * v[0] + m1[1] * v[1] + m1[2] * v[2]);
+        r->k2 = (float)-(m2[0] * v[0] + m2[1] * v[1] + m2[2] * v[2]);
+    }
+}
+
+static hit_t hit_tri(const tri_rec* r, v3 o, v3 d) {
+    hit_t h; memset(&h, 0, sizeof h);
+    float denom = r->n[0] * d.x + r->n[1] * d.y + r->n[2] * d.z;
+    if (fabsf(denom) < 1e-9f) return h;
+    float t = (r->dn - (r->n[0] * o.x + r->n[1] * o.y + r->n[2] * o.z)) / denom;
+    if (!(t >= 1e-4f && t <= 10000.f)) return h;
+    float Px = o.x + d.x * t, Py = o.y + d.y * t, Pz = o.z + d.z * t;
+    float u = (r->m1[0] * Px + r->m1[1] * Py + r->m1[2] * Pz) + r->k1;
+    float v = (r->m2[0] * Px + r->m2[1] * Py + r->m2[2] * Pz) + r->k2;
+    if (!(u >= 0.f && v >= 0.f && u + v <= 1.f)) return h;
+    h.valid = 1; h.distance = t; h.point = V(Px, Py, Pz);
+    h.normal = denom < 0.f ? V(r->n[0], r->n[1], r->n[2]) : V(r->n[0] * -1.f, r->n[1] * -1.f, r->n[2] * -1.f);
+    return h;
+}
+
+/* Mesh::Raytrace: closest triangle of object `obj`, index order, strict < */
+static hit_t hit_mesh(int obj, v3 o, v3 d) {
+    hit_t best; memset(&best, 0, sizeof best);
+    float shortest = INFINITY;
+    for (int t = 0; t < g_ntri; ++t) {
+        if (g_tri_obj[t] != obj) continue;
+        hit_t h = hit_tri(&g_tri[t], o, d);
+        if (h.valid && h.distance < shortest) { shortest = h.distance; best = h; }
+    }
+    return best;
+}
+
 /* GetClosestObject (Raytracer.cpp:123-140): strict <, list order, +inf start */
 static int closest(const orc_object* objs, int n, v3 o, v3 d, hit_t* out, long long* segs) {
     int best = -1;
@@ -187,6 +252,7 @@ static int closest(const orc_object* objs, int n, v3 o, v3 d, hit_t* out, long l
         hit_t h;
         if (objs[i].type == 1) h = hit_sphere(&objs[i], o, d);
         else if (objs[i].type == 2) h = hit_box(&objs[i], o, d);
+        else if (objs[i].type == 3) h = hit_mesh(i, o, d);           /* extension */
         else continue;                                               /* Object::Raytrace: never valid (Object.hpp:21-23) */
         if (h.valid && h.distance < shortest) { best = i; shortest = h.distance; res = h; }
     }

@@ -127,7 +127,7 @@ struct Builder {
 
 }  // namespace
 
-void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf) {
+void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf, const TriRecords* tris) {
     out = HostBvh();
     Builder b; b.out = &out;
     b.kMaxLeaf = max_leaf < 1 ? 1 : (max_leaf > 64 ? 64 : max_leaf);
@@ -154,6 +154,22 @@ void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostB
         }
         scene.grow(p.box);
         b.prims.push_back(p);
+    }
+    if (tris) {
+        b.prims.reserve(b.prims.size() + (size_t)tris->count());
+        for (int t = 0; t < tris->count(); ++t) {
+            Prim p;
+            const float* bb = tris->bounds.data() + (size_t)6 * t;
+            bool finite = true;
+            for (int k = 0; k < 3; ++k) {
+                p.box.lo[k] = bb[k]; p.box.hi[k] = bb[3 + k]; p.centroid[k] = 0.5f * (bb[k] + bb[3 + k]);
+                finite = finite && std::isfinite(bb[k]) && std::isfinite(bb[3 + k]);
+            }
+            if (!finite) for (int k = 0; k < 3; ++k) { p.box.lo[k] = -1e30f; p.box.hi[k] = 1e30f; p.centroid[k] = 0.f; }
+            p.ref = kTriRefBase + t;
+            scene.grow(p.box);
+            b.prims.push_back(p);
+        }
     }
     out.n_prims = (int)b.prims.size();
     float extent = std::fabs(origin_extent);

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/rt_b200.h"
+#include "mesh.h"
 
 namespace rtb {
 
@@ -28,7 +29,7 @@ static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
 struct HostBvh {
     std::vector<BvhNode> nodes;      // nodes[0] is the root (always an inner node)
-    std::vector<int32_t> refs;       // leaf entries: >= 0 sphere slot, < 0 ~cube slot (slots = SoA list indices)
+    std::vector<int32_t> refs;       // leaf entries: [0, kTriRefBase) sphere slot, >= kTriRefBase triangle, < 0 ~cube slot
     int max_depth = 0;
     int n_prims = 0;
     float inflate_abs = 0.f;         // the absolute inflation that was applied
@@ -37,10 +38,12 @@ struct HostBvh {
 };
 
 constexpr float kInflate = 4e-5f;    // relative box inflation
+constexpr int32_t kTriRefBase = 0x40000000;   // leaf ref of triangle i = kTriRefBase + i
 constexpr int kMaxBvhDepth = 40;     // traversal stack entries per thread
 
 // objects: the scene in list order. origin_extent: largest |coordinate| of any ray origin that will be
 // traced from outside the scene bounds (the camera position); secondary origins lie on surfaces.
-void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf = 4);
+void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf = 4,
+               const TriRecords* tris = nullptr);
 
 }  // namespace rtb

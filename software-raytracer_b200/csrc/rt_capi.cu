@@ -16,6 +16,7 @@
 #include "rt_kernels.h"
 #include "bvh_build.h"
 #include "flat_build.h"
+#include "mesh.h"
 #include "scene_json.h"
 
 using namespace rtb;
@@ -40,6 +41,10 @@ struct rt_ctx {
     float4* d_box = nullptr; int* d_box_id = nullptr;
     float4* d_mat = nullptr;
     size_t cap_sph = 0, cap_sph_id = 0, cap_box = 0, cap_box_id = 0, cap_mat = 0;
+    // mesh extension: triangle records (mesh.h)
+    TriRecords tris;
+    float4* d_tri = nullptr; int* d_tri_obj = nullptr;
+    size_t cap_tri = 0, cap_tri_obj = 0;
 
     // BVH (built lazily; see bvh_build.h)
     HostBvh bvh;
@@ -146,11 +151,21 @@ int upload_scene(rt_ctx* c) {
     }
     if (!mat.empty())
         RT_CUDA(c, cudaMemcpyAsync(c->d_mat, mat.data(), mat.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    c->scene.meshes.resize(objs.size());
+    build_tri_records(objs, c->scene.meshes, c->tris);
+    const size_t nt = (size_t)c->tris.count();
+    RT_CUDA(c, ensure_capacity(c->d_tri, c->cap_tri, nt * 3));
+    RT_CUDA(c, ensure_capacity(c->d_tri_obj, c->cap_tri_obj, nt));
+    if (nt) {
+        RT_CUDA(c, cudaMemcpyAsync(c->d_tri, c->tris.rec.data(), nt * 48, cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(c, cudaMemcpyAsync(c->d_tri_obj, c->tris.obj.data(), nt * 4, cudaMemcpyHostToDevice, c->stream));
+    }
     RT_CUDA(c, cudaStreamSynchronize(c->stream));             // host vectors die at return
     c->view.sph = c->d_sph; c->view.sph_id = c->d_sph_id;
     c->view.box = c->d_box; c->view.box_id = c->d_box_id;
     c->view.mat = c->d_mat;
     c->view.n_sph = (int)sph_id.size(); c->view.n_box = (int)box_id.size(); c->view.n_obj = (int)objs.size();
+    c->view.tri = c->d_tri; c->view.tri_obj = c->d_tri_obj; c->view.n_tri = (int)nt;
     c->bvh_valid = false; c->flat_valid = false; c->tuned_accel = -1;
     return RT_OK;
 }
@@ -159,7 +174,7 @@ int upload_scene(rt_ctx* c) {
 // box inflation was derived from.
 int ensure_bvh(rt_ctx* c, float origin_extent) {
     if (c->bvh_valid && origin_extent <= c->bvh.extent) return RT_OK;
-    build_bvh(c->scene.objects, origin_extent, c->bvh, c->opt_bvh_leaf);
+    build_bvh(c->scene.objects, origin_extent, c->bvh, c->opt_bvh_leaf, &c->tris);
     if (c->bvh.max_depth + 2 > 62) return fail(c, RT_ERR_INVALID, "BVH too deep for the traversal stack");
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     RT_CUDA(c, ensure_capacity(c->d_bvh_nodes, c->cap_bvh_nodes, c->bvh.nodes.size() * 4));
@@ -211,7 +226,7 @@ int make_accel(rt_ctx* c, int rt_accel, float origin_extent, AccelSel& ac) {
     int rc;
     if (rt_accel == RT_ACCEL_FLAT) {
         if ((rc = ensure_flat(c, origin_extent)) != RT_OK) return rc;
-        if (c->flat.usable) { ac.kind = kAccelFlat; ac.flat = c->fview; return RT_OK; }
+        if (c->flat.usable && c->view.n_tri == 0) { ac.kind = kAccelFlat; ac.flat = c->fview; return RT_OK; }
         rt_accel = RT_ACCEL_BVH;
     }
     if (rt_accel == RT_ACCEL_BVH) {
@@ -230,8 +245,8 @@ int accel_of(const AccelSel& ac) { return ac.kind == kAccelFlat ? RT_ACCEL_FLAT 
 int want_accel(rt_ctx* c) {
     if (c->opt_accel != RT_ACCEL_AUTO) return c->opt_accel;
     if (c->tuned_accel >= 0) return c->tuned_accel;
-    const int n = c->view.n_sph + c->view.n_box;
-    if (n >= c->opt_bvh_threshold) return RT_ACCEL_BVH;
+    const int n = c->view.n_sph + c->view.n_box + c->view.n_tri;
+    if (n >= c->opt_bvh_threshold || c->view.n_tri > 0) return RT_ACCEL_BVH;
     if (n >= 8 && n <= kFlatMaxPrims) return RT_ACCEL_FLAT;
     return RT_ACCEL_BRUTE;
 }
@@ -242,9 +257,9 @@ int want_accel(rt_ctx* c) {
 // threshold the BVH.
 int autotune_accel(rt_ctx* c) {
     if (c->opt_accel != RT_ACCEL_AUTO || c->tuned_accel >= 0) return RT_OK;
-    const int n = c->view.n_sph + c->view.n_box;
+    const int n = c->view.n_sph + c->view.n_box + c->view.n_tri;
     if (n < 8) { c->tuned_accel = RT_ACCEL_BRUTE; return RT_OK; }
-    if (n >= c->opt_bvh_threshold) { c->tuned_accel = RT_ACCEL_BVH; return RT_OK; }
+    if (n >= c->opt_bvh_threshold || c->view.n_tri > 0) { c->tuned_accel = RT_ACCEL_BVH; return RT_OK; }
     const int kinds[3] = {RT_ACCEL_BRUTE, RT_ACCEL_BVH, RT_ACCEL_FLAT};
     AccelSel sel[3];
     int rc;
@@ -382,6 +397,7 @@ int rt_destroy(rt_ctx* c) {
     cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
     cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_tune);
+    cudaFree(c->d_tri); cudaFree(c->d_tri_obj);
     cudaFree(c->d_flat_boxes); cudaFree(c->d_flat_cull); cudaFree(c->d_flat_slots); cudaFree(c->d_flat_ids);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -414,10 +430,11 @@ int rt_set_scene(rt_ctx* c, const rt_object* objects, int n) {
     RT_CUDA(c, cudaSetDevice(c->device));
     // identical content (a host that re-submits its object array every frame): the device copy is still
     // refreshed, but the BVH and the back-end choice stay valid
-    const bool same = (size_t)n == c->scene.objects.size() && c->bvh_valid &&
+    const bool same = (size_t)n == c->scene.objects.size() && c->bvh_valid && c->view.n_tri == 0 &&
                       (n == 0 || memcmp(objects, c->scene.objects.data(), (size_t)n * sizeof(rt_object)) == 0);
     c->scene.objects.assign(objects, objects + n);
     c->scene.names.resize((size_t)n);
+    c->scene.meshes.assign((size_t)n, HostMesh());             // mesh data is attached afterwards (rt_set_mesh)
     for (rt_object& o : c->scene.objects) {                    // Color ctor clamp (Common.hpp:253-262)
         for (int k = 0; k < 3; ++k) {
             if (o.base[k] < 0) o.base[k] = 0;
@@ -489,6 +506,49 @@ int rt_set_object_name(rt_ctx* c, int index, const char* name) {
     return RT_OK;
 }
 const char* rt_scene_name(rt_ctx* c) { return c ? c->scene.scene_name.c_str() : nullptr; }
+
+// ---- mesh extension ------------------------------------------------------------------------------
+static int mesh_changed(rt_ctx* c) {
+    int rc = upload_scene(c);
+    if (rc != RT_OK) return rc;
+    return rt_reset_accumulation(c);
+}
+
+int rt_set_mesh(rt_ctx* c, int object_index, const float* vertices_xyz, int n_vertices, const int32_t* indices, int n_triangles) {
+    if (!c || object_index < 0 || (size_t)object_index >= c->scene.objects.size() || n_vertices < 0 || n_triangles < 0 ||
+        (n_vertices > 0 && !vertices_xyz) || (n_triangles > 0 && !indices))
+        return fail(c, RT_ERR_INVALID, "rt_set_mesh: bad arguments");
+    if (c->scene.objects[(size_t)object_index].type != RT_OBJ_MESH) return fail(c, RT_ERR_INVALID, "rt_set_mesh: object is not of type RT_OBJ_MESH");
+    for (int i = 0; i < 3 * n_triangles; ++i)
+        if (indices[i] < 0 || indices[i] >= n_vertices) return fail(c, RT_ERR_INVALID, "rt_set_mesh: vertex index out of range");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    c->scene.meshes.resize(c->scene.objects.size());
+    HostMesh& m = c->scene.meshes[(size_t)object_index];
+    m.vertices.assign(vertices_xyz, vertices_xyz + (size_t)3 * n_vertices);
+    m.indices.assign(indices, indices + (size_t)3 * n_triangles);
+    m.file.clear();
+    return mesh_changed(c);
+}
+
+int rt_load_mesh_obj(rt_ctx* c, int object_index, const char* obj_path) {
+    if (!c || !obj_path || object_index < 0 || (size_t)object_index >= c->scene.objects.size())
+        return fail(c, RT_ERR_INVALID, "rt_load_mesh_obj: bad arguments");
+    if (c->scene.objects[(size_t)object_index].type != RT_OBJ_MESH) return fail(c, RT_ERR_INVALID, "rt_load_mesh_obj: object is not of type RT_OBJ_MESH");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    HostMesh m; std::string err;
+    if (!load_obj(obj_path, m, err)) return fail(c, RT_ERR_IO, err);
+    c->scene.meshes.resize(c->scene.objects.size());
+    c->scene.meshes[(size_t)object_index] = std::move(m);
+    return mesh_changed(c);
+}
+
+int rt_get_mesh_info(rt_ctx* c, int object_index, int* n_vertices, int* n_triangles) {
+    if (!c || object_index < 0 || (size_t)object_index >= c->scene.objects.size()) return RT_ERR_INVALID;
+    const HostMesh* m = (size_t)object_index < c->scene.meshes.size() ? &c->scene.meshes[(size_t)object_index] : nullptr;
+    if (n_vertices) *n_vertices = m ? (int)(m->vertices.size() / 3) : 0;
+    if (n_triangles) *n_triangles = m ? (int)(m->indices.size() / 3) : 0;
+    return RT_OK;
+}
 
 int rt_set_camera(rt_ctx* c, const rt_camera* cam) {
     if (!c || !cam) return RT_ERR_INVALID;
@@ -577,7 +637,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
         // this rank's slice of the global sample indices [next, next+spp)
         int mine = 0; uint32_t first = 0;
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
-        if (ac.kind == kAccelBvh && c->opt_bvh_sched)
+        if (ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0)
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else
             RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream));
@@ -727,7 +787,9 @@ int rt_pick(rt_ctx* c, int x, int y_window, int* id) {
     // and closest-hit code as the render path.
     const int y = c->par.height - y_window;
     int* d_id = (int*)c->d_scratch;
-    RT_CUDA(c, launch_pick(c->view, c->frame, x, y, d_id, c->stream));
+    AccelSel ac;
+    if ((rc = make_accel(c, want_accel(c), camera_extent(c), ac)) != RT_OK) return rc;
+    RT_CUDA(c, launch_pick(c->view, ac, c->frame, x, y, d_id, c->stream));
     RT_CUDA(c, cudaMemcpyAsync(id, d_id, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     return RT_OK;

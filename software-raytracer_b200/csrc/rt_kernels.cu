@@ -145,8 +145,11 @@ __global__ void k_env_color(FrameView fr, const float* __restrict__ dir, int n, 
     out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
 }
 
-__global__ void k_pick(SceneView sc, FrameView fr, int px, int py, int* out_id) {
-    *out_id = closest_hit(sc, sc.sph, sc.box, fr.cam_pos, ray_dir(fr, px, py)).id;
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_pick(SceneView sc, BvhView bv, FlatView fl, FrameView fr, int px, int py, int* out_id) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);       // all threads stage; thread 0 traces the one ray
+    if (threadIdx.x == 0) *out_id = trace<MODE>(sc, tc, fr.cam_pos, ray_dir(fr, px, py)).id;
 }
 
 __global__ void k_selftest_uniform(int* failures) {
@@ -548,7 +551,7 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(K<2, false>)) != cudaSuccess) return e; if ((e = optin(K<2, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<3, false>)) != cudaSuccess) return e; if ((e = optin(K<3, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<4, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true>)) != cudaSuccess) return e;
-    RTB_OPTIN2(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays)
+    RTB_OPTIN2(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick)
     if ((e = optin(k_render_bvh<2>)) != cudaSuccess) return e;
     if ((e = optin(k_render_bvh<3>)) != cudaSuccess) return e;
 #undef RTB_OPTIN
@@ -616,8 +619,11 @@ cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_pick(const SceneView& sc, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st) {
-    k_pick<<<1, 1, 0, st>>>(sc, fr, px, py, dev_id);
+cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st) {
+    cudaError_t e = ensure_smem_optin();
+    if (e != cudaSuccess) return e;
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    RTB_DISPATCH(mode, k_pick, 1, sb, st, sc, ac.bvh, ac.flat, fr, px, py, dev_id)
     return cudaGetLastError();
 }
 

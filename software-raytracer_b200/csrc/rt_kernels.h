@@ -34,7 +34,7 @@ cudaError_t launch_trace_rays(const SceneView& sc, const AccelSel& ac, const flo
 cudaError_t launch_env_color(const FrameView& fr, const float* dir, int n, float* out, cudaStream_t st);
 cudaError_t launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t* dev_out4, cudaStream_t st);
 cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st);
-cudaError_t launch_pick(const SceneView& sc, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st);
+cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st);
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                 uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st);
 cudaError_t launch_render_bvh(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum, uint32_t s_begin,

@@ -315,6 +315,7 @@ int HostScene::LoadFromString(const std::string& text, std::string& err) {
             const JVal& value = *entries[i];
             try {
                 float pos[3];
+                HostMesh mesh;
                 as_float3(value.find("Position"), "Position", pos);          // Scene.hpp:40,57
                 const JVal* rend = value.find("Renderer");
                 const JVal* type = rend ? rend->find("Type") : nullptr;
@@ -325,6 +326,25 @@ int HostScene::LoadFromString(const std::string& text, std::string& err) {
                 } else if (type && type->type == JVal::Str && type->str == "Cube") {        // Scene.hpp:46-52
                     o = make_object(RT_OBJ_CUBE);
                     as_float3(rend->find("Size"), "Renderer.Size", o.half);
+                } else if (type && type->type == JVal::Str && type->str == "Mesh") {        // extension (mesh.h)
+                    o = make_object(RT_OBJ_MESH);
+                    const JVal* file = rend->find("File");
+                    if (file && file->type == JVal::Str) {
+                        std::string path = file->str;
+                        if (!path.empty() && path[0] != '/') {                              // relative to the scene file
+                            const size_t slash = file_name.find_last_of('/');
+                            if (slash != std::string::npos) path = file_name.substr(0, slash + 1) + path;
+                        }
+                        std::string merr;
+                        if (!load_obj(path, mesh, merr)) throw EntryError{merr};
+                        mesh.file = file->str;
+                    } else {
+                        const JVal* vs = rend->find("Vertices"); const JVal* ts = rend->find("Triangles");
+                        if (!vs || vs->type != JVal::Arr || !ts || ts->type != JVal::Arr) throw EntryError{"Mesh needs File or Vertices + Triangles"};
+                        for (const JVal& x : vs->arr) mesh.vertices.push_back(as_float(&x, "Renderer.Vertices"));
+                        for (const JVal& x : ts->arr) mesh.indices.push_back((int32_t)as_float(&x, "Renderer.Triangles"));
+                        if (mesh.vertices.size() % 3 || mesh.indices.size() % 3) throw EntryError{"Mesh arrays must hold triples"};
+                    }
                 } else {
                     o = make_object(RT_OBJ_NONE);                                           // Scene.hpp:53-55
                 }
@@ -344,6 +364,8 @@ int HostScene::LoadFromString(const std::string& text, std::string& err) {
                 if (!name || name->type != JVal::Str) throw EntryError{"Name missing or not a string"};
                 objects.push_back(o);
                 names.push_back(name->str);
+                meshes.resize(objects.size());
+                meshes.back() = std::move(mesh);
             } catch (const EntryError& e) {
                 // Scene.hpp:75-77: the exception ends the load; earlier objects stay.
                 err = "SceneObjects[" + std::to_string(i) + "]: " + e.msg;
@@ -389,6 +411,20 @@ std::string HostScene::Dump() const {
         } else if (o.type == RT_OBJ_CUBE) {
             indent(out, 16); out += "\"Size\": "; dump_vec3(out, o.half, 16); out += ",\n";
             indent(out, 16); out += "\"Type\": \"Cube\"\n";
+        } else if (o.type == RT_OBJ_MESH && i < meshes.size()) {
+            const HostMesh& m = meshes[i];
+            if (!m.file.empty()) {
+                indent(out, 16); out += "\"File\": "; dump_string(out, m.file); out += ",\n";
+                indent(out, 16); out += "\"Type\": \"Mesh\"\n";
+            } else {
+                indent(out, 16); out += "\"Triangles\": [";
+                for (size_t k = 0; k < m.indices.size(); ++k) { if (k) out += ", "; out += std::to_string(m.indices[k]); }
+                out += "],\n";
+                indent(out, 16); out += "\"Type\": \"Mesh\",\n";
+                indent(out, 16); out += "\"Vertices\": [";
+                for (size_t k = 0; k < m.vertices.size(); ++k) { if (k) out += ", "; dump_number(out, m.vertices[k]); }
+                out += "]\n";
+            }
         } else {
             indent(out, 16); out += "\"Type\": \"None\"\n";
         }

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/rt_b200.h"
+#include "mesh.h"
 
 namespace rtb {
 
@@ -17,6 +18,7 @@ struct HostScene {
     std::string scene_name;                // Scene::sceneName  ("SceneName")
     std::vector<rt_object> objects;        // Scene::sceneObjects, JSON order
     std::vector<std::string> names;        // Object::name      ("Name")
+    std::vector<HostMesh> meshes;          // per object; empty unless type == RT_OBJ_MESH (extension, mesh.h)
 
     // Scene::Load (Scene.hpp:27-80). Returns RT_OK, RT_ERR_IO (file missing: scene left empty,
     // like the reference's silent return) or RT_ERR_PARSE (objects parsed before the bad entry
@@ -26,13 +28,14 @@ struct HostScene {
     // Scene::SaveAs / Save (Scene.hpp:88-104): dump(4) formatting, keys in byte order.
     int SaveAs(const std::string& path, std::string& err);
     std::string Dump() const;
-    void Unload() { objects.clear(); names.clear(); }                       // Scene.hpp:81-87
+    void Unload() { objects.clear(); names.clear(); meshes.clear(); }                       // Scene.hpp:81-87
     void AddObject(const rt_object& o, const std::string& name = "") {      // Scene.hpp:105-107
-        objects.push_back(o); names.push_back(name);
+        objects.push_back(o); names.push_back(name); meshes.resize(objects.size());
     }
     bool RemoveObject(size_t index) {                                        // Scene.hpp:108-115
         if (index >= objects.size()) return false;
         objects.erase(objects.begin() + index); names.erase(names.begin() + index);
+        if (index < meshes.size()) meshes.erase(meshes.begin() + index);
         return true;
     }
 };

@@ -15,7 +15,7 @@ REPO_ROOT = os.path.normpath(os.path.join(PRODUCT_DIR, ".."))
 LIB_PATH = os.path.join(PRODUCT_DIR, "lib", "librt_b200.so")
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_NOMEM = 0, -1, -2, -3, -4, -5
-RT_OBJ_NONE, RT_OBJ_SPHERE, RT_OBJ_CUBE = 0, 1, 2
+RT_OBJ_NONE, RT_OBJ_SPHERE, RT_OBJ_CUBE, RT_OBJ_MESH = 0, 1, 2, 3
 RT_MODE_PATH, RT_MODE_PREVIEW = 0, 1
 RT_OPT_PIPELINE, RT_OPT_ACCEL, RT_OPT_BVH_THRESHOLD, RT_OPT_BVH_SCHED, RT_OPT_BVH_WAIT_K, RT_OPT_BVH_LEAF, RT_OPT_PRIMARY_REUSE = 1, 2, 3, 4, 5, 6, 7
 RT_PIPELINE_AUTO, RT_PIPELINE_REGEN, RT_PIPELINE_WAVEFRONT = 0, 1, 2
@@ -61,6 +61,7 @@ EXPORTS = [
     "rt_read_accum", "rt_read_aov", "rt_read_ray_dirs", "rt_trace_rays", "rt_env_color", "rt_philox_block",
     "rt_scene_file_read", "rt_scene_file_read_names", "rt_scene_file_write", "rt_object_name", "rt_set_object_name", "rt_scene_name",
     "rt_write_accum", "rt_selftest", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
+    "rt_set_mesh", "rt_load_mesh_obj", "rt_get_mesh_info",
     "rt_argb_device_ptr", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_resolve_fused", "rt_read_surface",
 ]
 
@@ -209,6 +210,20 @@ class PathTracer:
     def set_scene(self, objs):
         objs = np.ascontiguousarray(objs, OBJECT_DTYPE)
         return self._chk(self.lib.rt_set_scene(self.h, _p(objs), len(objs)))
+
+    def set_mesh(self, object_index, vertices, triangles):
+        """mesh extension: attach triangles (object-space float32 xyz, int32 index triples) to an RT_OBJ_MESH object."""
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, np.int32).reshape(-1, 3)
+        return self._chk(self.lib.rt_set_mesh(self.h, object_index, _p(v), len(v), _p(t), len(t)))
+
+    def load_mesh_obj(self, object_index, path):
+        return self._chk(self.lib.rt_load_mesh_obj(self.h, object_index, str(path).encode()))
+
+    def mesh_info(self, object_index):
+        nv, nt = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.rt_get_mesh_info(self.h, object_index, C.byref(nv), C.byref(nt)))
+        return nv.value, nt.value
 
     def get_scene(self):
         n = self._chk(self.lib.rt_get_scene(self.h, None, 0))

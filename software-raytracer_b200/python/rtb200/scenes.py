@@ -37,3 +37,34 @@ def config3_camera(default_camera):
     cam = default_camera(60)
     cam.pos[0], cam.pos[1], cam.pos[2] = 0.0, 8.0, -20.0
     return cam
+
+
+def heightfield_mesh(nx=1024, nz=512, seed=12345, size=(20.0, 10.0), amplitude=0.6):
+    """Config 4: tessellated, displaced heightfield: (nx x nz) quads -> 2*nx*nz triangles (1024 x 512 -> 1.05 M),
+    object space: x in [-size0/2, size0/2], z in [0, size1], y = smooth pseudo-random displacement.
+    Returns (vertices float32 (n,3), triangles int32 (m,3))."""
+    rng = np.random.default_rng(seed)
+    xs = np.linspace(-size[0] / 2, size[0] / 2, nx + 1, dtype=np.float64)
+    zs = np.linspace(0, size[1], nz + 1, dtype=np.float64)
+    X, Z = np.meshgrid(xs, zs)
+    Y = np.zeros_like(X)
+    for _ in range(6):                                  # a few random sine waves: smooth hills
+        kx, kz = rng.uniform(0.3, 2.5, 2); ph = rng.uniform(0, 2 * np.pi, 2); a = rng.uniform(0.2, 1.0)
+        Y += a * np.sin(kx * X + ph[0]) * np.cos(kz * Z + ph[1])
+    Y *= amplitude / 3.0
+    v = np.stack([X, Y, Z], -1).reshape(-1, 3).astype(np.float32)
+    i = (np.arange(nz)[:, None] * (nx + 1) + np.arange(nx)[None, :]).reshape(-1)
+    t = np.concatenate([np.stack([i, i + nx + 1, i + 1], -1), np.stack([i + 1, i + nx + 1, i + nx + 2], -1)]).astype(np.int32)
+    return v, t
+
+
+def mesh_scene():
+    """Object list of config 4: the mesh object (index 0, diffuse-ish), an emissive sphere and two reflective spheres
+    above it. Attach heightfield_mesh() to object 0 with PathTracer.set_mesh."""
+    o = np.zeros(4, OBJECT_DTYPE)
+    o["spec_color"] = 1
+    o["type"][0] = 3; o["pos"][0] = [0, -1.0, 3.0]; o["base"][0] = [0.75, 0.7, 0.6]; o["smoothness"][0] = 0.3; o["spec_amount"][0] = 0.1
+    o["type"][1] = 1; o["pos"][1] = [3.0, 5.0, 9.0]; o["radius"][1] = 1.5; o["emissive"][1] = 40; o["base"][1] = 1
+    o["type"][2] = 1; o["pos"][2] = [-1.5, 0.4, 6.0]; o["radius"][2] = 0.9; o["base"][2] = [0.9, 0.3, 0.3]; o["smoothness"][2] = 1; o["spec_amount"][2] = 0.6
+    o["type"][3] = 1; o["pos"][3] = [1.8, 0.2, 7.5]; o["radius"][3] = 0.8; o["base"][3] = [0.3, 0.5, 0.9]; o["smoothness"][3] = 0.9; o["spec_amount"][3] = 1
+    return o

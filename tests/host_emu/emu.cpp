@@ -9,32 +9,50 @@
 #include "../../software-raytracer_b200/csrc/rt_host_pack.h"
 #include "../../software-raytracer_b200/csrc/bvh_build.h"
 #include "../../software-raytracer_b200/csrc/flat_build.h"
+#include "../../software-raytracer_b200/csrc/mesh.h"
 
 using namespace rtb;
 
 extern "C" {
 // Sum over samples [s0, s0+n) for every pixel (float3 per pixel, y-up); accel 0 = brute force,
 // 1 = BVH candidates, 2 = flat two-level accelerator. Also returns primary AOVs when the pointers are given. Returns segments traced.
+// Optional mesh (extension): object `mesh_object` (type RT_OBJ_MESH) gets the given triangles.
+long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* cam, const rt_params* par, int accel,
+                          uint32_t s0, int n, float* out_rgb, int32_t* aov_id, float* aov_t, float* aov_n, float* aov_p,
+                          const float* mverts, int n_mverts, const int32_t* mtris, int n_mtris, int mesh_object);
 long long emu_render(const rt_object* objects, int n_obj, const rt_camera* cam, const rt_params* par, int accel,
                      uint32_t s0, int n, float* out_rgb, int32_t* aov_id, float* aov_t, float* aov_n, float* aov_p) {
+    return emu_render_mesh(objects, n_obj, cam, par, accel, s0, n, out_rgb, aov_id, aov_t, aov_n, aov_p, nullptr, 0, nullptr, 0, -1);
+}
+long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* cam, const rt_params* par, int accel,
+                          uint32_t s0, int n, float* out_rgb, int32_t* aov_id, float* aov_t, float* aov_n, float* aov_p,
+                          const float* mverts, int n_mverts, const int32_t* mtris, int n_mtris, int mesh_object) {
     std::vector<rt_object> objs(objects, objects + n_obj);
+    std::vector<HostMesh> meshes((size_t)n_obj);
+    if (mesh_object >= 0 && mesh_object < n_obj) {
+        meshes[(size_t)mesh_object].vertices.assign(mverts, mverts + (size_t)3 * n_mverts);
+        meshes[(size_t)mesh_object].indices.assign(mtris, mtris + (size_t)3 * n_mtris);
+    }
+    TriRecords tris;
+    build_tri_records(objs, meshes, tris);
     std::vector<float4> sph, box, mat; std::vector<int> sph_id, box_id;
     pack_scene(objs, sph, sph_id, box, box_id, mat);
     SceneView sc;
     sc.sph = sph.data(); sc.sph_id = sph_id.data(); sc.box = box.data(); sc.box_id = box_id.data(); sc.mat = mat.data();
     sc.n_sph = (int)sph_id.size(); sc.n_box = (int)box_id.size(); sc.n_obj = n_obj;
+    sc.tri = reinterpret_cast<const float4*>(tris.rec.data()); sc.tri_obj = tris.obj.data(); sc.n_tri = tris.count();
     FrameView fr;
     fill_frame_view(*cam, *par, fr);
     HostBvh bvh;
     float ext = 0.f;
     for (int k = 0; k < 3; ++k) ext = fmaxf(ext, fabsf(cam->pos[k]));
-    build_bvh(objs, ext, bvh);
+    build_bvh(objs, ext, bvh, 4, &tris);
     const float4* nodes = reinterpret_cast<const float4*>(bvh.nodes.data());
     std::vector<int> stack((size_t)bvh.max_depth + 8);
     unsigned char queue[64];
     HostFlat flat;
     build_flat(objs, ext, flat);
-    if (accel == 2 && !flat.usable) return -1;
+    if (accel == 2 && (!flat.usable || sc.n_tri > 0)) return -1;
     FlatView fv;
     fv.boxes = reinterpret_cast<const float4*>(flat.boxes.data()); fv.cull = reinterpret_cast<const float4*>(flat.cull.data());
     fv.cull_slot = flat.cull_slot.data(); fv.prim_id = flat.prim_id.data();

@@ -20,21 +20,29 @@ EMU_SO = os.path.join(EMU_DIR, "libemu.so")
 @pytest.fixture(scope="session")
 def emu():
     srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(ROOT, "software-raytracer_b200", "csrc", "bvh_build.cpp"),
-            os.path.join(ROOT, "software-raytracer_b200", "csrc", "flat_build.cpp")]
+            os.path.join(ROOT, "software-raytracer_b200", "csrc", "flat_build.cpp"),
+            os.path.join(ROOT, "software-raytracer_b200", "csrc", "mesh.cpp")]
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
                            "-o", EMU_SO] + srcs)
     lib = C.CDLL(EMU_SO)
     lib.emu_render.restype = C.c_longlong
+    lib.emu_render_mesh.restype = C.c_longlong
 
-    def render(objs, cam, par, accel, s0, n, aov=False):
+    def render(objs, cam, par, accel, s0, n, aov=False, mesh=None):
         w, h = par.width, par.height
         objs = np.ascontiguousarray(objs, rtb200.OBJECT_DTYPE)
         out = np.zeros((h, w, 3), np.float32)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         ids = np.zeros((h, w), np.int32); t = np.zeros((h, w), np.float32)
         nrm = np.zeros((h, w, 3), np.float32); pt = np.zeros((h, w, 3), np.float32)
-        segs = lib.emu_render(p(objs), len(objs), C.byref(cam), C.byref(par), accel, C.c_uint32(s0), n, p(out),
-                              p(ids) if aov else None, p(t), p(nrm), p(pt))
+        if mesh is None:
+            segs = lib.emu_render(p(objs), len(objs), C.byref(cam), C.byref(par), accel, C.c_uint32(s0), n, p(out),
+                                  p(ids) if aov else None, p(t), p(nrm), p(pt))
+        else:
+            oi, v, tr = mesh
+            v = np.ascontiguousarray(v, np.float32).reshape(-1, 3); tr = np.ascontiguousarray(tr, np.int32).reshape(-1, 3)
+            segs = lib.emu_render_mesh(p(objs), len(objs), C.byref(cam), C.byref(par), accel, C.c_uint32(s0), n, p(out),
+                                       p(ids) if aov else None, p(t), p(nrm), p(pt), p(v), len(v), p(tr), len(tr), oi)
         return out, segs, (ids, t, nrm, pt)
     return render
 
@@ -103,3 +111,33 @@ def test_device_logic_flat_equals_brute_on_random_scenes(emu, n, spread, seed):
     assert sa == sb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     for x, y in zip(aa, ab):
         assert np.array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32))
+
+
+def test_device_logic_mesh_bvh_equals_brute_and_oracle(emu, oracle):
+    """mesh extension: triangles through the BVH vs the in-order brute-force loop vs the oracle's restatement
+    (ids, t, normals, points bit-equal; radiance bit-equal between the two back ends)."""
+    from rtb200.scenes import heightfield_mesh, mesh_scene
+    v, tr = heightfield_mesh(24, 16, seed=3)
+    objs = mesh_scene()
+    cam = rtb200.default_camera(55); cam.pos[1] = 1.5; cam.pos[2] = -1.0
+    par = rtb200.default_params(width=96, height=64, mode=0, max_bounces=4, seed_lo=5, seed_hi=6)
+    a, sa, aa = emu(objs, cam, par, 0, 0, 3, aov=True, mesh=(0, v, tr))
+    b, sb, ab = emu(objs, cam, par, 1, 0, 3, aov=True, mesh=(0, v, tr))
+    assert sa == sb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for x, y in zip(aa, ab):
+        assert np.array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32))
+    assert (aa[0] == 0).mean() > 0.2                         # the mesh is visible
+    ocam = OrcCamera(); ocam.right[0] = 1; ocam.up[1] = 1; ocam.forward[2] = 1; ocam.fov_deg = 55; ocam.pos[1] = 1.5; ocam.pos[2] = -1.0
+    oracle.set_triangles(objs, {0: (v, tr)})
+    try:
+        oid, ot, on, op = oracle.primary_aov(objs, ocam, 96, 64)
+        op_ = oracle.default_params(width=96, height=64, max_bounces=4, mode=0, seed_lo=5, seed_hi=6)
+        want, _, segs = oracle.render(objs, ocam, op_, 0, 3)
+    finally:
+        oracle.set_triangles(objs, {})
+    assert np.array_equal(aa[0], oid)
+    hit = oid >= 0
+    assert np.array_equal(aa[1][hit].view(np.uint32), ot[hit].view(np.uint32))
+    assert np.array_equal(aa[2][hit].view(np.uint32), on[hit].view(np.uint32))
+    assert np.array_equal(aa[3][hit].view(np.uint32), op[hit].view(np.uint32))
+    assert segs == sa and np.array_equal(a.view(np.uint32), want.view(np.uint32))

@@ -561,3 +561,141 @@ def test_flat_accel_far_camera_and_inside_sphere(tracer, scenes):
         a, b = out[rtb200.RT_ACCEL_FLAT], out[rtb200.RT_ACCEL_BRUTE]
         assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(bits(a[0][1]), bits(b[0][1]))
         assert np.array_equal(bits(a[1]), bits(b[1]))
+
+
+# ---- triangle meshes (extension, BASELINE.json config 4): BVH == in-order brute force == oracle restatement -------
+from rtb200.scenes import heightfield_mesh, mesh_scene  # noqa: E402
+
+
+def _mesh_cam(cls):
+    cam = make_camera(cls)
+    cam.pos[1] = 1.5; cam.pos[2] = -1.0
+    return cam
+
+
+def test_mesh_bvh_equals_brute_and_oracle(tracer, oracle):
+    v, tr = heightfield_mesh(24, 16, seed=3)
+    objs = mesh_scene()
+    res = {}
+    try:
+        for accel in (rtb200.RT_ACCEL_BVH, rtb200.RT_ACCEL_BRUTE):
+            tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+            setup(tracer, objs, 96, 64, _mesh_cam(rtb200.RtCamera), max_bounces=4, seed_lo=5, seed_hi=6)
+            tracer.set_mesh(0, v, tr)
+            assert tracer.mesh_info(0) == (len(v), len(tr))
+            aov = tracer.read_aov()
+            tracer.render_spp(3)
+            st = tracer.stats()
+            assert st.accel == accel
+            res[accel] = (aov, tracer.read_accum()[0], st.segments)
+            assert tracer.pick(48, 40) == aov[0][64 - 40, 48]           # picking goes through the same back end
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+    a, b = res[rtb200.RT_ACCEL_BVH], res[rtb200.RT_ACCEL_BRUTE]
+    assert np.array_equal(a[0][0], b[0][0]) and (a[0][0] == 0).mean() > 0.2
+    for x, y in zip(a[0][1:], b[0][1:]):
+        assert np.array_equal(bits(x), bits(y))
+    assert np.array_equal(bits(a[1]), bits(b[1])) and a[2] == b[2]
+    oracle.set_triangles(objs, {0: (v, tr)})
+    try:
+        oid, ot, on, op = oracle.primary_aov(objs, _mesh_cam(OrcCamera), 96, 64)
+        p = oracle.default_params(width=96, height=64, max_bounces=4, mode=0, seed_lo=5, seed_hi=6)
+        want, _, segs = oracle.render(objs, _mesh_cam(OrcCamera), p, 0, 3)
+    finally:
+        oracle.set_triangles(objs, {})
+    hit = oid >= 0
+    assert np.array_equal(a[0][0], oid)
+    for x, y in ((a[0][1], ot), (a[0][2], on), (a[0][3], op)):
+        assert np.array_equal(bits(x[hit]), bits(y[hit]))
+    assert segs == a[2] and close(a[1][..., :3], want)
+
+
+def test_mesh_sampled_rays_vs_oracle_65k_triangles(tracer, oracle):
+    v, tr = heightfield_mesh(256, 128, seed=11)
+    objs = mesh_scene()
+    rng = np.random.default_rng(4)
+    n = 3000
+    org = rng.uniform([-8, 0.5, 0], [8, 4, 12], (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d[:, 1] = -np.abs(d[:, 1]) * 0.7
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d = (d / np.sqrt((d.astype(np.float32) ** 2).sum(1, dtype=np.float32))[:, None]).astype(np.float32)
+    try:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_BVH)
+        setup(tracer, objs, 64, 48, _mesh_cam(rtb200.RtCamera))
+        tracer.set_mesh(0, v, tr)
+        ids, t, nrm, pt = tracer.trace_rays(org, d)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+    oracle.set_triangles(objs, {0: (v, tr)})
+    try:
+        oid, ot, on, op = oracle.trace_rays(objs, org, d)
+    finally:
+        oracle.set_triangles(objs, {})
+    assert np.array_equal(ids, oid) and (ids == 0).mean() > 0.3
+    hit = oid >= 0
+    for x, y in ((t, ot), (nrm, on), (pt, op)):
+        assert np.array_equal(bits(x[hit]), bits(y[hit]))
+
+
+def test_mesh_one_million_triangles_bvh_vs_brute_on_device(tracer):
+    """Config 4 size: 2 x 1024 x 512 triangles. The BVH answer must equal the in-order brute-force loop over all
+    1.05 M triangles (run on the device) on sampled rays, and a render must deliver sane statistics."""
+    v, tr = heightfield_mesh(1024, 512)
+    assert len(tr) == 2 * 1024 * 512
+    objs = mesh_scene()
+    rng = np.random.default_rng(9)
+    n = 512
+    org = rng.uniform([-8, 0.5, 0], [8, 4, 12], (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d[:, 1] = -np.abs(d[:, 1]) * 0.7
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    out = {}
+    try:
+        for accel in (rtb200.RT_ACCEL_BVH, rtb200.RT_ACCEL_BRUTE):
+            tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+            setup(tracer, objs, 320, 180, _mesh_cam(rtb200.RtCamera))
+            tracer.set_mesh(0, v, tr)
+            out[accel] = tracer.trace_rays(org, d)
+            if accel == rtb200.RT_ACCEL_BVH:
+                tracer.render_spp(2)
+                st = tracer.stats()
+                acc, ns = tracer.read_accum()
+                assert ns == 2 and st.paths == 320 * 180 * 2 and st.segments > st.paths and np.isfinite(acc).all()
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        tracer.set_scene(mesh_scene()[1:])                   # drop the big mesh
+    a, b = out[rtb200.RT_ACCEL_BVH], out[rtb200.RT_ACCEL_BRUTE]
+    assert np.array_equal(a[0], b[0]) and (a[0] == 0).mean() > 0.3
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(bits(x), bits(y))
+
+
+def test_mesh_scene_json_round_trip(tracer, tmp_path):
+    v, tr = heightfield_mesh(4, 3, seed=2)
+    objs = mesh_scene()
+    setup(tracer, objs, 64, 48, _mesh_cam(rtb200.RtCamera))
+    tracer.set_mesh(0, v, tr)
+    want = tracer.read_aov()
+    p1 = tmp_path / "mesh_inline.json"
+    tracer.save_scene(p1)                                     # inline "Vertices"/"Triangles"
+    assert '"Type": "Mesh"' in p1.read_text()
+    assert tracer.load_scene(p1) == len(objs) and tracer.mesh_info(0) == (len(v), len(tr))
+    tracer.set_camera(_mesh_cam(rtb200.RtCamera))
+    got = tracer.read_aov()
+    for x, y in zip(want, got):
+        assert np.array_equal(bits(x), bits(y))
+    # OBJ file form: "File" relative to the scene file
+    with open(tmp_path / "hf.obj", "w") as f:
+        for a in v:
+            f.write("v %.9g %.9g %.9g\n" % tuple(a))
+        for a in tr:
+            f.write("f %d %d %d\n" % tuple(a + 1))
+    text = p1.read_text()
+    i0 = text.index('"Triangles"'); i1 = text.index(']', text.index('"Vertices"')) + 1
+    p2 = tmp_path / "mesh_file.json"
+    p2.write_text(text[:i0] + '"File": "hf.obj",\n                "Type": "Mesh"' + text[i1:])
+    assert tracer.load_scene(p2) == len(objs) and tracer.mesh_info(0) == (len(v), len(tr))
+    tracer.set_camera(_mesh_cam(rtb200.RtCamera))
+    got = tracer.read_aov()
+    for x, y in zip(want, got):
+        assert np.array_equal(bits(x), bits(y))
+    tracer.set_scene(objs[1:])
