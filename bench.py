@@ -174,6 +174,7 @@ def run_b200(args):
     tr.set_option(rtb200.RT_OPT_ACCEL, {"auto": rtb200.RT_ACCEL_AUTO, "brute": rtb200.RT_ACCEL_BRUTE, "bvh": rtb200.RT_ACCEL_BVH,
                                         "flat": rtb200.RT_ACCEL_FLAT}[args.accel])
     tr.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 0 if args.no_primary_reuse else 1)
+    tr.set_option(rtb200.RT_OPT_PIPELINE, {"auto": rtb200.RT_PIPELINE_AUTO, "regen": rtb200.RT_PIPELINE_REGEN, "wavefront": rtb200.RT_PIPELINE_WAVEFRONT}[args.pipeline])
     if args.bvh_sched >= 0:
         tr.set_option(rtb200.RT_OPT_BVH_SCHED, args.bvh_sched)
     if args.wait_k >= 0:
@@ -323,6 +324,7 @@ def run_b200(args):
                                          "on: the reference has no pixel jitter, so the primary closest-hit query of a pixel is identical for "
                                          "all samples; it runs once per pixel per launch and every sample shades/scatters from it "
                                          "(bit-identical radiance; `value` counts path segments delivered, traced_segments_per_s_M the queries executed)"),
+                       "pipeline": {rtb200.RT_PIPELINE_REGEN: "regeneration megakernel", rtb200.RT_PIPELINE_WAVEFRONT: "wavefront (raygen / persistent intersect / shade + ballot compaction)"}[st.pipeline],
                        "scene": args.scene},
             "paths_per_s_M": paths_rank * world / (total_ms * 1e-3) / 1e6,
             "ms_per_1spp_frame": total_ms / args.steps / spp,
@@ -398,6 +400,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=24, help="1-spp frames of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh", "flat"], help="closest-hit back end (results are identical)")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "regen", "wavefront"],
+                    help="regen: persistent-lane regeneration megakernel (default); wavefront: raygen/intersect/shade kernels over device queues (bit-identical)")
     ap.add_argument("--no-primary-reuse", action="store_true", help="re-trace the (identical) primary ray for every sample, like the reference")
     ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"], help="N > 1 exchange: fused peer-memory reduce+resolve kernel, or NCCL all-reduce")
     ap.add_argument("--bvh-sched", type=int, default=-1, help="RT_OPT_BVH_SCHED override")

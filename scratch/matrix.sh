@@ -7,7 +7,7 @@ for scene in $SCENES; do
  for accel in $ACCELS; do
   for r in "${REUSE[@]}"; do
     flag=""; [ "$r" = "off" ] && flag="--no-primary-reuse"
-    timeout 300 python bench.py --steps 2 --warmup 3 --spp $SPP --no-cpu --accel $accel $flag --scene $scene 2>/dev/null | python -c "
+    timeout 300 python bench.py --steps 2 --warmup 3 --spp $SPP --no-cpu --accel $accel $flag --scene $scene $EXTRA 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)

@@ -60,6 +60,8 @@ struct rt_ctx {
     size_t cap_flat_boxes = 0, cap_flat_cull = 0, cap_flat_slots = 0, cap_flat_ids = 0;
     bool flat_valid = false;
 
+    WavefrontBuffers* wf = nullptr;    // RT_PIPELINE_WAVEFRONT state (rt_wavefront.cu), allocated on first use
+
     // frame buffers
     float4* d_accum = nullptr;
     uint32_t* d_argb = nullptr;
@@ -398,6 +400,7 @@ int rt_destroy(rt_ctx* c) {
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
     cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_tune);
     cudaFree(c->d_tri); cudaFree(c->d_tri_obj);
+    wavefront_destroy(c->wf);
     cudaFree(c->d_flat_boxes); cudaFree(c->d_flat_cull); cudaFree(c->d_flat_slots); cudaFree(c->d_flat_ids);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -637,11 +640,15 @@ int rt_render_spp(rt_ctx* c, int spp) {
         // this rank's slice of the global sample indices [next, next+spp)
         int mine = 0; uint32_t first = 0;
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
-        if (ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0)
+        if (c->opt_pipeline == RT_PIPELINE_WAVEFRONT) {
+            if (!c->wf) c->wf = wavefront_create();
+            RT_CUDA(c, launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream));
+            c->used_pipeline = RT_PIPELINE_WAVEFRONT;
+        } else if (ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0)
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else
             RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream));
-        c->used_pipeline = RT_PIPELINE_REGEN;
+        if (c->opt_pipeline != RT_PIPELINE_WAVEFRONT) c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce
         c->paths += (uint64_t)mine * px; c->total_paths += (uint64_t)mine * px;

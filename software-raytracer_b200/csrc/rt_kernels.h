@@ -21,8 +21,6 @@ constexpr size_t kMaxStagedBytes = 128 * 1024;
 // A BVH (stack + geometry + nodes + refs) up to this size is staged whole; smaller keeps more CTAs per SM.
 constexpr size_t kMaxBvhStagedBytes = 48 * 1024;
 
-size_t staged_bytes(const SceneView& sc);
-size_t flat_staged_bytes(const SceneView& sc, const FlatView& fl);
 
 struct PeerPtrs { const float4* p[16]; };      // every rank's accumulation buffer, rank order (RT_MAX_PEERS)
 
@@ -47,4 +45,15 @@ cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int
 cudaError_t launch_resolve_fused(const PeerPtrs& peers, int world, uint32_t samples, int width, int height, int first, int n,
                                  int flip_y, uint32_t* out, cudaStream_t st);
 
+}  // namespace rtb
+
+namespace rtb {
+// ---- wavefront pipeline (rt_wavefront.cu) ----------------------------------------------------------
+struct WavefrontBuffers;                        // device buffers of one context, owned by the C-ABI layer
+WavefrontBuffers* wavefront_create();
+void wavefront_destroy(WavefrontBuffers* wb);
+// Adds samples [s_begin, s_begin + n_samples) of every pixel into accum, bit-identical to launch_render_regen.
+cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
+                                    float4* accum, uint32_t s_begin, int n_samples, bool reuse_primary,
+                                    unsigned long long* seg_counter, cudaStream_t st);
 }  // namespace rtb

@@ -1,0 +1,353 @@
+// rt_wavefront.cu - the WAVEFRONT pipeline (RT_PIPELINE_WAVEFRONT): the same path tracer as the regeneration
+// megakernel (rt_kernels.cu k_render_regen), split into stream-ordered stages over device-resident queues:
+//
+//   k_wf_primary    (REUSE) one primary closest-hit query per pixel per launch
+//   k_wf_generate   raygen: one path per (pixel, sample) of the wave; with REUSE it shades the cached primary hit
+//                   and emits the first SECONDARY ray; live paths are appended to the ray queue
+//   k_wf_intersect  persistent threads: every warp pulls batches of 32 queue entries through an atomic cursor
+//                   and runs the closest-hit back end (brute / BVH / flat, scene staged per CTA once)
+//   k_wf_shade      path_ends / scatter_segment per entry; surviving paths are COMPACTED into the next queue
+//                   with one warp ballot + prefix popcount + one atomicAdd per warp
+//   k_wf_accumulate per pixel, the wave's samples are added in sample order; k_wf_commit adds the launch's sum
+//                   into the accumulation buffer
+//
+// A wave is all pixels x S samples (about 8 M paths). No host synchronisation anywhere: queue lengths stay
+// in device memory (one counter and one cursor per bounce round, zeroed per wave) and the persistent kernels
+// read them there. Per-path state lives in SoA float4 arrays indexed by path id (wave-local sample x tile-major
+// pixel), so queue order is almost memory order. Every path's arithmetic is the megakernel's (same device
+// functions, same Philox counters) and samples are summed in the same order: the result is BIT-IDENTICAL to
+// k_render_regen (asserted by tests/test_gpu_parity.py), whichever order the queues end up in.
+#include "rt_kernels.h"
+
+#include "rt_device.cuh"
+#include "rt_trace.cuh"
+
+namespace rtb {
+
+struct WavefrontBuffers {
+    size_t cap_paths = 0, cap_px = 0, cap_tiles = 0;
+    float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *rad = nullptr;   // per path: o, (d, depth), T, L
+    float4 *hit_nt = nullptr; int* hit_id = nullptr;                              // per path: (normal, t), object id
+    float4* wave_rad = nullptr;                                                   // per path: radiance of the finished path
+    uint32_t* q[2] = {nullptr, nullptr};                                          // ping-pong ray queues (path ids)
+    unsigned int* counters = nullptr;                                             // [0..63] queue lengths per round, [64..127] cursors
+    float4* launch_acc = nullptr;                                                 // per pixel: this launch's sum
+    float4* prim_nt = nullptr; int* prim_id = nullptr;                            // REUSE: primary hit per tile-major pixel
+};
+
+namespace {
+
+constexpr int kMaxRounds = 64;
+
+struct WaveGeom { int tiles_x, tiles_y, npad; };
+__host__ __device__ inline WaveGeom wave_geom(int w, int h) {
+    WaveGeom g; g.tiles_x = (w + 7) / 8; g.tiles_y = (h + 3) / 4; g.npad = g.tiles_x * g.tiles_y * 32;
+    return g;
+}
+// tile-major pixel index -> pixel: 8x4 tiles, so the 32 lanes of a warp cover a compact block like the megakernel's
+__device__ __forceinline__ bool tile_to_pixel(const FrameView& fr, int tiles_x, int ti, int& px, int& py) {
+    const int tile = ti >> 5, lane = ti & 31;
+    px = (tile % tiles_x) * 8 + (lane & 7);
+    py = (tile / tiles_x) * 4 + (lane >> 3);
+    return px < fr.width && py < fr.height;
+}
+
+// append `pid` to a queue for the lanes with want == true: one atomicAdd per warp
+__device__ __forceinline__ void warp_push(bool want, uint32_t pid, uint32_t* __restrict__ q, unsigned int* __restrict__ count) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == (__ffs((int)mask) - 1)) base = atomicAdd(count, (unsigned int)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, __ffs((int)mask) - 1);
+    if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = pid;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_wf_primary(SceneView sc, BvhView bv, FlatView fl, FrameView fr, int tiles_x, int npad,
+                                                          float4* __restrict__ prim_nt, int* __restrict__ prim_id) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= npad) return;
+    int px, py;
+    if (!tile_to_pixel(fr, tiles_x, ti, px, py)) { prim_id[ti] = -1; return; }
+    const Hit h = trace<MODE>(sc, tc, fr.cam_pos, ray_dir(fr, px, py));
+    prim_nt[ti] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
+    prim_id[ti] = h.id;
+}
+
+template <bool REUSE>
+__global__ void __launch_bounds__(256) k_wf_generate(SceneView sc, FrameView fr, int tiles_x, int npad, uint32_t s_first, int s_wave,
+                                                      const float4* __restrict__ prim_nt, const int* __restrict__ prim_id,
+                                                      float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ thr,
+                                                      float4* __restrict__ rad, float4* __restrict__ wave_rad,
+                                                      uint32_t* __restrict__ q0, unsigned int* __restrict__ counters,
+                                                      unsigned long long* __restrict__ seg_counter) {
+    const uint32_t np = (uint32_t)npad * (uint32_t)s_wave;
+    const uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;             // the grid covers np rounded up to warps
+    bool live = false;
+    unsigned int delivered = 0;
+    if (pid < np) {
+        const int ti = (int)(pid % (uint32_t)npad);
+        const uint32_t s = s_first + pid / (uint32_t)npad;
+        int px, py;
+        if (tile_to_pixel(fr, tiles_x, ti, px, py)) {
+            const uint32_t pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
+            float3 o = fr.cam_pos, d = ray_dir(fr, px, py);
+            float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
+            int depth = 0;
+            live = true;
+            if (REUSE) {
+                const float4 nt = prim_nt[ti];
+                Hit h0;
+                h0.id = prim_id[ti]; h0.t = nt.w; h0.n = f3(nt.x, nt.y, nt.z);
+                h0.p = f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w);
+                delivered = 1;                                               // the reused primary segment
+                float3 c;
+                if (path_ends(sc, fr, h0, d, T, L, 0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
+                else scatter_segment(sc, fr, h0, pixel, s, o, d, T, L, depth);
+            }
+            if (live) {
+                ray_o[pid] = make_float4(o.x, o.y, o.z, 0.f);
+                ray_d[pid] = make_float4(d.x, d.y, d.z, __int_as_float(depth));
+                thr[pid] = make_float4(T.x, T.y, T.z, 0.f);
+                rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
+            }
+        }
+    }
+    warp_push(live, pid, q0, counters);
+    if (REUSE) {
+        unsigned int total = delivered;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(0xffffffffu, total, off);
+        if ((threadIdx.x & 31) == 0 && total) { atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total); }
+    }
+}
+
+// Persistent threads: the grid is sized to the machine, not to the queue. Each warp claims 32 consecutive entries.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 6) k_wf_intersect(SceneView sc, BvhView bv, FlatView fl, const uint32_t* __restrict__ q,
+                                                               const unsigned int* __restrict__ count_ptr, unsigned int* __restrict__ cursor,
+                                                               const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                               float4* __restrict__ hit_nt, int* __restrict__ hit_id) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
+    const unsigned int count = *count_ptr;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const unsigned int i = base + (unsigned int)lane;
+        if (i < count) {
+            const uint32_t pid = q[i];
+            const float4 o4 = ray_o[pid], d4 = ray_d[pid];
+            const Hit h = trace<MODE>(sc, tc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+            hit_nt[pid] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
+            hit_id[pid] = h.id;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_wf_shade(SceneView sc, FrameView fr, int tiles_x, int npad, uint32_t s_first,
+                                                   const uint32_t* __restrict__ q_in, const unsigned int* __restrict__ count_ptr,
+                                                   uint32_t* __restrict__ q_out, unsigned int* __restrict__ count_out,
+                                                   float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ thr,
+                                                   float4* __restrict__ rad, const float4* __restrict__ hit_nt, const int* __restrict__ hit_id,
+                                                   float4* __restrict__ wave_rad, unsigned long long* __restrict__ seg_counter) {
+    const unsigned int count = *count_ptr;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    unsigned int done = 0;
+    // whole warps stay in the loop together: the compaction ballots need every lane
+    for (unsigned int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += stride) {
+        const unsigned int i = base + (threadIdx.x & 31u);
+        bool live = false;
+        uint32_t pid = 0;
+        if (i < count) {
+            pid = q_in[i];
+            const int ti = (int)(pid % (uint32_t)npad);
+            const uint32_t s = s_first + pid / (uint32_t)npad;
+            int px, py;
+            tile_to_pixel(fr, tiles_x, ti, px, py);
+            const uint32_t pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
+            const float4 o4 = ray_o[pid], d4 = ray_d[pid], T4 = thr[pid], L4 = rad[pid], nt = hit_nt[pid];
+            float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z), T = f3(T4.x, T4.y, T4.z), L = f3(L4.x, L4.y, L4.z);
+            int depth = __float_as_int(d4.w);
+            Hit h;
+            h.id = hit_id[pid]; h.t = nt.w; h.n = f3(nt.x, nt.y, nt.z);
+            h.p = f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w);            // as in closest_hit*()
+            ++done;
+            float3 c;
+            if (path_ends(sc, fr, h, d, T, L, depth, c)) wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f);
+            else {
+                scatter_segment(sc, fr, h, pixel, s, o, d, T, L, depth);
+                ray_o[pid] = make_float4(o.x, o.y, o.z, 0.f);
+                ray_d[pid] = make_float4(d.x, d.y, d.z, __int_as_float(depth));
+                thr[pid] = make_float4(T.x, T.y, T.z, 0.f);
+                rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
+                live = true;
+            }
+        }
+        warp_push(live, pid, q_out, count_out);                                         // ray compaction
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) done += __shfl_down_sync(0xffffffffu, done, off);
+    if ((threadIdx.x & 31) == 0 && done) {
+        for (int k = 0; k < 4; ++k) atomicAdd(seg_counter + k, (unsigned long long)done);
+    }
+}
+
+__global__ void k_wf_accumulate(FrameView fr, int tiles_x, int npad, int s_wave, const float4* __restrict__ wave_rad,
+                                float4* __restrict__ launch_acc) {
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= npad) return;
+    int px, py;
+    if (!tile_to_pixel(fr, tiles_x, ti, px, py)) return;
+    const size_t pixel = (size_t)px + (size_t)py * fr.width;
+    float4 a = launch_acc[pixel];
+    for (int s = 0; s < s_wave; ++s) {                       // sample order: the megakernel's summation order
+        const float4 c = wave_rad[(size_t)s * npad + ti];
+        a.x += c.x; a.y += c.y; a.z += c.z;
+    }
+    launch_acc[pixel] = a;
+}
+
+__global__ void k_wf_commit(int n, const float4* __restrict__ launch_acc, float4* __restrict__ accum) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float4 a = accum[p];
+    const float4 c = launch_acc[p];
+    a.x += c.x; a.y += c.y; a.z += c.z;
+    accum[p] = a;
+}
+
+__global__ void k_wf_count_primaries(int n_inside, unsigned long long* seg_counter) {
+    atomicAdd(seg_counter + 2, (unsigned long long)n_inside); atomicAdd(seg_counter + 3, (unsigned long long)n_inside);
+}
+
+template <typename T>
+cudaError_t grow(T*& p, size_t n) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc((void**)&p, n * sizeof(T));
+}
+
+template <typename K>
+cudaError_t optin(K kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes); }
+
+cudaError_t ensure_optin() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e;
+#define RTB_WF_OPTIN(K) \
+    if ((e = optin(K<0>)) != cudaSuccess) return e; if ((e = optin(K<1>)) != cudaSuccess) return e; \
+    if ((e = optin(K<2>)) != cudaSuccess) return e; if ((e = optin(K<3>)) != cudaSuccess) return e; \
+    if ((e = optin(K<4>)) != cudaSuccess) return e;
+    RTB_WF_OPTIN(k_wf_primary) RTB_WF_OPTIN(k_wf_intersect)
+#undef RTB_WF_OPTIN
+    done = true;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+WavefrontBuffers* wavefront_create() { return new WavefrontBuffers(); }
+
+void wavefront_destroy(WavefrontBuffers* wb) {
+    if (!wb) return;
+    cudaFree(wb->ray_o); cudaFree(wb->ray_d); cudaFree(wb->thr); cudaFree(wb->rad); cudaFree(wb->hit_nt); cudaFree(wb->hit_id);
+    cudaFree(wb->wave_rad); cudaFree(wb->q[0]); cudaFree(wb->q[1]); cudaFree(wb->counters); cudaFree(wb->launch_acc);
+    cudaFree(wb->prim_nt); cudaFree(wb->prim_id);
+    delete wb;
+}
+
+cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
+                                    float4* accum, uint32_t s_begin, int n_samples, bool reuse, unsigned long long* seg_counter,
+                                    cudaStream_t st) {
+    if (n_samples <= 0) return cudaSuccess;
+    cudaError_t e = ensure_optin();
+    if (e != cudaSuccess) return e;
+    const WaveGeom g = wave_geom(fr.width, fr.height);
+    const size_t npix = (size_t)fr.width * fr.height;
+    // samples per wave: about 8 M paths in flight
+    int s_cap = (int)((size_t)(8u << 20) / (size_t)g.npad);
+    if (s_cap < 1) s_cap = 1;
+    if (s_cap > 16) s_cap = 16;
+    if (s_cap > n_samples) s_cap = n_samples;
+    const size_t np_cap = (size_t)g.npad * s_cap;
+    if (np_cap >= (size_t)1 << 32) return cudaErrorInvalidValue;
+    if (wb->cap_paths < np_cap) {
+        cudaStreamSynchronize(st);
+        if ((e = grow(wb->ray_o, np_cap)) != cudaSuccess || (e = grow(wb->ray_d, np_cap)) != cudaSuccess ||
+            (e = grow(wb->thr, np_cap)) != cudaSuccess || (e = grow(wb->rad, np_cap)) != cudaSuccess ||
+            (e = grow(wb->hit_nt, np_cap)) != cudaSuccess || (e = grow(wb->hit_id, np_cap)) != cudaSuccess ||
+            (e = grow(wb->wave_rad, np_cap)) != cudaSuccess || (e = grow(wb->q[0], np_cap)) != cudaSuccess ||
+            (e = grow(wb->q[1], np_cap)) != cudaSuccess) { wb->cap_paths = 0; return e; }
+        wb->cap_paths = np_cap;
+    }
+    if (wb->cap_px < npix) {
+        cudaStreamSynchronize(st);
+        if ((e = grow(wb->launch_acc, npix)) != cudaSuccess) { wb->cap_px = 0; return e; }
+        wb->cap_px = npix;
+    }
+    if (wb->cap_tiles < (size_t)g.npad) {
+        cudaStreamSynchronize(st);
+        if ((e = grow(wb->prim_nt, (size_t)g.npad)) != cudaSuccess || (e = grow(wb->prim_id, (size_t)g.npad)) != cudaSuccess) { wb->cap_tiles = 0; return e; }
+        wb->cap_tiles = (size_t)g.npad;
+    }
+    if (!wb->counters && (e = cudaMalloc((void**)&wb->counters, 2 * kMaxRounds * sizeof(unsigned int))) != cudaSuccess) return e;
+    const int rounds = reuse ? fr.max_bounces : fr.max_bounces + 1;
+    if (rounds > kMaxRounds - 1) return cudaErrorInvalidValue;
+
+    int device = 0, sms = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    const int persistent_blocks = sms * 8;
+
+    if ((e = cudaMemsetAsync(wb->launch_acc, 0, npix * sizeof(float4), st)) != cudaSuccess) return e;
+    if (reuse) {
+        const int blocks = (g.npad + kThreads - 1) / kThreads;
+        switch (mode) {
+            case 0: k_wf_primary<0><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
+            case 1: k_wf_primary<1><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
+            case 2: k_wf_primary<2><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
+            case 3: k_wf_primary<3><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
+            default: k_wf_primary<4><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
+        }
+        k_wf_count_primaries<<<1, 1, 0, st>>>((int)npix, seg_counter);
+    }
+    for (int s0 = 0; s0 < n_samples; s0 += s_cap) {
+        const int sw = n_samples - s0 < s_cap ? n_samples - s0 : s_cap;
+        const uint32_t s_first = s_begin + (uint32_t)s0;
+        const size_t np = (size_t)g.npad * sw;
+        if ((e = cudaMemsetAsync(wb->counters, 0, 2 * kMaxRounds * sizeof(unsigned int), st)) != cudaSuccess) return e;
+        const int gen_blocks = (int)((np + 255) / 256);
+        if (reuse) k_wf_generate<true><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, wb->prim_nt, wb->prim_id, wb->ray_o, wb->ray_d,
+                                                                    wb->thr, wb->rad, wb->wave_rad, wb->q[0], wb->counters, seg_counter);
+        else k_wf_generate<false><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, wb->prim_nt, wb->prim_id, wb->ray_o, wb->ray_d,
+                                                               wb->thr, wb->rad, wb->wave_rad, wb->q[0], wb->counters, seg_counter);
+        for (int r = 0; r < rounds; ++r) {
+            const uint32_t* qin = wb->q[r & 1];
+            uint32_t* qout = wb->q[(r + 1) & 1];
+            unsigned int* cnt = wb->counters + r;
+            unsigned int* cur = wb->counters + kMaxRounds + r;
+            switch (mode) {
+                case 0: k_wf_intersect<0><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
+                case 1: k_wf_intersect<1><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
+                case 2: k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
+                case 3: k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
+                default: k_wf_intersect<4><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
+            }
+            k_wf_shade<<<sms * 8, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, qin, cnt, qout, cnt + 1, wb->ray_o, wb->ray_d, wb->thr, wb->rad,
+                                                 wb->hit_nt, wb->hit_id, wb->wave_rad, seg_counter);
+        }
+        k_wf_accumulate<<<(g.npad + 255) / 256, 256, 0, st>>>(fr, g.tiles_x, g.npad, sw, wb->wave_rad, wb->launch_acc);
+    }
+    k_wf_commit<<<(int)((npix + 255) / 256), 256, 0, st>>>((int)npix, wb->launch_acc, accum);
+    return cudaGetLastError();
+}
+
+}  // namespace rtb

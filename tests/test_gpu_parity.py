@@ -699,3 +699,55 @@ def test_mesh_scene_json_round_trip(tracer, tmp_path):
     for x, y in zip(want, got):
         assert np.array_equal(bits(x), bits(y))
     tracer.set_scene(objs[1:])
+
+
+# ---- wavefront pipeline (raygen -> persistent intersect -> shade + ballot compaction): same bits as the megakernel ----
+@pytest.mark.parametrize("scene,accel", [("Scene1", rtb200.RT_ACCEL_FLAT), ("Scene3_indirect", rtb200.RT_ACCEL_BVH),
+                                         ("Scene_indirect", rtb200.RT_ACCEL_BRUTE), ("Scene2", rtb200.RT_ACCEL_AUTO)])
+@pytest.mark.parametrize("reuse", [1, 0])
+def test_wavefront_pipeline_is_bit_identical(tracer, scenes, scene, accel, reuse):
+    out = {}
+    try:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+        tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, reuse)
+        for pipe in (rtb200.RT_PIPELINE_REGEN, rtb200.RT_PIPELINE_WAVEFRONT):
+            tracer.set_option(rtb200.RT_OPT_PIPELINE, pipe)
+            for (w, h, mb) in ((333, 77, 8), (160, 120, 0), (64, 48, 2)):      # not tile multiples; no bounce; shallow
+                setup(tracer, scenes[scene], w, h, max_bounces=mb)
+                tracer.render_spp(5); tracer.render_spp(19)                     # 19 > one wave at small sizes? several waves at 16/wave
+                st = tracer.stats()
+                assert st.pipeline == pipe
+                out[(pipe, w, mb)] = (tracer.read_accum()[0], st.segments, st.traced_segments, st.paths)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_PIPELINE, rtb200.RT_PIPELINE_AUTO)
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 1)
+    for (pipe, w, mb), v in out.items():
+        if pipe != rtb200.RT_PIPELINE_WAVEFRONT:
+            continue
+        base = out[(rtb200.RT_PIPELINE_REGEN, w, mb)]
+        assert np.array_equal(bits(v[0]), bits(base[0])), (w, mb)
+        assert v[1:] == base[1:], (w, mb)
+
+
+def test_wavefront_mesh_and_large_scene(tracer):
+    objs = synthetic_spheres(3000, cubes_every=9)
+    cam = rtb200.default_camera(60)
+    cam.pos[0], cam.pos[1], cam.pos[2] = 0.0, 8.0, -20.0
+    out = []
+    try:
+        for pipe in (rtb200.RT_PIPELINE_REGEN, rtb200.RT_PIPELINE_WAVEFRONT):
+            tracer.set_option(rtb200.RT_OPT_PIPELINE, pipe)
+            setup(tracer, objs, 256, 144, cam)
+            tracer.render_spp(6)
+            a = tracer.read_accum()[0]; s1 = tracer.stats().segments
+            v, tr = heightfield_mesh(48, 32, seed=5)
+            setup(tracer, mesh_scene(), 200, 120, _mesh_cam(rtb200.RtCamera), max_bounces=5)
+            tracer.set_mesh(0, v, tr)
+            tracer.render_spp(4)
+            out.append((a, s1, tracer.read_accum()[0], tracer.stats().segments))
+    finally:
+        tracer.set_option(rtb200.RT_OPT_PIPELINE, rtb200.RT_PIPELINE_AUTO)
+        tracer.set_scene(mesh_scene()[1:])
+    assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and out[0][1] == out[1][1]
+    assert np.array_equal(bits(out[0][2]), bits(out[1][2])) and out[0][3] == out[1][3]
