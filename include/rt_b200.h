@@ -170,6 +170,17 @@ int rt_set_camera(rt_ctx* ctx, const rt_camera* cam);
 int rt_set_params(rt_ctx* ctx, const rt_params* p);
 int rt_set_option(rt_ctx* ctx, int option, int value);
 
+/* Block-filled frames - the reference's SCREEN_SCALE slider and progressive-resolution first frame
+ * (Raytracer.cpp:30,47,233-248,576-590): with steps = ceil(1 / (SCREEN_SCALE * progressiveResolutionScaler)) > 1,
+ * every rt_render_spp traces ONE path per steps x steps block (through the block's first pixel) and writes it
+ * to all pixels of the block. Blocks start at the first column of each worker strip and are clipped to it:
+ * strip_columns = 0 treats the image as one strip, rt_reference_strip_columns(width) gives the reference's 16
+ * strips (ceil(width / 16) + 1 columns, :330). steps = 1 (default) is the full-resolution path; the C-ABI's
+ * default is full resolution, the reference's default SCREEN_SCALE of .5 corresponds to steps = 2. */
+int rt_set_pixel_step(rt_ctx* ctx, int steps, int strip_columns);
+int rt_reference_pixel_step(float screen_scale, float progressive_scaler);
+int rt_reference_strip_columns(int width);
+
 /* Multi-GPU sharding by samples-per-pixel: rank r of `world` renders its slice of the global
  * sample indices of every rt_render_spp call, so the reduced image does not depend on the
  * GPU count (up to float summation order). Default (0, 1). */

@@ -305,10 +305,11 @@ class Reference:
         self.lib.ref_get_color_buffer(_p(buf))
         return surf, buf
 
-    def render_frames(self, frames, rng_mode=0, start_frame=1, count_segments=False, thread_seed=1):
+    def render_frames(self, frames, rng_mode=0, start_frame=1, count_segments=False, thread_seed=1, progressive_scaler=1.0):
         """The reference's own 16-thread frame loop; returns (seconds, segments|None).
         thread_seed 1 = MSVC semantics (every worker's rand() starts at seed 1)."""
         self.lib.ref_set_thread_seed(C.c_uint32(thread_seed))
+        self.lib.ref_set_progressive_scaler(C.c_float(progressive_scaler))
         self.lib.ref_count_segments(int(count_segments))
         sec = self.lib.ref_render_frames(frames, rng_mode, start_frame)
         segs = self.lib.ref_segments() if count_segments else None

@@ -277,12 +277,14 @@ long long ref_segments() { long long v = g_segment_calls.load() + t_segment_call
 // :572-595). rng_mode 0 = per-thread MSVC LCG (what the shipped Windows binary does),
 // 2 = glibc's global locked rand(). first frame overwrites (setFrame), the rest accumulate.
 // Returns wall seconds over the frame loop only.
+static float g_prog_scaler = 1.0f;     // progressiveResolutionScaler for the next ref_render_frames (Raytracer.cpp:233,580)
+void ref_set_progressive_scaler(float s) { g_prog_scaler = s; }
 static uint32_t g_thread_seed = 1u;   // MSVC: every new thread's rand() state starts at 1
 void ref_set_thread_seed(uint32_t s) { g_thread_seed = s; }
 double ref_render_frames(int frames, int rng_mode, int start_frame) {
     ref_rng_mode(rng_mode);
     suspendAllThreads = false;
-    progressiveResolutionScaler = 1;
+    progressiveResolutionScaler = g_prog_scaler;
     std::vector<std::thread*> workers(THREADS);
     volatile bool* status = threadGroupStatus;
     for (int i = 0; i < THREADS; ++i) status[i] = true;   // parked until the first release

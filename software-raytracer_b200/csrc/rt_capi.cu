@@ -74,6 +74,7 @@ struct rt_ctx {
     uint32_t next_sample = 0;      // next global sample index
     uint64_t paths = 0, total_paths = 0, total_segments_base = 0;
     int rank = 0, world = 1;
+    int pixel_step = 1, strip_columns = 0;   // block-filled frames (rt_set_pixel_step)
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
     int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4, opt_primary_reuse = 1;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
@@ -595,6 +596,18 @@ int rt_set_option(rt_ctx* c, int option, int value) {
     return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
 }
 
+int rt_set_pixel_step(rt_ctx* c, int steps, int strip_columns) {
+    if (!c || steps < 1 || strip_columns < 0) return fail(c, RT_ERR_INVALID, "rt_set_pixel_step: bad arguments");
+    c->pixel_step = steps; c->strip_columns = strip_columns;
+    return RT_OK;
+}
+
+int rt_reference_pixel_step(float screen_scale, float progressive_scaler) {
+    return (int)ceil(1 / ((float)screen_scale * progressive_scaler));             // Raytracer.cpp:233
+}
+
+int rt_reference_strip_columns(int width) { return (int)ceil(width / 16) + 1; }   // Raytracer.cpp:28,330 (integer division first)
+
 int rt_set_shard(rt_ctx* c, int rank, int world) {
     if (!c || world < 1 || rank < 0 || rank >= world) return fail(c, RT_ERR_INVALID, "rt_set_shard: bad rank/world");
     c->rank = rank; c->world = world;
@@ -632,7 +645,23 @@ int rt_render_spp(rt_ctx* c, int spp) {
     if ((rc = make_accel(c, want_accel(c), camera_extent(c), ac)) != RT_OK) return rc;
     c->used_accel = accel_of(ac);
     RT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    if (c->par.mode == RT_MODE_PREVIEW) {
+    if (c->pixel_step > 1) {
+        // SCREEN_SCALE / progressive resolution: one path per block, block-filled (Raytracer.cpp:233-248)
+        int mine = 1; uint32_t first = 0;
+        if (c->par.mode == RT_MODE_PATH) rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
+        RT_CUDA(c, launch_render_blocks(c->view, ac, c->frame, c->d_accum, first, mine, c->pixel_step, c->strip_columns, c->d_counters, c->stream));
+        const int sw = c->strip_columns > 0 && c->strip_columns < c->par.width ? c->strip_columns : c->par.width;
+        uint64_t blocks = 0;
+        for (int x0 = 0; x0 < c->par.width; x0 += sw) {
+            const int len = (x0 + sw < c->par.width ? sw : c->par.width - x0);
+            blocks += (uint64_t)((len + c->pixel_step - 1) / c->pixel_step);
+        }
+        blocks *= (uint64_t)((c->par.height + c->pixel_step - 1) / c->pixel_step);
+        if (c->par.mode == RT_MODE_PREVIEW) { c->samples = 1; c->next_sample = 0; }
+        else { c->next_sample += (uint32_t)spp; c->samples += (uint32_t)mine; }
+        c->paths += blocks * (uint64_t)mine; c->total_paths += blocks * (uint64_t)mine;
+        c->used_pipeline = RT_PIPELINE_REGEN;
+    } else if (c->par.mode == RT_MODE_PREVIEW) {
         // SIMPLEDRAW: ACCUMULATIONFRAMES stays 1, every frame overwrites (Raytracer.cpp:66-67,589)
         RT_CUDA(c, launch_render_preview(c->view, ac, c->frame, c->d_accum, c->d_counters, c->stream));
         c->samples = 1; c->next_sample = 0; c->paths += px; c->total_paths += px;

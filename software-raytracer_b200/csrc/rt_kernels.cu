@@ -347,6 +347,22 @@ __global__ void __launch_bounds__(kThreads, RTB_BVH_MIN_BLOCKS) k_render_bvh(Sce
 }
 
 // ---- preview mode (SIMPLEDRAW, Raytracer.cpp:147-160): one primary ray, overwrite ----------
+__device__ __forceinline__ float3 preview_color(const SceneView& sc, const FrameView& fr, const Hit& h, float3 d) {
+    if (h.id < 0) return env_color(fr, d);
+    const float4 m0 = __ldg(sc.mat + 3 * h.id), m1 = __ldg(sc.mat + 3 * h.id + 1);
+    const float3 base = f3(m0.x, m0.y, m0.z), emis = f3(m1.x, m1.y, m1.z);
+    const float k = m1.w, sm = m0.w;
+    const float3 refl = env_color(fr, reflect3(d, h.n));                       // :148
+    float fres = 0.f;
+    if (h.id == fr.selected_id) {                                              // :153-157
+        fres = 1.f - dot3(scale3(h.n, -1.f), d);
+        fres = maxsel(fres, 0.f);
+        fres = smoothstep1(0.f, 0.5f, fres);
+    }
+    const float3 a = cadd(cadd(cscale(base, 1.f - k), cscale(cscale(refl, k), sm)), emis);
+    return clerp(a, col(3.f, 3.f, 0.f), fres);                                 // :159
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
                                                               unsigned long long* __restrict__ seg_counter) {
@@ -356,27 +372,59 @@ __global__ void __launch_bounds__(kThreads) k_render_preview(SceneView sc, BvhVi
     if (!tile_pixel(fr, px, py)) return;
     const size_t pixel = (size_t)px + (size_t)py * fr.width;
     const float3 d = ray_dir(fr, px, py);
-    const Hit h = trace<MODE>(sc, tc, fr.cam_pos, d);
-    float3 c;
-    if (h.id < 0) c = env_color(fr, d);
-    else {
-        const float4 m0 = __ldg(sc.mat + 3 * h.id), m1 = __ldg(sc.mat + 3 * h.id + 1);
-        const float3 base = f3(m0.x, m0.y, m0.z), emis = f3(m1.x, m1.y, m1.z);
-        const float k = m1.w, sm = m0.w;
-        const float3 refl = env_color(fr, reflect3(d, h.n));                       // :148
-        float fres = 0.f;
-        if (h.id == fr.selected_id) {                                              // :153-157
-            fres = 1.f - dot3(scale3(h.n, -1.f), d);
-            fres = maxsel(fres, 0.f);
-            fres = smoothstep1(0.f, 0.5f, fres);
-        }
-        const float3 a = cadd(cadd(cscale(base, 1.f - k), cscale(cscale(refl, k), sm)), emis);
-        c = clerp(a, col(3.f, 3.f, 0.f), fres);                                    // :159
-    }
+    const float3 c = preview_color(sc, fr, trace<MODE>(sc, tc, fr.cam_pos, d), d);
     accum[pixel] = make_float4(c.x, c.y, c.z, 0.f);
     if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
         for (int k = 0; k < 4; ++k) atomicAdd(seg_counter + k, (unsigned long long)fr.width * fr.height);
     }
+}
+
+// ---- block-filled frames: SCREEN_SCALE / progressive resolution (Raytracer.cpp:233-248, 330-341) -------------
+// `steps` = ceil(1 / (SCREEN_SCALE * progressiveResolutionScaler)): one path per steps x steps block, traced
+// through the block's first pixel and written to every pixel of the block. Blocks start at each column strip's
+// first column (the reference's 16 worker strips) and are clipped to the strip and the image. One thread per
+// block; path mode adds the block's sample sum to all its pixels, preview mode overwrites them.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_render_blocks(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
+                                                             uint32_t s_begin, int n_samples, int steps, int strip_w, int bps, int n_strips,
+                                                             unsigned long long* __restrict__ seg_counter) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
+    const int cols = n_strips * bps, rows = (fr.height + steps - 1) / steps;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int col_i = t % cols, row = t / cols;
+    const int strip = col_i / bps, x0 = strip * strip_w, x1 = min(x0 + strip_w, fr.width);
+    const int px = x0 + (col_i % bps) * steps, py = row * steps;
+    const bool valid = row < rows && px < x1 && py < fr.height;
+    unsigned int segs = 0;
+    if (valid) {
+        const uint32_t pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
+        const float3 d0 = ray_dir(fr, px, py);
+        float3 acc = f3(0.f, 0.f, 0.f);
+        if (fr.mode == 1) {
+            acc = preview_color(sc, fr, trace<MODE>(sc, tc, fr.cam_pos, d0), d0);
+            segs = 1;
+        } else {
+            float3 o = fr.cam_pos, d = d0, T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
+            int s = 0, depth = 0;
+            while (s < n_samples) {
+                const Hit h = trace<MODE>(sc, tc, o, d);
+                ++segs;
+                float3 c;
+                if (shade_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth, c)) {
+                    acc.x += c.x; acc.y += c.y; acc.z += c.z;
+                    ++s; depth = 0; o = fr.cam_pos; d = d0;
+                }
+            }
+        }
+        for (int j = py; j < py + steps && j < fr.height; ++j)
+            for (int i = px; i < px + steps && i < x1; ++i) {
+                const size_t p = (size_t)i + (size_t)j * fr.width;
+                if (fr.mode == 1) accum[p] = make_float4(acc.x, acc.y, acc.z, 0.f);
+                else { float4 a = accum[p]; a.x += acc.x; a.y += acc.y; a.z += acc.z; accum[p] = a; }
+            }
+    }
+    if (segs) for (int k = 0; k < 4; ++k) atomicAdd(seg_counter + k, (unsigned long long)segs);
 }
 
 // ---- resolve: sum/count -> Reinhard -> truncating ARGB8 pack (Raytracer.cpp:73-75) -----------
@@ -451,7 +499,7 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(K<2, false>)) != cudaSuccess) return e; if ((e = optin(K<2, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<3, false>)) != cudaSuccess) return e; if ((e = optin(K<3, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<4, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true>)) != cudaSuccess) return e;
-    RTB_OPTIN2(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick)
+    RTB_OPTIN2(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick) RTB_OPTIN(k_render_blocks)
     if ((e = optin(k_render_bvh<2>)) != cudaSuccess) return e;
     if ((e = optin(k_render_bvh<3>)) != cudaSuccess) return e;
 #undef RTB_OPTIN
@@ -555,6 +603,21 @@ cudaError_t launch_render_preview(const SceneView& sc, const AccelSel& ac, const
     if (e != cudaSuccess) return e;
     size_t sb; const int mode = pick_mode(sc, ac, sb);
     RTB_DISPATCH(mode, k_render_preview, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, accum, seg_counter)
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_blocks(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum, uint32_t s_begin,
+                                 int n_samples, int steps, int strip_w, unsigned long long* seg_counter, cudaStream_t st) {
+    cudaError_t e = ensure_smem_optin();
+    if (e != cudaSuccess) return e;
+    if (steps < 1) steps = 1;
+    if (strip_w <= 0 || strip_w > fr.width) strip_w = fr.width;
+    const int n_strips = (fr.width + strip_w - 1) / strip_w, bps = (strip_w + steps - 1) / steps;
+    const int rows = (fr.height + steps - 1) / steps;
+    const long long threads = (long long)n_strips * bps * rows;
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    RTB_DISPATCH(mode, k_render_blocks, (unsigned int)((threads + kThreads - 1) / kThreads), sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples,
+                 steps, strip_w, bps, n_strips, seg_counter)
     return cudaGetLastError();
 }
 

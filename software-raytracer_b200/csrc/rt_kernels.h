@@ -39,6 +39,8 @@ cudaError_t launch_render_bvh(const SceneView& sc, const AccelSel& ac, const Fra
                               int n_samples, unsigned long long* seg_counter, int wait_k, cudaStream_t st);
 cudaError_t launch_render_preview(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                   unsigned long long* seg_counter, cudaStream_t st);
+cudaError_t launch_render_blocks(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum, uint32_t s_begin,
+                                 int n_samples, int steps, int strip_w, unsigned long long* seg_counter, cudaStream_t st);
 cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int height, int first, int n, int flip_y,
                            uint32_t* out, int out_is_slice, cudaStream_t st);
 

@@ -1,6 +1,7 @@
 // rt_headless - headless driver over the C-ABI: the reference's main loop without SDL/ImGui.
 //   rt_headless --scene Scenes/Scene1.json [--width 1280 --height 720 --spp 64 --bounces 8]
-//               [--preview] [--out frame.ppm] [--interactive N]
+//               [--preview] [--scale S] [--out frame.ppm] [--interactive N]
+// --scale S: the reference's SCREEN_SCALE (render scale slider, default here 1.0 = every pixel; the reference's is 0.5).
 // --interactive N: N frames of 1 spp + resolve + download each (the viewer's per-frame work,
 // BASELINE config 5) and prints p50/p99 frame latency.
 #include <algorithm>
@@ -16,6 +17,7 @@ int main(int argc, char** argv) {
     std::string scene_path, out_path;
     int w = 1280, h = 720, spp = 64, bounces = 8, interactive = 0;
     bool preview = false;
+    float scale = 1.0f;
     for (int i = 1; i < argc; ++i) {
         auto arg = [&](const char* n) { return !strcmp(argv[i], n) && i + 1 < argc; };
         if (arg("--scene")) scene_path = argv[++i];
@@ -25,6 +27,7 @@ int main(int argc, char** argv) {
         else if (arg("--bounces")) bounces = atoi(argv[++i]);
         else if (arg("--out")) out_path = argv[++i];
         else if (arg("--interactive")) interactive = atoi(argv[++i]);
+        else if (arg("--scale")) scale = (float)atof(argv[++i]);
         else if (!strcmp(argv[i], "--preview")) preview = true;
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
@@ -36,7 +39,7 @@ int main(int argc, char** argv) {
                                                 scene1.lastError.c_str(), scene1.GetObjects().size());
         rtb200::Raytracer rt(w, h);
         rt.SetObjectsToRender(scene1.GetObjects());
-        rt.SIMPLEDRAW = preview; rt.MAXBOUNCES = bounces; rt.TARGETFRAMES = 1 << 30;
+        rt.SIMPLEDRAW = preview; rt.MAXBOUNCES = bounces; rt.TARGETFRAMES = 1 << 30; rt.SCREEN_SCALE = scale;
         std::vector<uint32_t> surface((size_t)w * h);
         using clk = std::chrono::steady_clock;
         if (interactive > 0) {
@@ -53,7 +56,8 @@ int main(int argc, char** argv) {
                    ms[ms.size() / 2], ms[(size_t)(ms.size() * 0.99)], [&] { double s = 0; for (double v : ms) s += v; return s / ms.size(); }());
         } else {
             auto t0 = clk::now();
-            rt.RenderFrame();                                        // first frame: overwrite
+            rt.RenderFrame();                                        // first frame after a change: 1/4 scale, overwrite
+            rt.RenderFrame();                                        // second frame: full render scale, overwrite
             if (!preview && spp > 1) {                               // the rest of the accumulation in one call
                 if (rt_render_spp(rt.Context(), spp - 1) < 0) throw std::runtime_error(rt_last_error(rt.Context()));
                 rt.ACCUMULATIONFRAMES = spp;

@@ -145,17 +145,32 @@ public:
     }
     void Invalidate() { doSetFrame = true; }         // any edit: doSetFrame = true (Raytracer.cpp:393,422,454,...)
 
-    // One iteration of the main loop's render step (Raytracer.cpp:572-595 + the workers' frame :231-252):
-    // returns false when paused by the frame cap. The progressive 1/4-resolution first frame (:580) is
-    // not reproduced - the first frame after a change is already full resolution here.
+    float SCREEN_SCALE = .5f;                                                       // :30 (slider 0.25 .. 1.0, :479)
+    bool pause = false;                                                             // :50 ('P')
+    float progressiveResolutionScaler = 1;                                          // :47
+
+    // One iteration of the main loop's render step (Raytracer.cpp:572-595 + the workers' frame :231-252): returns
+    // false when nothing was rendered (paused, or the frame cap reached). As in the reference the first frame after
+    // a change is traced at 1/4 of the render scale and overwrites (:576-581), the next one is at full render scale
+    // and overwrites again (:585-587), and later frames accumulate; every frame is block-filled with
+    // steps = ceil(1 / (SCREEN_SCALE * progressiveResolutionScaler)) over the reference's 16 column strips (:233,330).
+    // One deviation, on purpose: the reference's running mean counts that second frame twice (ACCUMULATIONFRAMES is
+    // already 2 when it overwrites); here every accumulated frame has the same weight.
     bool RenderFrame() {
-        if (!doSetFrame && ACCUMULATIONFRAMES == TARGETFRAMES) return false;        // :572
+        if (pause || (!doSetFrame && ACCUMULATIONFRAMES == TARGETFRAMES)) return false;     // :572
         par.max_bounces = MAXBOUNCES; par.mode = SIMPLEDRAW ? RT_MODE_PREVIEW : RT_MODE_PATH; par.selected_id = selectedObject;
         check(rt_set_params(ctx, &par), ctx);
         rt_camera cam = camera.ToCamera(FOV);
         check(rt_set_camera(ctx, &cam), ctx);
-        if (doSetFrame) { check(rt_reset_accumulation(ctx), ctx); ACCUMULATIONFRAMES = 1; doSetFrame = false; }   // :576-581
-        else ACCUMULATIONFRAMES += SIMPLEDRAW ? 0 : 1;                              // :589
+        bool setFrame;
+        if (doSetFrame) { setFrame = true; ACCUMULATIONFRAMES = 1; progressiveResolutionScaler = 1.0f / 4.0f; doSetFrame = false; }   // :576-581
+        else {
+            setFrame = progressiveResolutionScaler != 1;                            // :584-587
+            progressiveResolutionScaler = 1;
+            ACCUMULATIONFRAMES += SIMPLEDRAW ? 0 : 1;                               // :589
+        }
+        if (setFrame) check(rt_reset_accumulation(ctx), ctx);
+        check(rt_set_pixel_step(ctx, rt_reference_pixel_step(SCREEN_SCALE, progressiveResolutionScaler), rt_reference_strip_columns(par.width)), ctx);
         check(rt_render_spp(ctx, 1), ctx);
         return true;
     }

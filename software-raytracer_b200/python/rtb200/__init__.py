@@ -61,7 +61,7 @@ EXPORTS = [
     "rt_read_accum", "rt_read_aov", "rt_read_ray_dirs", "rt_trace_rays", "rt_env_color", "rt_philox_block",
     "rt_scene_file_read", "rt_scene_file_read_names", "rt_scene_file_write", "rt_object_name", "rt_set_object_name", "rt_scene_name",
     "rt_write_accum", "rt_selftest", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
-    "rt_set_mesh", "rt_load_mesh_obj", "rt_get_mesh_info",
+    "rt_set_mesh", "rt_load_mesh_obj", "rt_get_mesh_info", "rt_set_pixel_step", "rt_reference_pixel_step", "rt_reference_strip_columns",
     "rt_argb_device_ptr", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_resolve_fused", "rt_read_surface",
 ]
 
@@ -163,6 +163,16 @@ def scene_file_write(path, objs, names=None, scene_name=""):
     return lib.rt_scene_file_write(str(path).encode(), scene_name.encode(), _p(objs), arr, len(objs))
 
 
+def reference_pixel_step(screen_scale, progressive_scaler=1.0):
+    lib = load_library()
+    lib.rt_reference_pixel_step.argtypes = [C.c_float, C.c_float]
+    return lib.rt_reference_pixel_step(screen_scale, progressive_scaler)
+
+
+def reference_strip_columns(width):
+    return load_library().rt_reference_strip_columns(width)
+
+
 def shard_range(spp, rank, world, next_sample=0):
     first, count = C.c_uint32(0), C.c_int(0)
     rc = load_library().rt_shard_range(spp, rank, world, C.c_uint32(next_sample), C.byref(first), C.byref(count))
@@ -245,6 +255,9 @@ class PathTracer:
 
     def set_option(self, opt, value):
         return self._chk(self.lib.rt_set_option(self.h, opt, value))
+
+    def set_pixel_step(self, steps, strip_columns=0):
+        return self._chk(self.lib.rt_set_pixel_step(self.h, steps, strip_columns))
 
     def set_shard(self, rank, world):
         return self._chk(self.lib.rt_set_shard(self.h, rank, world))

@@ -179,3 +179,12 @@ int main(int argc, char** argv) {
     r = meta["rotated_camera_by_reference"]["forward"]
     assert [np.float32(v) for v in out[3:6]] == [np.float32(v) for v in r]
     assert hashlib.sha256((tmp_path / "out.json").read_bytes()).hexdigest() == meta["scenes"]["Scene1"]["save_sha256"]
+
+
+def test_reference_block_geometry_helpers():
+    """Raytracer.cpp:233 steps = ceil(1 / (SCREEN_SCALE * progressiveResolutionScaler)); :330 strip = ceil(W / 16) + 1."""
+    assert rtb200.reference_pixel_step(0.5, 1.0) == 2 and rtb200.reference_pixel_step(0.5, 0.25) == 8
+    assert rtb200.reference_pixel_step(1.0, 1.0) == 1 and rtb200.reference_pixel_step(0.3, 1.0) == 4
+    assert rtb200.reference_pixel_step(0.25, 0.25) == 16
+    assert rtb200.reference_strip_columns(1280) == 81 and rtb200.reference_strip_columns(160) == 11
+    assert rtb200.reference_strip_columns(333) == 21
