@@ -671,7 +671,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
         if (c->opt_pipeline == RT_PIPELINE_WAVEFRONT) {
             if (!c->wf) c->wf = wavefront_create();
-            RT_CUDA(c, launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream));
+            RT_CUDA(c, launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_bvh_sched == 0));
             c->used_pipeline = RT_PIPELINE_WAVEFRONT;
         } else if (ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0)
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));

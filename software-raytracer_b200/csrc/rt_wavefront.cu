@@ -151,6 +151,157 @@ __global__ void __launch_bounds__(kThreads, 6) k_wf_intersect(SceneView sc, BvhV
     }
 }
 
+// BVH scenes: persistent threads with PER-LANE ray replacement. With one ray per lane per batch (above) a warp
+// runs until its longest traversal ends: on the 10 000-sphere scene 5 of 32 lanes are active on average
+// (profiles/r1l_summary_c3_bvh.txt). Here every lane is a small state machine - IDLE (needs a ray), ACTIVE (one BVH
+// step per iteration: an inner node, or a whole leaf), DONE (hit pending) - and the warp refills: as soon as
+// kRefill lanes are not traversing, the DONE lanes write their hits together and every free lane claims the
+// next queue entry (one atomicAdd per warp). Same candidate semantics and strict tests as closest_hit_bvh().
+constexpr int kRefill = 8;          // free lanes that trigger a refill pass
+constexpr int kBurst = 4;           // traversal steps between two refill checks
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 6) k_wf_intersect_bvh(SceneView sc, BvhView bv, FlatView fl, const uint32_t* __restrict__ q,
+                                                                   const unsigned int* __restrict__ count_ptr, unsigned int* __restrict__ cursor,
+                                                                   const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                                   float4* __restrict__ hit_nt, int* __restrict__ hit_id) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
+    const float4* __restrict__ nodes = tc.nodes;
+    const int* __restrict__ refs = tc.refs;
+    int* const stk = tc.stack;
+    float* const stk_t = tc.stack_t;
+    const int stride = tc.stride;
+    const unsigned int count = *count_ptr;
+    const int lane = threadIdx.x & 31;
+    constexpr unsigned FULL = 0xffffffffu;
+    enum { IDLE = 0, ACTIVE = 1, DONE = 2 };
+
+    int state = IDLE, cur = 0, sp = 0;
+    uint32_t pid = 0;
+    float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f), bn = f3(0.f, 0.f, 0.f);
+    float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+    float best_t = 0.f; int best_id = 0, best_ref = 0; bool have = false;
+    bool exhausted = false;
+
+    auto pop = [&]() {
+        for (;;) {
+            if (sp == 0) { state = DONE; return; }
+            --sp;
+            if (stk_t[sp * stride] > best_t) continue;      // entered after the best hit found since the push
+            cur = stk[sp * stride];
+            return;
+        }
+    };
+
+    for (;;) {
+        const unsigned m_free = __ballot_sync(FULL, state != ACTIVE);
+        if (__popc(m_free) >= kRefill || m_free == FULL) {
+            if (state == DONE) {                             // write the pending hits together
+                Hit h;
+                h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f);
+                if (have) {
+                    h.id = best_id; h.t = best_t;
+                    if (best_ref >= 0 && best_ref < kTriRef) {
+                        const float4 s4 = tc.sph[best_ref];
+                        const float3 p = f3(o.x + d.x * best_t, o.y + d.y * best_t, o.z + d.z * best_t);      // Object.hpp:136
+                        h.n = normalized3(f3(p.x - s4.x, p.y - s4.y, p.z - s4.z));                         // Object.hpp:137
+                    } else h.n = bn;
+                }
+                hit_nt[pid] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
+                hit_id[pid] = h.id;
+                state = IDLE;
+            }
+            if (!exhausted) {
+                const unsigned m_idle = __ballot_sync(FULL, state == IDLE);
+                unsigned int base = 0;
+                const int leader = __ffs((int)m_idle) - 1;
+                if (lane == leader) base = atomicAdd(cursor, (unsigned int)__popc(m_idle));
+                base = __shfl_sync(FULL, base, leader);
+                if (state == IDLE) {
+                    const unsigned int i = base + (unsigned int)__popc(m_idle & ((1u << lane) - 1u));
+                    if (i < count) {
+                        pid = q[i];
+                        const float4 o4 = ray_o[pid], d4 = ray_d[pid];
+                        o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
+                        const float big = 1e30f;
+                        ix = fabsf(d.x) > 1e-30f ? 1.f / d.x : copysignf(big, d.x);
+                        iy = fabsf(d.y) > 1e-30f ? 1.f / d.y : copysignf(big, d.y);
+                        iz = fabsf(d.z) > 1e-30f ? 1.f / d.z : copysignf(big, d.z);
+                        ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
+                        best_t = __int_as_float(0x7f800000); best_id = 0x7fffffff; best_ref = 0; have = false;
+                        cur = 0; sp = 0; state = ACTIVE;
+                    }
+                }
+                if (base + (unsigned int)__popc(m_idle) >= count) exhausted = true;       // warp-uniform
+            }
+            if (!__any_sync(FULL, state == ACTIVE)) break;    // nothing left to traverse (DONE lanes were flushed above)
+        }
+#pragma unroll 1
+        for (int it = 0; it < kBurst; ++it) {
+            if (state != ACTIVE) continue;
+            if (cur >= 0) {                                   // inner node: both children's slabs
+                const float4 n0 = nodes[4 * cur], n1 = nodes[4 * cur + 1], n2 = nodes[4 * cur + 2];
+                const int2 ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
+                float a, b;
+                a = fmaf(n0.x, ix, ox); b = fmaf(n0.y, ix, ox);
+                float lo0 = fminf(a, b), hi0 = fmaxf(a, b);
+                a = fmaf(n0.z, iy, oy); b = fmaf(n0.w, iy, oy);
+                lo0 = fmaxf(lo0, fminf(a, b)); hi0 = fminf(hi0, fmaxf(a, b));
+                a = fmaf(n1.x, iz, oz); b = fmaf(n1.y, iz, oz);
+                lo0 = fmaxf(lo0, fminf(a, b)); hi0 = fminf(hi0, fmaxf(a, b));
+                a = fmaf(n1.z, ix, ox); b = fmaf(n1.w, ix, ox);
+                float lo1 = fminf(a, b), hi1 = fmaxf(a, b);
+                a = fmaf(n2.x, iy, oy); b = fmaf(n2.y, iy, oy);
+                lo1 = fmaxf(lo1, fminf(a, b)); hi1 = fminf(hi1, fmaxf(a, b));
+                a = fmaf(n2.z, iz, oz); b = fmaf(n2.w, iz, oz);
+                lo1 = fmaxf(lo1, fminf(a, b)); hi1 = fminf(hi1, fmaxf(a, b));
+                const bool h0 = lo0 <= hi0 && hi0 >= 0.f && lo0 <= best_t;
+                const bool h1 = lo1 <= hi1 && hi1 >= 0.f && lo1 <= best_t;
+                if (h0 && h1) {
+                    const bool swap = lo1 < lo0;
+                    stk[sp * stride] = swap ? ch.x : ch.y;
+                    stk_t[sp * stride] = swap ? lo0 : lo1;
+                    ++sp;
+                    cur = swap ? ch.y : ch.x;
+                } else if (h0) cur = ch.x;
+                else if (h1) cur = ch.y;
+                else pop();
+            } else {                                          // leaf: strict tests on its primitives, then pop
+                const unsigned int v = (unsigned int)(~cur);
+                const int first = (int)(v & 0xffffffu), cnt = (int)(v >> 24);
+                for (int i = 0; i < cnt; ++i) {
+                    const int r = refs[first + i];
+                    if (r >= kTriRef) {
+                        const int k = r - kTriRef;
+                        float t; float3 nrm;
+                        if (tri_hit(__ldg(sc.tri + 3 * k), __ldg(sc.tri + 3 * k + 1), __ldg(sc.tri + 3 * k + 2), o, d, t, nrm)) {
+                            const int oid = __ldg(sc.tri_obj + k);
+                            if (t < best_t || (t == best_t && (oid < best_id || (oid == best_id && r < best_ref)))) {
+                                best_t = t; best_id = oid; best_ref = r; bn = nrm; have = true;
+                            }
+                        }
+                    } else if (r >= 0) {
+                        float t;
+                        if (sphere_t(tc.sph[r], o, d, t)) {
+                            const int oid = sc.sph_id[r];
+                            if (t < best_t || (t == best_t && oid < best_id)) { best_t = t; best_id = oid; best_ref = r; have = true; }
+                        }
+                    } else {
+                        const int j = ~r;
+                        float dist; float3 nrm;
+                        if (box_hit(tc.box[2 * j], tc.box[2 * j + 1], o, d, dist, nrm)) {
+                            const int oid = sc.box_id[j];
+                            if (dist < best_t || (dist == best_t && oid < best_id)) { best_t = dist; best_id = oid; best_ref = r; bn = nrm; have = true; }
+                        }
+                    }
+                }
+                pop();
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_wf_shade(SceneView sc, FrameView fr, int tiles_x, int npad, uint32_t s_first,
                                                    const uint32_t* __restrict__ q_in, const unsigned int* __restrict__ count_ptr,
                                                    uint32_t* __restrict__ q_out, unsigned int* __restrict__ count_out,
@@ -246,6 +397,8 @@ cudaError_t ensure_optin() {
     if ((e = optin(K<2>)) != cudaSuccess) return e; if ((e = optin(K<3>)) != cudaSuccess) return e; \
     if ((e = optin(K<4>)) != cudaSuccess) return e;
     RTB_WF_OPTIN(k_wf_primary) RTB_WF_OPTIN(k_wf_intersect)
+    if ((e = optin(k_wf_intersect_bvh<2>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_intersect_bvh<3>)) != cudaSuccess) return e;
 #undef RTB_WF_OPTIN
     done = true;
     return cudaSuccess;
@@ -265,7 +418,7 @@ void wavefront_destroy(WavefrontBuffers* wb) {
 
 cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
                                     float4* accum, uint32_t s_begin, int n_samples, bool reuse, unsigned long long* seg_counter,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, bool bvh_refill) {
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_optin();
     if (e != cudaSuccess) return e;
@@ -337,8 +490,12 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
             switch (mode) {
                 case 0: k_wf_intersect<0><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
                 case 1: k_wf_intersect<1><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
-                case 2: k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
-                case 3: k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
+                case 2: if (bvh_refill) k_wf_intersect_bvh<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
+                        else k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
+                        break;
+                case 3: if (bvh_refill) k_wf_intersect_bvh<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
+                        else k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
+                        break;
                 default: k_wf_intersect<4><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
             }
             k_wf_shade<<<sms * 8, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, qin, cnt, qout, cnt + 1, wb->ray_o, wb->ray_d, wb->thr, wb->rad,
