@@ -6,8 +6,8 @@
 // than the current best is guaranteed to be visited, and each candidate is then tested with the
 // same strict-IEEE code the brute-force loop uses, with the reference's tie rule (lowest object
 // id wins on equal distance, Raytracer.cpp:127-137). Conservativeness comes from inflating every
-// box by kInflate * (largest coordinate magnitude of the scene bounds and the ray origins), two
-// orders of magnitude above the float rounding error of either computation.
+// box by kInflate * (largest coordinate magnitude of the scene bounds and the ray origins), several
+// times the float rounding error of either computation (derivation at kInflate below).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -37,7 +37,14 @@ struct HostBvh {
     // traversal statistics hooks are on the device side
 };
 
-constexpr float kInflate = 4e-5f;    // relative box inflation
+// Relative box inflation. What it has to cover (slab test of rt_device.cuh, per axis): the computed plane parameter
+// a = fma(plane, i, -o*i) with i = 1/d from MUFU.RCP differs from (plane - o)/d by at most 2.4e-7 |t| (reciprocal,
+// 2 ulp) + u (|o| + |plane|) |i| (the two roundings, u = 2^-24); moving a plane outwards by eps shifts its parameter by
+// eps |i|, and |t| / |i| is the distance travelled along that axis <= |o| + |plane| <= 2 extent. So eps >= 6e-7 x
+// extent is enough; 4e-6 keeps a factor 6 on top (and the reference's own sphere test accepts points at most
+// ~1e-7 x extent outside the sphere, flat_build.h). The first version used 4e-5, which made the boxes of the
+// 0.2-radius spheres of Scene1 (extent 2001 because of the ground sphere) 0.08 larger per side than needed.
+constexpr float kInflate = 4e-6f;
 constexpr int32_t kTriRefBase = 0x40000000;   // leaf ref of triangle i = kTriRefBase + i
 constexpr int kMaxBvhDepth = 40;     // traversal stack entries per thread
 

@@ -31,7 +31,7 @@
 // and below 1e15 in magnitude, at most 255 primitives.
 //
 // BOXES (cluster bounds and cubes) use the BVH's inflated slab test with the same inflation rule
-// (bvh_build.h): 4e-5 x the largest coordinate magnitude of scene bounds and origins.
+// (bvh_build.h kInflate): 4e-6 x the largest coordinate magnitude of scene bounds and origins.
 #pragma once
 #include <cstdint>
 #include <vector>
