@@ -80,7 +80,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("RTB200_LIB") or LIB_PATH     # RTB200_LIB: A/B builds of the same library (benchmarks)
     if not os.path.exists(p):
         raise FileNotFoundError("%s not built: run `make -C %s` (or __graft_entry__.build())" % (p, PRODUCT_DIR))
     lib = C.CDLL(p)

@@ -797,3 +797,52 @@ def test_block_filled_path_frames_are_the_block_origin_paths(tracer, scenes):
                 nblocks += 1
     assert close(blk, want, rtol=1e-6)                       # same paths; 2+4 vs 6 samples differ in summation order only
     assert st.paths == nblocks * 6
+
+
+def test_flat_accel_degenerate_scenes(tracer):
+    """Scenes the flat builder must either handle or hand to the BVH: duplicates, zero / negative radii, cubes only,
+    more level-1 entries than its queue takes, coordinates beyond its finite-arithmetic precondition."""
+    rng = np.random.default_rng(12)
+
+    def spheres(n):
+        o = np.zeros(n, rtb200.OBJECT_DTYPE); o["type"] = 1; o["spec_color"] = 1; o["base"] = 0.7
+        o["pos"] = rng.uniform([-3, -1, 3], [3, 3, 9], (n, 3)).astype(np.float32)
+        o["radius"] = rng.uniform(0.2, 0.6, n).astype(np.float32)
+        return o
+    cases = {}
+    a = spheres(24); a["pos"][1] = a["pos"][0]; a["radius"][1] = a["radius"][0]          # exact duplicates: lowest id wins
+    a["radius"][2] = 0.0; a["radius"][3] = -0.4; a["emissive"][5] = 9
+    cases["duplicates_zero_negative_radius"] = a
+    b = spheres(20); b["type"] = 2; b["half"] = rng.uniform(0.1, 0.5, (20, 3)).astype(np.float32); b["half"][4] = [-0.3, 0.2, 0.2]
+    cases["cubes_only"] = b
+    c = spheres(200); c["radius"] = np.where(np.arange(200) % 3 == 0, 3.0, 0.05).astype(np.float32)   # 67 big "singles" > 56
+    cases["too_many_singles"] = c
+    d = spheres(12); d["pos"][7] = [1e16, 0, 5]
+    cases["beyond_finite_precondition"] = d
+    e = spheres(9); e["pos"][:, 2] += 2000.0                                                # far from the origin
+    cases["far_from_origin"] = e
+    cam = rtb200.default_camera(60)
+    for name, objs in cases.items():
+        out = {}
+        try:
+            for accel in (rtb200.RT_ACCEL_FLAT, rtb200.RT_ACCEL_BRUTE):
+                tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+                camx = rtb200.default_camera(60)
+                if name == "far_from_origin":
+                    camx.pos[2] = 1990.0
+                setup(tracer, objs, 160, 96, camx, max_bounces=4)
+                aov = tracer.read_aov()
+                tracer.render_spp(4)
+                out[accel] = (aov, tracer.read_accum()[0], tracer.stats().segments, tracer.stats().accel)
+        finally:
+            tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        f, b_ = out[rtb200.RT_ACCEL_FLAT], out[rtb200.RT_ACCEL_BRUTE]
+        assert np.array_equal(f[0][0], b_[0][0]), name
+        for x, y in zip(f[0][1:], b_[0][1:]):
+            assert np.array_equal(bits(x), bits(y)), name
+        assert np.array_equal(bits(f[1]), bits(b_[1])) and f[2] == b_[2], name
+        if name in ("too_many_singles", "beyond_finite_precondition"):
+            assert f[3] == rtb200.RT_ACCEL_BVH, name                                       # handed over
+        else:
+            assert f[3] == rtb200.RT_ACCEL_FLAT, name
+    assert (out[rtb200.RT_ACCEL_FLAT][0][0] >= 0).any()
