@@ -78,6 +78,8 @@ struct rt_ctx {
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
     int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4, opt_primary_reuse = 1;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
+    int tuned_pipeline = -1;       // RT_PIPELINE_AUTO decision for large BVH scenes (-1: not measured yet)
+    float tune_pipe_ms[2] = {0.f, 0.f};
     float4* d_tune = nullptr; size_t cap_tune = 0;
     float tune_ms[3] = {0.f, 0.f, 0.f};
     int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;
@@ -169,7 +171,7 @@ int upload_scene(rt_ctx* c) {
     c->view.mat = c->d_mat;
     c->view.n_sph = (int)sph_id.size(); c->view.n_box = (int)box_id.size(); c->view.n_obj = (int)objs.size();
     c->view.tri = c->d_tri; c->view.tri_obj = c->d_tri_obj; c->view.n_tri = (int)nt;
-    c->bvh_valid = false; c->flat_valid = false; c->tuned_accel = -1;
+    c->bvh_valid = false; c->flat_valid = false; c->tuned_accel = c->tuned_pipeline = -1;
     return RT_OK;
 }
 
@@ -291,6 +293,38 @@ int autotune_accel(rt_ctx* c) {
         if (c->tune_ms[k] < c->tune_ms[best]) best = k;
     }
     c->tuned_accel = kinds[best];
+    return RT_OK;
+}
+
+// RT_PIPELINE_AUTO: the regeneration megakernel, except for BVH scenes too large to stage in shared memory
+// (thousands of primitives), where the first path-mode render times 2 spp of the megakernel and of the wavefront
+// pipeline and keeps the faster (identical results). On the 10 000-sphere scene the wavefront wins by about 10 %,
+// on the 1 M-triangle mesh the megakernel by about 25 %.
+int autotune_pipeline(rt_ctx* c, const AccelSel& ac) {
+    if (c->opt_pipeline != RT_PIPELINE_AUTO) return RT_OK;
+    if (c->tuned_pipeline >= 0) return RT_OK;
+    const size_t prims = (size_t)c->view.n_sph + c->view.n_box + c->view.n_tri;
+    if (ac.kind != kAccelBvh || prims < 2048 || c->pixel_step > 1) { c->tuned_pipeline = RT_PIPELINE_REGEN; return RT_OK; }
+    const size_t px = (size_t)c->par.width * c->par.height;
+    RT_CUDA(c, ensure_capacity(c->d_tune, c->cap_tune, px));
+    if (!c->wf) c->wf = wavefront_create();
+    cudaEvent_t e[3];
+    for (auto& ev : e) RT_CUDA(c, cudaEventCreate(&ev));
+    unsigned long long* dummy = c->d_counters + 4;
+    const bool reuse = c->opt_primary_reuse != 0;
+    cudaError_t err = cudaSuccess;
+    for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 allocates the wavefront buffers and warms up
+        cudaEventRecord(e[0], c->stream);
+        err = launch_render_regen(c->view, ac, c->frame, c->d_tune, 0u, 2, reuse, dummy, c->stream);
+        cudaEventRecord(e[1], c->stream);
+        if (err == cudaSuccess) err = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_tune, 0u, 2, reuse, dummy, c->stream, c->opt_bvh_sched == 0);
+        cudaEventRecord(e[2], c->stream);
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+    if (err == cudaSuccess) { cudaEventElapsedTime(&c->tune_pipe_ms[0], e[0], e[1]); cudaEventElapsedTime(&c->tune_pipe_ms[1], e[1], e[2]); }
+    for (auto& ev : e) cudaEventDestroy(ev);
+    if (err != cudaSuccess) return cuda_fail(c, err, "autotune_pipeline");
+    c->tuned_pipeline = c->tune_pipe_ms[1] < c->tune_pipe_ms[0] ? RT_PIPELINE_WAVEFRONT : RT_PIPELINE_REGEN;
     return RT_OK;
 }
 
@@ -446,11 +480,11 @@ int rt_set_scene(rt_ctx* c, const rt_object* objects, int n) {
             if (o.spec_color[k] < 0) o.spec_color[k] = 0;
         }
     }
-    const int keep_tuned = same ? c->tuned_accel : -1;
+    const int keep_tuned = same ? c->tuned_accel : -1, keep_pipe = same ? c->tuned_pipeline : -1;
     int rc = upload_scene(c);
     if (rc != RT_OK) return rc;
     if (same) c->bvh_valid = true;
-    c->tuned_accel = keep_tuned;
+    c->tuned_accel = keep_tuned; c->tuned_pipeline = keep_pipe;
     return rt_reset_accumulation(c);
 }
 
@@ -556,7 +590,7 @@ int rt_get_mesh_info(rt_ctx* c, int object_index, int* n_vertices, int* n_triang
 
 int rt_set_camera(rt_ctx* c, const rt_camera* cam) {
     if (!c || !cam) return RT_ERR_INVALID;
-    if (memcmp(&c->cam, cam, sizeof *cam) != 0) c->tuned_accel = -1;
+    if (memcmp(&c->cam, cam, sizeof *cam) != 0) c->tuned_accel = c->tuned_pipeline = -1;
     c->cam = *cam;
     c->frame_dirty = true;
     return RT_OK;
@@ -568,7 +602,7 @@ int rt_set_params(rt_ctx* c, const rt_params* p) {
         return fail(c, RT_ERR_INVALID, "rt_set_params: bad resolution");
     if (p->mode != RT_MODE_PATH && p->mode != RT_MODE_PREVIEW) return fail(c, RT_ERR_INVALID, "rt_set_params: bad mode");
     bool resized = p->width != c->par.width || p->height != c->par.height;
-    if (resized || p->max_bounces != c->par.max_bounces || p->mode != c->par.mode) c->tuned_accel = -1;
+    if (resized || p->max_bounces != c->par.max_bounces || p->mode != c->par.mode) c->tuned_accel = c->tuned_pipeline = -1;
     c->par = *p;
     if (c->par.max_bounces < 0) c->par.max_bounces = 0;        // MAXBOUNCES = max(MAXBOUNCES, 0) Raytracer.cpp:475
     c->frame_dirty = true;
@@ -589,8 +623,8 @@ int rt_set_option(rt_ctx* c, int option, int value) {
         case RT_OPT_ACCEL: c->opt_accel = value; return RT_OK;
         case RT_OPT_BVH_THRESHOLD: c->opt_bvh_threshold = value; return RT_OK;
         case RT_OPT_BVH_SCHED: c->opt_bvh_sched = value; return RT_OK;
-        case RT_OPT_BVH_LEAF: c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = -1; return RT_OK;
-        case RT_OPT_PRIMARY_REUSE: c->opt_primary_reuse = value != 0; c->tuned_accel = -1; return RT_OK;
+        case RT_OPT_BVH_LEAF: c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
+        case RT_OPT_PRIMARY_REUSE: c->opt_primary_reuse = value != 0; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
         case RT_OPT_BVH_WAIT_K: c->opt_bvh_wait_k = value < 1 ? 1 : value; return RT_OK;
     }
     return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
@@ -644,6 +678,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
     AccelSel ac;
     if ((rc = make_accel(c, want_accel(c), camera_extent(c), ac)) != RT_OK) return rc;
     c->used_accel = accel_of(ac);
+    if (c->par.mode == RT_MODE_PATH && (rc = autotune_pipeline(c, ac)) != RT_OK) return rc;
     RT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if (c->pixel_step > 1) {
         // SCREEN_SCALE / progressive resolution: one path per block, block-filled (Raytracer.cpp:233-248)
@@ -669,7 +704,8 @@ int rt_render_spp(rt_ctx* c, int spp) {
         // this rank's slice of the global sample indices [next, next+spp)
         int mine = 0; uint32_t first = 0;
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
-        if (c->opt_pipeline == RT_PIPELINE_WAVEFRONT) {
+        const bool wavefront = c->opt_pipeline == RT_PIPELINE_WAVEFRONT || (c->opt_pipeline == RT_PIPELINE_AUTO && c->tuned_pipeline == RT_PIPELINE_WAVEFRONT);
+        if (wavefront) {
             if (!c->wf) c->wf = wavefront_create();
             RT_CUDA(c, launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_bvh_sched == 0));
             c->used_pipeline = RT_PIPELINE_WAVEFRONT;
@@ -677,7 +713,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else
             RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream));
-        if (c->opt_pipeline != RT_PIPELINE_WAVEFRONT) c->used_pipeline = RT_PIPELINE_REGEN;
+        if (!wavefront) c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce
         c->paths += (uint64_t)mine * px; c->total_paths += (uint64_t)mine * px;
