@@ -179,6 +179,10 @@ def run_b200(args):
         tr.set_option(rtb200.RT_OPT_BVH_SCHED, args.bvh_sched)
     if args.wait_k >= 0:
         tr.set_option(rtb200.RT_OPT_BVH_WAIT_K, args.wait_k)
+    if args.wf_refill >= 0:
+        tr.set_option(rtb200.RT_OPT_WF_REFILL, args.wf_refill)
+    if args.wf_node_min >= 0:
+        tr.set_option(rtb200.RT_OPT_WF_NODE_MIN, args.wf_node_min)
     tr.set_scene(objs)
     if mesh is not None:
         tr.set_mesh(0, mesh[0], mesh[1])
@@ -409,6 +413,8 @@ def main():
     ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"], help="N > 1 exchange: fused peer-memory reduce+resolve kernel, or NCCL all-reduce")
     ap.add_argument("--bvh-sched", type=int, default=-1, help="RT_OPT_BVH_SCHED override")
     ap.add_argument("--wait-k", type=int, default=-1, help="RT_OPT_BVH_WAIT_K override")
+    ap.add_argument("--wf-refill", type=int, default=-1, help="RT_OPT_WF_REFILL override")
+    ap.add_argument("--wf-node-min", type=int, default=-1, help="RT_OPT_WF_NODE_MIN override")
     ap.add_argument("--scene", default="Scene1", help="bundled scene fixture (the headline config is Scene1)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -57,5 +57,6 @@ void wavefront_destroy(WavefrontBuffers* wb);
 // Adds samples [s_begin, s_begin + n_samples) of every pixel into accum, bit-identical to launch_render_regen.
 cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
                                     float4* accum, uint32_t s_begin, int n_samples, bool reuse_primary,
-                                    unsigned long long* seg_counter, cudaStream_t st, bool bvh_refill = true);
+                                    unsigned long long* seg_counter, cudaStream_t st, bool bvh_refill = true,
+                                    int k_refill = 8, int k_node_min = 8);
 }  // namespace rtb

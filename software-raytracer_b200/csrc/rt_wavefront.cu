@@ -151,20 +151,31 @@ __global__ void __launch_bounds__(kThreads, 6) k_wf_intersect(SceneView sc, BvhV
     }
 }
 
-// BVH scenes: persistent threads with PER-LANE ray replacement. With one ray per lane per batch (above) a warp
-// runs until its longest traversal ends: on the 10 000-sphere scene 5 of 32 lanes are active on average
-// (profiles/r1l_summary_c3_bvh.txt). Here every lane is a small state machine - IDLE (needs a ray), ACTIVE (one BVH
-// step per iteration: an inner node, or a whole leaf), DONE (hit pending) - and the warp refills: as soon as
-// kRefill lanes are not traversing, the DONE lanes write their hits together and every free lane claims the
-// next queue entry (one atomicAdd per warp). Same candidate semantics and strict tests as closest_hit_bvh().
-constexpr int kRefill = 8;          // free lanes that trigger a refill pass
-constexpr int kBurst = 4;           // traversal steps between two refill checks
+// BVH scenes: persistent threads with PER-LANE ray replacement and POSTPONED leaves ("speculative while-while").
+// With one ray per lane per batch (k_wf_intersect above) a warp runs until its longest traversal ends: on the
+// 10 000-sphere scene 5 of 32 lanes are active on average (profiles/r1l_summary_c3_bvh.txt). Here every lane is
+// a small state machine - IDLE (needs a ray), ACTIVE, DONE (hit pending):
+//   node phase  lanes holding an inner node step through it together; a lane that reaches a leaf stashes it
+//               (one pending leaf) and keeps traversing - culling against a best distance that is merely not
+//               yet as tight as it could be, so the candidate set stays conservative; the phase ends when
+//               fewer than kNodeMin lanes still hold an inner node;
+//   leaf phase  the stashed leaves are tested together with the strict reference arithmetic (with ~70 node
+//               visits and ~5 leaves per ray, testing a leaf the moment one lane reaches it would drag the whole
+//               warp through the leaf code at almost every step);
+//   refill      as soon as kRefill lanes are free, the DONE lanes write their hits together and every free lane
+//               claims the next queue entry (one atomicAdd per warp).
+// Same candidate semantics, strict tests and tie rule as closest_hit_bvh(): bit-identical results (tested).
+// k_refill: free lanes that trigger a refill pass; k_node_min: lanes with inner-node work below which the warp turns
+// to its pending leaves (RT_OPT_WF_REFILL / RT_OPT_WF_NODE_MIN; defaults measured on the 10k-sphere scene)
 
+#ifndef RTB_WF_BVH_MIN_BLOCKS
+#define RTB_WF_BVH_MIN_BLOCKS 8      // 63 registers, no spills: the kernel waits on node fetches (issue slots 52 % busy at 6), +8 % at 8
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 6) k_wf_intersect_bvh(SceneView sc, BvhView bv, FlatView fl, const uint32_t* __restrict__ q,
+__global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersect_bvh(SceneView sc, BvhView bv, FlatView fl, const uint32_t* __restrict__ q,
                                                                    const unsigned int* __restrict__ count_ptr, unsigned int* __restrict__ cursor,
                                                                    const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                                                                   float4* __restrict__ hit_nt, int* __restrict__ hit_id) {
+                                                                   float4* __restrict__ hit_nt, int* __restrict__ hit_id, int kRefill, int kNodeMin) {
     extern __shared__ float4 smem[];
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     const float4* __restrict__ nodes = tc.nodes;
@@ -175,26 +186,63 @@ __global__ void __launch_bounds__(kThreads, 6) k_wf_intersect_bvh(SceneView sc, 
     const unsigned int count = *count_ptr;
     const int lane = threadIdx.x & 31;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NONE = (int)0x80000000;                     // "no link": never a real leaf (a leaf's count is <= 127)
     enum { IDLE = 0, ACTIVE = 1, DONE = 2 };
 
-    int state = IDLE, cur = 0, sp = 0;
+    int state = IDLE, cur = NONE, leaf0 = NONE, sp = 0;
     uint32_t pid = 0;
     float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f), bn = f3(0.f, 0.f, 0.f);
     float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
     float best_t = 0.f; int best_id = 0, best_ref = 0; bool have = false;
     bool exhausted = false;
 
-    auto pop = [&]() {
-        for (;;) {
-            if (sp == 0) { state = DONE; return; }
+    auto pop = [&]() -> int {
+        while (sp > 0) {
             --sp;
-            if (stk_t[sp * stride] > best_t) continue;      // entered after the best hit found since the push
-            cur = stk[sp * stride];
-            return;
+            if (stk_t[sp * stride] > best_t) continue;       // entered after the best hit found since the push
+            return stk[sp * stride];
+        }
+        return NONE;
+    };
+    // keep at most one stashed leaf and, if there is more work, an inner node (or a second leaf) in `cur`
+    auto settle = [&]() {
+        if (cur == NONE) cur = pop();
+        if (cur < 0 && cur != NONE && leaf0 == NONE) { leaf0 = cur; cur = pop(); }
+        if (cur == NONE && leaf0 == NONE) state = DONE;
+    };
+    auto test_leaf = [&](int link) {
+        const unsigned int v = (unsigned int)(~link);
+        const int first = (int)(v & 0xffffffu), cnt = (int)(v >> 24);
+        for (int i = 0; i < cnt; ++i) {
+            const int r = refs[first + i];
+            if (r >= kTriRef) {
+                const int k = r - kTriRef;
+                float t; float3 nrm;
+                if (tri_hit(__ldg(sc.tri + 3 * k), __ldg(sc.tri + 3 * k + 1), __ldg(sc.tri + 3 * k + 2), o, d, t, nrm)) {
+                    const int oid = __ldg(sc.tri_obj + k);
+                    if (t < best_t || (t == best_t && (oid < best_id || (oid == best_id && r < best_ref)))) {
+                        best_t = t; best_id = oid; best_ref = r; bn = nrm; have = true;
+                    }
+                }
+            } else if (r >= 0) {
+                float t;
+                if (sphere_t(tc.sph[r], o, d, t)) {
+                    const int oid = sc.sph_id[r];
+                    if (t < best_t || (t == best_t && oid < best_id)) { best_t = t; best_id = oid; best_ref = r; have = true; }
+                }
+            } else {
+                const int j = ~r;
+                float dist; float3 nrm;
+                if (box_hit(tc.box[2 * j], tc.box[2 * j + 1], o, d, dist, nrm)) {
+                    const int oid = sc.box_id[j];
+                    if (dist < best_t || (dist == best_t && oid < best_id)) { best_t = dist; best_id = oid; best_ref = r; bn = nrm; have = true; }
+                }
+            }
         }
     };
 
     for (;;) {
+        // ---- refill ---------------------------------------------------------------------------------------
         const unsigned m_free = __ballot_sync(FULL, state != ACTIVE);
         if (__popc(m_free) >= kRefill || m_free == FULL) {
             if (state == DONE) {                             // write the pending hits together
@@ -225,79 +273,53 @@ __global__ void __launch_bounds__(kThreads, 6) k_wf_intersect_bvh(SceneView sc, 
                         const float4 o4 = ray_o[pid], d4 = ray_d[pid];
                         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
                         const float big = 1e30f;
-                        ix = fabsf(d.x) > 1e-30f ? 1.f / d.x : copysignf(big, d.x);
-                        iy = fabsf(d.y) > 1e-30f ? 1.f / d.y : copysignf(big, d.y);
-                        iz = fabsf(d.z) > 1e-30f ? 1.f / d.z : copysignf(big, d.z);
+                        ix = fabsf(d.x) > 1e-30f ? RTB_FAST_RCP(d.x) : copysignf(big, d.x);
+                        iy = fabsf(d.y) > 1e-30f ? RTB_FAST_RCP(d.y) : copysignf(big, d.y);
+                        iz = fabsf(d.z) > 1e-30f ? RTB_FAST_RCP(d.z) : copysignf(big, d.z);
                         ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
                         best_t = __int_as_float(0x7f800000); best_id = 0x7fffffff; best_ref = 0; have = false;
-                        cur = 0; sp = 0; state = ACTIVE;
+                        cur = 0; leaf0 = NONE; sp = 0; state = ACTIVE;
                     }
                 }
                 if (base + (unsigned int)__popc(m_idle) >= count) exhausted = true;       // warp-uniform
             }
             if (!__any_sync(FULL, state == ACTIVE)) break;    // nothing left to traverse (DONE lanes were flushed above)
         }
-#pragma unroll 1
-        for (int it = 0; it < kBurst; ++it) {
-            if (state != ACTIVE) continue;
-            if (cur >= 0) {                                   // inner node: both children's slabs
+        // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
+        for (;;) {
+            const bool in_node = state == ACTIVE && cur >= 0;
+            if (in_node) {
                 const float4 n0 = nodes[4 * cur], n1 = nodes[4 * cur + 1], n2 = nodes[4 * cur + 2];
                 const int2 ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
-                float a, b;
-                a = fmaf(n0.x, ix, ox); b = fmaf(n0.y, ix, ox);
-                float lo0 = fminf(a, b), hi0 = fmaxf(a, b);
-                a = fmaf(n0.z, iy, oy); b = fmaf(n0.w, iy, oy);
-                lo0 = fmaxf(lo0, fminf(a, b)); hi0 = fminf(hi0, fmaxf(a, b));
-                a = fmaf(n1.x, iz, oz); b = fmaf(n1.y, iz, oz);
-                lo0 = fmaxf(lo0, fminf(a, b)); hi0 = fminf(hi0, fmaxf(a, b));
-                a = fmaf(n1.z, ix, ox); b = fmaf(n1.w, ix, ox);
-                float lo1 = fminf(a, b), hi1 = fmaxf(a, b);
-                a = fmaf(n2.x, iy, oy); b = fmaf(n2.y, iy, oy);
-                lo1 = fmaxf(lo1, fminf(a, b)); hi1 = fminf(hi1, fmaxf(a, b));
-                a = fmaf(n2.z, iz, oz); b = fmaf(n2.w, iz, oz);
-                lo1 = fmaxf(lo1, fminf(a, b)); hi1 = fminf(hi1, fmaxf(a, b));
+                const float ax0 = fmaf(n0.x, ix, ox), bx0 = fmaf(n0.y, ix, ox), ay0 = fmaf(n0.z, iy, oy), by0 = fmaf(n0.w, iy, oy);
+                const float az0 = fmaf(n1.x, iz, oz), bz0 = fmaf(n1.y, iz, oz);
+                const float ax1 = fmaf(n1.z, ix, ox), bx1 = fmaf(n1.w, ix, ox), ay1 = fmaf(n2.x, iy, oy), by1 = fmaf(n2.y, iy, oy);
+                const float az1 = fmaf(n2.z, iz, oz), bz1 = fmaf(n2.w, iz, oz);
+                const float lo0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fminf(az0, bz0));
+                const float hi0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fmaxf(az0, bz0));
+                const float lo1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fminf(az1, bz1));
+                const float hi1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fmaxf(az1, bz1));
                 const bool h0 = lo0 <= hi0 && hi0 >= 0.f && lo0 <= best_t;
                 const bool h1 = lo1 <= hi1 && hi1 >= 0.f && lo1 <= best_t;
                 if (h0 && h1) {
                     const bool swap = lo1 < lo0;
-                    stk[sp * stride] = swap ? ch.x : ch.y;
+                    const int far_link = swap ? ch.x : ch.y;
+                    stk[sp * stride] = far_link;
                     stk_t[sp * stride] = swap ? lo0 : lo1;
                     ++sp;
                     cur = swap ? ch.y : ch.x;
                 } else if (h0) cur = ch.x;
                 else if (h1) cur = ch.y;
-                else pop();
-            } else {                                          // leaf: strict tests on its primitives, then pop
-                const unsigned int v = (unsigned int)(~cur);
-                const int first = (int)(v & 0xffffffu), cnt = (int)(v >> 24);
-                for (int i = 0; i < cnt; ++i) {
-                    const int r = refs[first + i];
-                    if (r >= kTriRef) {
-                        const int k = r - kTriRef;
-                        float t; float3 nrm;
-                        if (tri_hit(__ldg(sc.tri + 3 * k), __ldg(sc.tri + 3 * k + 1), __ldg(sc.tri + 3 * k + 2), o, d, t, nrm)) {
-                            const int oid = __ldg(sc.tri_obj + k);
-                            if (t < best_t || (t == best_t && (oid < best_id || (oid == best_id && r < best_ref)))) {
-                                best_t = t; best_id = oid; best_ref = r; bn = nrm; have = true;
-                            }
-                        }
-                    } else if (r >= 0) {
-                        float t;
-                        if (sphere_t(tc.sph[r], o, d, t)) {
-                            const int oid = sc.sph_id[r];
-                            if (t < best_t || (t == best_t && oid < best_id)) { best_t = t; best_id = oid; best_ref = r; have = true; }
-                        }
-                    } else {
-                        const int j = ~r;
-                        float dist; float3 nrm;
-                        if (box_hit(tc.box[2 * j], tc.box[2 * j + 1], o, d, dist, nrm)) {
-                            const int oid = sc.box_id[j];
-                            if (dist < best_t || (dist == best_t && oid < best_id)) { best_t = dist; best_id = oid; best_ref = r; bn = nrm; have = true; }
-                        }
-                    }
-                }
-                pop();
+                else cur = NONE;
+                settle();
             }
+            if (__popc(__ballot_sync(FULL, state == ACTIVE && cur >= 0)) < kNodeMin) break;
+        }
+        // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
+        if (state == ACTIVE) {
+            if (leaf0 != NONE) { test_leaf(leaf0); leaf0 = NONE; }
+            if (cur < 0 && cur != NONE) { test_leaf(cur); cur = NONE; }
+            settle();
         }
     }
 }
@@ -418,7 +440,9 @@ void wavefront_destroy(WavefrontBuffers* wb) {
 
 cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
                                     float4* accum, uint32_t s_begin, int n_samples, bool reuse, unsigned long long* seg_counter,
-                                    cudaStream_t st, bool bvh_refill) {
+                                    cudaStream_t st, bool bvh_refill, int k_refill, int k_node_min) {
+    if (k_refill < 1) k_refill = 1; if (k_refill > 32) k_refill = 32;
+    if (k_node_min < 1) k_node_min = 1; if (k_node_min > 32) k_node_min = 32;
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_optin();
     if (e != cudaSuccess) return e;
@@ -490,10 +514,10 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
             switch (mode) {
                 case 0: k_wf_intersect<0><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
                 case 1: k_wf_intersect<1><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
-                case 2: if (bvh_refill) k_wf_intersect_bvh<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
+                case 2: if (bvh_refill) k_wf_intersect_bvh<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id, k_refill, k_node_min);
                         else k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
                         break;
-                case 3: if (bvh_refill) k_wf_intersect_bvh<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
+                case 3: if (bvh_refill) k_wf_intersect_bvh<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id, k_refill, k_node_min);
                         else k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
                         break;
                 default: k_wf_intersect<4><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
