@@ -758,6 +758,14 @@ int rt_resolve_rgba8(rt_ctx* c, uint32_t* host_out, int pitch_bytes, int flip_y)
     return RT_OK;
 }
 
+void* rt_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void rt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int rt_read_accum(rt_ctx* c, float* host_rgba, uint32_t* samples) {
     int rc = prepare(c);
     if (rc != RT_OK) return rc;

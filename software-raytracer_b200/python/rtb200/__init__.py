@@ -62,7 +62,7 @@ EXPORTS = [
     "rt_read_accum", "rt_read_aov", "rt_read_ray_dirs", "rt_trace_rays", "rt_env_color", "rt_philox_block",
     "rt_scene_file_read", "rt_scene_file_read_names", "rt_scene_file_write", "rt_object_name", "rt_set_object_name", "rt_scene_name",
     "rt_write_accum", "rt_selftest", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
-    "rt_set_mesh", "rt_load_mesh_obj", "rt_get_mesh_info", "rt_set_pixel_step", "rt_reference_pixel_step", "rt_reference_strip_columns",
+    "rt_host_alloc", "rt_host_free", "rt_set_mesh", "rt_load_mesh_obj", "rt_get_mesh_info", "rt_set_pixel_step", "rt_reference_pixel_step", "rt_reference_strip_columns",
     "rt_argb_device_ptr", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_resolve_fused", "rt_read_surface",
 ]
 
@@ -94,7 +94,7 @@ def load_library(path=None):
     lib.rt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name in ("rt_last_error", "rt_accum_device_ptr", "rt_argb_device_ptr", "rt_create", "rt_default_params", "rt_default_camera",
+        if name in ("rt_host_alloc", "rt_host_free", "rt_last_error", "rt_accum_device_ptr", "rt_argb_device_ptr", "rt_create", "rt_default_params", "rt_default_camera",
                     "rt_rotate_camera", "rt_abi_version", "rt_object_name", "rt_scene_name"):
             continue
         fn.restype = C.c_int
@@ -102,6 +102,10 @@ def load_library(path=None):
     lib.rt_object_name.argtypes = [C.c_void_p, C.c_int]
     lib.rt_scene_name.restype = C.c_char_p
     lib.rt_scene_name.argtypes = [C.c_void_p]
+    lib.rt_host_alloc.restype = C.c_void_p
+    lib.rt_host_alloc.argtypes = [C.c_size_t]
+    lib.rt_host_free.restype = None
+    lib.rt_host_free.argtypes = [C.c_void_p]
     lib.rt_default_params.restype = None
     lib.rt_default_camera.restype = None
     lib.rt_rotate_camera.restype = None
@@ -162,6 +166,20 @@ def scene_file_write(path, objs, names=None, scene_name=""):
     if names is not None:
         arr = (C.c_char_p * len(objs))(*[n.encode() for n in names])
     return lib.rt_scene_file_write(str(path).encode(), scene_name.encode(), _p(objs), arr, len(objs))
+
+
+def host_surface(width, height):
+    """A page-locked (height, width) uint32 array for resolve_rgba8 / read_surface; keep the returned owner alive."""
+    lib = load_library()
+    ptr = lib.rt_host_alloc(width * height * 4)
+    if not ptr:
+        raise MemoryError("rt_host_alloc failed")
+
+    class _Owner:
+        def __del__(self):
+            lib.rt_host_free(ptr)
+    arr = np.ctypeslib.as_array((C.c_uint32 * (width * height)).from_address(ptr)).reshape(height, width)
+    return arr, _Owner()
 
 
 def reference_pixel_step(screen_scale, progressive_scaler=1.0):
