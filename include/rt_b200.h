@@ -114,6 +114,7 @@ enum {
     RT_OPT_BVH_LEAF = 6,           /* BVH builder: maximum primitives per leaf (default 4) */
     RT_OPT_WF_REFILL = 8,          /* wavefront BVH intersect: free lanes that trigger a ray refill (default 8) */
     RT_OPT_WF_NODE_MIN = 9,        /* wavefront BVH intersect: lanes with inner-node work below which pending leaves are tested (default 8) */
+    RT_OPT_POOL_TILES = 10,        /* megakernel, few samples per call: 8x4 pixel tiles per warp-level pixel pool; 0 (default) automatic, 1 one pixel per lane */
     RT_OPT_PRIMARY_REUSE = 7       /* 1 (default): one primary closest-hit query per pixel per rt_render_spp call,
                                       reused by every sample (identical ray: the reference has no pixel jitter);
                                       0: re-trace it for every sample like the reference. Results are bit-identical. */

@@ -77,7 +77,7 @@ struct rt_ctx {
     int pixel_step = 1, strip_columns = 0;   // block-filled frames (rt_set_pixel_step)
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
     int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4, opt_primary_reuse = 1;
-    int opt_wf_refill = 8, opt_wf_node_min = 8;
+    int opt_wf_refill = 8, opt_wf_node_min = 8, opt_pool_tiles = 0;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
     int tuned_pipeline = -1;       // RT_PIPELINE_AUTO decision for large BVH scenes (-1: not measured yet)
     float tune_pipe_ms[2] = {0.f, 0.f};
@@ -627,6 +627,7 @@ int rt_set_option(rt_ctx* c, int option, int value) {
         case RT_OPT_BVH_SCHED: c->opt_bvh_sched = value; return RT_OK;
         case RT_OPT_BVH_LEAF: c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
         case RT_OPT_PRIMARY_REUSE: c->opt_primary_reuse = value != 0; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
+        case RT_OPT_POOL_TILES: c->opt_pool_tiles = value < 0 ? 0 : value; return RT_OK;
         case RT_OPT_WF_REFILL: c->opt_wf_refill = value; return RT_OK;
         case RT_OPT_WF_NODE_MIN: c->opt_wf_node_min = value; return RT_OK;
         case RT_OPT_BVH_WAIT_K: c->opt_bvh_wait_k = value < 1 ? 1 : value; return RT_OK;
@@ -717,7 +718,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
         } else if (ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0)
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else
-            RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream));
+            RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_pool_tiles));
         if (!wavefront) c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce

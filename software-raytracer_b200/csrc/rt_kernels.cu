@@ -169,6 +169,94 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     }
 }
 
+// ---- few samples per pixel: warp-level pixel pool -------------------------------------------------------------
+// With one lane per pixel a launch of n samples keeps a warp busy for the LONGEST of its 32 pixels' work; for large
+// n that averages out (29.8 of 32 lanes alive at 1024 spp), but an interactive 1-spp frame runs ~4.5 warp iterations
+// for 2.1 segments per path. Here a warp owns `pool_tiles` consecutive 8x4 pixel tiles and its lanes pull PIXELS
+// from that pool (one ballot + popcount, no atomics): a lane that finishes a pixel's n samples starts the next
+// pixel at once. One pixel is still traced by one lane, samples in order, one write: the same bits as k_render_regen.
+template <int MODE, bool REUSE>
+__global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
+                                                           uint32_t s_begin, int n_samples, int pool_tiles,
+                                                           unsigned long long* __restrict__ seg_counter) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = (fr.width + 7) / 8, tiles_y = (fr.height + 3) / 4;
+    const long long warp_id = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long tile0 = warp_id * pool_tiles;
+    const long long n_tiles = (long long)tiles_x * tiles_y;
+    long long rem = n_tiles - tile0;
+    const int total = rem <= 0 ? 0 : (int)(rem < pool_tiles ? rem : pool_tiles) * 32;     // pool entries (some outside the image)
+    int next = 0;                                                                           // warp-uniform
+
+    bool busy = false, primary = false;
+    uint32_t pixel = 0;
+    float3 d0 = f3(0.f, 0.f, 1.f), acc = f3(0.f, 0.f, 0.f), o = fr.cam_pos, d = d0;
+    float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
+    int s = 0, depth = 0;
+    unsigned int segs = 0, traced = 0;
+    Hit h0;
+    h0.id = -1; h0.t = 0.f; h0.n = f3(0.f, 0.f, 0.f); h0.p = f3(0.f, 0.f, 0.f);
+
+    for (;;) {
+        const unsigned m_need = __ballot_sync(FULL, !busy);
+        if (m_need != 0u && next < total) {
+            const int idx = next + __popc(m_need & ((1u << lane) - 1u));
+            next += __popc(m_need);
+            if (!busy && idx < total) {
+                const long long tile = tile0 + (idx >> 5);
+                const int px = (int)(tile % tiles_x) * 8 + (idx & 7), py = (int)(tile / tiles_x) * 4 + ((idx & 31) >> 3);
+                if (px < fr.width && py < fr.height) {
+                    pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
+                    d0 = ray_dir(fr, px, py);
+                    acc = f3(0.f, 0.f, 0.f); o = fr.cam_pos; d = d0; s = 0; depth = 0;
+                    busy = true; primary = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, busy)) { if (next >= total) break; else continue; }
+        if (busy) {
+            Hit h = trace<MODE>(sc, tc, o, d);
+            ++segs; ++traced;
+            bool scatter = true;
+            if (REUSE && primary) h0 = h;
+            float3 c;
+            if (path_ends(sc, fr, h, d, T, L, depth, c)) {
+                scatter = false;
+                if (REUSE && primary) {
+                    // the primary ray misses (or max_bounces == 0): every sample of the pixel has the value c
+                    for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
+                    segs += (unsigned int)(n_samples - 1);
+                } else {
+                    acc.x += c.x; acc.y += c.y; acc.z += c.z;
+                    ++s; depth = 0; o = fr.cam_pos; d = d0;
+                    if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }     // next sample from the cached primary hit
+                }
+            }
+            primary = false;
+            if (s >= n_samples) {
+                float4 a = accum[pixel];
+                a.x += acc.x; a.y += acc.y; a.z += acc.z;
+                accum[pixel] = a;
+                busy = false;
+            } else if (scatter) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
+        }
+    }
+
+    unsigned int total_s = segs, total_tr = traced;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        total_s += __shfl_down_sync(FULL, total_s, off);
+        total_tr += __shfl_down_sync(FULL, total_tr, off);
+    }
+    if (lane == 0 && total_s) {
+        atomicAdd(seg_counter, (unsigned long long)total_s); atomicAdd(seg_counter + 1, (unsigned long long)total_s);
+        atomicAdd(seg_counter + 2, (unsigned long long)total_tr); atomicAdd(seg_counter + 3, (unsigned long long)total_tr);
+    }
+}
+
 // ---- BVH render kernel with warp-level phase scheduling ---------------------------------------
 // Same lane-owns-a-pixel / regeneration scheme as k_render_regen, but the BVH traversal is an
 // explicit per-lane state machine and the WARP decides what runs next, so no lane waits for the
@@ -499,7 +587,7 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(K<2, false>)) != cudaSuccess) return e; if ((e = optin(K<2, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<3, false>)) != cudaSuccess) return e; if ((e = optin(K<3, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<4, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true>)) != cudaSuccess) return e;
-    RTB_OPTIN2(k_render_regen) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick) RTB_OPTIN(k_render_blocks)
+    RTB_OPTIN2(k_render_regen) RTB_OPTIN2(k_render_pool) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick) RTB_OPTIN(k_render_blocks)
     if ((e = optin(k_render_bvh<2>)) != cudaSuccess) return e;
     if ((e = optin(k_render_bvh<3>)) != cudaSuccess) return e;
 #undef RTB_OPTIN
@@ -576,11 +664,27 @@ cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView
 }
 
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
-                                uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st) {
+                                uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st, int pool_override) {
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
     size_t sb; const int mode = pick_mode(sc, ac, sb);
+    // few samples per launch: lanes pull pixels from a warp-level pool (k_render_pool); many: one pixel per lane.
+    // Measured (scratch/pool_sweep.py, Scene1): pools pay while the grid still has several waves of warps - 2 tiles at
+    // 1 spp (720p 0.205 -> 0.181 ms), 4 tiles at 1080p (0.427 -> 0.329 ms), 2 tiles up to 4 spp at 1080p; larger pools
+    // lose to the imbalance between warps, and from 16 spp on one pixel per lane is as good.
+    const long long n_tiles_all = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
+    int pool_tiles = 1;
+    if (pool_override > 0) pool_tiles = pool_override > 32 ? 32 : pool_override;
+    else if (n_samples == 1) pool_tiles = n_tiles_all >= 50000 ? 4 : 2;
+    else if (n_samples <= 4 && n_tiles_all >= 50000) pool_tiles = 2;
+    if (pool_tiles >= 2) {
+        const long long n_tiles = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
+        const long long warps = (n_tiles + pool_tiles - 1) / pool_tiles;
+        const unsigned int blocks = (unsigned int)((warps + kThreads / 32 - 1) / (kThreads / 32));
+        RTB_DISPATCH2(mode, reuse_primary, k_render_pool, blocks, sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, seg_counter)
+        return cudaGetLastError();
+    }
     RTB_DISPATCH2(mode, reuse_primary, k_render_regen, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter)
     return cudaGetLastError();
 }

@@ -846,3 +846,25 @@ def test_flat_accel_degenerate_scenes(tracer):
         else:
             assert f[3] == rtb200.RT_ACCEL_FLAT, name
     assert (out[rtb200.RT_ACCEL_FLAT][0][0] >= 0).any()
+
+
+@pytest.mark.parametrize("scene", ["Scene1", "Scene_indirect"])
+def test_pixel_pool_kernel_is_bit_identical(tracer, scenes, scene):
+    """k_render_pool (lanes pull pixels from a warp-level pool, used for 1..4-spp launches) vs one pixel per lane."""
+    out = {}
+    try:
+        for reuse in (1, 0):
+            tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, reuse)
+            for pool in (1, 2, 5, 32):
+                tracer.set_option(rtb200.RT_OPT_POOL_TILES, pool)
+                for (w, h, mb) in ((333, 77, 8), (160, 120, 0)):
+                    setup(tracer, scenes[scene], w, h, max_bounces=mb)
+                    tracer.render_spp(1); tracer.render_spp(3); tracer.render_spp(7)
+                    st = tracer.stats()
+                    out[(reuse, pool, w)] = (tracer.read_accum()[0], st.segments, st.traced_segments, st.paths)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_POOL_TILES, 0)
+        tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 1)
+    for (reuse, pool, w), v in out.items():
+        base = out[(reuse, 1, w)]
+        assert np.array_equal(bits(v[0]), bits(base[0])) and v[1:] == base[1:], (reuse, pool, w)
