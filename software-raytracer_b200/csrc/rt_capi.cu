@@ -483,9 +483,10 @@ int rt_set_scene(rt_ctx* c, const rt_object* objects, int n) {
         }
     }
     const int keep_tuned = same ? c->tuned_accel : -1, keep_pipe = same ? c->tuned_pipeline : -1;
+    const bool keep_flat = same && c->flat_valid;
     int rc = upload_scene(c);
     if (rc != RT_OK) return rc;
-    if (same) c->bvh_valid = true;
+    if (same) { c->bvh_valid = true; c->flat_valid = keep_flat; }
     c->tuned_accel = keep_tuned; c->tuned_pipeline = keep_pipe;
     return rt_reset_accumulation(c);
 }
