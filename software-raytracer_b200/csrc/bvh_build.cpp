@@ -127,7 +127,8 @@ struct Builder {
 
 }  // namespace
 
-void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf, const TriRecords* tris) {
+void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf, const TriRecords* tris,
+               float origin_offset) {
     out = HostBvh();
     Builder b; b.out = &out;
     b.kMaxLeaf = max_leaf < 1 ? 1 : (max_leaf > 64 ? 64 : max_leaf);
@@ -175,7 +176,8 @@ void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostB
     float extent = std::fabs(origin_extent);
     if (scene.valid())
         for (int k = 0; k < 3; ++k) extent = std::max(extent, std::max(std::fabs(scene.lo[k]), std::fabs(scene.hi[k])));
-    if (extent > 1e29f) extent = 1e29f;
+    extent += std::isfinite(origin_offset) ? std::fabs(origin_offset) : 1e29f;     // secondary origins sit eps off their surface
+    if (!(extent <= 1e29f)) extent = 1e29f;
     out.extent = extent;
     out.inflate_abs = kInflate * std::max(extent, 1e-3f);
     b.eps = out.inflate_abs;

@@ -51,6 +51,6 @@ constexpr int kMaxBvhDepth = 40;     // traversal stack entries per thread
 // objects: the scene in list order. origin_extent: largest |coordinate| of any ray origin that will be
 // traced from outside the scene bounds (the camera position); secondary origins lie on surfaces.
 void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf = 4,
-               const TriRecords* tris = nullptr);
+               const TriRecords* tris = nullptr, float origin_offset = 0.f);   // origin_offset: |rt_params.eps|
 
 }  // namespace rtb

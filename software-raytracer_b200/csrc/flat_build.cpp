@@ -36,7 +36,7 @@ void split_groups(std::vector<Sph>& s, int first, int count, std::vector<std::pa
 
 }  // namespace
 
-void build_flat(const std::vector<rt_object>& objects, float origin_extent, HostFlat& out) {
+void build_flat(const std::vector<rt_object>& objects, float origin_extent, HostFlat& out, float origin_offset) {
     out = HostFlat();
     const double u = std::ldexp(1.0, -24);
     std::vector<Sph> sph;
@@ -75,8 +75,10 @@ void build_flat(const std::vector<rt_object>& objects, float origin_extent, Host
             cubes.push_back(c); ++n_box;
         }
     }
-    if (!finite || coord_max > 1e15 || n_sph + n_box > kFlatMaxPrims || n_sph + n_box == 0) return;
-    omax = omax * (1.0 + 1e-4) + 1e-2;                                 // eps offset along the normal, slack
+    if (!finite || !(std::fabs((double)origin_offset) < 1e15) || coord_max > 1e15 || n_sph + n_box > kFlatMaxPrims || n_sph + n_box == 0) return;
+    const double off = std::isfinite(origin_offset) ? std::fabs((double)origin_offset) : 1e30;
+    omax = omax * (1.0 + 1e-4) + 1e-2 + off;                           // eps offset along the normal, slack
+    coord_max += off;
     out.extent = (float)coord_max;
     out.inflate_abs = kInflate * std::max((float)coord_max, 1e-3f);
     out.kappa = (float)(1.0 - 64.0 * u);                               // 1 - 2^-18, exact in float

@@ -61,6 +61,7 @@ struct HostFlat {
 };
 
 // objects: the scene in list order; origin_extent: largest |coordinate| of any ray origin outside the scene.
-void build_flat(const std::vector<rt_object>& objects, float origin_extent, HostFlat& out);
+// origin_offset: |rt_params.eps|, how far a secondary origin may sit off its surface (Raytracer.cpp:177).
+void build_flat(const std::vector<rt_object>& objects, float origin_extent, HostFlat& out, float origin_offset = 0.f);
 
 }  // namespace rtb

@@ -180,7 +180,7 @@ int upload_scene(rt_ctx* c) {
 // box inflation was derived from.
 int ensure_bvh(rt_ctx* c, float origin_extent) {
     if (c->bvh_valid && origin_extent <= c->bvh.extent) return RT_OK;
-    build_bvh(c->scene.objects, origin_extent, c->bvh, c->opt_bvh_leaf, &c->tris);
+    build_bvh(c->scene.objects, origin_extent, c->bvh, c->opt_bvh_leaf, &c->tris, c->par.eps);
     if (c->bvh.max_depth + 2 > 62) return fail(c, RT_ERR_INVALID, "BVH too deep for the traversal stack");
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     RT_CUDA(c, ensure_capacity(c->d_bvh_nodes, c->cap_bvh_nodes, c->bvh.nodes.size() * 4));
@@ -199,7 +199,7 @@ int ensure_bvh(rt_ctx* c, float origin_extent) {
 // (Re)builds and uploads the flat accelerator; c->flat.usable tells whether the scene qualifies.
 int ensure_flat(rt_ctx* c, float origin_extent) {
     if (c->flat_valid && origin_extent <= c->flat.extent) return RT_OK;
-    build_flat(c->scene.objects, origin_extent, c->flat);
+    build_flat(c->scene.objects, origin_extent, c->flat, c->par.eps);
     c->flat_valid = true;
     memset(&c->fview, 0, sizeof c->fview);
     if (!c->flat.usable) return RT_OK;
@@ -605,6 +605,7 @@ int rt_set_params(rt_ctx* c, const rt_params* p) {
         return fail(c, RT_ERR_INVALID, "rt_set_params: bad resolution");
     if (p->mode != RT_MODE_PATH && p->mode != RT_MODE_PREVIEW) return fail(c, RT_ERR_INVALID, "rt_set_params: bad mode");
     bool resized = p->width != c->par.width || p->height != c->par.height;
+    if (!(fabsf(p->eps) <= fabsf(c->par.eps))) { c->bvh_valid = false; c->flat_valid = false; }   // margins were derived for the old offset
     if (resized || p->max_bounces != c->par.max_bounces || p->mode != c->par.mode) c->tuned_accel = c->tuned_pipeline = -1;
     c->par = *p;
     if (c->par.max_bounces < 0) c->par.max_bounces = 0;        // MAXBOUNCES = max(MAXBOUNCES, 0) Raytracer.cpp:475

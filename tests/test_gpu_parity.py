@@ -868,3 +868,21 @@ def test_pixel_pool_kernel_is_bit_identical(tracer, scenes, scene):
     for (reuse, pool, w), v in out.items():
         base = out[(reuse, 1, w)]
         assert np.array_equal(bits(v[0]), bits(base[0])) and v[1:] == base[1:], (reuse, pool, w)
+
+
+def test_large_secondary_offset_keeps_accelerators_exact(tracer, scenes):
+    """rt_params.eps (the secondary-origin offset, Raytracer.cpp:177) far larger than the reference's 1e-5: origins then sit
+    well off their surfaces (inside neighbouring spheres, outside the scene bounds); the accelerators' margins follow it."""
+    for eps in (0.3, 25.0):
+        out = {}
+        try:
+            for accel in (rtb200.RT_ACCEL_FLAT, rtb200.RT_ACCEL_BVH, rtb200.RT_ACCEL_BRUTE):
+                tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+                setup(tracer, scenes["Scene1"], 160, 120, eps=eps)
+                tracer.render_spp(6)
+                out[accel] = (tracer.read_accum()[0], tracer.stats().segments)
+        finally:
+            tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        b = out[rtb200.RT_ACCEL_BRUTE]
+        for accel in (rtb200.RT_ACCEL_FLAT, rtb200.RT_ACCEL_BVH):
+            assert np.array_equal(bits(out[accel][0]), bits(b[0])) and out[accel][1] == b[1], (eps, accel)
