@@ -179,6 +179,8 @@ def run_b200(args):
         tr.set_option(rtb200.RT_OPT_BVH_SCHED, args.bvh_sched)
     if args.wait_k >= 0:
         tr.set_option(rtb200.RT_OPT_BVH_WAIT_K, args.wait_k)
+    if args.flat_coop >= 0:
+        tr.set_option(rtb200.RT_OPT_FLAT_COOP, args.flat_coop)
     if args.wf_refill >= 0:
         tr.set_option(rtb200.RT_OPT_WF_REFILL, args.wf_refill)
     if args.wf_node_min >= 0:
@@ -413,6 +415,7 @@ def main():
     ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"], help="N > 1 exchange: fused peer-memory reduce+resolve kernel, or NCCL all-reduce")
     ap.add_argument("--bvh-sched", type=int, default=-1, help="RT_OPT_BVH_SCHED override")
     ap.add_argument("--wait-k", type=int, default=-1, help="RT_OPT_BVH_WAIT_K override")
+    ap.add_argument("--flat-coop", type=int, default=-1, help="RT_OPT_FLAT_COOP: 0 per-lane levels 2/3, 1 warp-cooperative, 2 measured per scene (default)")
     ap.add_argument("--wf-refill", type=int, default=-1, help="RT_OPT_WF_REFILL override")
     ap.add_argument("--wf-node-min", type=int, default=-1, help="RT_OPT_WF_NODE_MIN override")
     ap.add_argument("--scene", default="Scene1", help="bundled scene fixture (the headline config is Scene1)")

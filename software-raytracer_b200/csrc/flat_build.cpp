@@ -128,6 +128,9 @@ void build_flat(const std::vector<rt_object>& objects, float origin_extent, Host
                 out.cull_slot.push_back(255);
             }
         }
+        for (int pad = kFlatClusterSize; pad < kFlatClusterStride; ++pad) {   // bank-conflict padding, never read as a slot
+            out.cull.push_back(0.f); out.cull.push_back(0.f); out.cull.push_back(0.f); out.cull.push_back(-1e30f);
+        }
         push_box(lo, hi);
     }
     for (const Cube& c : cubes) push_box(c.lo, c.hi);

@@ -41,6 +41,8 @@
 namespace rtb {
 
 constexpr int kFlatClusterSize = 8;      // sphere slots per cluster (padded with never-hit dummies)
+constexpr int kFlatClusterStride = 9;    // cull records per cluster in memory: 8 + 1 pad, so that lanes reading the same slot of
+                                         // DIFFERENT clusters hit different shared-memory banks (stride 144 B instead of 128 B)
 constexpr int kFlatMaxPrims = 255;       // candidate codes are bytes
 constexpr int kFlatMaxClusters = 32;     // level-1 cluster boxes: one mask word
 constexpr int kFlatMaxLevel1 = 56;       // cubes + single spheres: they enter the 64-entry candidate queue before any cluster
@@ -51,9 +53,9 @@ struct HostFlat {
     // (cluster k owns cull slots [8k, 8k+8)), entries [n_clusters, n_clusters + n_cubes) are the cubes in
     // cube-slot order.
     std::vector<float> boxes;            // 8 floats per box
-    // conservative sphere records (cx, cy, cz, R'): first 8*n_clusters cluster slots, then the singles
-    std::vector<float> cull;             // 4 floats per slot
-    std::vector<uint8_t> cull_slot;      // sphere slot (index into the exact sphere list) per cull slot; 255 = dummy
+    // conservative sphere records (cx, cy, cz, R'): kFlatClusterStride records per cluster (8 slots + pad), then the singles
+    std::vector<float> cull;             // 4 floats per record
+    std::vector<uint8_t> cull_slot;      // sphere slot (index into the exact sphere list): 8 per cluster (no pad; 255 = dummy), then the singles
     std::vector<int32_t> prim_id;        // candidate code (sphere slot, or n_spheres + cube slot) -> object id
     int n_clusters = 0, n_cubes = 0, n_singles = 0;
     float kappa = 1.f;

@@ -77,12 +77,13 @@ struct rt_ctx {
     int pixel_step = 1, strip_columns = 0;   // block-filled frames (rt_set_pixel_step)
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
     int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4, opt_primary_reuse = 1;
-    int opt_wf_refill = 8, opt_wf_node_min = 8, opt_pool_tiles = 0;
+    int opt_wf_refill = 8, opt_wf_node_min = 8, opt_pool_tiles = 0, opt_flat_coop = 2;   // flat_coop: 0 off, 1 on, 2 measured per scene
+    int tuned_flat_coop = 1;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
     int tuned_pipeline = -1;       // RT_PIPELINE_AUTO decision for large BVH scenes (-1: not measured yet)
     float tune_pipe_ms[2] = {0.f, 0.f};
     float4* d_tune = nullptr; size_t cap_tune = 0;
-    float tune_ms[3] = {0.f, 0.f, 0.f};
+    float tune_ms[4] = {0.f, 0.f, 0.f, 0.f};
     int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;
     float last_render_ms = 0.f, last_resolve_ms = 0.f;
     bool render_timed = false, resolve_timed = false;
@@ -266,33 +267,37 @@ int autotune_accel(rt_ctx* c) {
     const int n = c->view.n_sph + c->view.n_box + c->view.n_tri;
     if (n < 8) { c->tuned_accel = RT_ACCEL_BRUTE; return RT_OK; }
     if (n >= c->opt_bvh_threshold || c->view.n_tri > 0) { c->tuned_accel = RT_ACCEL_BVH; return RT_OK; }
-    const int kinds[3] = {RT_ACCEL_BRUTE, RT_ACCEL_BVH, RT_ACCEL_FLAT};
-    AccelSel sel[3];
+    // candidates: brute force, BVH, flat with warp-cooperative levels 2/3, flat with per-lane levels 2/3
+    const int kinds[4] = {RT_ACCEL_BRUTE, RT_ACCEL_BVH, RT_ACCEL_FLAT, RT_ACCEL_FLAT};
+    const bool coop[4] = {false, false, c->opt_flat_coop != 0, false};
+    const int n_cand = c->opt_flat_coop == 2 ? 4 : 3;
+    AccelSel sel[4];
     int rc;
-    for (int k = 0; k < 3; ++k) if ((rc = make_accel(c, kinds[k], camera_extent(c), sel[k])) != RT_OK) return rc;
+    for (int k = 0; k < n_cand; ++k) if ((rc = make_accel(c, kinds[k], camera_extent(c), sel[k])) != RT_OK) return rc;
     const size_t px = (size_t)c->par.width * c->par.height;
     RT_CUDA(c, ensure_capacity(c->d_tune, c->cap_tune, px));
-    cudaEvent_t e[4];
+    cudaEvent_t e[5];
     for (auto& ev : e) RT_CUDA(c, cudaEventCreate(&ev));
     unsigned long long* dummy = c->d_counters + 4;            // not part of the reported statistics
     cudaError_t err = cudaSuccess;
     const bool reuse = c->opt_primary_reuse != 0;
     for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 warms the instruction cache
         cudaEventRecord(e[0], c->stream);
-        for (int k = 0; k < 3 && err == cudaSuccess; ++k) {
-            err = launch_render_regen(c->view, sel[k], c->frame, c->d_tune, 0u, 4, reuse, dummy, c->stream);
+        for (int k = 0; k < n_cand && err == cudaSuccess; ++k) {
+            err = launch_render_regen(c->view, sel[k], c->frame, c->d_tune, 0u, 8, reuse, dummy, c->stream, 1, coop[k]);
             cudaEventRecord(e[k + 1], c->stream);
         }
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
-    if (err == cudaSuccess) for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&c->tune_ms[k], e[k], e[k + 1]);
+    if (err == cudaSuccess) for (int k = 0; k < n_cand; ++k) cudaEventElapsedTime(&c->tune_ms[k], e[k], e[k + 1]);
     for (auto& ev : e) cudaEventDestroy(ev);
     if (err != cudaSuccess) return cuda_fail(c, err, "autotune_accel");
     int best = 0;
-    for (int k = 1; k < 3; ++k) {
+    for (int k = 1; k < n_cand; ++k) {
         if (kinds[k] == RT_ACCEL_FLAT && sel[k].kind != kAccelFlat) continue;   // scene does not qualify
         if (c->tune_ms[k] < c->tune_ms[best]) best = k;
     }
+    c->tuned_flat_coop = coop[best] ? 1 : 0;
     c->tuned_accel = kinds[best];
     return RT_OK;
 }
@@ -629,6 +634,7 @@ int rt_set_option(rt_ctx* c, int option, int value) {
         case RT_OPT_BVH_SCHED: c->opt_bvh_sched = value; return RT_OK;
         case RT_OPT_BVH_LEAF: c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
         case RT_OPT_PRIMARY_REUSE: c->opt_primary_reuse = value != 0; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
+        case RT_OPT_FLAT_COOP: c->opt_flat_coop = value < 0 || value > 2 ? 2 : value; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
         case RT_OPT_POOL_TILES: c->opt_pool_tiles = value < 0 ? 0 : value; return RT_OK;
         case RT_OPT_WF_REFILL: c->opt_wf_refill = value; return RT_OK;
         case RT_OPT_WF_NODE_MIN: c->opt_wf_node_min = value; return RT_OK;
@@ -720,7 +726,8 @@ int rt_render_spp(rt_ctx* c, int spp) {
         } else if (ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0)
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else
-            RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_pool_tiles));
+            RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_pool_tiles,
+                                           c->opt_flat_coop == 2 ? (c->opt_accel == RT_ACCEL_AUTO ? c->tuned_flat_coop != 0 : true) : c->opt_flat_coop != 0));
         if (!wavefront) c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce

@@ -122,32 +122,37 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     // every sample of the pixel has the same value: add it n times, in order, and the lane is done.
     Hit h0;
     h0.id = -1; h0.t = 0.f; h0.n = f3(0.f, 0.f, 0.f); h0.p = f3(0.f, 0.f, 0.f);
-    if (REUSE && n_samples > 0) {
-        h0 = trace<MODE>(sc, tc, o, d);
-        traced = 1;
-        float3 c;
-        if (path_ends(sc, fr, h0, d, T, L, 0, c)) {
-            for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
-            segs = (unsigned int)n_samples;
-        } else {
-            scatter_segment(sc, fr, h0, pixel, s_begin, o, d, T, L, depth);
-            segs = 1;
+    if (REUSE) {
+        h0 = trace_all<MODE>(sc, tc, o, d, n_samples > 0);  // all lanes call: MODE 5 pools the work across the warp
+        if (n_samples > 0) {
+            traced = 1;
+            float3 c;
+            if (path_ends(sc, fr, h0, d, T, L, 0, c)) {
+                for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
+                segs = (unsigned int)n_samples;
+            } else {
+                scatter_segment(sc, fr, h0, pixel, s_begin, o, d, T, L, depth);
+                segs = 1;
+            }
         }
     }
     // Main loop: one closest-hit query per lane per iteration, then ONE pass through each shading block - the
     // flag (instead of continue/break) lets the warp reconverge before the scatter block.
-    while (s < n_samples) {
-        Hit h = trace<MODE>(sc, tc, o, d);
-        ++segs; ++traced;
-        bool scatter = true;
-        float3 c;
-        if (path_ends(sc, fr, h, d, T, L, depth, c)) {
-            acc.x += c.x; acc.y += c.y; acc.z += c.z;
-            ++s; depth = 0; o = fr.cam_pos; d = d0;
-            scatter = false;                                 // no reuse: trace the primary ray again
-            if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }   // next sample starts from the cached primary hit
+    while (__any_sync(0xffffffffu, s < n_samples)) {
+        const bool live = s < n_samples;                     // lanes that are done keep serving the others in MODE 5
+        Hit h = trace_all<MODE>(sc, tc, o, d, live);
+        if (live) {
+            ++segs; ++traced;
+            bool scatter = true;
+            float3 c;
+            if (path_ends(sc, fr, h, d, T, L, depth, c)) {
+                acc.x += c.x; acc.y += c.y; acc.z += c.z;
+                ++s; depth = 0; o = fr.cam_pos; d = d0;
+                scatter = false;                             // no reuse: trace the primary ray again
+                if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }   // next sample starts from the cached primary hit
+            }
+            if (scatter) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
         }
-        if (scatter) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
     }
 
     if (inside) {
@@ -217,8 +222,8 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
             }
         }
         if (!__any_sync(FULL, busy)) { if (next >= total) break; else continue; }
+        Hit h = trace_all<MODE>(sc, tc, o, d, busy);
         if (busy) {
-            Hit h = trace<MODE>(sc, tc, o, d);
             ++segs; ++traced;
             bool scatter = true;
             if (REUSE && primary) h0 = h;
@@ -586,7 +591,8 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(K<1, false>)) != cudaSuccess) return e; if ((e = optin(K<1, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<2, false>)) != cudaSuccess) return e; if ((e = optin(K<2, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<3, false>)) != cudaSuccess) return e; if ((e = optin(K<3, true>)) != cudaSuccess) return e; \
-    if ((e = optin(K<4, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true>)) != cudaSuccess) return e;
+    if ((e = optin(K<4, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<5, false>)) != cudaSuccess) return e; if ((e = optin(K<5, true>)) != cudaSuccess) return e;
     RTB_OPTIN2(k_render_regen) RTB_OPTIN2(k_render_pool) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick) RTB_OPTIN(k_render_blocks)
     if ((e = optin(k_render_bvh<2>)) != cudaSuccess) return e;
     if ((e = optin(k_render_bvh<3>)) != cudaSuccess) return e;
@@ -610,7 +616,8 @@ static cudaError_t ensure_smem_optin() {
         case 1: if (FLAG) K<1, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<1, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
         case 2: if (FLAG) K<2, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<2, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
         case 3: if (FLAG) K<3, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<3, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
-        default: if (FLAG) K<4, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<4, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
+        case 4: if (FLAG) K<4, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<4, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
+        default: if (FLAG) K<5, true><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); else K<5, false><<<GRID, kThreads, SMEM, ST>>>(__VA_ARGS__); break; \
     }
 
 cudaError_t launch_primary_aov(const SceneView& sc, const AccelSel& ac, const FrameView& fr, int* id, float* t,
@@ -664,11 +671,11 @@ cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView
 }
 
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
-                                uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st, int pool_override) {
+                                uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st, int pool_override, bool flat_coop) {
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    size_t sb; const int mode = pick_mode(sc, ac, sb, kThreads, flat_coop);
     // few samples per launch: lanes pull pixels from a warp-level pool (k_render_pool); many: one pixel per lane.
     // Measured (scratch/pool_sweep.py, Scene1): pools pay while the grid still has several waves of warps - 2 tiles at
     // 1 spp (720p 0.205 -> 0.181 ms), 4 tiles at 1080p (0.427 -> 0.329 ms), 2 tiles up to 4 spp at 1080p; larger pools

@@ -35,7 +35,8 @@ cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st);
 cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st);
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                 uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st,
-                                int pool_override = 0);   // 0: automatic; 1: always one pixel per lane; n >= 2: pool of n tiles per warp
+                                int pool_override = 0,    // 0: automatic; 1: always one pixel per lane; n >= 2: pool of n tiles per warp
+                                bool flat_coop = true);   // flat accelerator: warp-cooperative levels 2/3 (rt_trace.cuh)
 cudaError_t launch_render_bvh(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum, uint32_t s_begin,
                               int n_samples, unsigned long long* seg_counter, int wait_k, cudaStream_t st);
 cudaError_t launch_render_preview(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,

@@ -25,8 +25,15 @@ struct TraceCtx {
     const float4* sph; const float4* box; const float4* nodes; const int* refs;
     int* stack; float* stack_t; int stride;
     FlatView fl;
-    unsigned char* q;          // MODE 4: this thread's candidate queue, entries `stride` bytes apart
+    unsigned char* q;          // MODE 4/5: this thread's candidate queue, entries `stride` bytes apart
+    unsigned char* coop;       // MODE 5: this WARP's scratch for the cooperative levels 2/3
 };
+
+// MODE 5 = MODE 4 with warp-cooperative levels 2 and 3 (closest_hit_flat_coop below); per-warp scratch layout:
+// [ray: 6 x 32 floats][pairs: kCoopPairs x u16][candidates: kCoopCands x u16][best key: 32 x u64]
+constexpr int kCoopPairs = 64;                  // (owner lane, cluster) pairs per call; more -> per-lane fallback
+constexpr int kCoopCands = 64 * 8 + 32 * 56;    // every pair full + every lane's level-1 queue full: cannot overflow
+constexpr int kCoopBytesPerWarp = 6 * 32 * 4 + kCoopPairs * 2 + kCoopCands * 2 + 32 * 8;
 
 template <int MODE>
 __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhView& bv, const FlatView& fl, float4* smem) {
@@ -34,10 +41,16 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
     t.sph = sc.sph; t.box = sc.box; t.nodes = bv.nodes; t.refs = bv.refs; t.stack = nullptr; t.stack_t = nullptr; t.stride = blockDim.x;
     t.fl = fl; t.q = nullptr;
     float4* p = smem;
-    if (MODE == 4) {
+    t.coop = nullptr;
+    if (MODE == 4 || MODE == 5) {
         t.q = reinterpret_cast<unsigned char*>(p) + threadIdx.x;
         p += (kFlatQueue * blockDim.x + 15) / 16;
-        const int ng = sc.n_sph + 2 * sc.n_box, nb = 2 * (fl.n_clusters + fl.n_cubes), ncull = 8 * fl.n_clusters + fl.n_singles;
+        if (MODE == 5) {
+            t.coop = reinterpret_cast<unsigned char*>(p) + (threadIdx.x >> 5) * kCoopBytesPerWarp;
+            p += ((blockDim.x >> 5) * kCoopBytesPerWarp + 15) / 16;
+        }
+        const int ng = sc.n_sph + 2 * sc.n_box, nb = 2 * (fl.n_clusters + fl.n_cubes), ncull = kClusterStride * fl.n_clusters + fl.n_singles;
+        const int nslot = 8 * fl.n_clusters + fl.n_singles;
         const int np = sc.n_sph + sc.n_box;
         for (int i = threadIdx.x; i < ng; i += blockDim.x) p[i] = i < sc.n_sph ? __ldg(sc.sph + i) : __ldg(sc.box + (i - sc.n_sph));
         t.sph = p; t.box = p + sc.n_sph; p += ng;
@@ -49,7 +62,7 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
         for (int i = threadIdx.x; i < np; i += blockDim.x) ids[i] = __ldg(fl.prim_id + i);
         t.fl.prim_id = ids;
         unsigned char* slots = reinterpret_cast<unsigned char*>(ids + np);
-        for (int i = threadIdx.x; i < ncull; i += blockDim.x) slots[i] = __ldg(fl.cull_slot + i);
+        for (int i = threadIdx.x; i < nslot; i += blockDim.x) slots[i] = __ldg(fl.cull_slot + i);
         t.fl.cull_slot = slots;
         __syncthreads();
         return t;
@@ -80,21 +93,155 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
 
 template <int MODE>
 __device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d) {
-    if (MODE == 4) return closest_hit_flat(sc, t.fl, t.sph, t.box, t.q, t.stride, o, d);
+    if (MODE == 4 || MODE == 5) return closest_hit_flat(sc, t.fl, t.sph, t.box, t.q, t.stride, o, d);
     if (MODE >= 2) return closest_hit_bvh(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr);
     return closest_hit(sc, t.sph, t.box, o, d);
 }
 
 
+// ---- warp-cooperative flat traversal ------------------------------------------------------------------------------
+// Levels 2 and 3 of the flat accelerator per lane leave most of the warp idle: a lane has 0.9 hit clusters and 0.9
+// candidates on average but the warp loops for the lane with the most (2.5 and 3.9 iterations on Scene1, 9 and 7 lanes
+// active; profiles/r1q_summary_flat_reuse_1024spp.txt). Here the warp pools the work: every lane publishes its ray,
+// the (lane, cluster) pairs of all lanes are enumerated with a prefix sum into one list and each lane culls ONE pair
+// (whoever's it is); the surviving (lane, primitive) candidates are appended to a second list the same way and each
+// lane runs ONE strict test per pass, returning the result to the owning lane with a 64-bit atomicMin on
+// (order-preserving bits of t, object id) - exactly the reference's "closest, lowest id on ties". Lanes without work
+// of their own (sky pixels, finished pixels) serve the others. Must be called by all 32 lanes; `active` = has a ray.
+__device__ __forceinline__ unsigned int warp_incl_scan(unsigned int v, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int n = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v += n;
+    }
+    return v;
+}
+
+// the rare per-lane fallback, kept out of line so it does not dilute the instruction cache of the hot loop
+static __device__ __noinline__ Hit flat_levels23_outlined(const SceneView& sc, const FlatView& fv, const float4* __restrict__ sph,
+                                                   const float4* __restrict__ box, unsigned char* __restrict__ q, int qstride,
+                                                   float3 o, float3 d, unsigned int cm, int nq) {
+    return flat_levels23(sc, fv, sph, box, q, qstride, o, d, cm, nq);
+}
+
+__device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const FlatView& fv, const float4* __restrict__ sph,
+                                                     const float4* __restrict__ box, unsigned char* __restrict__ q, int qstride,
+                                                     unsigned char* __restrict__ coop, float3 o, float3 d, bool active) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned long long kNoHit = 0xffffffffffffffffull;
+    const int lane = threadIdx.x & 31;
+    float* const ray_s = reinterpret_cast<float*>(coop);
+    unsigned short* const pairs = reinterpret_cast<unsigned short*>(coop + 6 * 32 * 4);
+    unsigned short* const cand = pairs + kCoopPairs;
+    unsigned long long* const key = reinterpret_cast<unsigned long long*>(cand + kCoopCands);
+
+    int nq = 0;
+    unsigned int cm = 0u;
+    if (active) cm = flat_level1(sc, fv, q, qstride, o, d, nq);
+    // ---- level 2: (lane, cluster) pairs, one per lane per pass ----
+    const unsigned int cnt = (unsigned int)__popc(cm);
+    const unsigned int incl = warp_incl_scan(cnt, lane);
+    const unsigned int n_pairs = __shfl_sync(FULL, incl, 31);
+    if (n_pairs > (unsigned int)kCoopPairs) {                 // rare: every lane works for itself
+        Hit h;
+        h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f); h.p = f3(0.f, 0.f, 0.f);
+        if (active) h = flat_levels23_outlined(sc, fv, sph, box, q, qstride, o, d, cm, nq);
+        return h;
+    }
+    ray_s[lane] = o.x; ray_s[32 + lane] = o.y; ray_s[64 + lane] = o.z;
+    ray_s[96 + lane] = d.x; ray_s[128 + lane] = d.y; ray_s[160 + lane] = d.z;
+    key[lane] = kNoHit;
+    {
+        unsigned int m = cm, j = incl - cnt;
+        while (m) { const int k = __ffs((int)m) - 1; m &= m - 1u; pairs[j++] = (unsigned short)((lane << 8) | k); }
+    }
+    __syncwarp();
+    // candidate list: every lane's level-1 candidates (pass 0, as owner) + the survivors of the pair it culls (as worker)
+    unsigned int n_cand = 0u;                                 // warp-uniform
+    unsigned int base = 0u;
+    do {
+        unsigned int m8 = 0u, pr = 0u;
+        if (base + (unsigned int)lane < n_pairs) {
+            pr = pairs[base + lane];
+            const int ow = (int)(pr >> 8);
+            m8 = flat_cull8(fv, (int)(pr & 255u), f3(ray_s[ow], ray_s[32 + ow], ray_s[64 + ow]), f3(ray_s[96 + ow], ray_s[128 + ow], ray_s[160 + ow]));
+        }
+        const unsigned int own = base == 0u ? (unsigned int)nq : 0u;
+        const unsigned int contrib = own + (unsigned int)__popc(m8);
+        const unsigned int incl2 = warp_incl_scan(contrib, lane);
+        unsigned int j = n_cand + incl2 - contrib;
+        for (unsigned int i = 0; i < own; ++i) cand[j++] = (unsigned short)((lane << 8) | q[i * qstride]);
+        while (m8) { const int b = __clz((int)m8) - 24; m8 &= ~(0x80u >> b); cand[j++] = (unsigned short)((pr & 0xff00u) | fv.cull_slot[8 * (pr & 255u) + b]); }
+        n_cand += __shfl_sync(FULL, incl2, 31);
+        base += 32u;
+    } while (base < n_pairs);
+    __syncwarp();
+    // ---- level 3: one strict test per lane per pass; the owner gets the minimum of (t, object id) ----
+    for (base = 0u; base < n_cand; base += 32u) {
+        const unsigned int i = base + (unsigned int)lane;
+        if (i < n_cand) {
+            const unsigned int e = cand[i];
+            const int ow = (int)(e >> 8), code = (int)(e & 255u);
+            const float3 ro = f3(ray_s[ow], ray_s[32 + ow], ray_s[64 + ow]), rd = f3(ray_s[96 + ow], ray_s[128 + ow], ray_s[160 + ow]);
+            float t = 0.f; bool hit; unsigned int nbits = 0u;
+            if (code < sc.n_sph) hit = sphere_t(sph[code], ro, rd, t);
+            else {
+                float3 nrm = f3(0.f, 0.f, 0.f); const int j = code - sc.n_sph;
+                hit = box_hit(box[2 * j], box[2 * j + 1], ro, rd, t, nrm);
+                // a cube normal has components in {+-0, +-1}: 2 bits each travel in the key
+                nbits = ((__float_as_uint(nrm.x) >> 31) << 5) | ((nrm.x != 0.f ? 1u : 0u) << 4) | ((__float_as_uint(nrm.y) >> 31) << 3) |
+                        ((nrm.y != 0.f ? 1u : 0u) << 2) | ((__float_as_uint(nrm.z) >> 31) << 1) | (nrm.z != 0.f ? 1u : 0u);
+            }
+            if (hit && t == t) {                              // NaN distances never win (`<` is false), as in the per-lane loop
+                unsigned int ob = __float_as_uint(t);
+                ob ^= (unsigned int)((int)ob >> 31) | 0x80000000u;                        // order-preserving bits
+                const unsigned long long kb = ((unsigned long long)ob << 32) |
+                                              (unsigned long long)(((unsigned int)fv.prim_id[code] << 14) | ((unsigned int)code << 6) | nbits);
+                if (kb < *reinterpret_cast<volatile unsigned long long*>(key + ow)) atomicMin(key + ow, kb);
+            }
+        }
+    }
+    __syncwarp();
+    const unsigned long long kb = key[lane];
+    float best_t = 0.f; int best_id = 0, best_code = -1;
+    float3 bn = f3(0.f, 0.f, 0.f);
+    if (active && kb != kNoHit) {
+        unsigned int ob = (unsigned int)(kb >> 32);
+        ob ^= (unsigned int)((int)~ob >> 31) | 0x80000000u;
+        best_t = __uint_as_float(ob);
+        const unsigned int lo = (unsigned int)kb;
+        best_code = (int)((lo >> 6) & 255u);
+        best_id = (int)(lo >> 14);
+        bn = f3(__uint_as_float(((lo >> 5) & 1u) << 31 | ((lo >> 4) & 1u) * 0x3f800000u), __uint_as_float(((lo >> 3) & 1u) << 31 | ((lo >> 2) & 1u) * 0x3f800000u),
+                __uint_as_float(((lo >> 1) & 1u) << 31 | (lo & 1u) * 0x3f800000u));
+    }
+    __syncwarp();                                             // everyone is done with the scratch before the next call
+    return flat_finish(sc, sph, o, d, best_t, best_id, best_code, bn);
+}
+
+// Per-lane trace for all lanes of a warp (inactive lanes get a miss); MODE 5 pools levels 2/3 across the warp.
+template <int MODE>
+__device__ __forceinline__ Hit trace_all(const SceneView& sc, const TraceCtx& t, float3 o, float3 d, bool active) {
+    if (MODE == 5) return closest_hit_flat_coop(sc, t.fl, t.sph, t.box, t.q, t.stride, t.coop, o, d, active);
+    Hit h;
+    h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f); h.p = f3(0.f, 0.f, 0.f);
+    if (active) h = trace<MODE>(sc, t, o, d);
+    return h;
+}
+
 // ---- host: variant + dynamic shared memory size for a back end -----------------------------------
 inline size_t staged_bytes(const SceneView& sc) { return (size_t)(sc.n_sph + 2 * sc.n_box) * sizeof(float4); }
 inline size_t flat_staged_bytes(const SceneView& sc, const FlatView& fl, int threads) {
-    const size_t ncull = (size_t)8 * fl.n_clusters + fl.n_singles;
+    const size_t ncull = (size_t)kClusterStride * fl.n_clusters + fl.n_singles;
     return (size_t)kFlatQueue * threads + staged_bytes(sc) + (size_t)2 * (fl.n_clusters + fl.n_cubes) * 16 + ncull * 16 + (size_t)(sc.n_sph + sc.n_box) * 4 + ncull + 16;
 }
-inline int pick_mode(const SceneView& sc, const AccelSel& ac, size_t& smem, int threads = kThreads) {
+inline int pick_mode(const SceneView& sc, const AccelSel& ac, size_t& smem, int threads = kThreads, bool coop = false) {
     const size_t geo = staged_bytes(sc);
-    if (ac.kind == kAccelFlat) { smem = flat_staged_bytes(sc, ac.flat, threads); return 4; }
+    if (ac.kind == kAccelFlat) {
+        smem = flat_staged_bytes(sc, ac.flat, threads);
+        if (coop) { smem += (size_t)(threads / 32) * kCoopBytesPerWarp + 16; return 5; }
+        return 4;
+    }
     if (ac.kind == kAccelBrute) {
         if (geo <= kMaxStagedBytes) { smem = geo; return 0; }
         smem = 0; return 1;
