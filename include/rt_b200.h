@@ -116,7 +116,7 @@ enum {
     RT_OPT_WF_NODE_MIN = 9,        /* wavefront BVH intersect: lanes with inner-node work below which pending leaves are tested (default 8) */
     RT_OPT_POOL_TILES = 10,        /* megakernel, few samples per call: 8x4 pixel tiles per warp-level pixel pool; 0 (default) automatic, 1 one pixel per lane */
     RT_OPT_FLAT_COOP = 11,         /* flat accelerator in the megakernel: 1 the warp pools the cluster culls and strict tests of its 32 rays, 0 every lane for itself,
-                                      2 (default) measured per scene with RT_ACCEL_AUTO (open scenes gain ~8 %, cube rooms lose) */
+                                      2 (default) pooled for scenes without cubes (open sphere scenes gain ~8 %, cube rooms lose ~10 %) */
     RT_OPT_PRIMARY_REUSE = 7       /* 1 (default): one primary closest-hit query per pixel per rt_render_spp call,
                                       reused by every sample (identical ray: the reference has no pixel jitter);
                                       0: re-trace it for every sample like the reference. Results are bit-identical. */

@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -260,17 +261,23 @@ int want_accel(rt_ctx* c) {
 
 // RT_ACCEL_AUTO between 8 and `bvh_threshold` primitives: all back ends give identical results and which
 // one is fastest depends on the scene, so the first path-mode render after a scene/camera/parameter change
-// times 4 spp of each into a scratch buffer and keeps the fastest. Below 8 primitives brute force, above the
-// threshold the BVH.
-int autotune_accel(rt_ctx* c) {
+// of at least 64 spp times 16 spp of each into a scratch buffer and keeps the fastest. Below 8 primitives brute force,
+// above the threshold the BVH.
+int autotune_accel(rt_ctx* c, int spp) {
     if (c->opt_accel != RT_ACCEL_AUTO || c->tuned_accel >= 0) return RT_OK;
+    // Measuring costs about 100 samples per pixel of work: only when the call itself is long enough to amortise it
+    // (an interactive 1-spp frame loop keeps the heuristic choice of want_accel()); camera moves do not re-trigger it.
+    if (spp < 64) { c->tuned_flat_coop = c->view.n_box == 0; return RT_OK; }
     const int n = c->view.n_sph + c->view.n_box + c->view.n_tri;
     if (n < 8) { c->tuned_accel = RT_ACCEL_BRUTE; return RT_OK; }
     if (n >= c->opt_bvh_threshold || c->view.n_tri > 0) { c->tuned_accel = RT_ACCEL_BVH; return RT_OK; }
-    // candidates: brute force, BVH, flat with warp-cooperative levels 2/3, flat with per-lane levels 2/3
+    // candidates: brute force, BVH, flat. Whether the flat back end pools levels 2/3 across the warp is NOT measured here:
+    // the two variants differ by less than the noise of a 16-spp run (2.618 vs 2.614 ms on Scene1) although the pooled one
+    // is 8 % faster over 256+ spp; RT_OPT_FLAT_COOP 2 uses it for scenes without cubes (cube rooms lose ~10 % with it).
     const int kinds[4] = {RT_ACCEL_BRUTE, RT_ACCEL_BVH, RT_ACCEL_FLAT, RT_ACCEL_FLAT};
-    const bool coop[4] = {false, false, c->opt_flat_coop != 0, false};
-    const int n_cand = c->opt_flat_coop == 2 ? 4 : 3;
+    const bool flat_coop = c->opt_flat_coop == 2 ? c->view.n_box == 0 : c->opt_flat_coop != 0;
+    const bool coop[4] = {false, false, flat_coop, false};
+    const int n_cand = 3;
     AccelSel sel[4];
     int rc;
     for (int k = 0; k < n_cand; ++k) if ((rc = make_accel(c, kinds[k], camera_extent(c), sel[k])) != RT_OK) return rc;
@@ -284,7 +291,7 @@ int autotune_accel(rt_ctx* c) {
     for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 warms the instruction cache
         cudaEventRecord(e[0], c->stream);
         for (int k = 0; k < n_cand && err == cudaSuccess; ++k) {
-            err = launch_render_regen(c->view, sel[k], c->frame, c->d_tune, 0u, 8, reuse, dummy, c->stream, 1, coop[k]);
+            err = launch_render_regen(c->view, sel[k], c->frame, c->d_tune, 0u, 16, reuse, dummy, c->stream, 1, coop[k]);
             cudaEventRecord(e[k + 1], c->stream);
         }
     }
@@ -297,7 +304,9 @@ int autotune_accel(rt_ctx* c) {
         if (kinds[k] == RT_ACCEL_FLAT && sel[k].kind != kAccelFlat) continue;   // scene does not qualify
         if (c->tune_ms[k] < c->tune_ms[best]) best = k;
     }
-    c->tuned_flat_coop = coop[best] ? 1 : 0;
+    c->tuned_flat_coop = flat_coop ? 1 : 0;
+    if (getenv("RTB200_DEBUG"))
+        fprintf(stderr, "[rtb200] autotune: brute %.3f ms, bvh %.3f ms, flat %.3f ms -> candidate %d\n", c->tune_ms[0], c->tune_ms[1], c->tune_ms[2], best);
     c->tuned_accel = kinds[best];
     return RT_OK;
 }
@@ -306,9 +315,9 @@ int autotune_accel(rt_ctx* c) {
 // (thousands of primitives), where the first path-mode render times 2 spp of the megakernel and of the wavefront
 // pipeline and keeps the faster (identical results). On the 10 000-sphere scene the wavefront wins by about 10 %,
 // on the 1 M-triangle mesh the megakernel by about 25 %.
-int autotune_pipeline(rt_ctx* c, const AccelSel& ac) {
+int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     if (c->opt_pipeline != RT_PIPELINE_AUTO) return RT_OK;
-    if (c->tuned_pipeline >= 0) return RT_OK;
+    if (c->tuned_pipeline >= 0 || spp < 8) return RT_OK;      // short calls keep the megakernel until a longer one measures
     const size_t prims = (size_t)c->view.n_sph + c->view.n_box + c->view.n_tri;
     if (ac.kind != kAccelBvh || prims < 2048 || c->pixel_step > 1) { c->tuned_pipeline = RT_PIPELINE_REGEN; return RT_OK; }
     const size_t px = (size_t)c->par.width * c->par.height;
@@ -598,7 +607,6 @@ int rt_get_mesh_info(rt_ctx* c, int object_index, int* n_vertices, int* n_triang
 
 int rt_set_camera(rt_ctx* c, const rt_camera* cam) {
     if (!c || !cam) return RT_ERR_INVALID;
-    if (memcmp(&c->cam, cam, sizeof *cam) != 0) c->tuned_accel = c->tuned_pipeline = -1;
     c->cam = *cam;
     c->frame_dirty = true;
     return RT_OK;
@@ -687,11 +695,11 @@ int rt_render_spp(rt_ctx* c, int spp) {
     if (spp < 0) return fail(c, RT_ERR_INVALID, "rt_render_spp: negative spp");
     if (spp == 0) return RT_OK;
     const size_t px = (size_t)c->par.width * c->par.height;
-    if (c->par.mode == RT_MODE_PATH && (rc = autotune_accel(c)) != RT_OK) return rc;
+    if (c->par.mode == RT_MODE_PATH && (rc = autotune_accel(c, spp)) != RT_OK) return rc;
     AccelSel ac;
     if ((rc = make_accel(c, want_accel(c), camera_extent(c), ac)) != RT_OK) return rc;
     c->used_accel = accel_of(ac);
-    if (c->par.mode == RT_MODE_PATH && (rc = autotune_pipeline(c, ac)) != RT_OK) return rc;
+    if (c->par.mode == RT_MODE_PATH && (rc = autotune_pipeline(c, ac, spp)) != RT_OK) return rc;
     RT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if (c->pixel_step > 1) {
         // SCREEN_SCALE / progressive resolution: one path per block, block-filled (Raytracer.cpp:233-248)
@@ -727,7 +735,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else
             RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_pool_tiles,
-                                           c->opt_flat_coop == 2 ? (c->opt_accel == RT_ACCEL_AUTO ? c->tuned_flat_coop != 0 : true) : c->opt_flat_coop != 0));
+                                           c->opt_flat_coop == 2 ? (c->opt_accel == RT_ACCEL_AUTO ? c->tuned_flat_coop != 0 : c->view.n_box == 0) : c->opt_flat_coop != 0));
         if (!wavefront) c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce

@@ -675,7 +675,6 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    size_t sb; const int mode = pick_mode(sc, ac, sb, kThreads, flat_coop);
     // few samples per launch: lanes pull pixels from a warp-level pool (k_render_pool); many: one pixel per lane.
     // Measured (scratch/pool_sweep.py, Scene1): pools pay while the grid still has several waves of warps - 2 tiles at
     // 1 spp (720p 0.205 -> 0.181 ms), 4 tiles at 1080p (0.427 -> 0.329 ms), 2 tiles up to 4 spp at 1080p; larger pools
@@ -685,6 +684,8 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
     if (pool_override > 0) pool_tiles = pool_override > 32 ? 32 : pool_override;
     else if (n_samples == 1) pool_tiles = n_tiles_all >= 50000 ? 4 : 2;
     else if (n_samples <= 4 && n_tiles_all >= 50000) pool_tiles = 2;
+    // the pooled flat traversal pays from ~16 spp per launch on; short launches (the pixel pool's) run the per-lane form
+    size_t sb; const int mode = pick_mode(sc, ac, sb, kThreads, flat_coop && pool_tiles < 2 && n_samples >= 16);
     if (pool_tiles >= 2) {
         const long long n_tiles = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
         const long long warps = (n_tiles + pool_tiles - 1) / pool_tiles;

@@ -30,10 +30,10 @@ struct TraceCtx {
 };
 
 // MODE 5 = MODE 4 with warp-cooperative levels 2 and 3 (closest_hit_flat_coop below); per-warp scratch layout:
-// [ray: 6 x 32 floats][pairs: kCoopPairs x u16][candidates: kCoopCands x u16][best key: 32 x u64]
+// [ray: 9 x 32 floats (o, d, iBox's m)][pairs: kCoopPairs x u16][candidates: kCoopCands x u16][best key: 32 x u64]
 constexpr int kCoopPairs = 64;                  // (owner lane, cluster) pairs per call; more -> per-lane fallback
 constexpr int kCoopCands = 64 * 8 + 32 * 56;    // every pair full + every lane's level-1 queue full: cannot overflow
-constexpr int kCoopBytesPerWarp = 6 * 32 * 4 + kCoopPairs * 2 + kCoopCands * 2 + 32 * 8;
+constexpr int kCoopBytesPerWarp = 9 * 32 * 4 + kCoopPairs * 2 + kCoopCands * 2 + 32 * 8;
 
 template <int MODE>
 __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhView& bv, const FlatView& fl, float4* smem) {
@@ -131,7 +131,7 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
     constexpr unsigned long long kNoHit = 0xffffffffffffffffull;
     const int lane = threadIdx.x & 31;
     float* const ray_s = reinterpret_cast<float*>(coop);
-    unsigned short* const pairs = reinterpret_cast<unsigned short*>(coop + 6 * 32 * 4);
+    unsigned short* const pairs = reinterpret_cast<unsigned short*>(coop + 9 * 32 * 4);
     unsigned short* const cand = pairs + kCoopPairs;
     unsigned long long* const key = reinterpret_cast<unsigned long long*>(cand + kCoopCands);
 
@@ -150,6 +150,10 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
     }
     ray_s[lane] = o.x; ray_s[32 + lane] = o.y; ray_s[64 + lane] = o.z;
     ray_s[96 + lane] = d.x; ray_s[128 + lane] = d.y; ray_s[160 + lane] = d.z;
+    if (sc.n_box > 0) {                                       // cubes: the ray-only half of iBox, once per ray
+        const BoxRay br = box_ray(d);
+        ray_s[192 + lane] = br.m.x; ray_s[224 + lane] = br.m.y; ray_s[256 + lane] = br.m.z;
+    }
     key[lane] = kNoHit;
     {
         unsigned int m = cm, j = incl - cnt;
@@ -187,7 +191,7 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
             if (code < sc.n_sph) hit = sphere_t(sph[code], ro, rd, t);
             else {
                 float3 nrm = f3(0.f, 0.f, 0.f); const int j = code - sc.n_sph;
-                hit = box_hit(box[2 * j], box[2 * j + 1], ro, rd, t, nrm);
+                hit = box_hit_pre(box[2 * j], box[2 * j + 1], ro, box_ray_from_m(f3(ray_s[192 + ow], ray_s[224 + ow], ray_s[256 + ow])), t, nrm);
                 // a cube normal has components in {+-0, +-1}: 2 bits each travel in the key
                 nbits = ((__float_as_uint(nrm.x) >> 31) << 5) | ((nrm.x != 0.f ? 1u : 0u) << 4) | ((__float_as_uint(nrm.y) >> 31) << 3) |
                         ((nrm.y != 0.f ? 1u : 0u) << 2) | ((__float_as_uint(nrm.z) >> 31) << 1) | (nrm.z != 0.f ? 1u : 0u);
