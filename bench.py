@@ -345,16 +345,16 @@ def run_b200(args):
             "gpu_launches_detail": "per rank. timed value region: 1 k_render_regen per step (+ 1 k_resolve_fused at N > 1); e2e region: k_render_regen + k_resolve (N = 1) or k_resolve_fused (N > 1) per step",
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "traffic": 33.44e6, "traffic_note": "dram read+write per launch at 1080p x 64 spp, ncu --set full (profiles/r1f_*): the float4 accumulation buffer once; independent of spp",
+                         "traffic": 33.3e6, "traffic_note": "dram read+write per launch at 1080p x 1024 spp, ncu --set full (profiles/r1y_summary_final_1024spp.txt): the float4 accumulation buffer once (the write-back of the other 33 MB is still in L2 when the kernel ends); independent of spp",
                          "kernel": "k_render_regen", "kernel_ms": kern_s * 1e3,
                          "flop_per_segment": fps,
                          "peak_source": "%d SMs x 128 lanes x 2 (FMA) x %.0f MHz (%s MEASURED_PEAKS.json sm_max_mhz)" % (st.sm_count, sm_mhz, peaks_src),
                          "note": "path is FP32-CUDA-core issue bound, not HBM or tensor (SURVEY.md 8d). `achieved` is ALGORITHMIC: the reference's "
                                  "brute-force op count per segment (23/sphere + 30/cube + 110) x path segments delivered. The flat accelerator's conservative "
-                                 "culls and the primary-hit reuse execute far fewer operations than that (ncu, profiles/r1f_summary_flat_reuse.txt: 538 thread "
-                                 "instructions per delivered segment, issue slots 80% busy, 13.8 of 32 threads active per instruction), so frac says how much "
+                                 "culls and the primary-hit reuse execute far fewer operations than that (ncu, profiles/r1y_summary_final_1024spp.txt: 25 warp "
+                                 "instructions per delivered segment, issue slots 78% busy, 22.7 of 32 threads active per instruction), so frac says how much "
                                  "reference-equivalent work is delivered per peak FLOP, not how busy the FP32 pipe is",
-                         "executed_thread_instr_per_segment_ncu": 538, "issue_active_pct_ncu": 79.5, "active_threads_per_inst_ncu": 13.8,
+                         "executed_warp_instr_per_segment_ncu": 25.1, "issue_active_pct_ncu": 78.4, "active_threads_per_inst_ncu": 22.65,
                          "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_algorithmic_gbs": (W * H * 32 / kern_s) / 1e9},
         }
         if world == 1 and not args.no_cpu and args.config == "c2":
