@@ -886,3 +886,53 @@ def test_large_secondary_offset_keeps_accelerators_exact(tracer, scenes):
         b = out[rtb200.RT_ACCEL_BRUTE]
         for accel in (rtb200.RT_ACCEL_FLAT, rtb200.RT_ACCEL_BVH):
             assert np.array_equal(bits(out[accel][0]), bits(b[0])) and out[accel][1] == b[1], (eps, accel)
+
+
+def _dense_scene(n, spread, seed):
+    rng = np.random.default_rng(seed)
+    o = np.zeros(n + 1, rtb200.OBJECT_DTYPE)
+    o["type"] = 1
+    o["pos"][:n] = rng.uniform([-spread, 0, 4], [spread, spread, 4 + 2 * spread], (n, 3)).astype(np.float32)
+    o["radius"][:n] = rng.uniform(0.1, 0.8, n).astype(np.float32)
+    o["base"] = rng.uniform(0.1, 0.9, (n + 1, 3)).astype(np.float32); o["spec_color"] = 1
+    o["spec_amount"][::3] = 1; o["smoothness"][::3] = 0.9
+    cubes = np.arange(2, n, 7)
+    o["type"][cubes] = 2; o["half"][cubes] = rng.uniform(0.2, 0.7, (len(cubes), 3)).astype(np.float32)
+    o["emissive"][::10] = 20
+    o["pos"][n] = [0, -500, 20]; o["radius"][n] = 500
+    return o
+
+
+@pytest.mark.parametrize("case", SCENES + ["dense250", "dense120", "dense40"])
+def test_pooled_flat_traversal_is_bit_identical(tracer, scenes, case):
+    """closest_hit_flat_coop (the warp pools its cluster culls and strict tests; launches of >= 16 spp) vs the per-lane
+    form vs the brute-force loop. The dense scenes push a warp beyond 64 (lane, cluster) pairs (per-lane fallback inside
+    the pooled kernel), fill candidate lists over several passes and mix cubes with spheres."""
+    if case.startswith("dense"):
+        n = int(case[5:])
+        objs = _dense_scene(n, {250: 12.0, 120: 2.0, 40: 0.6}[n], n)
+        cam = rtb200.default_camera(60); cam.pos[1] = 0.5 * {250: 12.0, 120: 2.0, 40: 0.6}[n]; cam.pos[2] = -2.0
+    else:
+        objs, cam = scenes[case], rtb200.default_camera()
+    out = {}
+    try:
+        for key, accel, coop in (("coop", rtb200.RT_ACCEL_FLAT, 1), ("lane", rtb200.RT_ACCEL_FLAT, 0), ("brute", rtb200.RT_ACCEL_BRUTE, 0)):
+            tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+            tracer.set_option(rtb200.RT_OPT_FLAT_COOP, coop)
+            for reuse in (1, 0):
+                tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, reuse)
+                setup(tracer, objs, 200, 104, cam, max_bounces=6)
+                tracer.render_spp(16); tracer.render_spp(21)
+                st = tracer.stats()
+                assert st.accel == accel
+                out[(key, reuse)] = (tracer.read_accum()[0], st.segments, st.traced_segments)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        tracer.set_option(rtb200.RT_OPT_FLAT_COOP, 2)
+        tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 1)
+    for reuse in (1, 0):
+        base = out[("brute", reuse)]
+        for key in ("coop", "lane"):
+            v = out[(key, reuse)]
+            assert np.array_equal(bits(v[0]), bits(base[0])) and v[1:] == base[1:], (case, key, reuse)
+    assert np.array_equal(bits(out[("coop", 1)][0]), bits(out[("coop", 0)][0]))
