@@ -90,3 +90,43 @@ long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* 
     return segs;
 }
 }
+
+// ---- host-logic hooks for the CPU tests (builders only, no tracing) ----------------------------------------------
+extern "C" {
+// Flat accelerator of a scene: returns usable (0/1); counts[0..3] = clusters, cubes, singles, cull records;
+// cull (4 floats per record, up to max_records) and cull_slot (up to max_slots) copied out; kappa and inflation returned.
+int emu_flat_info(const rt_object* objects, int n_obj, float origin_extent, float origin_offset, int* counts, float* cull,
+                  int max_records, unsigned char* cull_slot, int max_slots, float* boxes, int max_boxes, float* kappa_inflate) {
+    std::vector<rt_object> objs(objects, objects + n_obj);
+    HostFlat f;
+    build_flat(objs, origin_extent, f, origin_offset);
+    counts[0] = f.n_clusters; counts[1] = f.n_cubes; counts[2] = f.n_singles; counts[3] = (int)(f.cull.size() / 4);
+    for (size_t i = 0; i < f.cull.size() && i < (size_t)4 * max_records; ++i) cull[i] = f.cull[i];
+    for (size_t i = 0; i < f.cull_slot.size() && i < (size_t)max_slots; ++i) cull_slot[i] = f.cull_slot[i];
+    for (size_t i = 0; i < f.boxes.size() && i < (size_t)8 * max_boxes; ++i) boxes[i] = f.boxes[i];
+    kappa_inflate[0] = f.kappa; kappa_inflate[1] = f.inflate_abs;
+    return f.usable ? 1 : 0;
+}
+// OBJ subset reader/writer and the triangle records (mesh.h). Returns triangles (or -1 on a load error).
+int emu_obj_round_trip(const char* path_in, const char* path_out, float* verts, int max_verts, int32_t* tris, int max_tris) {
+    HostMesh m; std::string err;
+    if (!load_obj(path_in, m, err)) return -1;
+    if (path_out && !save_obj(path_out, m, err)) return -2;
+    for (size_t i = 0; i < m.vertices.size() && i < (size_t)3 * max_verts; ++i) verts[i] = m.vertices[i];
+    for (size_t i = 0; i < m.indices.size() && i < (size_t)3 * max_tris; ++i) tris[i] = m.indices[i];
+    return (int)(m.indices.size() / 3) | ((int)(m.vertices.size() / 3) << 16);
+}
+int emu_tri_records(const float* pos3, const float* verts, int n_verts, const int32_t* tris, int n_tris, float* rec12, float* bounds6) {
+    std::vector<rt_object> objs(1);
+    memset(&objs[0], 0, sizeof(rt_object));
+    objs[0].type = RT_OBJ_MESH; objs[0].pos[0] = pos3[0]; objs[0].pos[1] = pos3[1]; objs[0].pos[2] = pos3[2];
+    std::vector<HostMesh> meshes(1);
+    meshes[0].vertices.assign(verts, verts + (size_t)3 * n_verts);
+    meshes[0].indices.assign(tris, tris + (size_t)3 * n_tris);
+    TriRecords t;
+    build_tri_records(objs, meshes, t);
+    for (size_t i = 0; i < t.rec.size(); ++i) rec12[i] = t.rec[i];
+    for (size_t i = 0; i < t.bounds.size(); ++i) bounds6[i] = t.bounds[i];
+    return t.count();
+}
+}

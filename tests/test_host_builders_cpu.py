@@ -1,0 +1,120 @@
+"""CPU: the product's HOST builders (flat accelerator, triangle records, OBJ subset), compiled for the host with the
+emulation library. Invariants the device code relies on, checked without a GPU."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import rtb200
+from conftest import SCENES
+from test_device_logic_cpu import emu, EMU_SO  # noqa: F401  (session fixture builds the library)
+
+
+@pytest.fixture(scope="module")
+def lib(emu):  # noqa: F811
+    return C.CDLL(EMU_SO)
+
+
+def flat_info(lib, objs, extent=0.0, offset=1e-5):
+    objs = np.ascontiguousarray(objs, rtb200.OBJECT_DTYPE)
+    counts = (C.c_int * 4)()
+    cull = np.zeros((4096, 4), np.float32); slots = np.zeros(4096, np.uint8); boxes = np.zeros((256, 8), np.float32)
+    ki = (C.c_float * 2)()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ok = lib.emu_flat_info(p(objs), len(objs), C.c_float(extent), C.c_float(offset), counts, p(cull), 4096, p(slots), 4096, p(boxes), 256, ki)
+    nc, ncube, ns, nrec = list(counts)
+    return ok, nc, ncube, ns, cull[:nrec], slots[:8 * nc + ns], boxes[:nc + ncube], ki[0], ki[1]
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_flat_builder_invariants_on_bundled_scenes(lib, scenes, scene):
+    objs = scenes[scene]
+    ok, nc, ncube, ns, cull, slots, boxes, kappa, inflate = flat_info(lib, objs)
+    assert ok == 1 and nc <= 32 and ncube + ns <= 56
+    sph = np.flatnonzero(objs["type"] == 1)
+    assert ncube == int((objs["type"] == 2).sum())
+    assert len(cull) == 9 * nc + ns                           # 8 slots + 1 bank-conflict pad per cluster, then the singles
+    real = slots[slots != 255]
+    assert sorted(real.tolist()) == list(range(len(sph)))     # every sphere exactly once
+    assert kappa == np.float32(1.0 - 2.0 ** -18) and inflate > 0
+    # every record: same centre as its sphere, inflated r^2 slightly above the exact one; every cluster box contains its spheres
+    for k in range(nc):
+        for j in range(8):
+            s = slots[8 * k + j]
+            rec = cull[9 * k + j]
+            if s == 255:
+                assert rec[3] < -1e29
+                continue
+            o = objs[sph[s]]
+            r2 = np.float32(o["radius"]) * np.float32(o["radius"])
+            assert np.array_equal(rec[:3], o["pos"]) and r2 < rec[3] <= r2 * 1.05 + 1e-6   # a few per cent: 4 D with D from the 3000-unit origin bound of the ground sphere
+            assert np.all(boxes[k][:3] <= o["pos"] - abs(o["radius"])) and np.all(boxes[k][4:7] >= o["pos"] + abs(o["radius"]))
+        assert cull[9 * k + 8][3] < -1e29                     # the pad record can never be a candidate
+    for j in range(ns):
+        o = objs[sph[slots[8 * nc + j]]]
+        assert np.array_equal(cull[9 * nc + j][:3], o["pos"])
+
+
+def test_flat_builder_limits(lib):
+    rng = np.random.default_rng(3)
+
+    def spheres(n, r=0.3):
+        o = np.zeros(n, rtb200.OBJECT_DTYPE); o["type"] = 1
+        o["pos"] = rng.uniform(-5, 5, (n, 3)).astype(np.float32); o["radius"] = r
+        return o
+    assert flat_info(lib, spheres(255))[0] == 1
+    assert flat_info(lib, spheres(256))[0] == 0               # candidate codes are bytes
+    assert flat_info(lib, spheres(0))[0] == 0
+    o = spheres(10); o["pos"][3, 0] = np.inf
+    assert flat_info(lib, o)[0] == 0                          # finite-arithmetic precondition
+    o = spheres(10); o["pos"][3, 0] = 1e16
+    assert flat_info(lib, o)[0] == 0
+    big = spheres(200); big["radius"] = np.where(np.arange(200) % 3 == 0, 3.0, 0.05)
+    assert flat_info(lib, big)[0] == 0                        # 67 level-1 singles > 56
+    # margins grow with the origin extent and offset they have to cover
+    a = flat_info(lib, spheres(20), extent=0.0)[4][:, 3]
+    rng = np.random.default_rng(3)
+    b = flat_info(lib, spheres(20), extent=1e4)[4][:, 3]
+    rng = np.random.default_rng(3)
+    c = flat_info(lib, spheres(20), extent=0.0, offset=50.0)[4][:, 3]
+    live = a > 0
+    assert np.all(b[live] > a[live]) and np.all(c[live] > a[live])
+
+
+def test_obj_subset_and_triangle_records(lib, tmp_path):
+    src = tmp_path / "m.obj"
+    src.write_text("# comment\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0.5\nvn 0 0 1\nf 1 2 3 4\nf -4/1/1 -3/1/1 -1/1/1\n")
+    verts = np.zeros((16, 3), np.float32); tris = np.zeros((16, 3), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    out = tmp_path / "m2.obj"
+    r = lib.emu_obj_round_trip(str(src).encode(), str(out).encode(), p(verts), 16, p(tris), 16)
+    nt, nv = r & 0xffff, r >> 16
+    assert (nv, nt) == (4, 3)                                 # the quad is fanned into two triangles; negative indices are relative
+    assert tris[:3].tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 3]]
+    v2 = np.zeros((16, 3), np.float32); t2 = np.zeros((16, 3), np.int32)
+    assert lib.emu_obj_round_trip(str(out).encode(), None, p(v2), 16, p(t2), 16) == r
+    assert np.array_equal(v2, verts) and np.array_equal(t2, tris)
+    assert lib.emu_obj_round_trip(str(tmp_path / "missing.obj").encode(), None, p(v2), 16, p(t2), 16) == -1
+    (tmp_path / "bad.obj").write_text("v 0 0 0\nf 1 2 3\n")
+    assert lib.emu_obj_round_trip(str(tmp_path / "bad.obj").encode(), None, p(v2), 16, p(t2), 16) == -1   # index out of range
+    # triangle records against an independent double-precision evaluation
+    rng = np.random.default_rng(5)
+    v = rng.uniform(-3, 3, (30, 3)).astype(np.float32); t = rng.integers(0, 30, (40, 3)).astype(np.int32)
+    t[7] = [2, 2, 5]                                          # degenerate
+    pos = np.array([0.5, -1.0, 2.0], np.float32)
+    rec = np.zeros((40, 12), np.float32); bounds = np.zeros((40, 6), np.float32)
+    assert lib.emu_tri_records(p(pos), p(v), 30, p(t), 40, p(rec), p(bounds)) == 40
+    w = (v + pos).astype(np.float32).astype(np.float64)
+    for i in range(40):
+        a, b, c = w[t[i]]
+        n = np.cross(b - a, c - a)
+        if not n.any():
+            assert not rec[i].any()
+            continue
+        nn = n / np.linalg.norm(n)
+        assert np.allclose(rec[i][:3], nn, rtol=0, atol=1e-7) and abs(rec[i][3] - nn @ a) < 1e-5
+        for (px, u_want, v_want) in ((a, 0, 0), (b, 1, 0), (c, 0, 1), ((a + b + c) / 3, 1 / 3, 1 / 3)):
+            u = rec[i][4:7].astype(np.float64) @ px + rec[i][7]; vv = rec[i][8:11].astype(np.float64) @ px + rec[i][11]
+            assert abs(u - u_want) < 1e-4 * max(1, np.abs(rec[i][4:7]).max() * 3) and abs(vv - v_want) < 1e-4 * max(1, np.abs(rec[i][8:11]).max() * 3)
+        assert np.allclose(bounds[i][:3], w[t[i]].min(0)) and np.allclose(bounds[i][3:], w[t[i]].max(0))
