@@ -411,9 +411,13 @@ template <typename K>
 cudaError_t optin(K kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes); }
 
 cudaError_t ensure_optin() {
-    static bool done = false;
+    // the attribute is per DEVICE: a process may hold contexts on several GPUs (tests/multigpu, rt_resolve_fused)
+    static bool done_on[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    bool& done = done_on[dev & 63];
     if (done) return cudaSuccess;
-    cudaError_t e;
 #define RTB_WF_OPTIN(K) \
     if ((e = optin(K<0>)) != cudaSuccess) return e; if ((e = optin(K<1>)) != cudaSuccess) return e; \
     if ((e = optin(K<2>)) != cudaSuccess) return e; if ((e = optin(K<3>)) != cudaSuccess) return e; \
