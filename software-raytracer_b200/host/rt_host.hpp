@@ -143,6 +143,19 @@ public:
         check(rt_set_scene(ctx, pods.data(), (int)pods.size()), ctx);
         doSetFrame = true;
     }
+    // Scene files with the Mesh extension ("Renderer": {"Type": "Mesh", ...}, csrc/mesh.h) carry geometry the POD object
+    // list cannot: load them inside the library. Returns the object count; throws on I/O or parse errors.
+    int LoadSceneFile(const std::string& path) {
+        int n = rt_load_scene(ctx, path.c_str());
+        check(n, ctx);
+        doSetFrame = true;
+        return n;
+    }
+    // Attach triangles (object-space xyz, index triples) to object `index`, which must be of type RT_OBJ_MESH.
+    void SetMesh(int index, const std::vector<float>& vertices, const std::vector<int32_t>& indices) {
+        check(rt_set_mesh(ctx, index, vertices.data(), (int)(vertices.size() / 3), indices.data(), (int)(indices.size() / 3)), ctx);
+        doSetFrame = true;
+    }
     void Invalidate() { doSetFrame = true; }         // any edit: doSetFrame = true (Raytracer.cpp:393,422,454,...)
 
     float SCREEN_SCALE = .5f;                                                       // :30 (slider 0.25 .. 1.0, :479)
