@@ -109,7 +109,8 @@ enum {
     RT_OPT_PIPELINE = 1,           /* RT_PIPELINE_* */
     RT_OPT_ACCEL = 2,              /* RT_ACCEL_* */
     RT_OPT_BVH_THRESHOLD = 3,      /* object count at which RT_ACCEL_AUTO switches to the BVH */
-    RT_OPT_BVH_SCHED = 4,          /* 0 (default): per-ray traversal loop, 1: experimental warp-scheduled BVH kernel */
+    RT_OPT_BVH_SCHED = 4,          /* 0 (default): megakernel per-ray BVH loop / wavefront intersect with ray refill + postponed leaves;
+                                      1: experimental warp-scheduled BVH megakernel / wavefront intersect one ray per lane per batch */
     RT_OPT_BVH_WAIT_K = 5,         /* scheduled kernel: waiting lanes that trigger a shading pass (default 20) */
     RT_OPT_BVH_LEAF = 6,           /* BVH builder: maximum primitives per leaf (default 4) */
     RT_OPT_WF_REFILL = 8,          /* wavefront BVH intersect: free lanes that trigger a ray refill (default 8) */
@@ -124,7 +125,10 @@ enum {
 enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
 /* BRUTE: the reference's object loop. BVH: host-built BVH2. FLAT: two-level flat accelerator for scenes of up
  * to 255 objects (conservative culls with warp-uniform control flow, then the strict tests). All three give
- * bit-identical hits; AUTO measures them on the first render of a scene. */
+ * bit-identical hits; AUTO measures them on the first rt_render_spp call of at least 64 samples after a scene or parameter
+ * change (shorter calls, and camera moves, keep a heuristic choice: flat up to 255 objects, BVH from `bvh_threshold`).
+ * RT_PIPELINE_AUTO is the regeneration megakernel, except that BVH scenes of 2048+ primitives also time the wavefront
+ * pipeline (raygen / persistent-thread intersect / shade + ray compaction kernels) and keep the faster. */
 enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2, RT_ACCEL_FLAT = 3 };
 
 /* ---- lifetime: replaces the worker spawn/join (Raytracer.cpp:331-342, 598-607) -------- */
