@@ -168,6 +168,10 @@ def run_b200(args):
         workload = "config 4: 1 048 576-triangle heightfield mesh + 3 spheres"
     elif args.config == "c5":                            # configs[4]: interactive 1 spp frames at 720p
         W, H = 1280, 720
+    elif args.config == "c1":                            # configs[0]: the reference's own CPU-runnable case
+        W, H = 640, 480
+        if spp == SPP:
+            spp = 64
     stream = torch.cuda.Stream()
     tr = rtb200.PathTracer(local)
     tr.set_stream(stream.cuda_stream)
@@ -318,7 +322,7 @@ def run_b200(args):
         sm_mhz = peaks.get("sm_max_mhz", 1965.0)
         peak_tf = st.sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if (W, H) == (1920, 1080) else METRIC.replace("1920x1080", "%dx%d" % (W, H)), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic: bundled Scene1 fixture (tests/golden/bundled_scenes.npz), default camera, Philox seeds",
             "config": {"workload": "%s %dx%d, %d spp per GPU per step, depth %d, path mode" % (workload, W, H, spp, DEPTH),
@@ -357,7 +361,7 @@ def run_b200(args):
                          "executed_warp_instr_per_segment_ncu": 25.1, "issue_active_pct_ncu": 78.4, "active_threads_per_inst_ncu": 22.65,
                          "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_algorithmic_gbs": (W * H * 32 / kern_s) / 1e9},
         }
-        if world == 1 and not args.no_cpu and args.config == "c2":
+        if world == 1 and not args.no_cpu and args.config in ("c1", "c2"):
             rate, info = cpu_reference_run(objs, args.cpu_frames)
             line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"], "threads": info["threads"]}
@@ -399,8 +403,8 @@ def run_interactive(args, tr, stream, torch):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
-                    help="BASELINE.json configs[1..4]; the headline (and default) is c2, the others are report-only lines")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configs[0..4]; the headline (and default) is c2, the others are report-only lines")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
