@@ -319,7 +319,8 @@ int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     if (c->opt_pipeline != RT_PIPELINE_AUTO) return RT_OK;
     if (c->tuned_pipeline >= 0 || spp < 8) return RT_OK;      // short calls keep the megakernel until a longer one measures
     const size_t prims = (size_t)c->view.n_sph + c->view.n_box + c->view.n_tri;
-    if (ac.kind != kAccelBvh || prims < 2048 || c->pixel_step > 1) { c->tuned_pipeline = RT_PIPELINE_REGEN; return RT_OK; }
+    // (the wavefront pipeline keeps one queue counter per bounce round: 60 rounds at most)
+    if (ac.kind != kAccelBvh || prims < 2048 || c->pixel_step > 1 || c->par.max_bounces > 60) { c->tuned_pipeline = RT_PIPELINE_REGEN; return RT_OK; }
     const size_t px = (size_t)c->par.width * c->par.height;
     RT_CUDA(c, ensure_capacity(c->d_tune, c->cap_tune, px));
     if (!c->wf) c->wf = wavefront_create();
@@ -725,7 +726,8 @@ int rt_render_spp(rt_ctx* c, int spp) {
         // this rank's slice of the global sample indices [next, next+spp)
         int mine = 0; uint32_t first = 0;
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
-        const bool wavefront = c->opt_pipeline == RT_PIPELINE_WAVEFRONT || (c->opt_pipeline == RT_PIPELINE_AUTO && c->tuned_pipeline == RT_PIPELINE_WAVEFRONT);
+        const bool wavefront = (c->opt_pipeline == RT_PIPELINE_WAVEFRONT || (c->opt_pipeline == RT_PIPELINE_AUTO && c->tuned_pipeline == RT_PIPELINE_WAVEFRONT)) &&
+                               c->par.max_bounces <= 60;      // deeper paths: the megakernel (identical results)
         if (wavefront) {
             if (!c->wf) c->wf = wavefront_create();
             RT_CUDA(c, launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_bvh_sched == 0,
