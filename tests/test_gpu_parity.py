@@ -936,3 +936,24 @@ def test_pooled_flat_traversal_is_bit_identical(tracer, scenes, case):
             v = out[(key, reuse)]
             assert np.array_equal(bits(v[0]), bits(base[0])) and v[1:] == base[1:], (case, key, reuse)
     assert np.array_equal(bits(out[("coop", 1)][0]), bits(out[("coop", 0)][0]))
+
+
+def test_accumulation_checkpoint_and_resume(tracer, scenes):
+    """SURVEY.md 5 (checkpoint / resume): dump the float4 sum + sample counter mid-run, restore them into a NEW context
+    and continue - bit-identical to the uninterrupted run (sample indices continue where the checkpoint stopped)."""
+    setup(tracer, scenes["Scene2"], 200, 120)
+    tracer.render_spp(24); tracer.render_spp(40)
+    want, n_want = tracer.read_accum()
+    tracer.reset_accumulation()
+    tracer.render_spp(24)
+    ckpt, n_ckpt = tracer.read_accum()
+    assert n_ckpt == 24
+    other = rtb200.PathTracer(0)
+    try:
+        setup(other, scenes["Scene2"], 200, 120)
+        other.write_accum(ckpt, n_ckpt)
+        other.render_spp(40)
+        got, n_got = other.read_accum()
+    finally:
+        other.close()
+    assert n_got == n_want == 64 and np.array_equal(bits(got), bits(want))
