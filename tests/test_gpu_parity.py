@@ -957,3 +957,18 @@ def test_accumulation_checkpoint_and_resume(tracer, scenes):
     finally:
         other.close()
     assert n_got == n_want == 64 and np.array_equal(bits(got), bits(want))
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_primary_visibility_720p_and_1080p_all_scenes(tracer, oracle, scenes, meta, scene):
+    """ids, t, normals, points bit-exact at the reference's native 1280x720 and at 1920x1080 for every
+    bundled scene (the C oracle, itself pinned to the reference's output, is the checker at these sizes)."""
+    for (w, h), rotated in (((1280, 720), False), ((1920, 1080), True)):
+        cam = make_camera(rtb200.RtCamera, meta, rotated)
+        setup(tracer, scenes[scene], w, h, cam)
+        ids, t, nrm, pt = tracer.read_aov()
+        oid, ot, on, op = oracle.primary_aov(scenes[scene], make_camera(OrcCamera, meta, rotated), w, h)
+        assert np.array_equal(ids, oid)
+        hit = oid >= 0
+        for a, b in ((t, ot), (nrm, on), (pt, op)):
+            assert np.array_equal(bits(a[hit]), bits(b[hit]))
