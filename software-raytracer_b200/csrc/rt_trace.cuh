@@ -30,10 +30,10 @@ struct TraceCtx {
 };
 
 // MODE 5 = MODE 4 with warp-cooperative levels 2 and 3 (closest_hit_flat_coop below); per-warp scratch layout:
-// [ray: 9 x 32 floats (o, d, iBox's m)][pairs: kCoopPairs x u16][candidates: kCoopCands x u16][best key: 32 x u64]
+// [ray: 6 x 32 floats (o, d)][pairs: kCoopPairs x u16][sphere candidates: kCoopCands x u16][best key: 32 x u64]
 constexpr int kCoopPairs = 64;                  // (owner lane, cluster) pairs per call; more -> per-lane fallback
 constexpr int kCoopCands = 64 * 8 + 32 * 56;    // every pair full + every lane's level-1 queue full: cannot overflow
-constexpr int kCoopBytesPerWarp = 9 * 32 * 4 + kCoopPairs * 2 + kCoopCands * 2 + 32 * 8;
+constexpr int kCoopBytesPerWarp = 6 * 32 * 4 + kCoopPairs * 2 + kCoopCands * 2 + 32 * 8;
 
 template <int MODE>
 __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhView& bv, const FlatView& fl, float4* smem) {
@@ -131,13 +131,13 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
     constexpr unsigned long long kNoHit = 0xffffffffffffffffull;
     const int lane = threadIdx.x & 31;
     float* const ray_s = reinterpret_cast<float*>(coop);
-    unsigned short* const pairs = reinterpret_cast<unsigned short*>(coop + 9 * 32 * 4);
+    unsigned short* const pairs = reinterpret_cast<unsigned short*>(coop + 6 * 32 * 4);
     unsigned short* const cand = pairs + kCoopPairs;
     unsigned long long* const key = reinterpret_cast<unsigned long long*>(cand + kCoopCands);
 
-    int nq = 0;
+    int nq = 0, nq_cubes = 0;
     unsigned int cm = 0u;
-    if (active) cm = flat_level1(sc, fv, q, qstride, o, d, nq);
+    if (active) cm = flat_level1(sc, fv, q, qstride, o, d, nq, nq_cubes);
     // ---- level 2: (lane, cluster) pairs, one per lane per pass ----
     const unsigned int cnt = (unsigned int)__popc(cm);
     const unsigned int incl = warp_incl_scan(cnt, lane);
@@ -150,17 +150,13 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
     }
     ray_s[lane] = o.x; ray_s[32 + lane] = o.y; ray_s[64 + lane] = o.z;
     ray_s[96 + lane] = d.x; ray_s[128 + lane] = d.y; ray_s[160 + lane] = d.z;
-    if (sc.n_box > 0) {                                       // cubes: the ray-only half of iBox, once per ray
-        const BoxRay br = box_ray(d);
-        ray_s[192 + lane] = br.m.x; ray_s[224 + lane] = br.m.y; ray_s[256 + lane] = br.m.z;
-    }
     key[lane] = kNoHit;
     {
         unsigned int m = cm, j = incl - cnt;
         while (m) { const int k = __ffs((int)m) - 1; m &= m - 1u; pairs[j++] = (unsigned short)((lane << 8) | k); }
     }
     __syncwarp();
-    // candidate list: every lane's level-1 candidates (pass 0, as owner) + the survivors of the pair it culls (as worker)
+    // sphere candidates: every lane's level-1 singles (pass 0, as owner) + the survivors of the pair it culls (as worker)
     unsigned int n_cand = 0u;                                 // warp-uniform
     unsigned int base = 0u;
     do {
@@ -170,54 +166,56 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
             const int ow = (int)(pr >> 8);
             m8 = flat_cull8(fv, (int)(pr & 255u), f3(ray_s[ow], ray_s[32 + ow], ray_s[64 + ow]), f3(ray_s[96 + ow], ray_s[128 + ow], ray_s[160 + ow]));
         }
-        const unsigned int own = base == 0u ? (unsigned int)nq : 0u;
+        const unsigned int own = base == 0u ? (unsigned int)(nq - nq_cubes) : 0u;
         const unsigned int contrib = own + (unsigned int)__popc(m8);
         const unsigned int incl2 = warp_incl_scan(contrib, lane);
         unsigned int j = n_cand + incl2 - contrib;
-        for (unsigned int i = 0; i < own; ++i) cand[j++] = (unsigned short)((lane << 8) | q[i * qstride]);
+        for (unsigned int i = 0; i < own; ++i) cand[j++] = (unsigned short)((lane << 8) | q[(nq_cubes + (int)i) * qstride]);
         while (m8) { const int b = __clz((int)m8) - 24; m8 &= ~(0x80u >> b); cand[j++] = (unsigned short)((pr & 0xff00u) | fv.cull_slot[8 * (pr & 255u) + b]); }
         n_cand += __shfl_sync(FULL, incl2, 31);
         base += 32u;
     } while (base < n_pairs);
+    // cubes stay with their own lane: in rooms of cubes every ray has a similar number of them, so there is nothing to pool,
+    // and the ray-only half of the cube test is computed once
+    float cube_t = __int_as_float(0x7f800000);
+    int cube_id = 0x7fffffff, cube_code = -1;
+    float3 bn = f3(0.f, 0.f, 0.f);
+    if (nq_cubes > 0) {
+        const BoxRay br = box_ray(d);
+        for (int i = 0; i < nq_cubes; ++i) {
+            const int code = (int)q[i * qstride], j = code - sc.n_sph;
+            float dist; float3 nrm;
+            if (box_hit_pre(box[2 * j], box[2 * j + 1], o, br, dist, nrm)) {
+                const int oid = fv.prim_id[code];
+                if (dist < cube_t || (dist == cube_t && oid < cube_id)) { cube_t = dist; cube_id = oid; cube_code = code; bn = nrm; }
+            }
+        }
+    }
     __syncwarp();
-    // ---- level 3: one strict test per lane per pass; the owner gets the minimum of (t, object id) ----
+    // ---- level 3, spheres: one strict test per lane per pass; the owner gets the minimum of (t, object id) ----
     for (base = 0u; base < n_cand; base += 32u) {
         const unsigned int i = base + (unsigned int)lane;
         if (i < n_cand) {
             const unsigned int e = cand[i];
             const int ow = (int)(e >> 8), code = (int)(e & 255u);
-            const float3 ro = f3(ray_s[ow], ray_s[32 + ow], ray_s[64 + ow]), rd = f3(ray_s[96 + ow], ray_s[128 + ow], ray_s[160 + ow]);
-            float t = 0.f; bool hit; unsigned int nbits = 0u;
-            if (code < sc.n_sph) hit = sphere_t(sph[code], ro, rd, t);
-            else {
-                float3 nrm = f3(0.f, 0.f, 0.f); const int j = code - sc.n_sph;
-                hit = box_hit_pre(box[2 * j], box[2 * j + 1], ro, box_ray_from_m(f3(ray_s[192 + ow], ray_s[224 + ow], ray_s[256 + ow])), t, nrm);
-                // a cube normal has components in {+-0, +-1}: 2 bits each travel in the key
-                nbits = ((__float_as_uint(nrm.x) >> 31) << 5) | ((nrm.x != 0.f ? 1u : 0u) << 4) | ((__float_as_uint(nrm.y) >> 31) << 3) |
-                        ((nrm.y != 0.f ? 1u : 0u) << 2) | ((__float_as_uint(nrm.z) >> 31) << 1) | (nrm.z != 0.f ? 1u : 0u);
-            }
-            if (hit && t == t) {                              // NaN distances never win (`<` is false), as in the per-lane loop
-                unsigned int ob = __float_as_uint(t);
+            float t = 0.f;
+            if (sphere_t(sph[code], f3(ray_s[ow], ray_s[32 + ow], ray_s[64 + ow]), f3(ray_s[96 + ow], ray_s[128 + ow], ray_s[160 + ow]), t) && t == t) {
+                unsigned int ob = __float_as_uint(t);         // NaN distances never win (`<` is false), as in the per-lane loop
                 ob ^= (unsigned int)((int)ob >> 31) | 0x80000000u;                        // order-preserving bits
-                const unsigned long long kb = ((unsigned long long)ob << 32) |
-                                              (unsigned long long)(((unsigned int)fv.prim_id[code] << 14) | ((unsigned int)code << 6) | nbits);
+                const unsigned long long kb = ((unsigned long long)ob << 32) | (unsigned long long)(((unsigned int)fv.prim_id[code] << 8) | (unsigned int)code);
                 if (kb < *reinterpret_cast<volatile unsigned long long*>(key + ow)) atomicMin(key + ow, kb);
             }
         }
     }
     __syncwarp();
     const unsigned long long kb = key[lane];
-    float best_t = 0.f; int best_id = 0, best_code = -1;
-    float3 bn = f3(0.f, 0.f, 0.f);
+    float best_t = cube_t; int best_id = cube_id, best_code = cube_code;
     if (active && kb != kNoHit) {
         unsigned int ob = (unsigned int)(kb >> 32);
         ob ^= (unsigned int)((int)~ob >> 31) | 0x80000000u;
-        best_t = __uint_as_float(ob);
-        const unsigned int lo = (unsigned int)kb;
-        best_code = (int)((lo >> 6) & 255u);
-        best_id = (int)(lo >> 14);
-        bn = f3(__uint_as_float(((lo >> 5) & 1u) << 31 | ((lo >> 4) & 1u) * 0x3f800000u), __uint_as_float(((lo >> 3) & 1u) << 31 | ((lo >> 2) & 1u) * 0x3f800000u),
-                __uint_as_float(((lo >> 1) & 1u) << 31 | (lo & 1u) * 0x3f800000u));
+        const float st = __uint_as_float(ob);
+        const int sid = (int)(((unsigned int)kb) >> 8);
+        if (st < best_t || (st == best_t && sid < best_id)) { best_t = st; best_id = sid; best_code = (int)(kb & 255ull); }
     }
     __syncwarp();                                             // everyone is done with the scratch before the next call
     return flat_finish(sc, sph, o, d, best_t, best_id, best_code, bn);
