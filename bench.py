@@ -181,6 +181,8 @@ def run_b200(args):
     tr.set_option(rtb200.RT_OPT_PIPELINE, {"auto": rtb200.RT_PIPELINE_AUTO, "regen": rtb200.RT_PIPELINE_REGEN, "wavefront": rtb200.RT_PIPELINE_WAVEFRONT}[args.pipeline])
     if args.bvh_sched >= 0:
         tr.set_option(rtb200.RT_OPT_BVH_SCHED, args.bvh_sched)
+    if args.bvh_wide >= 0:
+        tr.set_option(rtb200.RT_OPT_BVH_WIDE, args.bvh_wide)
     if args.wait_k >= 0:
         tr.set_option(rtb200.RT_OPT_BVH_WAIT_K, args.wait_k)
     if args.flat_coop >= 0:
@@ -419,6 +421,7 @@ def main():
     ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"], help="N > 1 exchange: fused peer-memory reduce+resolve kernel, or NCCL all-reduce")
     ap.add_argument("--bvh-sched", type=int, default=-1, help="RT_OPT_BVH_SCHED override")
     ap.add_argument("--wait-k", type=int, default=-1, help="RT_OPT_BVH_WAIT_K override")
+    ap.add_argument("--bvh-wide", type=int, default=-1, help="RT_OPT_BVH_WIDE: 0 binary BVH nodes (default), 1 8-wide quantised nodes for 1024+ primitives, 2 always")
     ap.add_argument("--flat-coop", type=int, default=-1, help="RT_OPT_FLAT_COOP: 0 per-lane levels 2/3, 1 warp-cooperative, 2 measured per scene (default)")
     ap.add_argument("--wf-refill", type=int, default=-1, help="RT_OPT_WF_REFILL override")
     ap.add_argument("--wf-node-min", type=int, default=-1, help="RT_OPT_WF_NODE_MIN override")

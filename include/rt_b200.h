@@ -118,6 +118,9 @@ enum {
     RT_OPT_POOL_TILES = 10,        /* megakernel, few samples per call: 8x4 pixel tiles per warp-level pixel pool; 0 (default) automatic, 1 one pixel per lane */
     RT_OPT_FLAT_COOP = 11,         /* flat accelerator in the megakernel: 1 the warp pools the cluster culls and strict tests of its 32 rays, 0 every lane for itself,
                                       2 (default) pooled for scenes without cubes (open sphere scenes gain ~8 %, cube rooms lose ~10 %) */
+    RT_OPT_BVH_WIDE = 12,          /* BVH node format: 0 (default) 64-byte binary nodes; 1 scenes of 1024+ primitives traverse the 8-wide form with
+                                      quantised child boxes (80-byte nodes, csrc/bvh_wide.h); 2 every BVH scene. Identical results; on B200 the
+                                      wide form makes 2.2x fewer node visits but executes more instructions and measured slower */
     RT_OPT_PRIMARY_REUSE = 7       /* 1 (default): one primary closest-hit query per pixel per rt_render_spp call,
                                       reused by every sample (identical ray: the reference has no pixel jitter);
                                       0: re-trace it for every sample like the reference. Results are bit-identical. */

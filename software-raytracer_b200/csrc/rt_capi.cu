@@ -4,6 +4,7 @@
 // No CPU fallback lives here: every compute entry point launches kernels or fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,7 @@
 #include "rt_host_pack.h"
 #include "rt_kernels.h"
 #include "bvh_build.h"
+#include "bvh_wide.h"
 #include "flat_build.h"
 #include "mesh.h"
 #include "scene_json.h"
@@ -52,6 +54,9 @@ struct rt_ctx {
     BvhView bview;
     float4* d_bvh_nodes = nullptr; int* d_bvh_refs = nullptr;
     size_t cap_bvh_nodes = 0, cap_bvh_refs = 0;
+    HostWideBvh wide;                  // 8-wide quantised form for BVHs read from global memory (bvh_wide.h)
+    uint4* d_wide_nodes = nullptr; int* d_wide_refs = nullptr;
+    size_t cap_wide_nodes = 0, cap_wide_refs = 0;
     bool bvh_valid = false;
 
     // flat two-level accelerator for small scenes (built lazily; see flat_build.h)
@@ -78,6 +83,7 @@ struct rt_ctx {
     int pixel_step = 1, strip_columns = 0;   // block-filled frames (rt_set_pixel_step)
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
     int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4, opt_primary_reuse = 1;
+    int opt_bvh_wide = 0;              // 0 (default) binary nodes, 1 wide nodes for BVHs of kWideMinPrims+ primitives, 2 always (tests)
     int opt_wf_refill = 8, opt_wf_node_min = 8, opt_pool_tiles = 0, opt_flat_coop = 2;   // flat_coop: 0 off, 1 on, 2 measured per scene
     int tuned_flat_coop = 1;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
@@ -180,20 +186,35 @@ int upload_scene(rt_ctx* c) {
 
 // (Re)builds and uploads the BVH when the scene changed or a ray origin lies outside the extent its
 // box inflation was derived from.
+constexpr int kWideMinPrims = 1024;    // below this the whole BVH2 is staged in shared memory anyway (kMaxBvhStagedBytes)
 int ensure_bvh(rt_ctx* c, float origin_extent) {
     if (c->bvh_valid && origin_extent <= c->bvh.extent) return RT_OK;
-    build_bvh(c->scene.objects, origin_extent, c->bvh, c->opt_bvh_leaf, &c->tris, c->par.eps);
+    const size_t prims = (size_t)c->view.n_sph + c->view.n_box + c->view.n_tri;
+    const bool want_wide = c->opt_bvh_wide == 2 || (c->opt_bvh_wide == 1 && prims >= (size_t)kWideMinPrims);
+    build_bvh(c->scene.objects, origin_extent, c->bvh, want_wide ? std::min(c->opt_bvh_leaf, kWideMaxLeaf) : c->opt_bvh_leaf, &c->tris, c->par.eps);
     if (c->bvh.max_depth + 2 > 62) return fail(c, RT_ERR_INVALID, "BVH too deep for the traversal stack");
+    c->wide = HostWideBvh();
+    if (want_wide) build_wide_bvh(c->bvh, c->wide);           // not usable (huge extents, oversized leaves): the BVH2 is traversed
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     RT_CUDA(c, ensure_capacity(c->d_bvh_nodes, c->cap_bvh_nodes, c->bvh.nodes.size() * 4));
     RT_CUDA(c, ensure_capacity(c->d_bvh_refs, c->cap_bvh_refs, c->bvh.refs.size()));
     RT_CUDA(c, cudaMemcpyAsync(c->d_bvh_nodes, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, c->stream));
     if (!c->bvh.refs.empty())
         RT_CUDA(c, cudaMemcpyAsync(c->d_bvh_refs, c->bvh.refs.data(), c->bvh.refs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (c->wide.usable) {
+        RT_CUDA(c, ensure_capacity(c->d_wide_nodes, c->cap_wide_nodes, c->wide.nodes.size() * 5));
+        RT_CUDA(c, ensure_capacity(c->d_wide_refs, c->cap_wide_refs, c->wide.refs.size()));
+        RT_CUDA(c, cudaMemcpyAsync(c->d_wide_nodes, c->wide.nodes.data(), c->wide.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, c->stream));
+        if (!c->wide.refs.empty())
+            RT_CUDA(c, cudaMemcpyAsync(c->d_wide_refs, c->wide.refs.data(), c->wide.refs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->bview.nodes = c->d_bvh_nodes; c->bview.refs = c->d_bvh_refs;
     c->bview.n_nodes = (int)c->bvh.nodes.size(); c->bview.n_refs = (int)c->bvh.refs.size();
     c->bview.stack_entries = c->bvh.max_depth + 2;
+    c->bview.wnodes = c->wide.usable ? c->d_wide_nodes : nullptr; c->bview.wrefs = c->wide.usable ? c->d_wide_refs : nullptr;
+    c->bview.n_wnodes = c->wide.usable ? (int)c->wide.nodes.size() : 0; c->bview.n_wrefs = c->wide.usable ? (int)c->wide.refs.size() : 0;
+    c->bview.wstack_entries = c->wide.depth + 2;
     c->bvh_valid = true;
     return RT_OK;
 }
@@ -450,7 +471,7 @@ int rt_destroy(rt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
-    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_tune);
+    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_wide_nodes); cudaFree(c->d_wide_refs); cudaFree(c->d_tune);
     cudaFree(c->d_tri); cudaFree(c->d_tri_obj);
     wavefront_destroy(c->wf);
     cudaFree(c->d_flat_boxes); cudaFree(c->d_flat_cull); cudaFree(c->d_flat_slots); cudaFree(c->d_flat_ids);
@@ -641,6 +662,7 @@ int rt_set_option(rt_ctx* c, int option, int value) {
         case RT_OPT_ACCEL: c->opt_accel = value; return RT_OK;
         case RT_OPT_BVH_THRESHOLD: c->opt_bvh_threshold = value; return RT_OK;
         case RT_OPT_BVH_SCHED: c->opt_bvh_sched = value; return RT_OK;
+        case RT_OPT_BVH_WIDE: c->opt_bvh_wide = value < 0 || value > 2 ? 0 : value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
         case RT_OPT_BVH_LEAF: c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
         case RT_OPT_PRIMARY_REUSE: c->opt_primary_reuse = value != 0; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
         case RT_OPT_FLAT_COOP: c->opt_flat_coop = value < 0 || value > 2 ? 2 : value; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;

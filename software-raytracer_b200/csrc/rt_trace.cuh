@@ -17,7 +17,8 @@ constexpr int kThreads = 128;
 
 // ---- closest-hit back ends -------------------------------------------------------------------
 // MODE 0: brute force, geometry staged in shared memory      MODE 1: brute force from global (L1)
-// MODE 2: BVH, nodes + refs + geometry staged in shared mem  MODE 3: BVH from global (L1/L2)
+// MODE 2: BVH, nodes + refs + geometry staged in shared mem  MODE 3: BVH from global (L1/L2); when the 8-wide quantised
+//                                                                    form exists (bvh_wide.h) MODE 3 traverses that one
 // MODE 4: flat two-level accelerator (flat_build.h), everything staged in shared memory
 // Shared memory layout: [BVH stack: stack_entries x blockDim ints][spheres][cubes][nodes][refs]
 //                       MODE 4: [candidate queues: kFlatQueue x blockDim bytes][spheres][cubes][level-1 boxes][cull records][prim ids][cull slots]
@@ -27,6 +28,7 @@ struct TraceCtx {
     FlatView fl;
     unsigned char* q;          // MODE 4/5: this thread's candidate queue, entries `stride` bytes apart
     unsigned char* coop;       // MODE 5: this WARP's scratch for the cooperative levels 2/3
+    const uint4* wnodes; const int* wrefs; int wentries;   // MODE 3 with the wide BVH: stack = [3 * wentries][thread] words
 };
 
 // MODE 5 = MODE 4 with warp-cooperative levels 2 and 3 (closest_hit_flat_coop below); per-warp scratch layout:
@@ -40,6 +42,7 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
     TraceCtx t;
     t.sph = sc.sph; t.box = sc.box; t.nodes = bv.nodes; t.refs = bv.refs; t.stack = nullptr; t.stack_t = nullptr; t.stride = blockDim.x;
     t.fl = fl; t.q = nullptr;
+    t.wnodes = bv.wnodes; t.wrefs = bv.wrefs; t.wentries = bv.wstack_entries;
     float4* p = smem;
     t.coop = nullptr;
     if (MODE == 4 || MODE == 5) {
@@ -94,6 +97,7 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
 template <int MODE>
 __device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d) {
     if (MODE == 4 || MODE == 5) return closest_hit_flat(sc, t.fl, t.sph, t.box, t.q, t.stride, o, d);
+    if (MODE == 3 && t.wnodes) return closest_hit_bvh8(sc, t.sph, t.box, t.wnodes, t.wrefs, t.stack, t.stride, t.wentries, o, d);
     if (MODE >= 2) return closest_hit_bvh(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr);
     return closest_hit(sc, t.sph, t.box, o, d);
 }
@@ -249,6 +253,7 @@ inline int pick_mode(const SceneView& sc, const AccelSel& ac, size_t& smem, int 
         smem = 0; return 1;
     }
     const BvhView& bv = ac.bvh;
+    if (bv.wnodes) { smem = ((size_t)3 * bv.wstack_entries * threads * sizeof(int) + 15) / 16 * 16; return 3; }
     const size_t stack = ((size_t)2 * bv.stack_entries * threads * sizeof(int) + 15) / 16 * 16;
     const size_t all = stack + geo + (size_t)bv.n_nodes * 64 + (size_t)bv.n_refs * 4 + 16;
     if (all <= kMaxBvhStagedBytes) { smem = all; return 2; }

@@ -23,3 +23,17 @@ static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4);
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi; }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+// PRMT: nibble k of s selects result byte k from the 8 bytes of (y:x); bit 3 of the nibble replicates the byte's sign bit
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t src = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t sel = (s >> (4 * k)) & 0xf;
+        uint32_t b = (uint32_t)(src >> (8 * (sel & 7))) & 0xff;
+        // (the CUDA intrinsic ignores the replicate-sign flag of PTX prmt: only selector bits 2..0 count)
+        r |= b << (8 * k);
+    }
+    return r;
+}

@@ -8,6 +8,7 @@
 #include "../../software-raytracer_b200/csrc/rt_device.cuh"
 #include "../../software-raytracer_b200/csrc/rt_host_pack.h"
 #include "../../software-raytracer_b200/csrc/bvh_build.h"
+#include "../../software-raytracer_b200/csrc/bvh_wide.h"
 #include "../../software-raytracer_b200/csrc/flat_build.h"
 #include "../../software-raytracer_b200/csrc/mesh.h"
 
@@ -15,7 +16,7 @@ using namespace rtb;
 
 extern "C" {
 // Sum over samples [s0, s0+n) for every pixel (float3 per pixel, y-up); accel 0 = brute force,
-// 1 = BVH candidates, 2 = flat two-level accelerator. Also returns primary AOVs when the pointers are given. Returns segments traced.
+// 1 = BVH candidates, 2 = flat two-level accelerator, 3 = 8-wide quantised BVH (bvh_wide.h). Also returns primary AOVs when the pointers are given. Returns segments traced.
 // Optional mesh (extension): object `mesh_object` (type RT_OBJ_MESH) gets the given triangles.
 long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* cam, const rt_params* par, int accel,
                           uint32_t s0, int n, float* out_rgb, int32_t* aov_id, float* aov_t, float* aov_n, float* aov_p,
@@ -46,9 +47,12 @@ long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* 
     HostBvh bvh;
     float ext = 0.f;
     for (int k = 0; k < 3; ++k) ext = fmaxf(ext, fabsf(cam->pos[k]));
-    build_bvh(objs, ext, bvh, 4, &tris);
+    build_bvh(objs, ext, bvh, accel == 3 ? kWideMaxLeaf : 4, &tris);
     const float4* nodes = reinterpret_cast<const float4*>(bvh.nodes.data());
-    std::vector<int> stack((size_t)bvh.max_depth + 8);
+    HostWideBvh wide;
+    if (accel == 3) { build_wide_bvh(bvh, wide); if (!wide.usable) return -2; }
+    const int wentries = wide.depth + 2;
+    std::vector<int> stack((size_t)bvh.max_depth + 8 + 3 * (size_t)wentries);
     unsigned char queue[64];
     HostFlat flat;
     build_flat(objs, ext, flat);
@@ -64,6 +68,8 @@ long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* 
             const float3 d0 = ray_dir(fr, px, py);
             auto trace = [&](float3 o, float3 d) {
                 if (accel == 2) return closest_hit_flat(sc, fv, sc.sph, sc.box, queue, 1, o, d);
+                if (accel == 3) return closest_hit_bvh8(sc, sc.sph, sc.box, reinterpret_cast<const uint4*>(wide.nodes.data()), wide.refs.data(),
+                                                        stack.data(), 1, wentries, o, d);
                 return accel ? closest_hit_bvh(sc, sc.sph, sc.box, nodes, bvh.refs.data(), stack.data(), 1, o, d)
                              : closest_hit(sc, sc.sph, sc.box, o, d);
             };
@@ -89,6 +95,59 @@ long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* 
         }
     return segs;
 }
+}
+
+// traversal statistics of the emulated wide / binary BVH loops since the last call (test diagnostics)
+extern "C" void emu_bvh_stats(long long* out4) {
+    out4[0] = g_wide_node_visits; out4[1] = g_wide_prim_tests; out4[2] = g_bvh2_node_visits; out4[3] = g_wide_empty_visits; out4[4] = g_wide_stale_visits; g_wide_stale_visits = 0;
+    g_wide_node_visits = g_wide_prim_tests = g_bvh2_node_visits = g_wide_empty_visits = 0;
+}
+// wide BVH of a scene: counts[0..4] = usable, nodes, refs, depth, BVH2 nodes; returns the number of children whose decoded
+// box does NOT contain the BVH2 box it came from (must be 0), checked independently of the builder's own assert
+extern "C" int emu_wide_info(const rt_object* objects, int n_obj, float origin_extent, int* counts) {
+    std::vector<rt_object> objs(objects, objects + n_obj);
+    HostBvh b2; HostWideBvh w;
+    build_bvh(objs, origin_extent, b2, kWideMaxLeaf, nullptr);
+    build_wide_bvh(b2, w);
+    counts[0] = w.usable; counts[1] = (int)w.nodes.size(); counts[2] = (int)w.refs.size(); counts[3] = w.depth; counts[4] = (int)b2.nodes.size();
+    if (!w.usable) return 0;
+    // every primitive's own (uninflated) box must lie inside the decoded box of the leaf child that references it, and
+    // every ref must appear exactly once
+    std::vector<float> plo, phi;
+    for (const rt_object& o : objs) {
+        if (o.type != RT_OBJ_SPHERE && o.type != RT_OBJ_CUBE) continue;
+        for (int k = 0; k < 3; ++k) {
+            const float h = o.type == RT_OBJ_SPHERE ? fabsf(o.radius) : fabsf(o.half[k]);
+            plo.push_back(o.pos[k] - h); phi.push_back(o.pos[k] + h);
+        }
+    }
+    std::vector<int> seen(plo.size() / 3, 0);
+    int sph_n = 0; for (const rt_object& o : objs) sph_n += o.type == RT_OBJ_SPHERE;
+    // object order -> ref: spheres get slots in order, cubes ~slot; map back
+    std::vector<int> sph_obj, box_obj; { int i = 0; for (const rt_object& o : objs) { if (o.type == RT_OBJ_SPHERE) sph_obj.push_back(i), ++i; else if (o.type == RT_OBJ_CUBE) box_obj.push_back(i), ++i; } }
+    int bad = 0;
+    for (const WideNode& nd : w.nodes) {
+        const uint8_t* hdr = reinterpret_cast<const uint8_t*>(&nd.w[3]);
+        const uint8_t* meta = reinterpret_cast<const uint8_t*>(&nd.w[6]);
+        const uint8_t* qb = reinterpret_cast<const uint8_t*>(&nd.w[8]);
+        float org[3]; memcpy(org, &nd.w[0], 12);
+        for (int s = 0; s < 8; ++s) {
+            if (meta[s] == 0 || (hdr[3] >> s & 1)) continue;
+            const int cnt = __builtin_popcount(meta[s] >> 5), off = meta[s] & 31;
+            for (int j = 0; j < cnt; ++j) {
+                const int r = w.refs[(size_t)nd.w[5] + off + j];
+                const int prim = r >= 0 ? sph_obj[(size_t)r] : box_obj[(size_t)(~r)];
+                ++seen[(size_t)prim];
+                for (int k = 0; k < 3; ++k) {
+                    const double sc = ldexp(1.0, (int)hdr[k] - 127);
+                    const double lo = (double)org[k] + sc * qb[8 * k + s], hi = (double)org[k] + sc * qb[24 + 8 * k + s];
+                    if (!(lo <= plo[3 * (size_t)prim + k] && hi >= phi[3 * (size_t)prim + k])) ++bad;
+                }
+            }
+        }
+    }
+    for (int c : seen) if (c != 1) ++bad;
+    return bad;
 }
 
 // ---- host-logic hooks for the CPU tests (builders only, no tracing) ----------------------------------------------

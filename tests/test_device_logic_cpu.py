@@ -20,6 +20,7 @@ EMU_SO = os.path.join(EMU_DIR, "libemu.so")
 @pytest.fixture(scope="session")
 def emu():
     srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(ROOT, "software-raytracer_b200", "csrc", "bvh_build.cpp"),
+            os.path.join(ROOT, "software-raytracer_b200", "csrc", "bvh_wide.cpp"),
             os.path.join(ROOT, "software-raytracer_b200", "csrc", "flat_build.cpp"),
             os.path.join(ROOT, "software-raytracer_b200", "csrc", "mesh.cpp")]
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
@@ -48,7 +49,7 @@ def emu():
 
 
 @pytest.mark.parametrize("scene", SCENES)
-@pytest.mark.parametrize("accel", [0, 1, 2])
+@pytest.mark.parametrize("accel", [0, 1, 2, 3])
 def test_device_logic_matches_reference_goldens(emu, scenes, golden, meta, scene, accel):
     z = golden("radiance_philox")
     for cam_name, mb in (("default", 8), ("default", 2), ("rotated", 8)):
