@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for cfg in c3 c4; do for pipe in regen wavefront; do for wide in 0 1; do
   echo "== $cfg $pipe wide=$wide" >> gpurun_out/wide_ab.log
-  timeout 300 python bench.py --config $cfg --pipeline $pipe --bvh-wide $wide --no-cpu --steps 2 --warmup 3 2>&1 | tail -1 | python -c "
+  timeout 300 python bench.py --config $cfg --pipeline $pipe --bvh-wide $wide --no-cpu --steps 3 --warmup 3 --spp $([ $cfg = c3 ] && echo 16 || echo 64) 2>&1 | tail -1 | python -c "
 import sys, json
 l=sys.stdin.read().strip()
 try:

@@ -215,6 +215,7 @@ int ensure_bvh(rt_ctx* c, float origin_extent) {
     c->bview.wnodes = c->wide.usable ? c->d_wide_nodes : nullptr; c->bview.wrefs = c->wide.usable ? c->d_wide_refs : nullptr;
     c->bview.n_wnodes = c->wide.usable ? (int)c->wide.nodes.size() : 0; c->bview.n_wrefs = c->wide.usable ? (int)c->wide.refs.size() : 0;
     c->bview.wstack_entries = c->wide.depth + 2;
+    c->bview.q2f_hi = 0x47u;
     c->bvh_valid = true;
     return RT_OK;
 }

@@ -28,7 +28,7 @@ struct TraceCtx {
     FlatView fl;
     unsigned char* q;          // MODE 4/5: this thread's candidate queue, entries `stride` bytes apart
     unsigned char* coop;       // MODE 5: this WARP's scratch for the cooperative levels 2/3
-    const uint4* wnodes; const int* wrefs; int wentries;   // MODE 3 with the wide BVH: stack = [3 * wentries][thread] words
+    const uint4* wnodes; const int* wrefs; int wentries; uint32_t k47;   // MODE 3 with the wide BVH: stack = [3 * wentries][thread] words
 };
 
 // MODE 5 = MODE 4 with warp-cooperative levels 2 and 3 (closest_hit_flat_coop below); per-warp scratch layout:
@@ -42,7 +42,7 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
     TraceCtx t;
     t.sph = sc.sph; t.box = sc.box; t.nodes = bv.nodes; t.refs = bv.refs; t.stack = nullptr; t.stack_t = nullptr; t.stride = blockDim.x;
     t.fl = fl; t.q = nullptr;
-    t.wnodes = bv.wnodes; t.wrefs = bv.wrefs; t.wentries = bv.wstack_entries;
+    t.wnodes = bv.wnodes; t.wrefs = bv.wrefs; t.wentries = bv.wstack_entries; t.k47 = bv.q2f_hi;
     float4* p = smem;
     t.coop = nullptr;
     if (MODE == 4 || MODE == 5) {
@@ -97,7 +97,7 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
 template <int MODE>
 __device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d) {
     if (MODE == 4 || MODE == 5) return closest_hit_flat(sc, t.fl, t.sph, t.box, t.q, t.stride, o, d);
-    if (MODE == 3 && t.wnodes) return closest_hit_bvh8(sc, t.sph, t.box, t.wnodes, t.wrefs, t.stack, t.stride, t.wentries, o, d);
+    if (MODE == 3 && t.wnodes) return closest_hit_bvh8(sc, t.sph, t.box, t.wnodes, t.wrefs, t.stack, t.stride, t.wentries, t.k47, o, d);
     if (MODE >= 2) return closest_hit_bvh(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr);
     return closest_hit(sc, t.sph, t.box, o, d);
 }

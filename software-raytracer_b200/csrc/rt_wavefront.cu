@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH8_MIN_BLOCKS) k_wf_interse
     uint32_t pid = 0, node = NONE, t0x = 0, t0b = 0, t1x = 0, t1b = 0;
     float node_t = 0.f;
     float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
-    WideRay wr = wide_ray(d);
+    WideRay wr = wide_ray(d, bv.q2f_hi);
     BestHit b;
     b.t = 0.f; b.id = 0; b.ref = 0; b.have = false; b.n = f3(0.f, 0.f, 0.f);
     bool exhausted = false;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH8_MIN_BLOCKS) k_wf_interse
                         pid = q[i];
                         const float4 o4 = ray_o[pid], d4 = ray_d[pid];
                         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
-                        wr = wide_ray(d);
+                        wr = wide_ray(d, bv.q2f_hi);
                         b.t = __int_as_float(0x7f800000); b.id = 0x7fffffff; b.ref = 0; b.have = false;
                         node = 0u; node_t = -b.t; t0b = t1b = 0u; sp = 0; state = ACTIVE;
                     }

@@ -69,7 +69,7 @@ long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* 
             auto trace = [&](float3 o, float3 d) {
                 if (accel == 2) return closest_hit_flat(sc, fv, sc.sph, sc.box, queue, 1, o, d);
                 if (accel == 3) return closest_hit_bvh8(sc, sc.sph, sc.box, reinterpret_cast<const uint4*>(wide.nodes.data()), wide.refs.data(),
-                                                        stack.data(), 1, wentries, o, d);
+                                                        stack.data(), 1, wentries, 0x47u, o, d);
                 return accel ? closest_hit_bvh(sc, sc.sph, sc.box, nodes, bvh.refs.data(), stack.data(), 1, o, d)
                              : closest_hit(sc, sc.sph, sc.box, o, d);
             };

@@ -66,7 +66,8 @@ def test_device_logic_matches_reference_goldens(emu, scenes, golden, meta, scene
         assert sha(ids) == m["ids_sha256"] and sha(t) == m["t_sha256"] and sha(nrm) == m["normal_sha256"] and sha(pt) == m["point_sha256"]
 
 
-def test_device_logic_bvh_equals_brute_on_random_scene(emu):
+@pytest.mark.parametrize("accel", [1, 3])
+def test_device_logic_bvh_equals_brute_on_random_scene(emu, accel):
     rng = np.random.default_rng(7)
     n = 600
     o = np.zeros(n + 1, rtb200.OBJECT_DTYPE)
@@ -81,7 +82,7 @@ def test_device_logic_bvh_equals_brute_on_random_scene(emu):
     cam = rtb200.default_camera(60); cam.pos[1] = 3.0; cam.pos[2] = -6.0
     par = rtb200.default_params(width=96, height=64, mode=0, max_bounces=6, seed_lo=5, seed_hi=6)
     a, sa, aa = emu(o, cam, par, 0, 3, 3, aov=True)
-    b, sb, ab = emu(o, cam, par, 1, 3, 3, aov=True)
+    b, sb, ab = emu(o, cam, par, accel, 3, 3, aov=True)      # 1: binary BVH, 3: 8-wide quantised BVH
     assert sa == sb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     for x, y in zip(aa, ab):
         assert np.array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32))
@@ -123,10 +124,11 @@ def test_device_logic_mesh_bvh_equals_brute_and_oracle(emu, oracle):
     cam = rtb200.default_camera(55); cam.pos[1] = 1.5; cam.pos[2] = -1.0
     par = rtb200.default_params(width=96, height=64, mode=0, max_bounces=4, seed_lo=5, seed_hi=6)
     a, sa, aa = emu(objs, cam, par, 0, 0, 3, aov=True, mesh=(0, v, tr))
-    b, sb, ab = emu(objs, cam, par, 1, 0, 3, aov=True, mesh=(0, v, tr))
-    assert sa == sb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
-    for x, y in zip(aa, ab):
-        assert np.array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32))
+    for accel in (1, 3):                                     # binary BVH, 8-wide quantised BVH
+        b, sb, ab = emu(objs, cam, par, accel, 0, 3, aov=True, mesh=(0, v, tr))
+        assert sa == sb and np.array_equal(a.view(np.uint32), b.view(np.uint32)), accel
+        for x, y in zip(aa, ab):
+            assert np.array_equal(np.ascontiguousarray(x).view(np.uint32), np.ascontiguousarray(y).view(np.uint32)), accel
     assert (aa[0] == 0).mean() > 0.2                         # the mesh is visible
     ocam = OrcCamera(); ocam.right[0] = 1; ocam.up[1] = 1; ocam.forward[2] = 1; ocam.fov_deg = 55; ocam.pos[1] = 1.5; ocam.pos[2] = -1.0
     oracle.set_triangles(objs, {0: (v, tr)})

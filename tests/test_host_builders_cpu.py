@@ -118,3 +118,43 @@ def test_obj_subset_and_triangle_records(lib, tmp_path):
             u = rec[i][4:7].astype(np.float64) @ px + rec[i][7]; vv = rec[i][8:11].astype(np.float64) @ px + rec[i][11]
             assert abs(u - u_want) < 1e-4 * max(1, np.abs(rec[i][4:7]).max() * 3) and abs(vv - v_want) < 1e-4 * max(1, np.abs(rec[i][8:11]).max() * 3)
         assert np.allclose(bounds[i][:3], w[t[i]].min(0)) and np.allclose(bounds[i][3:], w[t[i]].max(0))
+
+
+# ---- 8-wide quantised BVH (csrc/bvh_wide.h): every primitive inside the decoded box of the leaf child that holds it ----
+def wide_info(lib, objs, extent=0.0):
+    objs = np.ascontiguousarray(objs, rtb200.OBJECT_DTYPE)
+    counts = (C.c_int * 5)()
+    bad = lib.emu_wide_info(objs.ctypes.data_as(C.c_void_p), len(objs), C.c_float(extent), counts)
+    return bad, list(counts)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_wide_bvh_builder_on_bundled_scenes(lib, scenes, scene):
+    bad, (usable, n_nodes, n_refs, depth, n_b2) = wide_info(lib, scenes[scene], extent=10.0)
+    prims = int(np.isin(scenes[scene]["type"], (1, 2)).sum())
+    assert usable == 1 and bad == 0 and n_refs == prims and 1 <= depth <= 8 and n_nodes <= n_b2
+
+
+def test_wide_bvh_builder_limits(lib):
+    rng = np.random.default_rng(11)
+
+    def spheres(n, spread=30.0):
+        o = np.zeros(n, rtb200.OBJECT_DTYPE); o["type"] = 1
+        o["pos"] = rng.uniform(-spread, spread, (n, 3)).astype(np.float32); o["radius"] = rng.uniform(0.05, 1.0, n).astype(np.float32)
+        return o
+    for n in (1, 2, 9, 64, 65, 4000):
+        o = spheres(n)
+        o["type"][::5] = 2; o["half"][::5] = rng.uniform(0.1, 2.0, (len(o["half"][::5]), 3)).astype(np.float32)
+        bad, (usable, n_nodes, n_refs, depth, n_b2) = wide_info(lib, o, extent=100.0)
+        assert usable == 1 and bad == 0 and n_refs == n, n
+        assert n_nodes * 2 <= max(n_b2, 2) or n < 9, (n, n_nodes, n_b2)       # the collapse really merges levels
+    # duplicates and flat (zero-extent) axes quantise without losing anything
+    o = spheres(200); o["pos"][:, 1] = 2.0; o["pos"][50:100] = o["pos"][0]
+    bad, (usable, *_rest) = wide_info(lib, o)
+    assert usable == 1 and bad == 0
+    # coordinates beyond 1e12 (or non-finite geometry, which the BVH2 keeps as a 1e30 box): not usable, callers keep the binary tree
+    o = spheres(50); o["pos"][7, 0] = 3e12
+    assert wide_info(lib, o)[1][0] == 0
+    o = spheres(50); o["pos"][7, 2] = np.inf
+    assert wide_info(lib, o)[1][0] == 0
+    assert wide_info(lib, spheres(0) if False else np.zeros(0, rtb200.OBJECT_DTYPE))[0] == 0     # empty scene
