@@ -118,6 +118,8 @@ enum {
     RT_OPT_POOL_TILES = 10,        /* megakernel, few samples per call: 8x4 pixel tiles per warp-level pixel pool; 0 (default) automatic, 1 one pixel per lane */
     RT_OPT_FLAT_COOP = 11,         /* flat accelerator in the megakernel: 1 the warp pools the cluster culls and strict tests of its 32 rays, 0 every lane for itself,
                                       2 (default) pooled for scenes without cubes (open sphere scenes gain ~8 %, cube rooms lose ~10 %) */
+    RT_OPT_WF_WAVE_MPATHS = 13,    /* wavefront pipeline: paths per wave in units of 2^20 (0 = default 128, i.e. ~15 GB of path state; at most 64 samples
+                                      per pixel per wave and a third of the free device memory). Larger waves keep the late bounce rounds filled */
     RT_OPT_BVH_WIDE = 12,          /* BVH node format: 0 (default) 64-byte binary nodes; 1 scenes of 1024+ primitives traverse the 8-wide form with
                                       quantised child boxes (80-byte nodes, csrc/bvh_wide.h); 2 every BVH scene. Identical results; on B200 the
                                       wide form makes 2.2x fewer node visits but executes more instructions and measured slower */

@@ -84,7 +84,7 @@ struct rt_ctx {
     int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
     int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4, opt_primary_reuse = 1;
     int opt_bvh_wide = 0;              // 0 (default) binary nodes, 1 wide nodes for BVHs of kWideMinPrims+ primitives, 2 always (tests)
-    int opt_wf_refill = 8, opt_wf_node_min = 8, opt_pool_tiles = 0, opt_flat_coop = 2;   // flat_coop: 0 off, 1 on, 2 measured per scene
+    int opt_wf_refill = 8, opt_wf_node_min = 8, opt_wf_wave_mpaths = 0, opt_pool_tiles = 0, opt_flat_coop = 2;   // flat_coop: 0 off, 1 on, 2 measured per scene
     int tuned_flat_coop = 1;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
     int tuned_pipeline = -1;       // RT_PIPELINE_AUTO decision for large BVH scenes (-1: not measured yet)
@@ -337,9 +337,10 @@ int autotune_accel(rt_ctx* c, int spp) {
 // (thousands of primitives), where the first path-mode render times 2 spp of the megakernel and of the wavefront
 // pipeline and keeps the faster (identical results). On the 10 000-sphere scene the wavefront wins by about 10 %,
 // on the 1 M-triangle mesh the megakernel by about 25 %.
+constexpr int kWavefrontMinSpp = 8;    // RT_PIPELINE_AUTO: calls shorter than this cannot fill a wave and stay on the megakernel
 int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     if (c->opt_pipeline != RT_PIPELINE_AUTO) return RT_OK;
-    if (c->tuned_pipeline >= 0 || spp < 8) return RT_OK;      // short calls keep the megakernel until a longer one measures
+    if (c->tuned_pipeline >= 0 || spp < kWavefrontMinSpp) return RT_OK;   // short calls always use the megakernel (rt_render_spp)
     const size_t prims = (size_t)c->view.n_sph + c->view.n_box + c->view.n_tri;
     // (the wavefront pipeline keeps one queue counter per bounce round: 60 rounds at most)
     if (ac.kind != kAccelBvh || prims < 2048 || c->pixel_step > 1 || c->par.max_bounces > 60) { c->tuned_pipeline = RT_PIPELINE_REGEN; return RT_OK; }
@@ -351,12 +352,15 @@ int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     unsigned long long* dummy = c->d_counters + 4;
     const bool reuse = c->opt_primary_reuse != 0;
     cudaError_t err = cudaSuccess;
+    // The wavefront pipeline's rate depends on how many samples share a wave (launch_render_wavefront), so it is measured with
+    // up to 16 samples per pixel - what a call of this length will really run.
+    const int n_tune = spp < 16 ? spp : 16;
     for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 allocates the wavefront buffers and warms up
         cudaEventRecord(e[0], c->stream);
-        err = launch_render_regen(c->view, ac, c->frame, c->d_tune, 0u, 2, reuse, dummy, c->stream);
+        err = launch_render_regen(c->view, ac, c->frame, c->d_tune, 0u, pass ? n_tune : 1, reuse, dummy, c->stream);
         cudaEventRecord(e[1], c->stream);
-        if (err == cudaSuccess) err = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_tune, 0u, 2, reuse, dummy, c->stream, c->opt_bvh_sched == 0,
-                                                             c->opt_wf_refill, c->opt_wf_node_min);
+        if (err == cudaSuccess) err = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_tune, 0u, n_tune, reuse, dummy, c->stream, c->opt_bvh_sched == 0,
+                                                             c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths);
         cudaEventRecord(e[2], c->stream);
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
@@ -670,6 +674,7 @@ int rt_set_option(rt_ctx* c, int option, int value) {
         case RT_OPT_POOL_TILES: c->opt_pool_tiles = value < 0 ? 0 : value; return RT_OK;
         case RT_OPT_WF_REFILL: c->opt_wf_refill = value; return RT_OK;
         case RT_OPT_WF_NODE_MIN: c->opt_wf_node_min = value; return RT_OK;
+        case RT_OPT_WF_WAVE_MPATHS: c->opt_wf_wave_mpaths = value; c->tuned_pipeline = -1; return RT_OK;
         case RT_OPT_BVH_WAIT_K: c->opt_bvh_wait_k = value < 1 ? 1 : value; return RT_OK;
     }
     return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
@@ -749,12 +754,13 @@ int rt_render_spp(rt_ctx* c, int spp) {
         // this rank's slice of the global sample indices [next, next+spp)
         int mine = 0; uint32_t first = 0;
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
-        const bool wavefront = (c->opt_pipeline == RT_PIPELINE_WAVEFRONT || (c->opt_pipeline == RT_PIPELINE_AUTO && c->tuned_pipeline == RT_PIPELINE_WAVEFRONT)) &&
+        const bool wavefront = (c->opt_pipeline == RT_PIPELINE_WAVEFRONT ||
+                                (c->opt_pipeline == RT_PIPELINE_AUTO && c->tuned_pipeline == RT_PIPELINE_WAVEFRONT && mine >= kWavefrontMinSpp)) &&
                                c->par.max_bounces <= 60;      // deeper paths: the megakernel (identical results)
         if (wavefront) {
             if (!c->wf) c->wf = wavefront_create();
             RT_CUDA(c, launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_bvh_sched == 0,
-                                               c->opt_wf_refill, c->opt_wf_node_min));
+                                               c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths));
             c->used_pipeline = RT_PIPELINE_WAVEFRONT;
         } else if (ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0)
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));

@@ -60,5 +60,6 @@ void wavefront_destroy(WavefrontBuffers* wb);
 cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
                                     float4* accum, uint32_t s_begin, int n_samples, bool reuse_primary,
                                     unsigned long long* seg_counter, cudaStream_t st, bool bvh_refill = true,
-                                    int k_refill = 8, int k_node_min = 8);
+                                    int k_refill = 8, int k_node_min = 8,
+                                    int wave_mpaths = 0);   // paths per wave in units of 2^20 (0: default 128, capped by free memory)
 }  // namespace rtb

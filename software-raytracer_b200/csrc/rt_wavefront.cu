@@ -576,7 +576,7 @@ void wavefront_destroy(WavefrontBuffers* wb) {
 
 cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
                                     float4* accum, uint32_t s_begin, int n_samples, bool reuse, unsigned long long* seg_counter,
-                                    cudaStream_t st, bool bvh_refill, int k_refill, int k_node_min) {
+                                    cudaStream_t st, bool bvh_refill, int k_refill, int k_node_min, int wave_mpaths) {
     if (k_refill < 1) k_refill = 1; if (k_refill > 32) k_refill = 32;
     if (k_node_min < 1) k_node_min = 1; if (k_node_min > 32) k_node_min = 32;
     if (n_samples <= 0) return cudaSuccess;
@@ -584,10 +584,22 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     if (e != cudaSuccess) return e;
     const WaveGeom g = wave_geom(fr.width, fr.height);
     const size_t npix = (size_t)fr.width * fr.height;
-    // samples per wave: about 8 M paths in flight
-    int s_cap = (int)((size_t)(8u << 20) / (size_t)g.npad);
+    // Samples per wave. The late bounce rounds of a wave hold a few per cent of its paths, and a persistent intersect kernel
+    // needs ~150 k rays just to fill the machine once, so small waves spend most of their rounds in the tail: on the
+    // 1 M-triangle mesh at 1080p 8 M / 34 M / 136 M paths per wave give 3.1 / 4.7 / 5.4 G segments/s (profiles/r1A_wave_sweep.log).
+    // Default 128 M paths (116 B each, ~15 GB), at most 64 samples per pixel, never more than a third of the free memory.
+    size_t wave_paths = (size_t)(wave_mpaths >= 1 && wave_mpaths <= 1024 ? wave_mpaths : 128) << 20;
+    if (const char* wp = getenv("RTB200_WAVE_MPATHS")) { const long v = atol(wp); if (v >= 1 && v <= 1024) wave_paths = (size_t)v << 20; }
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t budget = (free_b + wb->cap_paths * 116) / 3 / 116;
+            if (wave_paths > budget) wave_paths = budget;
+        }
+    }
+    int s_cap = (int)(wave_paths / (size_t)g.npad);
     if (s_cap < 1) s_cap = 1;
-    if (s_cap > 16) s_cap = 16;
+    if (s_cap > 64) s_cap = 64;
     if (s_cap > n_samples) s_cap = n_samples;
     const size_t np_cap = (size_t)g.npad * s_cap;
     if (np_cap >= (size_t)1 << 32) return cudaErrorInvalidValue;

@@ -18,7 +18,7 @@ RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_IO, RT_ERR_PARSE, RT_ERR_NOMEM = 0, -
 RT_OBJ_NONE, RT_OBJ_SPHERE, RT_OBJ_CUBE, RT_OBJ_MESH = 0, 1, 2, 3
 RT_MODE_PATH, RT_MODE_PREVIEW = 0, 1
 RT_OPT_PIPELINE, RT_OPT_ACCEL, RT_OPT_BVH_THRESHOLD, RT_OPT_BVH_SCHED, RT_OPT_BVH_WAIT_K, RT_OPT_BVH_LEAF, RT_OPT_PRIMARY_REUSE = 1, 2, 3, 4, 5, 6, 7
-RT_OPT_WF_REFILL, RT_OPT_WF_NODE_MIN, RT_OPT_POOL_TILES, RT_OPT_FLAT_COOP, RT_OPT_BVH_WIDE = 8, 9, 10, 11, 12
+RT_OPT_WF_REFILL, RT_OPT_WF_NODE_MIN, RT_OPT_POOL_TILES, RT_OPT_FLAT_COOP, RT_OPT_BVH_WIDE, RT_OPT_WF_WAVE_MPATHS = 8, 9, 10, 11, 12, 13
 RT_PIPELINE_AUTO, RT_PIPELINE_REGEN, RT_PIPELINE_WAVEFRONT = 0, 1, 2
 RT_ACCEL_AUTO, RT_ACCEL_BRUTE, RT_ACCEL_BVH, RT_ACCEL_FLAT = 0, 1, 2, 3
 

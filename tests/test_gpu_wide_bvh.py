@@ -115,3 +115,28 @@ def test_wide_bvh_mesh(tracer):
         for x, y, ids in [(a, b, ref[0][0]) for a, b in zip(val[0][1:], ref[0][1:])] + [(a, b, ref[1][0]) for a, b in zip(val[1][1:], ref[1][1:])]:
             assert np.array_equal(bits(x)[ids >= 0], bits(y)[ids >= 0]), k
         assert np.array_equal(bits(val[2]), bits(ref[2])) and val[3] == ref[3], k
+
+
+def test_wavefront_wave_size_does_not_change_the_sum(tracer):
+    """Samples per wave (RT_OPT_WF_WAVE_MPATHS) only change how the work is batched: per pixel the samples are still added in
+    sample order, so tiny waves, the default and the megakernel give the same bits; RT_PIPELINE_AUTO (which may pick either
+    pipeline for a long call, and always the megakernel for short ones) as well."""
+    objs = synthetic_spheres(3000, cubes_every=9)
+    cam = rtb200.default_camera(60)
+    cam.pos[0], cam.pos[1], cam.pos[2] = 0.0, 8.0, -20.0
+    out = {}
+    try:
+        for key, pipe, wave in (("regen", rtb200.RT_PIPELINE_REGEN, 0), ("wf_default", rtb200.RT_PIPELINE_WAVEFRONT, 0),
+                                ("wf_tiny", rtb200.RT_PIPELINE_WAVEFRONT, 1), ("auto", rtb200.RT_PIPELINE_AUTO, 0)):
+            tracer.set_option(rtb200.RT_OPT_PIPELINE, pipe); tracer.set_option(rtb200.RT_OPT_WF_WAVE_MPATHS, wave)
+            setup(tracer, objs, 512, 288, cam)                       # 147 456 pixels: 1 M paths = 7 samples per wave
+            tracer.render_spp(3); tracer.render_spp(37)
+            st = tracer.stats()
+            if key == "regen" or key.startswith("wf"):
+                assert st.pipeline == pipe
+            out[key] = (tracer.read_accum()[0], st.segments, st.paths)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_WF_WAVE_MPATHS, 0)
+        _reset(tracer)
+    for k, v in out.items():
+        assert np.array_equal(bits(v[0]), bits(out["regen"][0])) and v[1:] == out["regen"][1:], k
