@@ -63,6 +63,31 @@ __device__ __forceinline__ void warp_push(bool want, uint32_t pid, uint32_t* __r
     if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = pid;
 }
 
+// The same for a whole CTA of NW warps: ONE atomicAdd on the queue counter per CTA pass instead of one per warp (a wave of
+// 133 M paths is 4 M warps, all adding to the same word), and the segment counters ride along: `delivered` is summed over the
+// CTA and added to seg_counter[0 .. n_seg) by the same thread. Must be reached by every thread of the CTA.
+template <int NW>
+__device__ __forceinline__ void block_push(bool want, uint32_t pid, uint32_t* __restrict__ q, unsigned int* __restrict__ count,
+                                           unsigned int delivered, unsigned long long* __restrict__ seg_counter, int n_seg) {
+    __shared__ unsigned int s_cnt[NW], s_del[NW], s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) delivered += __shfl_down_sync(0xffffffffu, delivered, off);
+    __syncthreads();                                         // the previous pass has read s_base / s_cnt
+    if (lane == 0) { s_cnt[w] = (unsigned int)__popc(mask); s_del[w] = delivered; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int c = 0, dl = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { const unsigned int t = s_cnt[i]; s_cnt[i] = c; c += t; dl += s_del[i]; }
+        s_base = c ? atomicAdd(count, c) : 0u;
+        if (dl) for (int k = 0; k < n_seg; ++k) atomicAdd(seg_counter + k, (unsigned long long)dl);
+    }
+    __syncthreads();
+    if (want) q[s_base + s_cnt[w] + (unsigned int)__popc(mask & ((1u << lane) - 1u))] = pid;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) k_wf_primary(SceneView sc, BvhView bv, FlatView fl, FrameView fr, int tiles_x, int npad,
                                                           float4* __restrict__ prim_nt, int* __restrict__ prim_id) {
@@ -116,13 +141,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(SceneView sc, FrameView fr,
             }
         }
     }
-    warp_push(live, pid, q0, counters);
-    if (REUSE) {
-        unsigned int total = delivered;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) total += __shfl_down_sync(0xffffffffu, total, off);
-        if ((threadIdx.x & 31) == 0 && total) { atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total); }
-    }
+    block_push<8>(live, pid, q0, counters, delivered, seg_counter, REUSE ? 2 : 0);      // segments + reused (not traced) segments
 }
 
 // Persistent threads: the grid is sized to the machine, not to the queue. Each warp claims 32 consecutive entries.
@@ -463,11 +482,11 @@ __global__ void __launch_bounds__(256) k_wf_shade(SceneView sc, FrameView fr, in
                                                    float4* __restrict__ wave_rad, unsigned long long* __restrict__ seg_counter) {
     const unsigned int count = *count_ptr;
     const unsigned int stride = gridDim.x * blockDim.x;
-    unsigned int done = 0;
-    // whole warps stay in the loop together: the compaction ballots need every lane
-    for (unsigned int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += stride) {
-        const unsigned int i = base + (threadIdx.x & 31u);
+    // whole CTAs stay in the loop together: the compaction needs every thread
+    for (unsigned int base = blockIdx.x * blockDim.x; base < count; base += stride) {
+        const unsigned int i = base + threadIdx.x;
         bool live = false;
+        unsigned int done = 0;
         uint32_t pid = 0;
         if (i < count) {
             pid = q_in[i];
@@ -494,12 +513,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(SceneView sc, FrameView fr, in
                 live = true;
             }
         }
-        warp_push(live, pid, q_out, count_out);                                         // ray compaction
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) done += __shfl_down_sync(0xffffffffu, done, off);
-    if ((threadIdx.x & 31) == 0 && done) {
-        for (int k = 0; k < 4; ++k) atomicAdd(seg_counter + k, (unsigned long long)done);
+        block_push<8>(live, pid, q_out, count_out, done, seg_counter, 4);               // ray compaction + the four segment counters
     }
 }
 
