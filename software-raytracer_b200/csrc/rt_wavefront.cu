@@ -26,10 +26,14 @@ namespace rtb {
 
 struct WavefrontBuffers {
     size_t cap_paths = 0, cap_px = 0, cap_tiles = 0;
-    float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *rad = nullptr;   // per path: o, (d, depth), T, L
-    float4 *hit_nt = nullptr; int* hit_id = nullptr;                              // per path: (normal, t), object id
-    float4* wave_rad = nullptr;                                                   // per path: radiance of the finished path
-    uint32_t* q[2] = {nullptr, nullptr};                                          // ping-pong ray queues (path ids)
+    // Path state lives in DENSE ping-pong sets: slot i of round r's set is the i-th surviving path, so every kernel reads and
+    // writes consecutive records (with one fixed slot per path and a queue of path ids the survivors of the later rounds are
+    // scattered and a 32-byte sector carries one useful record: the shade kernel moved 3.8x its useful bytes).
+    float4 *ray_o[2] = {nullptr, nullptr}, *ray_d[2] = {nullptr, nullptr};         // per slot: o, (d, depth)
+    float4 *thr[2] = {nullptr, nullptr}, *rad[2] = {nullptr, nullptr};             // per slot: T, L
+    uint32_t* q[2] = {nullptr, nullptr};                                          // per slot: path id (tile-major pixel + npad * sample)
+    float4 *hit_nt = nullptr; int* hit_id = nullptr;                              // per slot of the current round: (normal, t), object id
+    float4* wave_rad = nullptr;                                                   // per PATH id: radiance of the finished path
     unsigned int* counters = nullptr;                                             // [0..63] queue lengths per round, [64..127] cursors
     float4* launch_acc = nullptr;                                                 // per pixel: this launch's sum
     float4* prim_nt = nullptr; int* prim_id = nullptr;                            // REUSE: primary hit per tile-major pixel
@@ -38,6 +42,7 @@ struct WavefrontBuffers {
 namespace {
 
 constexpr int kMaxRounds = 64;
+constexpr size_t kBytesPerPath = 2 * (4 * 16 + 4) + 16 + 4 + 16;   // two state sets + path id each, hit record, finished radiance: 172 B
 
 struct WaveGeom { int tiles_x, tiles_y, npad; };
 __host__ __device__ inline WaveGeom wave_geom(int w, int h) {
@@ -63,12 +68,12 @@ __device__ __forceinline__ void warp_push(bool want, uint32_t pid, uint32_t* __r
     if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = pid;
 }
 
-// The same for a whole CTA of NW warps: ONE atomicAdd on the queue counter per CTA pass instead of one per warp (a wave of
+// Slot allocation for a whole CTA of NW warps: ONE atomicAdd on the counter per CTA pass instead of one per warp (a wave of
 // 133 M paths is 4 M warps, all adding to the same word), and the segment counters ride along: `delivered` is summed over the
 // CTA and added to seg_counter[0 .. n_seg) by the same thread. Must be reached by every thread of the CTA.
 template <int NW>
-__device__ __forceinline__ void block_push(bool want, uint32_t pid, uint32_t* __restrict__ q, unsigned int* __restrict__ count,
-                                           unsigned int delivered, unsigned long long* __restrict__ seg_counter, int n_seg) {
+__device__ __forceinline__ unsigned int block_slot(bool want, unsigned int* __restrict__ count,
+                                                   unsigned int delivered, unsigned long long* __restrict__ seg_counter, int n_seg) {
     __shared__ unsigned int s_cnt[NW], s_del[NW], s_base;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned mask = __ballot_sync(0xffffffffu, want);
@@ -85,7 +90,7 @@ __device__ __forceinline__ void block_push(bool want, uint32_t pid, uint32_t* __
         if (dl) for (int k = 0; k < n_seg; ++k) atomicAdd(seg_counter + k, (unsigned long long)dl);
     }
     __syncthreads();
-    if (want) q[s_base + s_cnt[w] + (unsigned int)__popc(mask & ((1u << lane) - 1u))] = pid;
+    return s_base + s_cnt[w] + (unsigned int)__popc(mask & ((1u << lane) - 1u));      // this thread's slot in the next set, if it wants one
 }
 
 template <int MODE>
@@ -113,6 +118,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(SceneView sc, FrameView fr,
     const uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;             // the grid covers np rounded up to warps
     bool live = false;
     unsigned int delivered = 0;
+    float4 so = make_float4(0.f, 0.f, 0.f, 0.f), sd = so, sT = so, sL = so;
     if (pid < np) {
         const int ti = (int)(pid % (uint32_t)npad);
         const uint32_t s = s_first + pid / (uint32_t)npad;
@@ -133,15 +139,11 @@ __global__ void __launch_bounds__(256) k_wf_generate(SceneView sc, FrameView fr,
                 if (path_ends(sc, fr, h0, d, T, L, 0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
                 else scatter_segment(sc, fr, h0, pixel, s, o, d, T, L, depth);
             }
-            if (live) {
-                ray_o[pid] = make_float4(o.x, o.y, o.z, 0.f);
-                ray_d[pid] = make_float4(d.x, d.y, d.z, __int_as_float(depth));
-                thr[pid] = make_float4(T.x, T.y, T.z, 0.f);
-                rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
-            }
+            if (live) { so = make_float4(o.x, o.y, o.z, 0.f); sd = make_float4(d.x, d.y, d.z, __int_as_float(depth)); sT = make_float4(T.x, T.y, T.z, 0.f); sL = make_float4(L.x, L.y, L.z, 0.f); }
         }
     }
-    block_push<8>(live, pid, q0, counters, delivered, seg_counter, REUSE ? 2 : 0);      // segments + reused (not traced) segments
+    const unsigned int slot = block_slot<8>(live, counters, delivered, seg_counter, REUSE ? 2 : 0);      // segments + reused (not traced) segments
+    if (live) { ray_o[slot] = so; ray_d[slot] = sd; thr[slot] = sT; rad[slot] = sL; q0[slot] = pid; }
 }
 
 // Persistent threads: the grid is sized to the machine, not to the queue. Each warp claims 32 consecutive entries.
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_wf_intersect(SceneView sc, BvhV
         if (base >= count) break;
         const unsigned int i = base + (unsigned int)lane;
         if (i < count) {
-            const uint32_t pid = q[i];
+            const uint32_t pid = i;                          // dense state: slot = queue position
             const float4 o4 = ray_o[pid], d4 = ray_d[pid];
             const Hit h = trace<MODE>(sc, tc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
             hit_nt[pid] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
                 if (state == IDLE) {
                     const unsigned int i = base + (unsigned int)__popc(m_idle & ((1u << lane) - 1u));
                     if (i < count) {
-                        pid = q[i];
+                        pid = i;                             // dense state: slot = queue position
                         const float4 o4 = ray_o[pid], d4 = ray_d[pid];
                         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
                         const float big = 1e30f;
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH8_MIN_BLOCKS) k_wf_interse
                 if (state == IDLE) {
                     const unsigned int i = base + (unsigned int)__popc(m_idle & ((1u << lane) - 1u));
                     if (i < count) {
-                        pid = q[i];
+                        pid = i;                             // dense state: slot = queue position
                         const float4 o4 = ray_o[pid], d4 = ray_d[pid];
                         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
                         wr = wide_ray(d, bv.q2f_hi);
@@ -477,8 +479,10 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH8_MIN_BLOCKS) k_wf_interse
 __global__ void __launch_bounds__(256) k_wf_shade(SceneView sc, FrameView fr, int tiles_x, int npad, uint32_t s_first,
                                                    const uint32_t* __restrict__ q_in, const unsigned int* __restrict__ count_ptr,
                                                    uint32_t* __restrict__ q_out, unsigned int* __restrict__ count_out,
-                                                   float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ thr,
-                                                   float4* __restrict__ rad, const float4* __restrict__ hit_nt, const int* __restrict__ hit_id,
+                                                   const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ thr,
+                                                   const float4* __restrict__ rad, float4* __restrict__ ray_o2, float4* __restrict__ ray_d2,
+                                                   float4* __restrict__ thr2, float4* __restrict__ rad2,
+                                                   const float4* __restrict__ hit_nt, const int* __restrict__ hit_id,
                                                    float4* __restrict__ wave_rad, unsigned long long* __restrict__ seg_counter) {
     const unsigned int count = *count_ptr;
     const unsigned int stride = gridDim.x * blockDim.x;
@@ -488,6 +492,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(SceneView sc, FrameView fr, in
         bool live = false;
         unsigned int done = 0;
         uint32_t pid = 0;
+        float4 so = make_float4(0.f, 0.f, 0.f, 0.f), sd = so, sT = so, sL = so;
         if (i < count) {
             pid = q_in[i];
             const int ti = (int)(pid % (uint32_t)npad);
@@ -495,25 +500,24 @@ __global__ void __launch_bounds__(256) k_wf_shade(SceneView sc, FrameView fr, in
             int px, py;
             tile_to_pixel(fr, tiles_x, ti, px, py);
             const uint32_t pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
-            const float4 o4 = ray_o[pid], d4 = ray_d[pid], T4 = thr[pid], L4 = rad[pid], nt = hit_nt[pid];
+            const float4 o4 = ray_o[i], d4 = ray_d[i], T4 = thr[i], L4 = rad[i], nt = hit_nt[i];
             float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z), T = f3(T4.x, T4.y, T4.z), L = f3(L4.x, L4.y, L4.z);
             int depth = __float_as_int(d4.w);
             Hit h;
-            h.id = hit_id[pid]; h.t = nt.w; h.n = f3(nt.x, nt.y, nt.z);
+            h.id = hit_id[i]; h.t = nt.w; h.n = f3(nt.x, nt.y, nt.z);
             h.p = f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w);            // as in closest_hit*()
             ++done;
             float3 c;
             if (path_ends(sc, fr, h, d, T, L, depth, c)) wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f);
             else {
                 scatter_segment(sc, fr, h, pixel, s, o, d, T, L, depth);
-                ray_o[pid] = make_float4(o.x, o.y, o.z, 0.f);
-                ray_d[pid] = make_float4(d.x, d.y, d.z, __int_as_float(depth));
-                thr[pid] = make_float4(T.x, T.y, T.z, 0.f);
-                rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
+                so = make_float4(o.x, o.y, o.z, 0.f); sd = make_float4(d.x, d.y, d.z, __int_as_float(depth));
+                sT = make_float4(T.x, T.y, T.z, 0.f); sL = make_float4(L.x, L.y, L.z, 0.f);
                 live = true;
             }
         }
-        block_push<8>(live, pid, q_out, count_out, done, seg_counter, 4);               // ray compaction + the four segment counters
+        const unsigned int slot = block_slot<8>(live, count_out, done, seg_counter, 4);  // ray compaction + the four segment counters
+        if (live) { ray_o2[slot] = so; ray_d2[slot] = sd; thr2[slot] = sT; rad2[slot] = sL; q_out[slot] = pid; }
     }
 }
 
@@ -582,7 +586,8 @@ WavefrontBuffers* wavefront_create() { return new WavefrontBuffers(); }
 
 void wavefront_destroy(WavefrontBuffers* wb) {
     if (!wb) return;
-    cudaFree(wb->ray_o); cudaFree(wb->ray_d); cudaFree(wb->thr); cudaFree(wb->rad); cudaFree(wb->hit_nt); cudaFree(wb->hit_id);
+    for (int k = 0; k < 2; ++k) { cudaFree(wb->ray_o[k]); cudaFree(wb->ray_d[k]); cudaFree(wb->thr[k]); cudaFree(wb->rad[k]); }
+    cudaFree(wb->hit_nt); cudaFree(wb->hit_id);
     cudaFree(wb->wave_rad); cudaFree(wb->q[0]); cudaFree(wb->q[1]); cudaFree(wb->counters); cudaFree(wb->launch_acc);
     cudaFree(wb->prim_nt); cudaFree(wb->prim_id);
     delete wb;
@@ -601,13 +606,13 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     // Samples per wave. The late bounce rounds of a wave hold a few per cent of its paths, and a persistent intersect kernel
     // needs ~150 k rays just to fill the machine once, so small waves spend most of their rounds in the tail: on the
     // 1 M-triangle mesh at 1080p 8 M / 34 M / 136 M paths per wave give 3.1 / 4.7 / 5.4 G segments/s (profiles/r1A_wave_sweep.log).
-    // Default 128 M paths (116 B each, ~15 GB), at most 64 samples per pixel, never more than a third of the free memory.
+    // Default 128 M paths (172 B each, ~22 GB), at most 64 samples per pixel, never more than a third of the free memory.
     size_t wave_paths = (size_t)(wave_mpaths >= 1 && wave_mpaths <= 1024 ? wave_mpaths : 128) << 20;
     if (const char* wp = getenv("RTB200_WAVE_MPATHS")) { const long v = atol(wp); if (v >= 1 && v <= 1024) wave_paths = (size_t)v << 20; }
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t budget = (free_b + wb->cap_paths * 116) / 3 / 116;
+            const size_t budget = (free_b + wb->cap_paths * kBytesPerPath) / 3 / kBytesPerPath;
             if (wave_paths > budget) wave_paths = budget;
         }
     }
@@ -619,8 +624,10 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     if (np_cap >= (size_t)1 << 32) return cudaErrorInvalidValue;
     if (wb->cap_paths < np_cap) {
         cudaStreamSynchronize(st);
-        if ((e = grow(wb->ray_o, np_cap)) != cudaSuccess || (e = grow(wb->ray_d, np_cap)) != cudaSuccess ||
-            (e = grow(wb->thr, np_cap)) != cudaSuccess || (e = grow(wb->rad, np_cap)) != cudaSuccess ||
+        if ((e = grow(wb->ray_o[0], np_cap)) != cudaSuccess || (e = grow(wb->ray_d[0], np_cap)) != cudaSuccess ||
+            (e = grow(wb->thr[0], np_cap)) != cudaSuccess || (e = grow(wb->rad[0], np_cap)) != cudaSuccess ||
+            (e = grow(wb->ray_o[1], np_cap)) != cudaSuccess || (e = grow(wb->ray_d[1], np_cap)) != cudaSuccess ||
+            (e = grow(wb->thr[1], np_cap)) != cudaSuccess || (e = grow(wb->rad[1], np_cap)) != cudaSuccess ||
             (e = grow(wb->hit_nt, np_cap)) != cudaSuccess || (e = grow(wb->hit_id, np_cap)) != cudaSuccess ||
             (e = grow(wb->wave_rad, np_cap)) != cudaSuccess || (e = grow(wb->q[0], np_cap)) != cudaSuccess ||
             (e = grow(wb->q[1], np_cap)) != cudaSuccess) { wb->cap_paths = 0; return e; }
@@ -664,28 +671,29 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
         const size_t np = (size_t)g.npad * sw;
         if ((e = cudaMemsetAsync(wb->counters, 0, 2 * kMaxRounds * sizeof(unsigned int), st)) != cudaSuccess) return e;
         const int gen_blocks = (int)((np + 255) / 256);
-        if (reuse) k_wf_generate<true><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, wb->prim_nt, wb->prim_id, wb->ray_o, wb->ray_d,
-                                                                    wb->thr, wb->rad, wb->wave_rad, wb->q[0], wb->counters, seg_counter);
-        else k_wf_generate<false><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, wb->prim_nt, wb->prim_id, wb->ray_o, wb->ray_d,
-                                                               wb->thr, wb->rad, wb->wave_rad, wb->q[0], wb->counters, seg_counter);
+        if (reuse) k_wf_generate<true><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, wb->prim_nt, wb->prim_id, wb->ray_o[0], wb->ray_d[0],
+                                                                    wb->thr[0], wb->rad[0], wb->wave_rad, wb->q[0], wb->counters, seg_counter);
+        else k_wf_generate<false><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, wb->prim_nt, wb->prim_id, wb->ray_o[0], wb->ray_d[0],
+                                                               wb->thr[0], wb->rad[0], wb->wave_rad, wb->q[0], wb->counters, seg_counter);
         for (int r = 0; r < rounds; ++r) {
-            const uint32_t* qin = wb->q[r & 1];
-            uint32_t* qout = wb->q[(r + 1) & 1];
+            const int a = r & 1, b = a ^ 1;                  // this round's dense state set, the next round's
+            const uint32_t* qin = wb->q[a];
+            uint32_t* qout = wb->q[b];
             unsigned int* cnt = wb->counters + r;
             unsigned int* cur = wb->counters + kMaxRounds + r;
             switch (mode) {
-                case 0: k_wf_intersect<0><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
-                case 1: k_wf_intersect<1><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
-                case 2: if (bvh_refill) k_wf_intersect_bvh<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id, k_refill, k_node_min);
-                        else k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
+                case 0: k_wf_intersect<0><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id); break;
+                case 1: k_wf_intersect<1><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id); break;
+                case 2: if (bvh_refill) k_wf_intersect_bvh<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id, k_refill, k_node_min);
+                        else k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id);
                         break;
-                case 3: if (bvh_refill && ac.bvh.wnodes) k_wf_intersect_bvh8<<<sms * RTB_WF_BVH8_MIN_BLOCKS, kThreads, sb, st>>>(sc, ac.bvh, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id, k_refill, k_node_min);
-                        else if (bvh_refill) k_wf_intersect_bvh<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id, k_refill, k_node_min);
-                        else k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id);
+                case 3: if (bvh_refill && ac.bvh.wnodes) k_wf_intersect_bvh8<<<sms * RTB_WF_BVH8_MIN_BLOCKS, kThreads, sb, st>>>(sc, ac.bvh, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id, k_refill, k_node_min);
+                        else if (bvh_refill) k_wf_intersect_bvh<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id, k_refill, k_node_min);
+                        else k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id);
                         break;
-                default: k_wf_intersect<4><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o, wb->ray_d, wb->hit_nt, wb->hit_id); break;
+                default: k_wf_intersect<4><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id); break;
             }
-            k_wf_shade<<<sms * 8, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, qin, cnt, qout, cnt + 1, wb->ray_o, wb->ray_d, wb->thr, wb->rad,
+            k_wf_shade<<<sms * 8, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, qin, cnt, qout, cnt + 1, wb->ray_o[a], wb->ray_d[a], wb->thr[a], wb->rad[a], wb->ray_o[b], wb->ray_d[b], wb->thr[b], wb->rad[b],
                                                  wb->hit_nt, wb->hit_id, wb->wave_rad, seg_counter);
         }
         k_wf_accumulate<<<(g.npad + 255) / 256, 256, 0, st>>>(fr, g.tiles_x, g.npad, sw, wb->wave_rad, wb->launch_acc);
