@@ -157,15 +157,21 @@ def run_b200(args):
     cam0 = rtb200.default_camera()
     mesh = None
     workload = "Scene1 (67 spheres)" if args.scene == "Scene1" else args.scene
+    scene_label = "bundled %s" % args.scene
+    data_label = "synthetic: bundled %s fixture (tests/golden/bundled_scenes.npz), default camera, Philox seeds" % args.scene
     if args.config == "c3":                              # BASELINE.json configs[2]: 10k random spheres at 4K
         from rtb200.scenes import synthetic_spheres, config3_camera
         objs = synthetic_spheres(10000); cam0 = config3_camera(rtb200.default_camera); W, H = 3840, 2160
         workload = "config 3: 10 000 random spheres + ground + 8 lights"
+        scene_label = "synthetic 10k spheres"
+        data_label = "synthetic: rtb200.scenes.synthetic_spheres(10000) (seeded), config3_camera, Philox seeds"
     elif args.config == "c4":                            # configs[3]: ~1M-triangle mesh through the BVH
         from rtb200.scenes import heightfield_mesh, mesh_scene
         objs = mesh_scene(); mesh = heightfield_mesh(1024, 512)
         cam0.pos[1] = 1.5; cam0.pos[2] = -1.0
         workload = "config 4: 1 048 576-triangle heightfield mesh + 3 spheres"
+        scene_label = "synthetic 1M-triangle mesh"
+        data_label = "synthetic: rtb200.scenes.heightfield_mesh(1024, 512) (seeded) + mesh_scene(), Philox seeds"
     elif args.config == "c5":                            # configs[4]: interactive 1 spp frames at 720p
         W, H = 1280, 720
     elif args.config == "c1":                            # configs[0]: the reference's own CPU-runnable case
@@ -324,9 +330,9 @@ def run_b200(args):
         sm_mhz = peaks.get("sm_max_mhz", 1965.0)
         peak_tf = st.sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12
         line = {
-            "metric": METRIC if (W, H) == (1920, 1080) else METRIC.replace("1920x1080", "%dx%d" % (W, H)), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC.replace("bundled Scene1", scene_label).replace("1920x1080", "%dx%d" % (W, H)), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic: bundled Scene1 fixture (tests/golden/bundled_scenes.npz), default camera, Philox seeds",
+            "dtype": "f32", "data": data_label,
             "config": {"workload": "%s %dx%d, %d spp per GPU per step, depth %d, path mode" % (workload, W, H, spp, DEPTH),
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": ("spp-sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce+resolve kernel over NVLink peer memory" if fused else "one NCCL all-reduce per step"),
                        "build": "strict IEEE, -fmad=false (bit-exact geometry vs the reference)",
@@ -363,6 +369,20 @@ def run_b200(args):
                          "executed_warp_instr_per_segment_ncu": 25.1, "issue_active_pct_ncu": 78.4, "active_threads_per_inst_ncu": 22.65,
                          "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_algorithmic_gbs": (W * H * 32 / kern_s) / 1e9},
         }
+        if st.accel == rtb200.RT_ACCEL_BVH:
+            # BVH configs (3, 4): the brute-force FLOP count per segment (23 per sphere ...) is meaningless as a roofline numerator for
+            # a tree traversal; these kernels are bound by instruction issue + dependent node fetches, evidenced by ncu, not by a live figure
+            wf = st.pipeline == rtb200.RT_PIPELINE_WAVEFRONT
+            line["roofline"] = {"bound": "issue", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                                "kernel": "k_wf_intersect_bvh" if wf else "k_render_regen<3>",
+                                "note": ("wavefront pipeline: k_wf_intersect_bvh is 80 % of the step (ncu launch list profiles/r1B_launches_c3_c4.txt), issue slots "
+                                         "61 % (10k spheres) / 51 % (1M triangles) busy at 15.3 of 32 threads active per instruction; k_wf_shade (11-17 %) is HBM-bound on "
+                                         "the dense path state. BVH + primitives are L2-resident: neither HBM bandwidth nor FP32 peak bounds the traversal" if wf else
+                                         "megakernel per-ray BVH loop: 5.4-5.5 of 32 threads active per instruction (profiles/r1l_summary_c3_bvh.txt, r1l_summary_c4_bvh.txt)")}
+            line["gpu_launches_detail"] = ("per rank: the wavefront pipeline launches raygen + 2 kernels per bounce round per wave (about 20 per step) + accumulate/commit"
+                                           if wf else line["gpu_launches_detail"])
+            if wf:
+                line["gpu_launches"] = int(args.steps * (3 + 2 * DEPTH) * 2)
         if world == 1 and not args.no_cpu and args.config in ("c1", "c2"):
             rate, info = cpu_reference_run(objs, args.cpu_frames)
             line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
