@@ -706,7 +706,7 @@ cudaError_t launch_render_bvh(const SceneView& sc, const AccelSel& ac, const Fra
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    if (ac.bvh.wnodes) return launch_render_regen(sc, ac, fr, accum, s_begin, n_samples, true, seg_counter, st);   // the scheduled kernel walks binary nodes only
+    if (ac.bvh.wnodes) return launch_render_regen(sc, ac, fr, accum, s_begin, n_samples, false, seg_counter, st);   // the scheduled kernel walks binary nodes only (and, like it, re-traces every primary ray)
     size_t sb; const int mode = pick_mode(sc, ac, sb);
     if (mode == 2) k_render_bvh<2><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter, wait_k);
     else if (mode == 3) k_render_bvh<3><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter, wait_k);
