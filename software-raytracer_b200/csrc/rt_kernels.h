@@ -1,4 +1,4 @@
-// rt_kernels.h - host-visible launchers of the CUDA kernels in rt_kernels.cu / rt_bvh.cu.
+// rt_kernels.h - host-visible launchers of the CUDA kernels in rt_kernels.cu and rt_wavefront.cu.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

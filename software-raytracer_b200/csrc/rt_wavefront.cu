@@ -3,18 +3,19 @@
 //
 //   k_wf_primary    (REUSE) one primary closest-hit query per pixel per launch
 //   k_wf_generate   raygen: one path per (pixel, sample) of the wave; with REUSE it shades the cached primary hit
-//                   and emits the first SECONDARY ray; live paths are appended to the ray queue
+//                   and emits the first SECONDARY ray; live paths get consecutive slots of state set 0
 //   k_wf_intersect  persistent threads: every warp pulls batches of 32 queue entries through an atomic cursor
 //                   and runs the closest-hit back end (brute / BVH / flat, scene staged per CTA once)
-//   k_wf_shade      path_ends / scatter_segment per entry; surviving paths are COMPACTED into the next queue
-//                   with one warp ballot + prefix popcount + one atomicAdd per warp
+//   k_wf_shade      path_ends / scatter_segment per entry; surviving paths are COMPACTED into consecutive slots of
+//                   the other state set: warp ballot + prefix popcount, one atomicAdd per CTA pass (block_slot)
 //   k_wf_accumulate per pixel, the wave's samples are added in sample order; k_wf_commit adds the launch's sum
 //                   into the accumulation buffer
 //
-// A wave is all pixels x S samples (about 8 M paths). No host synchronisation anywhere: queue lengths stay
+// A wave is all pixels x S samples (S <= 64, up to 128 M paths). No host synchronisation anywhere: queue lengths stay
 // in device memory (one counter and one cursor per bounce round, zeroed per wave) and the persistent kernels
-// read them there. Per-path state lives in SoA float4 arrays indexed by path id (wave-local sample x tile-major
-// pixel), so queue order is almost memory order. Every path's arithmetic is the megakernel's (same device
+// read them there. Path state lives in two DENSE ping-pong sets of SoA float4 arrays: slot i of a round's set is its
+// i-th surviving path (plus its path id = wave-local sample x tile-major pixel), so every kernel reads and writes
+// consecutive records. Every path's arithmetic is the megakernel's (same device
 // functions, same Philox counters) and samples are summed in the same order: the result is BIT-IDENTICAL to
 // k_render_regen (asserted by tests/test_gpu_parity.py), whichever order the queues end up in.
 #include "rt_kernels.h"
