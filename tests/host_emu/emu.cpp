@@ -102,8 +102,9 @@ extern "C" void emu_bvh_stats(long long* out4) {
     out4[0] = g_wide_node_visits; out4[1] = g_wide_prim_tests; out4[2] = g_bvh2_node_visits; out4[3] = g_wide_empty_visits; out4[4] = g_wide_stale_visits; g_wide_stale_visits = 0;
     g_wide_node_visits = g_wide_prim_tests = g_bvh2_node_visits = g_wide_empty_visits = 0;
 }
-// wide BVH of a scene: counts[0..4] = usable, nodes, refs, depth, BVH2 nodes; returns the number of children whose decoded
-// box does NOT contain the BVH2 box it came from (must be 0), checked independently of the builder's own assert
+// Wide BVH of a scene (spheres and cubes): counts[0..4] = usable, wide nodes, refs, depth, BVH2 nodes. Returns the number of
+// violations of "every primitive is referenced exactly once, by a leaf child whose DECODED box contains the primitive's own box"
+// (must be 0) - checked here independently of the builder's own containment assert.
 extern "C" int emu_wide_info(const rt_object* objects, int n_obj, float origin_extent, int* counts) {
     std::vector<rt_object> objs(objects, objects + n_obj);
     HostBvh b2; HostWideBvh w;
@@ -111,42 +112,42 @@ extern "C" int emu_wide_info(const rt_object* objects, int n_obj, float origin_e
     build_wide_bvh(b2, w);
     counts[0] = w.usable; counts[1] = (int)w.nodes.size(); counts[2] = (int)w.refs.size(); counts[3] = w.depth; counts[4] = (int)b2.nodes.size();
     if (!w.usable) return 0;
-    // every primitive's own (uninflated) box must lie inside the decoded box of the leaf child that references it, and
-    // every ref must appear exactly once
-    std::vector<float> plo, phi;
+    // primitive boxes in build order; leaf refs address spheres by slot (>= 0) and cubes by ~slot (bvh_build.h)
+    struct PrimBox { float lo[3], hi[3]; };
+    std::vector<PrimBox> sph_box, cube_box;
     for (const rt_object& o : objs) {
         if (o.type != RT_OBJ_SPHERE && o.type != RT_OBJ_CUBE) continue;
+        PrimBox b;
         for (int k = 0; k < 3; ++k) {
             const float h = o.type == RT_OBJ_SPHERE ? fabsf(o.radius) : fabsf(o.half[k]);
-            plo.push_back(o.pos[k] - h); phi.push_back(o.pos[k] + h);
+            b.lo[k] = o.pos[k] - h; b.hi[k] = o.pos[k] + h;
         }
+        (o.type == RT_OBJ_SPHERE ? sph_box : cube_box).push_back(b);
     }
-    std::vector<int> seen(plo.size() / 3, 0);
-    int sph_n = 0; for (const rt_object& o : objs) sph_n += o.type == RT_OBJ_SPHERE;
-    // object order -> ref: spheres get slots in order, cubes ~slot; map back
-    std::vector<int> sph_obj, box_obj; { int i = 0; for (const rt_object& o : objs) { if (o.type == RT_OBJ_SPHERE) sph_obj.push_back(i), ++i; else if (o.type == RT_OBJ_CUBE) box_obj.push_back(i), ++i; } }
+    std::vector<int> sph_seen(sph_box.size(), 0), cube_seen(cube_box.size(), 0);
     int bad = 0;
     for (const WideNode& nd : w.nodes) {
-        const uint8_t* hdr = reinterpret_cast<const uint8_t*>(&nd.w[3]);
+        const uint8_t* hdr = reinterpret_cast<const uint8_t*>(&nd.w[3]);     // scale exponents x, y, z; imask
         const uint8_t* meta = reinterpret_cast<const uint8_t*>(&nd.w[6]);
-        const uint8_t* qb = reinterpret_cast<const uint8_t*>(&nd.w[8]);
+        const uint8_t* qb = reinterpret_cast<const uint8_t*>(&nd.w[8]);      // qlo.x qlo.y qlo.z qhi.x qhi.y qhi.z, 8 each
         float org[3]; memcpy(org, &nd.w[0], 12);
         for (int s = 0; s < 8; ++s) {
-            if (meta[s] == 0 || (hdr[3] >> s & 1)) continue;
+            if (meta[s] == 0 || ((hdr[3] >> s) & 1)) continue;               // empty slot or inner child
             const int cnt = __builtin_popcount(meta[s] >> 5), off = meta[s] & 31;
             for (int j = 0; j < cnt; ++j) {
                 const int r = w.refs[(size_t)nd.w[5] + off + j];
-                const int prim = r >= 0 ? sph_obj[(size_t)r] : box_obj[(size_t)(~r)];
-                ++seen[(size_t)prim];
+                const PrimBox& pb = r >= 0 ? sph_box[(size_t)r] : cube_box[(size_t)(~r)];
+                ++(r >= 0 ? sph_seen[(size_t)r] : cube_seen[(size_t)(~r)]);
                 for (int k = 0; k < 3; ++k) {
                     const double sc = ldexp(1.0, (int)hdr[k] - 127);
                     const double lo = (double)org[k] + sc * qb[8 * k + s], hi = (double)org[k] + sc * qb[24 + 8 * k + s];
-                    if (!(lo <= plo[3 * (size_t)prim + k] && hi >= phi[3 * (size_t)prim + k])) ++bad;
+                    if (!(lo <= pb.lo[k] && hi >= pb.hi[k])) ++bad;
                 }
             }
         }
     }
-    for (int c : seen) if (c != 1) ++bad;
+    for (int c : sph_seen) if (c != 1) ++bad;
+    for (int c : cube_seen) if (c != 1) ++bad;
     return bad;
 }
 
