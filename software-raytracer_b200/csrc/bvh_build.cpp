@@ -4,7 +4,11 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <future>
+#include <system_error>
+#include <thread>
 
 namespace rtb {
 namespace {
@@ -27,19 +31,44 @@ struct Prim {
     int32_t ref;          // >= 0 sphere slot, < 0 ~cube slot
 };
 
+// Nodes and refs of one subtree with subtree-local indices. The sequential builder allocates a node before it descends and
+// appends leaf refs as it meets them, i.e. nodes are laid out in pre-order and refs in leaf order; a subtree built on another
+// thread is appended to its parent's arrays with its links shifted (append_subtree), which gives exactly that layout again -
+// the tree is byte-identical whatever the number of threads.
+struct Subtree {
+    std::vector<BvhNode> nodes;
+    std::vector<int32_t> refs;
+    int max_depth = 0;
+};
+
 struct Builder {
     std::vector<Prim> prims;
-    HostBvh* out;
     float eps;
 
     static constexpr int kBins = 16;
     int kMaxLeaf = 4;
     static constexpr float kTravCost = 1.0f, kPrimCost = 0.7f;
 
-    int32_t make_leaf(int first, int count) {
-        int start = (int)out->refs.size();
-        for (int i = 0; i < count; ++i) out->refs.push_back(prims[(size_t)first + i].ref);
+    int32_t make_leaf(int first, int count, Subtree& out) const {
+        int start = (int)out.refs.size();
+        for (int i = 0; i < count; ++i) out.refs.push_back(prims[(size_t)first + i].ref);
         return ~(int32_t)((uint32_t)start | ((uint32_t)count << 24));
+    }
+
+    // appends subtree `s` (whose root link is `link`) to `out`; returns the link as seen from `out`
+    static int32_t append_subtree(Subtree& out, const Subtree& s, int32_t link) {
+        const int32_t node_off = (int32_t)out.nodes.size();
+        const uint32_t ref_off = (uint32_t)out.refs.size();
+        auto shift = [&](int32_t l) -> int32_t {
+            if (l >= 0) return l + node_off;
+            const uint32_t v = (uint32_t)(~l);
+            return ~(int32_t)(((v & 0xffffffu) + ref_off) | (v & 0xff000000u));
+        };
+        out.nodes.reserve(out.nodes.size() + s.nodes.size());
+        for (BvhNode n : s.nodes) { n.c[0] = shift(n.c[0]); n.c[1] = shift(n.c[1]); out.nodes.push_back(n); }
+        out.refs.insert(out.refs.end(), s.refs.begin(), s.refs.end());
+        out.max_depth = std::max(out.max_depth, s.max_depth);
+        return shift(link);
     }
 
     Box3 bounds(int first, int count) const {
@@ -99,38 +128,60 @@ struct Builder {
         return mid;
     }
 
-    // Builds the subtree over prims[first, first+count) and returns its link (inner index or encoded leaf).
-    int32_t build(int first, int count, int depth) {
-        out->max_depth = std::max(out->max_depth, depth);
-        if (count <= 0) return make_leaf(first, 0);
+    static constexpr int kParallelMinPrims = 1 << 14;      // smaller subtrees are not worth a thread
+
+    // Builds the subtree over prims[first, first+count) into `out` and returns its link (inner index or encoded leaf).
+    // par_levels > 0: the two children of a large node are built concurrently (they own disjoint slices of `prims`).
+    int32_t build(int first, int count, int depth, Subtree& out, int par_levels) {
+        out.max_depth = std::max(out.max_depth, depth);
+        if (count <= 0) return make_leaf(first, 0, out);
         const bool depth_left = depth < kMaxBvhDepth - 2;
         if (count == 1 || !depth_left) {
             // depth cap: emit (possibly several) leaves of <= 127 prims chained is not needed in practice;
             // a leaf holds up to 127 refs
-            if (count <= 127) return make_leaf(first, count);
+            if (count <= 127) return make_leaf(first, count, out);
         }
         Box3 nb = bounds(first, count);
         int mid = split(first, count, nb, count > 127);
-        if (mid < 0) return make_leaf(first, count);
-        int32_t idx = (int32_t)out->nodes.size();
-        out->nodes.emplace_back();
-        Box3 lb = bounds(first, mid - first), rb = bounds(mid, first + count - mid);
-        int32_t l = build(first, mid - first, depth + 1);
-        int32_t r = build(mid, first + count - mid, depth + 1);
-        BvhNode& n = out->nodes[(size_t)idx];
+        if (mid < 0) return make_leaf(first, count, out);
+        int32_t idx = (int32_t)out.nodes.size();
+        out.nodes.emplace_back();
+        int32_t l, r; Box3 lb, rb;
+        build_children(first, mid, first + count, depth, out, par_levels, lb, rb, l, r);
+        BvhNode& n = out.nodes[(size_t)idx];
         memset(&n, 0, sizeof n);
         store_child(n, 0, lb); store_child(n, 1, rb);
         n.c[0] = l; n.c[1] = r;
         return idx;
+    }
+
+    // children [first, mid) and [mid, end) of a node that already has its slot in out.nodes
+    void build_children(int first, int mid, int end, int depth, Subtree& out, int par_levels, Box3& lb, Box3& rb, int32_t& l, int32_t& r) {
+        if (par_levels > 0 && end - first >= kParallelMinPrims) {
+            Subtree ls, rs;
+            int32_t ll = 0, rl = 0;
+            auto build_left = [&] { lb = bounds(first, mid - first); ll = build(first, mid - first, depth + 1, ls, par_levels - 1); };
+            std::future<void> left;
+            try { left = std::async(std::launch::async, build_left); } catch (const std::system_error&) {}   // no thread to be had: build it here
+            rb = bounds(mid, end - mid);
+            rl = build(mid, end - mid, depth + 1, rs, par_levels - 1);
+            if (left.valid()) left.get(); else build_left();
+            l = append_subtree(out, ls, ll);
+            r = append_subtree(out, rs, rl);
+        } else {
+            lb = bounds(first, mid - first); rb = bounds(mid, end - mid);
+            l = build(first, mid - first, depth + 1, out, 0);
+            r = build(mid, end - mid, depth + 1, out, 0);
+        }
     }
 };
 
 }  // namespace
 
 void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf, const TriRecords* tris,
-               float origin_offset) {
+               float origin_offset, int threads) {
     out = HostBvh();
-    Builder b; b.out = &out;
+    Builder b;
     b.kMaxLeaf = max_leaf < 1 ? 1 : (max_leaf > 64 ? 64 : max_leaf);
     int sph_slot = 0, box_slot = 0;
     Box3 scene;
@@ -183,27 +234,31 @@ void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostB
     b.eps = out.inflate_abs;
 
     // the root is always an inner node so the traversal loop has a single entry shape
-    out.nodes.emplace_back();
+    Subtree t;
+    t.nodes.emplace_back();
     int n = (int)b.prims.size();
     if (n == 0) {
-        BvhNode& r = out.nodes[0];
+        BvhNode& r = t.nodes[0];
         memset(&r, 0, sizeof r);
         b.store_child(r, 0, Box3()); b.store_child(r, 1, Box3());
-        r.c[0] = b.make_leaf(0, 0); r.c[1] = r.c[0];
-        return;
+        r.c[0] = b.make_leaf(0, 0, t); r.c[1] = r.c[0];
+    } else {
+        // levels of the tree whose two children are built concurrently: 2^levels tasks at most (0 = sequential; same tree)
+        if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+        if (const char* e = getenv("RTB200_BVH_THREADS")) { const int v = atoi(e); if (v >= 1) threads = v; }
+        int par_levels = 0;
+        while ((1 << par_levels) < threads && par_levels < 6) ++par_levels;
+        Box3 nb = b.bounds(0, n);
+        int mid = n >= 2 ? b.split(0, n, nb, true) : -1;
+        int32_t l, rgt; Box3 lb, rb;
+        if (mid < 0) { lb = nb; l = b.build(0, n, 1, t, par_levels); rgt = b.make_leaf(0, 0, t); }
+        else b.build_children(0, mid, n, 0, t, par_levels, lb, rb, l, rgt);
+        BvhNode& r = t.nodes[0];
+        memset(&r, 0, sizeof r);
+        b.store_child(r, 0, lb); b.store_child(r, 1, rb);
+        r.c[0] = l; r.c[1] = rgt;
     }
-    Box3 nb = b.bounds(0, n);
-    int mid = n >= 2 ? b.split(0, n, nb, true) : -1;
-    int32_t l, rgt; Box3 lb, rb;
-    if (mid < 0) { lb = nb; l = b.build(0, n, 1); rgt = b.make_leaf(0, 0); }
-    else {
-        lb = b.bounds(0, mid); rb = b.bounds(mid, n - mid);
-        l = b.build(0, mid, 1); rgt = b.build(mid, n - mid, 1);
-    }
-    BvhNode& r = out.nodes[0];
-    memset(&r, 0, sizeof r);
-    b.store_child(r, 0, lb); b.store_child(r, 1, rb);
-    r.c[0] = l; r.c[1] = rgt;
+    out.nodes.swap(t.nodes); out.refs.swap(t.refs); out.max_depth = t.max_depth;
 }
 
 }  // namespace rtb

@@ -50,7 +50,9 @@ constexpr int kMaxBvhDepth = 40;     // traversal stack entries per thread
 
 // objects: the scene in list order. origin_extent: largest |coordinate| of any ray origin that will be
 // traced from outside the scene bounds (the camera position); secondary origins lie on surfaces.
+// threads: large subtrees are built concurrently (0 = all hardware threads, 1 = sequential; RTB200_BVH_THREADS overrides). The tree
+// is byte-identical for every thread count (bvh_build.cpp Subtree).
 void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf = 4,
-               const TriRecords* tris = nullptr, float origin_offset = 0.f);   // origin_offset: |rt_params.eps|
+               const TriRecords* tris = nullptr, float origin_offset = 0.f, int threads = 0);   // origin_offset: |rt_params.eps|
 
 }  // namespace rtb

@@ -151,6 +151,31 @@ extern "C" int emu_wide_info(const rt_object* objects, int n_obj, float origin_e
     return bad;
 }
 
+// BVH2 of a scene (optionally with one mesh object) built with `threads` threads: out[0..3] = FNV-1a 64 of the node array, of
+// the refs, node count, max depth. The parallel build must give the same bytes as the sequential one.
+extern "C" void emu_bvh_digest(const rt_object* objects, int n_obj, const float* mverts, int n_mverts, const int32_t* mtris, int n_mtris,
+                               int mesh_object, int threads, unsigned long long* out4) {
+    std::vector<rt_object> objs(objects, objects + n_obj);
+    std::vector<HostMesh> meshes((size_t)n_obj);
+    if (mesh_object >= 0 && mesh_object < n_obj) {
+        meshes[(size_t)mesh_object].vertices.assign(mverts, mverts + (size_t)3 * n_mverts);
+        meshes[(size_t)mesh_object].indices.assign(mtris, mtris + (size_t)3 * n_mtris);
+    }
+    TriRecords tris;
+    build_tri_records(objs, meshes, tris);
+    HostBvh b;
+    build_bvh(objs, 25.f, b, 4, &tris, 1e-5f, threads);
+    auto fnv = [](const void* p, size_t n) {
+        unsigned long long h = 1469598103934665603ull;
+        const unsigned char* c = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+        return h;
+    };
+    out4[0] = fnv(b.nodes.data(), b.nodes.size() * sizeof(BvhNode));
+    out4[1] = fnv(b.refs.data(), b.refs.size() * sizeof(int32_t));
+    out4[2] = b.nodes.size(); out4[3] = (unsigned long long)b.max_depth;
+}
+
 // ---- host-logic hooks for the CPU tests (builders only, no tracing) ----------------------------------------------
 extern "C" {
 // Flat accelerator of a scene: returns usable (0/1); counts[0..3] = clusters, cubes, singles, cull records;

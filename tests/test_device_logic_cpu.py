@@ -23,7 +23,7 @@ def emu():
             os.path.join(ROOT, "software-raytracer_b200", "csrc", "bvh_wide.cpp"),
             os.path.join(ROOT, "software-raytracer_b200", "csrc", "flat_build.cpp"),
             os.path.join(ROOT, "software-raytracer_b200", "csrc", "mesh.cpp")]
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + os.path.join(ROOT, "include"),
                            "-o", EMU_SO] + srcs)
     lib = C.CDLL(EMU_SO)
     lib.emu_render.restype = C.c_longlong

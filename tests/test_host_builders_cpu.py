@@ -158,3 +158,32 @@ def test_wide_bvh_builder_limits(lib):
     o = spheres(50); o["pos"][7, 2] = np.inf
     assert wide_info(lib, o)[1][0] == 0
     assert wide_info(lib, spheres(0) if False else np.zeros(0, rtb200.OBJECT_DTYPE))[0] == 0     # empty scene
+
+
+# ---- BVH2 builder: concurrent subtree builds give the same bytes as the sequential build -------------------------------------
+def bvh_digest(lib, objs, threads, mesh=None):
+    objs = np.ascontiguousarray(objs, rtb200.OBJECT_DTYPE)
+    out = (C.c_ulonglong * 4)()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    if mesh is None:
+        lib.emu_bvh_digest(p(objs), len(objs), None, 0, None, 0, -1, threads, out)
+    else:
+        v = np.ascontiguousarray(mesh[0], np.float32).reshape(-1, 3); t = np.ascontiguousarray(mesh[1], np.int32).reshape(-1, 3)
+        lib.emu_bvh_digest(p(objs), len(objs), p(v), len(v), p(t), len(t), 0, threads, out)
+    return tuple(out)
+
+
+def test_bvh_parallel_build_is_byte_identical(lib):
+    from rtb200.scenes import heightfield_mesh, mesh_scene, synthetic_spheres
+    objs = synthetic_spheres(60000, cubes_every=7)                    # well above the 16 384-primitive task threshold
+    want = bvh_digest(lib, objs, 1)
+    assert want[2] > 20000 and 10 < want[3] < 40
+    for threads in (2, 3, 8, 64, 0):
+        assert bvh_digest(lib, objs, threads) == want, threads
+    v, tr = heightfield_mesh(320, 200, seed=4)                         # 128 000 triangles
+    want = bvh_digest(lib, mesh_scene(), 1, (v, tr))
+    assert want[2] > 40000
+    for threads in (4, 16, 0):
+        assert bvh_digest(lib, mesh_scene(), threads, (v, tr)) == want, threads
+    small = synthetic_spheres(300)                                     # below the threshold: the sequential path whatever the count
+    assert bvh_digest(lib, small, 8) == bvh_digest(lib, small, 1)
