@@ -133,7 +133,8 @@ enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
  * bit-identical hits; AUTO measures them on the first rt_render_spp call of at least 64 samples after a scene or parameter
  * change (shorter calls, and camera moves, keep a heuristic choice: flat up to 255 objects, BVH from `bvh_threshold`).
  * RT_PIPELINE_AUTO is the regeneration megakernel, except that BVH scenes of 2048+ primitives also time the wavefront
- * pipeline (raygen / persistent-thread intersect / shade + ray compaction kernels) and keep the faster. */
+ * pipeline (raygen / persistent-thread intersect / shade + ray compaction kernels) on the first call of 8+ samples and keep
+ * the faster for calls of 8+ samples; shorter calls always use the megakernel. */
 enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2, RT_ACCEL_FLAT = 3 };
 
 /* ---- lifetime: replaces the worker spawn/join (Raytracer.cpp:331-342, 598-607) -------- */
