@@ -98,8 +98,8 @@ long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* 
 }
 
 // traversal statistics of the emulated wide / binary BVH loops since the last call (test diagnostics)
-extern "C" void emu_bvh_stats(long long* out4) {
-    out4[0] = g_wide_node_visits; out4[1] = g_wide_prim_tests; out4[2] = g_bvh2_node_visits; out4[3] = g_wide_empty_visits; out4[4] = g_wide_stale_visits; g_wide_stale_visits = 0;
+extern "C" void emu_bvh_stats(long long* out4) {   // six values
+    out4[0] = g_wide_node_visits; out4[1] = g_wide_prim_tests; out4[2] = g_bvh2_node_visits; out4[3] = g_wide_empty_visits; out4[4] = g_wide_stale_visits; out4[5] = g_bvh2_prim_tests; g_wide_stale_visits = g_bvh2_prim_tests = 0;
     g_wide_node_visits = g_wide_prim_tests = g_bvh2_node_visits = g_wide_empty_visits = 0;
 }
 // Wide BVH of a scene (spheres and cubes): counts[0..4] = usable, wide nodes, refs, depth, BVH2 nodes. Returns the number of
