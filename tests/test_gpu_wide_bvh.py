@@ -54,7 +54,10 @@ def _rays(n, seed, lo, hi):
     d = rng.normal(size=(n, 3)).astype(np.float32)
     d[::17, 0] = 0.0; d[5::29, 1] = 0.0; d[7::31, 2] = -0.0           # zero components: the clamped reciprocal path
     d[11::97] = (0.0, 0.0, 1.0); d[13::101] = (0.0, -1.0, 0.0)        # axis-parallel rays
+    d[np.linalg.norm(d, axis=1) == 0] = (1.0, 0.0, 0.0)               # (a row hit by all three zeroing patterns)
     d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    # rt_trace_rays sends a batch with ANY non-unit direction through the brute-force loop: make sure this one qualifies
+    assert np.all(np.abs((d.astype(np.float32) ** 2).sum(axis=1) - 1.0) <= 1e-6)
     return org, d
 
 
