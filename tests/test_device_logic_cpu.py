@@ -144,3 +144,28 @@ def test_device_logic_mesh_bvh_equals_brute_and_oracle(emu, oracle):
     assert np.array_equal(aa[2][hit].view(np.uint32), on[hit].view(np.uint32))
     assert np.array_equal(aa[3][hit].view(np.uint32), op[hit].view(np.uint32))
     assert segs == sa and np.array_equal(a.view(np.uint32), want.view(np.uint32))
+
+
+def test_wide_bvh_makes_about_half_the_node_visits(emu):
+    """DESIGN.md's claim about the 8-wide quantised BVH, from the emulated traversal loops' own counters: roughly 2.2x fewer
+    node visits per ray than the binary tree on a few thousand random spheres (each visit costs ~4x the instructions, which
+    is why it is not the default)."""
+    lib = C.CDLL(EMU_SO)
+    rng = np.random.default_rng(5)
+    n = 4000
+    o = np.zeros(n + 1, rtb200.OBJECT_DTYPE); o["type"] = 1
+    o["pos"] = rng.uniform(-20, 20, (n + 1, 3)).astype(np.float32); o["pos"][:, 1] = rng.uniform(0.2, 6, n + 1)
+    o["radius"] = rng.uniform(0.1, 0.6, n + 1).astype(np.float32)
+    o["pos"][n] = (0, -1000, 0); o["radius"][n] = 1000
+    o["base"] = 0.7; o["spec_color"] = 1
+    cam = rtb200.default_camera(60); cam.pos[1] = 3.0; cam.pos[2] = -26.0
+    par = rtb200.default_params(width=64, height=48, mode=0, max_bounces=4, seed_lo=5, seed_hi=6)
+    stats = (C.c_longlong * 6)()
+    lib.emu_bvh_stats(stats)                                  # reset
+    a, sa, _ = emu(o, cam, par, 1, 0, 2)
+    lib.emu_bvh_stats(stats); b2_visits, b2_prims = stats[2], stats[5]
+    b, sb, _ = emu(o, cam, par, 3, 0, 2)
+    lib.emu_bvh_stats(stats); w_visits, w_prims = stats[0], stats[1]
+    assert sa == sb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert b2_visits > 0 and 0.3 * b2_visits < w_visits < 0.6 * b2_visits, (b2_visits, w_visits)
+    assert w_prims < 2.0 * b2_prims, (b2_prims, w_prims)
