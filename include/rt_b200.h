@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 typedef struct rt_ctx rt_ctx;
 
@@ -123,9 +123,13 @@ enum {
     RT_OPT_BVH_WIDE = 12,          /* BVH node format: 0 (default) 64-byte binary nodes; 1 scenes of 1024+ primitives traverse the 8-wide form with
                                       quantised child boxes (80-byte nodes, csrc/bvh_wide.h); 2 every BVH scene. Identical results; on B200 the
                                       wide form makes 2.2x fewer node visits but executes more instructions and measured slower */
-    RT_OPT_PRIMARY_REUSE = 7       /* 1 (default): one primary closest-hit query per pixel per rt_render_spp call,
-                                      reused by every sample (identical ray: the reference has no pixel jitter);
-                                      0: re-trace it for every sample like the reference. Results are bit-identical. */
+    RT_OPT_PRIMARY_REUSE = 7,      /* 1 (default): ONE primary closest-hit query per pixel, kept in a per-pixel cache of the context
+                                      (id, t, normal) and reused by every sample of every rt_render_spp call until the camera, the
+                                      scene, the resolution or the secondary-origin offset changes (identical ray: the reference has
+                                      no pixel jitter, Raytracer.cpp:106-122); 0: re-trace it for every sample like the reference.
+                                      Results are bit-identical. */
+    RT_OPT_TRAVERSAL_STATS = 14    /* 1: BVH kernels count inner-node visits and primitive tests (rt_get_traversal_stats); a separate
+                                      instantiation of the kernels, ~3 % slower. 0 (default): off */
 };
 enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
 /* BRUTE: the reference's object loop. BVH: host-built BVH2. FLAT: two-level flat accelerator for scenes of up
@@ -251,6 +255,18 @@ int rt_philox_block(rt_ctx* ctx, const uint32_t ctr[4], const uint32_t key[2], u
  * which = 0: unit_from_word, (float)((double)k * (1.0/32767.0)) == (float)k / 32767.0f for all 32768 k. */
 int rt_selftest(rt_ctx* ctx, int which, int* failures);
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
+/* BVH traversal work actually executed by the render kernels since rt_reset_accumulation, counted on the device while
+ * RT_OPT_TRAVERSAL_STATS is 1 (bytes per segment = node bytes x <nodes visited> + primitive bytes x <primitives
+ * tested>). The per-ray loop (rt_trace_rays, megakernel) visits exactly the nodes the CPU emulation of the same code visits
+ * (tests/host_emu); the wavefront intersect kernel postpones leaves, so it visits a few more. */
+typedef struct {
+    uint64_t queries;              /* closest-hit queries that went through a counting BVH kernel */
+    uint64_t node_visits;          /* inner nodes fetched (64 B each: both children's boxes + links) */
+    uint64_t prim_tests;           /* leaf primitives tested with the strict intersectors */
+    uint64_t sphere_tests, cube_tests, tri_tests;   /* prim_tests by type (16 B + 4 B id, 32 B + 4 B, 48 B + 4 B per test) */
+    uint32_t node_bytes, reserved;
+} rt_traversal_stats;
+int rt_get_traversal_stats(rt_ctx* ctx, rt_traversal_stats* out);
 
 /* ---- device-side interop (multi-GPU reduce, benchmarks) -------------------------------- */
 void* rt_accum_device_ptr(rt_ctx* ctx);          /* float4[width*height] sum buffer, device memory */
@@ -272,18 +288,60 @@ int rt_resolve_device(rt_ctx* ctx, const void* dev_accum_rgba, uint32_t samples,
  * and stores the result straight into the destination surface (typically rank 0's, also
  * peer-mapped): 16 B read per pixel per rank, 4 B written, no intermediate buffer, deterministic
  * summation order. Buffers of other processes are mapped with the rt_ipc_* helpers (CUDA IPC);
- * buffers of other contexts in the same process can be passed as they are. The caller makes sure
- * every rank's render has completed (a barrier) before launching, and again before reading dst. */
+ * buffers of other contexts in the same process can be passed as they are: rt_resolve_fused looks every
+ * pointer up (cudaPointerGetAttributes) and enables peer access to its device, or fails with RT_ERR_CUDA
+ * when the devices cannot reach each other. With rt_resolve_fused the CALLER makes sure every rank's render
+ * has completed (a barrier) before launching, and again before reading dst; rt_exchange_* below and
+ * rt_group_* do that ordering themselves. */
 #define RT_IPC_HANDLE_BYTES 64
 #define RT_MAX_PEERS 16
 void* rt_argb_device_ptr(rt_ctx* ctx);                       /* uint32[width*height] resolved surface, device */
-int rt_ipc_export(rt_ctx* ctx, int which /* 0 accumulation, 1 surface */, unsigned char handle[RT_IPC_HANDLE_BYTES]);
+int rt_ipc_export(rt_ctx* ctx, int which /* 0 accumulation, 1 surface, 2 exchange flags */, unsigned char handle[RT_IPC_HANDLE_BYTES]);
 int rt_ipc_open(rt_ctx* ctx, const unsigned char handle[RT_IPC_HANDLE_BYTES], void** dev_ptr);
 int rt_ipc_close(rt_ctx* ctx, void* dev_ptr);
 int rt_resolve_fused(rt_ctx* ctx, const void* const* accum_ptrs, int world, uint32_t total_samples,
                      int first_pixel, int n_pixels, void* dst_argb_whole_image, int flip_y);
 /* Copies the context's device surface to the host (after a fused resolve wrote it). */
 int rt_read_surface(rt_ctx* ctx, uint32_t* host_out, int pitch_bytes);
+
+/* One process per GPU: the exchange step WITHOUT host synchronisation or a collective library. Every context owns a
+ * small block of flags in device memory (rt_ipc_export(ctx, 2, ..)). rt_exchange_setup gives a context the peer-mapped
+ * accumulation buffers and flag blocks of all ranks (rank order; its own entries may be NULL) and the destination
+ * surface (rank 0's). rt_exchange_resolve is then stream-ordered and asynchronous:
+ *   1. signal: "my samples are in my buffer" is stored into every peer's flag block (st.release.sys over NVLink);
+ *   2. k_resolve_fused waits on its OWN flag block until every rank has signalled this epoch, then reduces + resolves
+ *      its slice of the pixels from all ranks' buffers into the destination surface;
+ *   3. the last CTA signals "my slice is written and I have finished reading your buffers" to every peer;
+ *   4. a one-warp kernel waits until every rank has sent that, so whatever is enqueued next on the stream - rank 0's
+ *      rt_read_surface, any rank's next rt_reset_accumulation - is ordered after the whole exchange.
+ * Epochs only grow, nothing is reset. A wait gives up after ~4 s (a peer died) and the next rt_sync / rt_read_surface
+ * reports RT_ERR_CUDA. total_samples: samples per pixel summed over all ranks (the resolve's divisor). */
+int rt_exchange_setup(rt_ctx* ctx, int rank, int world, void* const* accum_ptrs, void* const* flag_ptrs, void* dst_argb_whole_image);
+int rt_exchange_resolve(rt_ctx* ctx, uint32_t total_samples, int flip_y);
+
+/* ---- library-owned multi-GPU: replaces the worker spawn / join of the reference (Raytracer.cpp:331-342, 598-607) ----
+ * "rt_create(int device_count, const int* devices, ..) owns streams, device buffers and the exchange". One
+ * host process, n devices: a group creates one context per device, enables peer access between them, shards every
+ * rt_group_render_spp call by samples per pixel (rt_set_shard(i, n)) and resolves with the fused reduce + resolve
+ * kernel, every device writing its slice of the pixels straight into device 0's surface; the ordering between the
+ * devices' streams is done with CUDA events (no host synchronisation until the download). No torch, no NCCL, no IPC.
+ * Setters are broadcast to every member; rt_group_ctx gives a member for anything else (options, statistics). */
+typedef struct rt_group rt_group;
+int rt_create_multi(int n_devices, const int* cuda_devices, rt_group** out);   /* cuda_devices NULL: 0 .. n-1 */
+int rt_group_destroy(rt_group* g);
+int rt_group_size(const rt_group* g);
+rt_ctx* rt_group_ctx(rt_group* g, int index);
+const char* rt_group_last_error(const rt_group* g);          /* g may be NULL: last rt_create_multi failure */
+int rt_group_set_scene(rt_group* g, const rt_object* objects, int n);
+int rt_group_load_scene(rt_group* g, const char* json_path);  /* returns object count */
+int rt_group_set_mesh(rt_group* g, int object_index, const float* vertices_xyz, int n_vertices, const int32_t* indices, int n_triangles);
+int rt_group_set_camera(rt_group* g, const rt_camera* cam);
+int rt_group_set_params(rt_group* g, const rt_params* p);
+int rt_group_set_option(rt_group* g, int option, int value);
+int rt_group_reset_accumulation(rt_group* g);
+int rt_group_render_spp(rt_group* g, int spp);               /* spp = GLOBAL samples per pixel, split over the devices */
+int rt_group_resolve_rgba8(rt_group* g, uint32_t* host_out, int pitch_bytes, int flip_y);
+int rt_group_get_stats(rt_group* g, rt_stats* out);           /* sums over the members; last_render_ms = the slowest */
 
 #ifdef __cplusplus
 }

@@ -12,98 +12,23 @@
 #include <string>
 #include <vector>
 
-#include "../../include/rt_b200.h"
-#include "rt_device.cuh"
+#include "rt_ctx.h"
 #include "rt_host_pack.h"
-#include "rt_kernels.h"
-#include "bvh_build.h"
-#include "bvh_wide.h"
-#include "flat_build.h"
-#include "mesh.h"
-#include "scene_json.h"
 
 using namespace rtb;
 
-struct rt_ctx {
-    int device = 0;
-    int sm_count = 0;
-    std::string err;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-
-    HostScene scene;
-    rt_camera cam;
-    rt_params par;
-    FrameView frame;
-    SceneView view;
-    bool frame_dirty = true;
-
-    // device scene
-    float4* d_sph = nullptr; int* d_sph_id = nullptr;
-    float4* d_box = nullptr; int* d_box_id = nullptr;
-    float4* d_mat = nullptr;
-    size_t cap_sph = 0, cap_sph_id = 0, cap_box = 0, cap_box_id = 0, cap_mat = 0;
-    // mesh extension: triangle records (mesh.h)
-    TriRecords tris;
-    float4* d_tri = nullptr; int* d_tri_obj = nullptr;
-    size_t cap_tri = 0, cap_tri_obj = 0;
-
-    // BVH (built lazily; see bvh_build.h)
-    HostBvh bvh;
-    BvhView bview;
-    float4* d_bvh_nodes = nullptr; int* d_bvh_refs = nullptr;
-    size_t cap_bvh_nodes = 0, cap_bvh_refs = 0;
-    HostWideBvh wide;                  // 8-wide quantised form for BVHs read from global memory (bvh_wide.h)
-    uint4* d_wide_nodes = nullptr; int* d_wide_refs = nullptr;
-    size_t cap_wide_nodes = 0, cap_wide_refs = 0;
-    bool bvh_valid = false;
-
-    // flat two-level accelerator for small scenes (built lazily; see flat_build.h)
-    HostFlat flat;
-    FlatView fview;
-    float4* d_flat_boxes = nullptr; float4* d_flat_cull = nullptr; unsigned char* d_flat_slots = nullptr; int* d_flat_ids = nullptr;
-    size_t cap_flat_boxes = 0, cap_flat_cull = 0, cap_flat_slots = 0, cap_flat_ids = 0;
-    bool flat_valid = false;
-
-    WavefrontBuffers* wf = nullptr;    // RT_PIPELINE_WAVEFRONT state (rt_wavefront.cu), allocated on first use
-
-    // frame buffers
-    float4* d_accum = nullptr;
-    uint32_t* d_argb = nullptr;
-    size_t cap_pixels = 0;
-    unsigned long long* d_counters = nullptr;     // [0] segments
-    uint32_t* d_scratch = nullptr;                // small device scratch (philox / pick)
-
-    // accumulation state
-    uint32_t samples = 0;          // samples per pixel in the buffer (global, after any external reduce)
-    uint32_t next_sample = 0;      // next global sample index
-    uint64_t paths = 0, total_paths = 0, total_segments_base = 0;
-    int rank = 0, world = 1;
-    int pixel_step = 1, strip_columns = 0;   // block-filled frames (rt_set_pixel_step)
-    int opt_pipeline = RT_PIPELINE_AUTO, opt_accel = RT_ACCEL_AUTO, opt_bvh_threshold = 512;
-    int opt_bvh_sched = 0, opt_bvh_wait_k = 20, opt_bvh_leaf = 4, opt_primary_reuse = 1;
-    int opt_bvh_wide = 0;              // 0 (default) binary nodes, 1 wide nodes for BVHs of kWideMinPrims+ primitives, 2 always (tests)
-    int opt_wf_refill = 8, opt_wf_node_min = 8, opt_wf_wave_mpaths = 0, opt_pool_tiles = 0, opt_flat_coop = 2;   // flat_coop: 0 off, 1 on, 2 measured per scene
-    int tuned_flat_coop = 1;
-    int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
-    int tuned_pipeline = -1;       // RT_PIPELINE_AUTO decision for large BVH scenes (-1: not measured yet)
-    float tune_pipe_ms[2] = {0.f, 0.f};
-    float4* d_tune = nullptr; size_t cap_tune = 0;
-    float tune_ms[4] = {0.f, 0.f, 0.f, 0.f};
-    int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;
-    float last_render_ms = 0.f, last_resolve_ms = 0.f;
-    bool render_timed = false, resolve_timed = false;
-};
-
 static thread_local std::string g_create_error;
 
-namespace {
-
+namespace rtb_capi {
 int fail(rt_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
 }
+}  // namespace rtb_capi
+using rtb_capi::fail;
+
+namespace {
+
 int cuda_fail(rt_ctx* c, cudaError_t e, const char* what) {
     return fail(c, RT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
@@ -121,6 +46,7 @@ cudaError_t ensure_capacity(T*& ptr, size_t& cap, size_t need) {
     size_t n = need < 16 ? 16 : need;
     cudaError_t e = cudaMalloc((void**)&ptr, n * sizeof(T));
     if (e == cudaSuccess) cap = n;
+    else { ptr = nullptr; cudaGetLastError(); }               // do not leave the failure for the next launch check to find
     return e;
 }
 
@@ -135,8 +61,14 @@ int ensure_buffers(rt_ctx* c) {
         if (c->d_accum) cudaFree(c->d_accum);
         if (c->d_argb) cudaFree(c->d_argb);
         c->d_accum = nullptr; c->d_argb = nullptr; c->cap_pixels = 0;
-        RT_CUDA(c, cudaMalloc((void**)&c->d_accum, px * sizeof(float4)));
-        RT_CUDA(c, cudaMalloc((void**)&c->d_argb, px * sizeof(uint32_t)));
+        c->exch.ready = false;                                 // peers hold mappings of the old buffers
+        cudaError_t e = cudaMalloc((void**)&c->d_accum, px * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_argb, px * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(c->d_accum); c->d_accum = nullptr;
+            return cuda_fail(c, e, "frame buffers");
+        }
         c->cap_pixels = px;
         RT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, px * sizeof(float4), c->stream));
         c->samples = 0; c->next_sample = 0; c->paths = 0;
@@ -181,6 +113,7 @@ int upload_scene(rt_ctx* c) {
     c->view.n_sph = (int)sph_id.size(); c->view.n_box = (int)box_id.size(); c->view.n_obj = (int)objs.size();
     c->view.tri = c->d_tri; c->view.tri_obj = c->d_tri_obj; c->view.n_tri = (int)nt;
     c->bvh_valid = false; c->flat_valid = false; c->tuned_accel = c->tuned_pipeline = -1;
+    c->prim_valid = false;
     return RT_OK;
 }
 
@@ -190,9 +123,12 @@ constexpr int kWideMinPrims = 1024;    // below this the whole BVH2 is staged in
 int ensure_bvh(rt_ctx* c, float origin_extent) {
     if (c->bvh_valid && origin_extent <= c->bvh.extent) return RT_OK;
     const size_t prims = (size_t)c->view.n_sph + c->view.n_box + c->view.n_tri;
+    if (prims >= ((size_t)1 << 24)) return fail(c, RT_ERR_INVALID, "scene has 2^24 or more primitives: not supported by the BVH's 24-bit leaf links");
     const bool want_wide = c->opt_bvh_wide == 2 || (c->opt_bvh_wide == 1 && prims >= (size_t)kWideMinPrims);
     build_bvh(c->scene.objects, origin_extent, c->bvh, want_wide ? std::min(c->opt_bvh_leaf, kWideMaxLeaf) : c->opt_bvh_leaf, &c->tris, c->par.eps);
     if (c->bvh.max_depth + 2 > 62) return fail(c, RT_ERR_INVALID, "BVH too deep for the traversal stack");
+    // leaf links carry the first ref index in 24 bits (bvh_build.h BvhNode): more refs would alias
+    if (c->bvh.refs.size() >= ((size_t)1 << 24)) return fail(c, RT_ERR_INVALID, "scene has 2^24 or more BVH leaf references: not supported by the 24-bit leaf links");
     c->wide = HostWideBvh();
     if (want_wide) build_wide_bvh(c->bvh, c->wide);           // not usable (huge extents, oversized leaves): the BVH2 is traversed
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -281,6 +217,32 @@ int want_accel(rt_ctx* c) {
     return RT_ACCEL_BRUTE;
 }
 
+// The per-pixel primary-hit cache (RT_OPT_PRIMARY_REUSE): traced once with the back end of the moment (all back ends give
+// identical hits) and kept until the camera, the scene or the resolution changes.
+int ensure_prim_cache(rt_ctx* c, const AccelSel& ac) {
+    const size_t px = (size_t)c->par.width * c->par.height;
+    if (c->prim_valid && c->cap_prim >= px) return RT_OK;
+    if (c->cap_prim < px) {
+        RT_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->d_prim_nt) cudaFree(c->d_prim_nt);
+        if (c->d_prim_id) cudaFree(c->d_prim_id);
+        c->d_prim_nt = nullptr; c->d_prim_id = nullptr; c->cap_prim = 0;
+        cudaError_t e = cudaMalloc((void**)&c->d_prim_nt, px * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_prim_id, px * sizeof(int));
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(c->d_prim_nt); c->d_prim_nt = nullptr; return cuda_fail(c, e, "primary-hit cache"); }
+        c->cap_prim = px;
+    }
+    RT_CUDA(c, launch_primary_cache(c->view, ac, c->frame, c->d_prim_nt, c->d_prim_id, c->d_counters, c->stream));
+    c->prim_valid = true;
+    return RT_OK;
+}
+// what the render launchers take: the cache when reuse is on, NULL when every sample re-traces its primary ray
+const PrimCache* prim_cache_arg(rt_ctx* c, PrimCache& pc) {
+    if (!c->opt_primary_reuse) return nullptr;
+    pc.nt = c->d_prim_nt; pc.id = c->d_prim_id;
+    return &pc;
+}
+
 // RT_ACCEL_AUTO between 8 and `bvh_threshold` primitives: all back ends give identical results and which
 // one is fastest depends on the scene, so the first path-mode render after a scene/camera/parameter change
 // of at least 64 spp times 16 spp of each into a scratch buffer and keeps the fastest. Below 8 primitives brute force,
@@ -305,21 +267,21 @@ int autotune_accel(rt_ctx* c, int spp) {
     for (int k = 0; k < n_cand; ++k) if ((rc = make_accel(c, kinds[k], camera_extent(c), sel[k])) != RT_OK) return rc;
     const size_t px = (size_t)c->par.width * c->par.height;
     RT_CUDA(c, ensure_capacity(c->d_tune, c->cap_tune, px));
-    cudaEvent_t e[5];
-    for (auto& ev : e) RT_CUDA(c, cudaEventCreate(&ev));
+    cudaEvent_t* e = c->ev_tune;
     unsigned long long* dummy = c->d_counters + 4;            // not part of the reported statistics
     cudaError_t err = cudaSuccess;
-    const bool reuse = c->opt_primary_reuse != 0;
+    PrimCache pc;
+    if (c->opt_primary_reuse && (rc = ensure_prim_cache(c, sel[n_cand - 1])) != RT_OK) return rc;
+    const PrimCache* prim = prim_cache_arg(c, pc);
     for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 warms the instruction cache
         cudaEventRecord(e[0], c->stream);
         for (int k = 0; k < n_cand && err == cudaSuccess; ++k) {
-            err = launch_render_regen(c->view, sel[k], c->frame, c->d_tune, 0u, 16, reuse, dummy, c->stream, 1, coop[k]);
+            err = launch_render_regen(c->view, sel[k], c->frame, c->d_tune, 0u, 16, prim, dummy, c->stream, 1, coop[k]);
             cudaEventRecord(e[k + 1], c->stream);
         }
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
     if (err == cudaSuccess) for (int k = 0; k < n_cand; ++k) cudaEventElapsedTime(&c->tune_ms[k], e[k], e[k + 1]);
-    for (auto& ev : e) cudaEventDestroy(ev);
     if (err != cudaSuccess) return cuda_fail(c, err, "autotune_accel");
     int best = 0;
     for (int k = 1; k < n_cand; ++k) {
@@ -347,30 +309,39 @@ int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     const size_t px = (size_t)c->par.width * c->par.height;
     RT_CUDA(c, ensure_capacity(c->d_tune, c->cap_tune, px));
     if (!c->wf) c->wf = wavefront_create();
-    cudaEvent_t e[3];
-    for (auto& ev : e) RT_CUDA(c, cudaEventCreate(&ev));
+    cudaEvent_t* e = c->ev_tune;
     unsigned long long* dummy = c->d_counters + 4;
-    const bool reuse = c->opt_primary_reuse != 0;
+    PrimCache pc;
+    int rc;
+    if (c->opt_primary_reuse && (rc = ensure_prim_cache(c, ac)) != RT_OK) return rc;
+    const PrimCache* prim = prim_cache_arg(c, pc);
     cudaError_t err = cudaSuccess;
     // The wavefront pipeline's rate depends on how many samples share a wave (launch_render_wavefront), so it is measured with
     // up to 16 samples per pixel - what a call of this length will really run.
     const int n_tune = spp < 16 ? spp : 16;
     for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 allocates the wavefront buffers and warms up
         cudaEventRecord(e[0], c->stream);
-        err = launch_render_regen(c->view, ac, c->frame, c->d_tune, 0u, pass ? n_tune : 1, reuse, dummy, c->stream);
+        err = launch_render_regen(c->view, ac, c->frame, c->d_tune, 0u, pass ? n_tune : 1, prim, dummy, c->stream);
         cudaEventRecord(e[1], c->stream);
-        if (err == cudaSuccess) err = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_tune, 0u, n_tune, reuse, dummy, c->stream, c->opt_bvh_sched == 0,
+        if (err == cudaSuccess) err = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_tune, 0u, n_tune, prim, dummy, c->stream, c->opt_bvh_sched == 0,
                                                              c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths);
         cudaEventRecord(e[2], c->stream);
     }
+    if (err == cudaErrorMemoryAllocation) {                    // no room for even the smallest wave: the megakernel gives the same image
+        cudaStreamSynchronize(c->stream);
+        c->tuned_pipeline = RT_PIPELINE_REGEN;
+        return RT_OK;
+    }
     if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
     if (err == cudaSuccess) { cudaEventElapsedTime(&c->tune_pipe_ms[0], e[0], e[1]); cudaEventElapsedTime(&c->tune_pipe_ms[1], e[1], e[2]); }
-    for (auto& ev : e) cudaEventDestroy(ev);
     if (err != cudaSuccess) return cuda_fail(c, err, "autotune_pipeline");
     c->tuned_pipeline = c->tune_pipe_ms[1] < c->tune_pipe_ms[0] ? RT_PIPELINE_WAVEFRONT : RT_PIPELINE_REGEN;
     return RT_OK;
 }
 
+}  // namespace
+
+namespace rtb_capi {
 int prepare(rt_ctx* c) {
     if (!c) return RT_ERR_INVALID;
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -378,7 +349,30 @@ int prepare(rt_ctx* c) {
     return ensure_buffers(c);
 }
 
-}  // namespace
+// Makes `ptr` (device memory of any context, or a CUDA-IPC mapping) loadable from kernels on this context's device.
+int enable_peer_access_to(rt_ctx* c, const void* ptr, const char* what) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+    if (e != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return fail(c, RT_ERR_INVALID, std::string(what) + ": not a device pointer");
+    }
+    if (at.device == c->device) return RT_OK;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, c->device, at.device) != cudaSuccess || !can) {
+        cudaGetLastError();
+        char buf[160];
+        snprintf(buf, sizeof buf, "%s: device %d cannot access memory of device %d (no peer path)", what, c->device, at.device);
+        return fail(c, RT_ERR_CUDA, buf);
+    }
+    e = cudaDeviceEnablePeerAccess(at.device, 0);              // for the current device = c->device (prepare() set it)
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaDeviceEnablePeerAccess");
+    return RT_OK;
+}
+}  // namespace rtb_capi
+using rtb_capi::prepare;
+using rtb_capi::enable_peer_access_to;
 
 extern "C" {
 
@@ -455,9 +449,15 @@ int rt_create(int cuda_device, rt_ctx** out) {
     memset(&c->bview, 0, sizeof c->bview);
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&c->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev2)) != cudaSuccess || (e = cudaEventCreate(&c->ev3)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev_tune[0])) != cudaSuccess || (e = cudaEventCreate(&c->ev_tune[1])) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev_tune[2])) != cudaSuccess || (e = cudaEventCreate(&c->ev_tune[3])) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev_tune[4])) != cudaSuccess ||
+        (e = cudaMalloc((void**)&c->d_counters, kCounters * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMalloc((void**)&c->d_scratch, 4096)) != cudaSuccess ||
-        (e = cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaMalloc((void**)&c->d_flags, sizeof(ExchFlags))) != cudaSuccess ||
+        (e = cudaMemset(c->d_flags, 0, sizeof(ExchFlags))) != cudaSuccess ||
+        (e = cudaMemset(c->d_counters, 0, kCounters * sizeof(unsigned long long))) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "rt_create");
         rt_destroy(c);
         return rc;
@@ -477,11 +477,14 @@ int rt_destroy(rt_ctx* c) {
     cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
     cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_wide_nodes); cudaFree(c->d_wide_refs); cudaFree(c->d_tune);
-    cudaFree(c->d_tri); cudaFree(c->d_tri_obj);
+    cudaFree(c->d_tri); cudaFree(c->d_tri_obj); cudaFree(c->d_prim_nt); cudaFree(c->d_prim_id); cudaFree(c->d_flags);
     wavefront_destroy(c->wf);
     cudaFree(c->d_flat_boxes); cudaFree(c->d_flat_cull); cudaFree(c->d_flat_slots); cudaFree(c->d_flat_ids);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
+    for (cudaEvent_t ev : c->ev_tune) if (ev) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return RT_OK;
@@ -634,6 +637,7 @@ int rt_get_mesh_info(rt_ctx* c, int object_index, int* n_vertices, int* n_triang
 
 int rt_set_camera(rt_ctx* c, const rt_camera* cam) {
     if (!c || !cam) return RT_ERR_INVALID;
+    if (memcmp(&c->cam, cam, sizeof *cam) != 0) c->prim_valid = false;   // a host that re-submits the same pose every frame keeps the cache
     c->cam = *cam;
     c->frame_dirty = true;
     return RT_OK;
@@ -656,26 +660,56 @@ int rt_set_params(rt_ctx* c, const rt_params* p) {
         if (c->d_accum) { cudaFree(c->d_accum); c->d_accum = nullptr; }
         if (c->d_argb) { cudaFree(c->d_argb); c->d_argb = nullptr; }
         c->cap_pixels = 0;
+        c->prim_valid = false;
+        c->exch.ready = false;
+        wavefront_release(c->wf);                              // sized for the old resolution (up to tens of GB)
     }
     return RT_OK;
 }
 
 int rt_set_option(rt_ctx* c, int option, int value) {
     if (!c) return RT_ERR_INVALID;
+    auto bad = [&](const char* what) { return fail(c, RT_ERR_INVALID, std::string("rt_set_option: ") + what); };
+    const int retune = -1;
     switch (option) {
-        case RT_OPT_PIPELINE: c->opt_pipeline = value; return RT_OK;
-        case RT_OPT_ACCEL: c->opt_accel = value; return RT_OK;
-        case RT_OPT_BVH_THRESHOLD: c->opt_bvh_threshold = value; return RT_OK;
-        case RT_OPT_BVH_SCHED: c->opt_bvh_sched = value; return RT_OK;
-        case RT_OPT_BVH_WIDE: c->opt_bvh_wide = value < 0 || value > 2 ? 0 : value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
-        case RT_OPT_BVH_LEAF: c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
-        case RT_OPT_PRIMARY_REUSE: c->opt_primary_reuse = value != 0; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
-        case RT_OPT_FLAT_COOP: c->opt_flat_coop = value < 0 || value > 2 ? 2 : value; c->tuned_accel = c->tuned_pipeline = -1; return RT_OK;
-        case RT_OPT_POOL_TILES: c->opt_pool_tiles = value < 0 ? 0 : value; return RT_OK;
-        case RT_OPT_WF_REFILL: c->opt_wf_refill = value; return RT_OK;
-        case RT_OPT_WF_NODE_MIN: c->opt_wf_node_min = value; return RT_OK;
-        case RT_OPT_WF_WAVE_MPATHS: c->opt_wf_wave_mpaths = value; c->tuned_pipeline = -1; return RT_OK;
-        case RT_OPT_BVH_WAIT_K: c->opt_bvh_wait_k = value < 1 ? 1 : value; return RT_OK;
+        case RT_OPT_PIPELINE:
+            if (value < RT_PIPELINE_AUTO || value > RT_PIPELINE_WAVEFRONT) return bad("RT_OPT_PIPELINE takes RT_PIPELINE_AUTO / REGEN / WAVEFRONT");
+            c->opt_pipeline = value; return RT_OK;
+        case RT_OPT_ACCEL:
+            if (value < RT_ACCEL_AUTO || value > RT_ACCEL_FLAT) return bad("RT_OPT_ACCEL takes RT_ACCEL_AUTO / BRUTE / BVH / FLAT");
+            c->opt_accel = value; return RT_OK;
+        case RT_OPT_BVH_THRESHOLD:
+            if (value < 1) return bad("RT_OPT_BVH_THRESHOLD must be at least 1");
+            c->opt_bvh_threshold = value; c->tuned_accel = retune; return RT_OK;
+        case RT_OPT_BVH_SCHED:
+            if (value != 0 && value != 1) return bad("RT_OPT_BVH_SCHED takes 0 or 1");
+            c->opt_bvh_sched = value; return RT_OK;
+        case RT_OPT_BVH_WIDE:
+            if (value < 0 || value > 2) return bad("RT_OPT_BVH_WIDE takes 0, 1 or 2");
+            c->opt_bvh_wide = value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = retune; return RT_OK;
+        case RT_OPT_BVH_LEAF:
+            if (value < 1 || value > 16) return bad("RT_OPT_BVH_LEAF takes 1 .. 16 primitives per leaf");
+            c->opt_bvh_leaf = value; c->bvh_valid = false; c->tuned_accel = c->tuned_pipeline = retune; return RT_OK;
+        case RT_OPT_PRIMARY_REUSE: c->opt_primary_reuse = value != 0; c->tuned_accel = c->tuned_pipeline = retune; return RT_OK;
+        case RT_OPT_FLAT_COOP:
+            if (value < 0 || value > 2) return bad("RT_OPT_FLAT_COOP takes 0, 1 or 2");
+            c->opt_flat_coop = value; c->tuned_accel = c->tuned_pipeline = retune; return RT_OK;
+        case RT_OPT_POOL_TILES:
+            if (value < 0 || value > 32) return bad("RT_OPT_POOL_TILES takes 0 (automatic) .. 32");
+            c->opt_pool_tiles = value; return RT_OK;
+        case RT_OPT_WF_REFILL:
+            if (value < 1 || value > 32) return bad("RT_OPT_WF_REFILL takes 1 .. 32 lanes");
+            c->opt_wf_refill = value; return RT_OK;
+        case RT_OPT_WF_NODE_MIN:
+            if (value < 1 || value > 32) return bad("RT_OPT_WF_NODE_MIN takes 1 .. 32 lanes");
+            c->opt_wf_node_min = value; return RT_OK;
+        case RT_OPT_WF_WAVE_MPATHS:
+            if (value < 0 || value > 1024) return bad("RT_OPT_WF_WAVE_MPATHS takes 0 (default) .. 1024");
+            c->opt_wf_wave_mpaths = value; c->tuned_pipeline = retune; return RT_OK;
+        case RT_OPT_BVH_WAIT_K:
+            if (value < 1 || value > 32) return bad("RT_OPT_BVH_WAIT_K takes 1 .. 32 lanes");
+            c->opt_bvh_wait_k = value; return RT_OK;
+        case RT_OPT_TRAVERSAL_STATS: c->opt_trav_stats = value != 0; return RT_OK;
     }
     return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
 }
@@ -711,9 +745,11 @@ int rt_reset_accumulation(rt_ctx* c) {
     if (rc != RT_OK) return rc;
     RT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)c->par.width * c->par.height * sizeof(float4), c->stream));
     // counters: [0] segments since the last reset, [1] since rt_create (never cleared); [2], [3] the same for the
-    // closest-hit queries actually executed (primary-hit reuse); [4..7] scratch for the autotuner
+    // closest-hit queries actually executed (primary-hit reuse); [4..7] scratch for the autotuner; [8..12] BVH traversal
+    // statistics since the last reset (RT_OPT_TRAVERSAL_STATS: queries, node visits, sphere / cube / triangle tests)
     RT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long), c->stream));
     RT_CUDA(c, cudaMemsetAsync(c->d_counters + 2, 0, sizeof(unsigned long long), c->stream));
+    RT_CUDA(c, cudaMemsetAsync(c->d_counters + 8, 0, 8 * sizeof(unsigned long long), c->stream));
     c->samples = 0; c->next_sample = 0; c->paths = 0;
     return RT_OK;
 }
@@ -754,19 +790,34 @@ int rt_render_spp(rt_ctx* c, int spp) {
         // this rank's slice of the global sample indices [next, next+spp)
         int mine = 0; uint32_t first = 0;
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
-        const bool wavefront = (c->opt_pipeline == RT_PIPELINE_WAVEFRONT ||
-                                (c->opt_pipeline == RT_PIPELINE_AUTO && c->tuned_pipeline == RT_PIPELINE_WAVEFRONT && mine >= kWavefrontMinSpp)) &&
-                               c->par.max_bounces <= 60;      // deeper paths: the megakernel (identical results)
+        bool wavefront = (c->opt_pipeline == RT_PIPELINE_WAVEFRONT ||
+                          (c->opt_pipeline == RT_PIPELINE_AUTO && c->tuned_pipeline == RT_PIPELINE_WAVEFRONT && mine >= kWavefrontMinSpp)) &&
+                         c->par.max_bounces <= 60;            // deeper paths: the megakernel (identical results)
+        const bool scheduled = !wavefront && ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0;   // experimental kernel, re-traces primaries
+        PrimCache pc;
+        if (c->opt_primary_reuse && !scheduled && mine > 0 && (rc = ensure_prim_cache(c, ac)) != RT_OK) return rc;
+        const PrimCache* prim = prim_cache_arg(c, pc);
         if (wavefront) {
             if (!c->wf) c->wf = wavefront_create();
-            RT_CUDA(c, launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_bvh_sched == 0,
-                                               c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths));
-            c->used_pipeline = RT_PIPELINE_WAVEFRONT;
-        } else if (ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0)
+            const cudaError_t we = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, prim, c->d_counters, c->stream, c->opt_bvh_sched == 0,
+                                                           c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths, c->opt_trav_stats != 0);
+            if (we == cudaErrorMemoryAllocation) {
+                // not even one sample per pixel of path state fits next to what else lives on the device: the megakernel
+                // needs no state and gives the same image (nothing was launched: allocation precedes the first kernel)
+                wavefront = false;
+                if (c->opt_pipeline == RT_PIPELINE_AUTO) c->tuned_pipeline = RT_PIPELINE_REGEN;
+            } else {
+                RT_CUDA(c, we);
+                c->used_pipeline = RT_PIPELINE_WAVEFRONT;
+            }
+        }
+        if (wavefront) {}
+        else if (scheduled)
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
         else
-            RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, c->opt_primary_reuse != 0, c->d_counters, c->stream, c->opt_pool_tiles,
-                                           c->opt_flat_coop == 2 ? (c->opt_accel == RT_ACCEL_AUTO ? c->tuned_flat_coop != 0 : c->view.n_box == 0) : c->opt_flat_coop != 0));
+            RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, prim, c->d_counters, c->stream, c->opt_pool_tiles,
+                                           c->opt_flat_coop == 2 ? (c->opt_accel == RT_ACCEL_AUTO ? c->tuned_flat_coop != 0 : c->view.n_box == 0) : c->opt_flat_coop != 0,
+                                           c->opt_trav_stats != 0));
         if (!wavefront) c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce
@@ -793,16 +844,17 @@ int rt_resolve_rgba8(rt_ctx* c, uint32_t* host_out, int pitch_bytes, int flip_y)
     if (rc != RT_OK) return rc;
     const int w = c->par.width, h = c->par.height;
     if (!host_out || pitch_bytes < w * 4) return fail(c, RT_ERR_INVALID, "rt_resolve_rgba8: bad output buffer");
-    cudaEvent_t r0, r1;
-    RT_CUDA(c, cudaEventCreate(&r0)); RT_CUDA(c, cudaEventCreate(&r1));
-    cudaEventRecord(r0, c->stream);
+    cudaEventRecord(c->ev2, c->stream);
     cudaError_t e = launch_resolve(c->d_accum, c->samples, w, h, 0, w * h, flip_y, c->d_argb, 0, c->stream);
-    cudaEventRecord(r1, c->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpy2DAsync(host_out, (size_t)pitch_bytes, c->d_argb, (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyDeviceToHost, c->stream);
+    cudaEventRecord(c->ev3, c->stream);
+    if (e == cudaSuccess) {
+        if (pitch_bytes == w * 4)                              // tightly packed surface: one linear copy
+            e = cudaMemcpyAsync(host_out, c->d_argb, (size_t)w * 4 * (size_t)h, cudaMemcpyDeviceToHost, c->stream);
+        else
+            e = cudaMemcpy2DAsync(host_out, (size_t)pitch_bytes, c->d_argb, (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyDeviceToHost, c->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e == cudaSuccess) cudaEventElapsedTime(&c->last_resolve_ms, r0, r1);
-    cudaEventDestroy(r0); cudaEventDestroy(r1);
+    if (e == cudaSuccess) cudaEventElapsedTime(&c->last_resolve_ms, c->ev2, c->ev3);
     if (e != cudaSuccess) return cuda_fail(c, e, "rt_resolve_rgba8");
     return RT_OK;
 }
@@ -901,7 +953,7 @@ int rt_trace_rays(rt_ctx* c, const float* origins, const float* dirs, int n, int
     int* d_id = (int*)(buf + 13 * N);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, origins, N * 12, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, N * 12, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = launch_trace_rays(c->view, ac, d_o, d_d, n, d_id, d_t, d_n, d_p, c->stream);
+    if (e == cudaSuccess) e = launch_trace_rays(c->view, ac, d_o, d_d, n, d_id, d_t, d_n, d_p, c->stream, c->opt_trav_stats ? c->d_counters : nullptr);
     if (e == cudaSuccess) e = cudaMemcpyAsync(id, d_id, N * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(t, d_t, N * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(normal, d_n, N * 12, cudaMemcpyDeviceToHost, c->stream);
@@ -968,7 +1020,7 @@ int rt_get_stats(rt_ctx* c, rt_stats* out) {
     if (!c || !out) return RT_ERR_INVALID;
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
-    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long counters[kCounters] = {};
     RT_CUDA(c, cudaMemcpy(counters, c->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
     if (c->render_timed) { cudaEventElapsedTime(&c->last_render_ms, c->ev0, c->ev1); }
     memset(out, 0, sizeof *out);
@@ -978,6 +1030,20 @@ int rt_get_stats(rt_ctx* c, rt_stats* out) {
     out->total_paths = c->total_paths; out->total_segments = counters[1];
     out->traced_segments = counters[2]; out->total_traced_segments = counters[3];
     out->pipeline = c->used_pipeline; out->accel = c->used_accel; out->sm_count = c->sm_count;
+    return RT_OK;
+}
+
+int rt_get_traversal_stats(rt_ctx* c, rt_traversal_stats* out) {
+    if (!c || !out) return RT_ERR_INVALID;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long counters[kCounters] = {};
+    RT_CUDA(c, cudaMemcpy(counters, c->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    out->queries = counters[8]; out->node_visits = counters[9];
+    out->sphere_tests = counters[10]; out->cube_tests = counters[11]; out->tri_tests = counters[12];
+    out->prim_tests = counters[10] + counters[11] + counters[12];
+    out->node_bytes = (uint32_t)sizeof(BvhNode);
     return RT_OK;
 }
 
@@ -994,10 +1060,10 @@ void* rt_argb_device_ptr(rt_ctx* c) {
 int rt_ipc_export(rt_ctx* c, int which, unsigned char handle[RT_IPC_HANDLE_BYTES]) {
     int rc = prepare(c);
     if (rc != RT_OK) return rc;
-    if (!handle || (which != 0 && which != 1)) return fail(c, RT_ERR_INVALID, "rt_ipc_export: bad arguments");
+    if (!handle || which < 0 || which > 2) return fail(c, RT_ERR_INVALID, "rt_ipc_export: bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == RT_IPC_HANDLE_BYTES, "IPC handle size");
     cudaIpcMemHandle_t h;
-    RT_CUDA(c, cudaIpcGetMemHandle(&h, which == 0 ? (void*)c->d_accum : (void*)c->d_argb));
+    RT_CUDA(c, cudaIpcGetMemHandle(&h, which == 0 ? (void*)c->d_accum : which == 1 ? (void*)c->d_argb : (void*)c->d_flags));
     memcpy(handle, &h, sizeof h);
     return RT_OK;
 }
@@ -1029,10 +1095,67 @@ int rt_resolve_fused(rt_ctx* c, const void* const* accum_ptrs, int world, uint32
     memset(&pp, 0, sizeof pp);
     for (int r = 0; r < world; ++r) {
         if (!accum_ptrs[r]) return fail(c, RT_ERR_INVALID, "rt_resolve_fused: NULL peer buffer");
+        if ((rc = enable_peer_access_to(c, accum_ptrs[r], "rt_resolve_fused: accumulation buffer")) != RT_OK) return rc;
         pp.p[r] = (const float4*)accum_ptrs[r];
     }
+    if ((rc = enable_peer_access_to(c, dst, "rt_resolve_fused: destination surface")) != RT_OK) return rc;
     RT_CUDA(c, launch_resolve_fused(pp, world, total_samples, c->par.width, c->par.height, first_pixel, n_pixels, flip_y,
                                     (uint32_t*)dst, c->stream));
+    return RT_OK;
+}
+
+int rt_exchange_setup(rt_ctx* c, int rank, int world, void* const* accum_ptrs, void* const* flag_ptrs, void* dst) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    if (world < 1 || world > RT_MAX_PEERS || rank < 0 || rank >= world || !accum_ptrs || !flag_ptrs)
+        return fail(c, RT_ERR_INVALID, "rt_exchange_setup: bad arguments");
+    ExchangeState& x = c->exch;
+    x.ready = false;
+    int devices[RT_MAX_PEERS];
+    for (int r = 0; r < world; ++r) {
+        const void* a = r == rank && !accum_ptrs[r] ? (const void*)c->d_accum : accum_ptrs[r];
+        void* f = r == rank && !flag_ptrs[r] ? (void*)c->d_flags : flag_ptrs[r];
+        if (!a || !f) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: NULL peer pointer");
+        if ((rc = enable_peer_access_to(c, a, "rt_exchange_setup: accumulation buffer")) != RT_OK) return rc;
+        if ((rc = enable_peer_access_to(c, f, "rt_exchange_setup: exchange flags")) != RT_OK) return rc;
+        cudaPointerAttributes at;
+        RT_CUDA(c, cudaPointerGetAttributes(&at, a));
+        devices[r] = at.device;
+        // ranks that share a GPU would wait for each other inside kernels that cannot be relied on to run concurrently
+        for (int q = 0; q < r; ++q)
+            if (devices[q] == devices[r]) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: two ranks on one device (every rank needs its own GPU; use rt_resolve_fused with host-side ordering instead)");
+        x.accum[r] = (const float4*)a; x.flags[r] = (ExchFlags*)f;
+    }
+    if (devices[rank] != c->device) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: entry `rank` is not this context's buffer");
+    if (!dst) dst = rank == 0 ? (void*)c->d_argb : nullptr;
+    if (!dst) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: NULL destination surface");
+    if ((rc = enable_peer_access_to(c, dst, "rt_exchange_setup: destination surface")) != RT_OK) return rc;
+    x.dst = (uint32_t*)dst; x.rank = rank; x.world = world;
+    x.ready = true;
+    return RT_OK;
+}
+
+int rt_exchange_resolve(rt_ctx* c, uint32_t total_samples, int flip_y) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    ExchangeState& x = c->exch;
+    if (!x.ready) return fail(c, RT_ERR_INVALID, "rt_exchange_resolve: rt_exchange_setup has not been called (or the frame buffers were reallocated since)");
+    PeerPtrs pp; ExchPeers fl;
+    memset(&pp, 0, sizeof pp); memset(&fl, 0, sizeof fl);
+    for (int r = 0; r < x.world; ++r) { pp.p[r] = x.accum[r]; fl.f[r] = x.flags[r]; }
+    const long long n_px = (long long)c->par.width * c->par.height;
+    const int first = (int)(n_px * x.rank / x.world), count = (int)(n_px * (x.rank + 1) / x.world) - first;
+    ++x.epoch;                                                 // every rank calls this the same number of times
+    RT_CUDA(c, launch_resolve_fused_sync(pp, fl, x.rank, x.world, x.epoch, total_samples, c->par.width, c->par.height, first, count, flip_y, x.dst, c->stream));
+    return RT_OK;
+}
+
+// a wait of the exchange timed out (a peer never signalled): reported by the calls that synchronise
+static int check_exchange_error(rt_ctx* c) {
+    if (!c->exch.ready) return RT_OK;
+    uint32_t err = 0;
+    RT_CUDA(c, cudaMemcpy(&err, &c->d_flags->error, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return fail(c, RT_ERR_CUDA, "exchange timed out: a peer rank did not signal within 4 s");
     return RT_OK;
 }
 
@@ -1043,7 +1166,7 @@ int rt_read_surface(rt_ctx* c, uint32_t* host_out, int pitch_bytes) {
     if (!host_out || pitch_bytes < w * 4) return fail(c, RT_ERR_INVALID, "rt_read_surface: bad output buffer");
     RT_CUDA(c, cudaMemcpy2DAsync(host_out, (size_t)pitch_bytes, c->d_argb, (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyDeviceToHost, c->stream));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
-    return RT_OK;
+    return check_exchange_error(c);
 }
 
 int rt_set_stream(rt_ctx* c, void* cuda_stream) {
@@ -1058,7 +1181,7 @@ int rt_sync(rt_ctx* c) {
     if (!c) return RT_ERR_INVALID;
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
-    return RT_OK;
+    return check_exchange_error(c);
 }
 
 int rt_set_sample_count(rt_ctx* c, uint32_t samples) {

@@ -5,6 +5,8 @@
 // Compiled with -fmad=false (see rt_device.cuh for the parity rules).
 #include "rt_kernels.h"
 
+#include <mutex>
+
 #include "rt_device.cuh"
 #include "rt_trace.cuh"
 
@@ -44,20 +46,54 @@ __global__ void k_ray_dirs(FrameView fr, float* __restrict__ out) {
     out[3 * p] = d.x; out[3 * p + 1] = d.y; out[3 * p + 2] = d.z;
 }
 
-template <int MODE>
+template <int MODE, bool COUNT = false>
 __global__ void __launch_bounds__(kThreads) k_trace_rays(SceneView sc, BvhView bv, FlatView fl, const float* __restrict__ org,
                                                           const float* __restrict__ dir, int n,
                                                           int* __restrict__ out_id, float* __restrict__ out_t,
-                                                          float* __restrict__ out_n, float* __restrict__ out_p) {
+                                                          float* __restrict__ out_n, float* __restrict__ out_p,
+                                                          unsigned long long* __restrict__ counters) {
     extern __shared__ float4 smem[];
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Hit h = trace<MODE>(sc, tc, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
-                        f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
-    out_id[i] = h.id; out_t[i] = h.t;
-    out_n[3 * i] = h.n.x; out_n[3 * i + 1] = h.n.y; out_n[3 * i + 2] = h.n.z;
-    out_p[3 * i] = h.p.x; out_p[3 * i + 1] = h.p.y; out_p[3 * i + 2] = h.p.z;
+    TravCount cnt = {0u, 0u, 0u, 0u};
+    if (i < n) {
+        Hit h = trace<MODE, COUNT>(sc, tc, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
+                                   f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), &cnt);
+        out_id[i] = h.id; out_t[i] = h.t;
+        out_n[3 * i] = h.n.x; out_n[3 * i + 1] = h.n.y; out_n[3 * i + 2] = h.n.z;
+        out_p[3 * i] = h.p.x; out_p[3 * i + 1] = h.p.y; out_p[3 * i + 2] = h.p.z;
+    }
+    if (COUNT) flush_trav_count(cnt, i < n ? 1u : 0u, counters);
+}
+
+// ---- the per-pixel primary-hit cache (RT_OPT_PRIMARY_REUSE) ------------------------------------------------------
+// GetRayDirection shoots every sample of a pixel through the pixel CORNER (no jitter, Raytracer.cpp:106-122), so the primary
+// closest-hit query of a pixel has the same inputs - and the same result - for every sample of every frame until the camera,
+// the scene or the resolution changes. It is traced ONCE, here, into (normal, t) + object id per pixel (20 B, y-up row-major
+// like the accumulation buffer); the render kernels start every sample from it. counters[2..3] (queries executed) += pixels.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_primary_cache(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ prim_nt,
+                                                             int* __restrict__ prim_id, unsigned long long* __restrict__ counters) {
+    extern __shared__ float4 smem[];
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
+    int px, py;
+    if (tile_pixel(fr, px, py)) {
+        const size_t p = (size_t)px + (size_t)py * fr.width;
+        const Hit h = trace<MODE>(sc, tc, fr.cam_pos, ray_dir(fr, px, py));
+        prim_nt[p] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
+        prim_id[p] = h.id;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        atomicAdd(counters + 2, (unsigned long long)fr.width * fr.height); atomicAdd(counters + 3, (unsigned long long)fr.width * fr.height);
+    }
+}
+// the cached primary hit of a pixel as the closest-hit functions return it (hit point = o + d * t, Object.hpp:136 / :229)
+__device__ __forceinline__ Hit cached_primary(const PrimCache& pc, uint32_t pixel, float3 o, float3 d) {
+    const float4 nt = __ldg(pc.nt + pixel);
+    Hit h;
+    h.id = __ldg(pc.id + pixel); h.t = nt.w; h.n = f3(nt.x, nt.y, nt.z);
+    h.p = h.id >= 0 ? f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w) : f3(0.f, 0.f, 0.f);
+    return h;
 }
 
 __global__ void k_env_color(FrameView fr, const float* __restrict__ dir, int n, float* __restrict__ out) {
@@ -92,17 +128,16 @@ __global__ void k_philox(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32_1
 // added to the float4 accumulation buffer once - no atomics, bit-reproducible for a given
 // (seed, sample range), independent of the launch shape.
 //
-// REUSE (primary-hit reuse): the reference shoots every sample of a pixel through the pixel CORNER
-// (GetRayDirection has no jitter, Raytracer.cpp:106-122), so the primary closest-hit query of a pixel
-// has the same inputs - and the same result - for every sample. With REUSE the query runs once per
-// pixel per launch; each sample still draws its own Philox block at the primary hit and scatters its
-// own secondary ray, so every sample's radiance is bit-identical to the non-reuse loop (asserted by
-// the tests). A pixel whose primary ray misses (or max_bounces == 0) has the same value for every
-// sample: the value is added n times, in order. seg_counter[0..1] count path segments DELIVERED (what
-// the reference traces), seg_counter[2..3] the closest-hit queries actually EXECUTED.
-template <int MODE, bool REUSE>
+// REUSE (primary-hit reuse): the primary closest-hit query of a pixel has the same inputs - and the same
+// result - for every sample (k_primary_cache above). With REUSE every sample starts from the cached hit:
+// it still draws its own Philox block there and scatters its own secondary ray, so every sample's radiance
+// is bit-identical to the non-reuse loop (asserted by the tests). A pixel whose primary ray misses (or
+// max_bounces == 0) has the same value for every sample: the value is added n times, in order.
+// seg_counter[0..1] count path segments DELIVERED (what the reference traces), seg_counter[2..3] the
+// closest-hit queries actually EXECUTED (with REUSE: the secondary and later segments; the cache pass adds its own).
+template <int MODE, bool REUSE, bool COUNT = false>
 __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
-                                                            uint32_t s_begin, int n_samples,
+                                                            uint32_t s_begin, int n_samples, PrimCache prim,
                                                             unsigned long long* __restrict__ seg_counter) {
     extern __shared__ float4 smem[];
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
@@ -118,14 +153,14 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     int s = 0, depth = 0;
     unsigned int segs = 0, traced = 0;
 
-    // REUSE prologue: the pixel's one primary query. A miss (or max_bounces == 0) consumes no random number, so
+    // REUSE prologue: the pixel's cached primary hit. A miss (or max_bounces == 0) consumes no random number, so
     // every sample of the pixel has the same value: add it n times, in order, and the lane is done.
     Hit h0;
     h0.id = -1; h0.t = 0.f; h0.n = f3(0.f, 0.f, 0.f); h0.p = f3(0.f, 0.f, 0.f);
+    TravCount cnt = {0u, 0u, 0u, 0u};
     if (REUSE) {
-        h0 = trace_all<MODE>(sc, tc, o, d, n_samples > 0);  // all lanes call: MODE 5 pools the work across the warp
         if (n_samples > 0) {
-            traced = 1;
+            h0 = cached_primary(prim, pixel, o, d);
             float3 c;
             if (path_ends(sc, fr, h0, d, T, L, 0, c)) {
                 for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
@@ -140,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     // flag (instead of continue/break) lets the warp reconverge before the scatter block.
     while (__any_sync(0xffffffffu, s < n_samples)) {
         const bool live = s < n_samples;                     // lanes that are done keep serving the others in MODE 5
-        Hit h = trace_all<MODE>(sc, tc, o, d, live);
+        Hit h = trace_all<MODE, COUNT>(sc, tc, o, d, live, &cnt);
         if (live) {
             ++segs; ++traced;
             bool scatter = true;
@@ -172,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
         atomicAdd(seg_counter, (unsigned long long)total); atomicAdd(seg_counter + 1, (unsigned long long)total);
         atomicAdd(seg_counter + 2, (unsigned long long)total_tr); atomicAdd(seg_counter + 3, (unsigned long long)total_tr);
     }
+    if (COUNT) flush_trav_count(cnt, traced, seg_counter);
 }
 
 // ---- few samples per pixel: warp-level pixel pool -------------------------------------------------------------
@@ -182,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
 // pixel at once. One pixel is still traced by one lane, samples in order, one write: the same bits as k_render_regen.
 template <int MODE, bool REUSE>
 __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
-                                                           uint32_t s_begin, int n_samples, int pool_tiles,
+                                                           uint32_t s_begin, int n_samples, int pool_tiles, PrimCache prim,
                                                            unsigned long long* __restrict__ seg_counter) {
     extern __shared__ float4 smem[];
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
@@ -196,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
     const int total = rem <= 0 ? 0 : (int)(rem < pool_tiles ? rem : pool_tiles) * 32;     // pool entries (some outside the image)
     int next = 0;                                                                           // warp-uniform
 
-    bool busy = false, primary = false;
+    bool busy = false;
     uint32_t pixel = 0;
     float3 d0 = f3(0.f, 0.f, 1.f), acc = f3(0.f, 0.f, 0.f), o = fr.cam_pos, d = d0;
     float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
@@ -217,7 +253,23 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
                     pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
                     d0 = ray_dir(fr, px, py);
                     acc = f3(0.f, 0.f, 0.f); o = fr.cam_pos; d = d0; s = 0; depth = 0;
-                    busy = true; primary = true;
+                    busy = true;
+                    if (REUSE) {
+                        h0 = cached_primary(prim, pixel, o, d);
+                        float3 c;
+                        if (path_ends(sc, fr, h0, d, T, L, 0, c)) {
+                            // the primary ray misses (or max_bounces == 0): every sample of the pixel has the value c
+                            for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
+                            segs += (unsigned int)n_samples;
+                            float4 a = accum[pixel];
+                            a.x += acc.x; a.y += acc.y; a.z += acc.z;
+                            accum[pixel] = a;
+                            busy = false;                    // takes another pixel in the next pass
+                        } else {
+                            scatter_segment(sc, fr, h0, pixel, s_begin, o, d, T, L, depth);
+                            ++segs;
+                        }
+                    }
                 }
             }
         }
@@ -226,21 +278,13 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
         if (busy) {
             ++segs; ++traced;
             bool scatter = true;
-            if (REUSE && primary) h0 = h;
             float3 c;
             if (path_ends(sc, fr, h, d, T, L, depth, c)) {
                 scatter = false;
-                if (REUSE && primary) {
-                    // the primary ray misses (or max_bounces == 0): every sample of the pixel has the value c
-                    for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
-                    segs += (unsigned int)(n_samples - 1);
-                } else {
-                    acc.x += c.x; acc.y += c.y; acc.z += c.z;
-                    ++s; depth = 0; o = fr.cam_pos; d = d0;
-                    if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }     // next sample from the cached primary hit
-                }
+                acc.x += c.x; acc.y += c.y; acc.z += c.z;
+                ++s; depth = 0; o = fr.cam_pos; d = d0;
+                if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }     // next sample from the cached primary hit
             }
-            primary = false;
             if (s >= n_samples) {
                 float4 a = accum[pixel];
                 a.x += acc.x; a.y += acc.y; a.z += acc.z;
@@ -568,6 +612,74 @@ __global__ void k_resolve_fused(PeerPtrs peers, int world, float count, int widt
     out[(size_t)x + (size_t)(flip_y ? height - 1 - y : y) * width] = resolve_pixel(sum, count);
 }
 
+// ---- the same with the inter-rank ordering on the device (rt_exchange_resolve; one process per GPU) -------------------------
+// No collective library and no host synchronisation: ranks signal each other through flag words in device memory that the
+// peers have mapped (CUDA IPC over NVLink). Epochs only grow, so nothing is ever reset and a late reader cannot see a stale
+// "ready". Every wait is bounded (kExchTimeoutNs): a peer that died makes the exchange fail instead of hanging the GPU.
+// NOTE: the ranks must run on DIFFERENT devices (kernels of two ranks on one GPU are not guaranteed to run concurrently).
+constexpr unsigned long long kExchTimeoutNs = 4000000000ull;
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// One warp: lane r < world polls flags[r] until it reaches `epoch` (wrap-safe compare). false: timed out, *error is set.
+__device__ __forceinline__ bool warp_wait_flags(const uint32_t* flags, int world, uint32_t epoch, uint32_t* error) {
+    const int lane = threadIdx.x & 31;
+    bool ok = lane >= world;
+    const unsigned long long t0 = global_ns();
+    while (!__all_sync(0xffffffffu, ok)) {
+        if (!ok) ok = (int)(ld_acquire_sys(flags + lane) - epoch) >= 0;
+        if (global_ns() - t0 > kExchTimeoutNs) {
+            if (lane == 0) atomicExch(error, 1u);
+            return false;
+        }
+    }
+    return true;
+}
+__global__ void __launch_bounds__(256) k_resolve_fused_sync(PeerPtrs peers, ExchPeers fl, int rank, int world, uint32_t epoch, float count,
+                                                             int width, int height, int first, int n, int flip_y, uint32_t* __restrict__ out) {
+    ExchFlags* const mine = fl.f[rank];
+    if (threadIdx.x < 32) {
+        if (blockIdx.x == 0 && threadIdx.x < world) {
+            // this rank's render finished before this kernel started (stream order): publish it to every rank
+            __threadfence_system();
+            st_release_sys(&fl.f[threadIdx.x]->arrive[rank], epoch);
+        }
+        warp_wait_flags(mine->arrive, world, epoch, &mine->error);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int p = first + i;
+        float4 sum = peers.p[0][p];
+        for (int r = 1; r < world; ++r) {
+            const float4 v = peers.p[r][p];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z;
+        }
+        const int x = p % width, y = p / width;
+        out[(size_t)x + (size_t)(flip_y ? height - 1 - y : y) * width] = resolve_pixel(sum, count);
+    }
+    // the last CTA tells every rank: my slice is in the surface, and I am done reading your buffers
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&mine->blocks_done, 1u);
+        if (prev == gridDim.x - 1) {
+            mine->blocks_done = 0u;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) st_release_sys(&fl.f[r]->done[rank], epoch);
+        }
+    }
+}
+__global__ void k_exchange_wait(ExchFlags* mine, int world, uint32_t epoch) { warp_wait_flags(mine->done, world, epoch, &mine->error); }
+
 }  // namespace
 
 // ---- launchers --------------------------------------------------------------------------------
@@ -577,11 +689,13 @@ template <typename K>
 static cudaError_t optin(K kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes); }
 
 static cudaError_t ensure_smem_optin() {
-    // the attribute is per DEVICE: a process may hold contexts on several GPUs (tests/multigpu, rt_resolve_fused)
+    // the attribute is per DEVICE: a process may hold contexts on several GPUs (rt_create_multi), used from several host threads
     static bool done_on[64] = {false};
+    static std::mutex mu;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
     bool& done = done_on[dev & 63];
     if (done) return cudaSuccess;
 #define RTB_OPTIN(K) \
@@ -598,8 +712,16 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(K<4, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<5, false>)) != cudaSuccess) return e; if ((e = optin(K<5, true>)) != cudaSuccess) return e;
     RTB_OPTIN2(k_render_regen) RTB_OPTIN2(k_render_pool) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick) RTB_OPTIN(k_render_blocks)
+    RTB_OPTIN(k_primary_cache)
     if ((e = optin(k_render_bvh<2>)) != cudaSuccess) return e;
     if ((e = optin(k_render_bvh<3>)) != cudaSuccess) return e;
+    // the counting instantiations (RT_OPT_TRAVERSAL_STATS): binary BVH only
+    if ((e = optin(k_trace_rays<2, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_trace_rays<3, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_render_regen<2, true, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_render_regen<3, true, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_render_regen<2, false, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_render_regen<3, false, true>)) != cudaSuccess) return e;
 #undef RTB_OPTIN
 #undef RTB_OPTIN2
     done = true;
@@ -639,12 +761,27 @@ cudaError_t launch_ray_dirs(const FrameView& fr, float* out, cudaStream_t st) {
 }
 
 cudaError_t launch_trace_rays(const SceneView& sc, const AccelSel& ac, const float* org, const float* dir, int n,
-                              int* id, float* t, float* nrm, float* pt, cudaStream_t st) {
+                              int* id, float* t, float* nrm, float* pt, cudaStream_t st, unsigned long long* counters) {
     if (n <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
     size_t sb; const int mode = pick_mode(sc, ac, sb);
-    RTB_DISPATCH(mode, k_trace_rays, dim3((n + kThreads - 1) / kThreads), sb, st, sc, ac.bvh, ac.flat, org, dir, n, id, t, nrm, pt)
+    const dim3 grid((n + kThreads - 1) / kThreads);
+    if (counters && (mode == 2 || mode == 3) && !ac.bvh.wnodes) {
+        if (mode == 2) k_trace_rays<2, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, org, dir, n, id, t, nrm, pt, counters);
+        else k_trace_rays<3, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, org, dir, n, id, t, nrm, pt, counters);
+        return cudaGetLastError();
+    }
+    RTB_DISPATCH(mode, k_trace_rays, grid, sb, st, sc, ac.bvh, ac.flat, org, dir, n, id, t, nrm, pt, nullptr)
+    return cudaGetLastError();
+}
+
+cudaError_t launch_primary_cache(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* prim_nt, int* prim_id,
+                                 unsigned long long* counters, cudaStream_t st) {
+    cudaError_t e = ensure_smem_optin();
+    if (e != cudaSuccess) return e;
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    RTB_DISPATCH(mode, k_primary_cache, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, prim_nt, prim_id, counters)
     return cudaGetLastError();
 }
 
@@ -675,8 +812,12 @@ cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView
 }
 
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
-                                uint32_t s_begin, int n_samples, bool reuse_primary, unsigned long long* seg_counter, cudaStream_t st, int pool_override, bool flat_coop) {
+                                uint32_t s_begin, int n_samples, const PrimCache* prim_cache, unsigned long long* seg_counter, cudaStream_t st, int pool_override, bool flat_coop,
+                                bool count_traversal) {
     if (n_samples <= 0) return cudaSuccess;
+    const bool reuse_primary = prim_cache != nullptr;
+    PrimCache prim;
+    prim.nt = prim_cache ? prim_cache->nt : nullptr; prim.id = prim_cache ? prim_cache->id : nullptr;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
     // few samples per launch: lanes pull pixels from a warp-level pool (k_render_pool); many: one pixel per lane.
@@ -685,6 +826,7 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
     // lose to the imbalance between warps, and from 16 spp on one pixel per lane is as good.
     const long long n_tiles_all = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
     int pool_tiles = 1;
+    if (count_traversal) pool_override = 1;                   // the counting instantiations exist for the one-pixel-per-lane kernel only
     if (pool_override > 0) pool_tiles = pool_override > 32 ? 32 : pool_override;
     else if (n_samples == 1) pool_tiles = n_tiles_all >= 50000 ? 4 : 2;
     else if (n_samples <= 4 && n_tiles_all >= 50000) pool_tiles = 2;
@@ -694,10 +836,18 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
         const long long n_tiles = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
         const long long warps = (n_tiles + pool_tiles - 1) / pool_tiles;
         const unsigned int blocks = (unsigned int)((warps + kThreads / 32 - 1) / (kThreads / 32));
-        RTB_DISPATCH2(mode, reuse_primary, k_render_pool, blocks, sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, seg_counter)
+        RTB_DISPATCH2(mode, reuse_primary, k_render_pool, blocks, sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, prim, seg_counter)
         return cudaGetLastError();
     }
-    RTB_DISPATCH2(mode, reuse_primary, k_render_regen, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter)
+    if (count_traversal && (mode == 2 || mode == 3) && !ac.bvh.wnodes) {
+        const dim3 grid = tile_grid(fr.width, fr.height);
+        if (mode == 2 && reuse_primary) k_render_regen<2, true, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
+        else if (mode == 2) k_render_regen<2, false, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
+        else if (reuse_primary) k_render_regen<3, true, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
+        else k_render_regen<3, false, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
+        return cudaGetLastError();
+    }
+    RTB_DISPATCH2(mode, reuse_primary, k_render_regen, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter)
     return cudaGetLastError();
 }
 
@@ -706,7 +856,7 @@ cudaError_t launch_render_bvh(const SceneView& sc, const AccelSel& ac, const Fra
     if (n_samples <= 0) return cudaSuccess;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    if (ac.bvh.wnodes) return launch_render_regen(sc, ac, fr, accum, s_begin, n_samples, false, seg_counter, st);   // the scheduled kernel walks binary nodes only (and, like it, re-traces every primary ray)
+    if (ac.bvh.wnodes) return launch_render_regen(sc, ac, fr, accum, s_begin, n_samples, nullptr, seg_counter, st);   // the scheduled kernel walks binary nodes only (and, like it, re-traces every primary ray)
     size_t sb; const int mode = pick_mode(sc, ac, sb);
     if (mode == 2) k_render_bvh<2><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter, wait_k);
     else if (mode == 3) k_render_bvh<3><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, seg_counter, wait_k);
@@ -749,6 +899,14 @@ cudaError_t launch_resolve_fused(const PeerPtrs& peers, int world, uint32_t samp
                                  int flip_y, uint32_t* out, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     k_resolve_fused<<<(n + 255) / 256, 256, 0, st>>>(peers, world, (float)samples, width, height, first, n, flip_y, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_fused_sync(const PeerPtrs& peers, const ExchPeers& flags, int rank, int world, uint32_t epoch, uint32_t samples,
+                                      int width, int height, int first, int n, int flip_y, uint32_t* out, cudaStream_t st) {
+    // n == 0 still signals: the other ranks wait for this one
+    k_resolve_fused_sync<<<n > 0 ? (n + 255) / 256 : 1, 256, 0, st>>>(peers, flags, rank, world, epoch, (float)samples, width, height, first, n, flip_y, out);
+    k_exchange_wait<<<1, 32, 0, st>>>(flags.f[rank], world, epoch);
     return cudaGetLastError();
 }
 

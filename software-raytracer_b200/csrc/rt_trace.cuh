@@ -94,12 +94,25 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
     return t;
 }
 
-template <int MODE>
-__device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d) {
+// COUNT (BVH modes 2 and 3 over the binary tree only): the lane's traversal work is added to *tcnt.
+template <int MODE, bool COUNT = false>
+__device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d, TravCount* tcnt = nullptr) {
     if (MODE == 4 || MODE == 5) return closest_hit_flat(sc, t.fl, t.sph, t.box, t.q, t.stride, o, d);
     if (MODE == 3 && t.wnodes) return closest_hit_bvh8(sc, t.sph, t.box, t.wnodes, t.wrefs, t.stack, t.stride, t.wentries, t.k47, o, d);
-    if (MODE >= 2) return closest_hit_bvh(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr);
+    if (MODE >= 2) return closest_hit_bvh<COUNT>(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr, tcnt);
     return closest_hit(sc, t.sph, t.box, o, d);
+}
+
+// Adds a lane's traversal counts to the context's counters [8..12] (queries, node visits, sphere / cube / triangle tests):
+// warp reduce, one atomic per warp and counter. Must be reached by all 32 lanes.
+__device__ __forceinline__ void flush_trav_count(const TravCount& tc, unsigned int queries, unsigned long long* __restrict__ counters) {
+    unsigned int v[5] = {queries, tc.nodes, tc.sph, tc.box, tc.tri};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+        if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(counters + 8 + k, (unsigned long long)v[k]);
+    }
 }
 
 
@@ -226,12 +239,12 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
 }
 
 // Per-lane trace for all lanes of a warp (inactive lanes get a miss); MODE 5 pools levels 2/3 across the warp.
-template <int MODE>
-__device__ __forceinline__ Hit trace_all(const SceneView& sc, const TraceCtx& t, float3 o, float3 d, bool active) {
+template <int MODE, bool COUNT = false>
+__device__ __forceinline__ Hit trace_all(const SceneView& sc, const TraceCtx& t, float3 o, float3 d, bool active, TravCount* tcnt = nullptr) {
     if (MODE == 5) return closest_hit_flat_coop(sc, t.fl, t.sph, t.box, t.q, t.stride, t.coop, o, d, active);
     Hit h;
     h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f); h.p = f3(0.f, 0.f, 0.f);
-    if (active) h = trace<MODE>(sc, t, o, d);
+    if (active) h = trace<MODE, COUNT>(sc, t, o, d, tcnt);
     return h;
 }
 

@@ -1,8 +1,8 @@
 // rt_wavefront.cu - the WAVEFRONT pipeline (RT_PIPELINE_WAVEFRONT): the same path tracer as the regeneration
 // megakernel (rt_kernels.cu k_render_regen), split into stream-ordered stages over device-resident queues:
 //
-//   k_wf_primary    (REUSE) one primary closest-hit query per pixel per launch
-//   k_wf_generate   raygen: one path per (pixel, sample) of the wave; with REUSE it shades the cached primary hit
+//   k_wf_generate   raygen: one path per (pixel, sample) of the wave; with REUSE it shades the pixel's cached primary hit
+//                   (the context's per-pixel cache, rt_kernels.cu k_primary_cache)
 //                   and emits the first SECONDARY ray; live paths get consecutive slots of state set 0
 //   k_wf_intersect  persistent threads: every warp pulls batches of 32 queue entries through an atomic cursor
 //                   and runs the closest-hit back end (brute / BVH / flat, scene staged per CTA once)
@@ -20,13 +20,15 @@
 // k_render_regen (asserted by tests/test_gpu_parity.py), whichever order the queues end up in.
 #include "rt_kernels.h"
 
+#include <mutex>
+
 #include "rt_device.cuh"
 #include "rt_trace.cuh"
 
 namespace rtb {
 
 struct WavefrontBuffers {
-    size_t cap_paths = 0, cap_px = 0, cap_tiles = 0;
+    size_t cap_paths = 0, cap_px = 0;
     // Path state lives in DENSE ping-pong sets: slot i of round r's set is the i-th surviving path, so every kernel reads and
     // writes consecutive records (with one fixed slot per path and a queue of path ids the survivors of the later rounds are
     // scattered and a 32-byte sector carries one useful record: the shade kernel moved 3.8x its useful bytes).
@@ -37,7 +39,6 @@ struct WavefrontBuffers {
     float4* wave_rad = nullptr;                                                   // per PATH id: radiance of the finished path
     unsigned int* counters = nullptr;                                             // [0..63] queue lengths per round, [64..127] cursors
     float4* launch_acc = nullptr;                                                 // per pixel: this launch's sum
-    float4* prim_nt = nullptr; int* prim_id = nullptr;                            // REUSE: primary hit per tile-major pixel
 };
 
 namespace {
@@ -94,20 +95,6 @@ __device__ __forceinline__ unsigned int block_slot(bool want, unsigned int* __re
     return s_base + s_cnt[w] + (unsigned int)__popc(mask & ((1u << lane) - 1u));      // this thread's slot in the next set, if it wants one
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_wf_primary(SceneView sc, BvhView bv, FlatView fl, FrameView fr, int tiles_x, int npad,
-                                                          float4* __restrict__ prim_nt, int* __restrict__ prim_id) {
-    extern __shared__ float4 smem[];
-    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
-    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ti >= npad) return;
-    int px, py;
-    if (!tile_to_pixel(fr, tiles_x, ti, px, py)) { prim_id[ti] = -1; return; }
-    const Hit h = trace<MODE>(sc, tc, fr.cam_pos, ray_dir(fr, px, py));
-    prim_nt[ti] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
-    prim_id[ti] = h.id;
-}
-
 template <bool REUSE>
 __global__ void __launch_bounds__(256) k_wf_generate(SceneView sc, FrameView fr, int tiles_x, int npad, uint32_t s_first, int s_wave,
                                                       const float4* __restrict__ prim_nt, const int* __restrict__ prim_id,
@@ -131,9 +118,9 @@ __global__ void __launch_bounds__(256) k_wf_generate(SceneView sc, FrameView fr,
             int depth = 0;
             live = true;
             if (REUSE) {
-                const float4 nt = prim_nt[ti];
+                const float4 nt = __ldg(prim_nt + pixel);
                 Hit h0;
-                h0.id = prim_id[ti]; h0.t = nt.w; h0.n = f3(nt.x, nt.y, nt.z);
+                h0.id = __ldg(prim_id + pixel); h0.t = nt.w; h0.n = f3(nt.x, nt.y, nt.z);
                 h0.p = f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w);
                 delivered = 1;                                               // the reused primary segment
                 float3 c;
@@ -193,11 +180,12 @@ __global__ void __launch_bounds__(kThreads, 6) k_wf_intersect(SceneView sc, BvhV
 #ifndef RTB_WF_BVH_MIN_BLOCKS
 #define RTB_WF_BVH_MIN_BLOCKS 8      // 63 registers, no spills: the kernel waits on node fetches (issue slots 52 % busy at 6), +8 % at 8
 #endif
-template <int MODE>
+template <int MODE, bool COUNT = false>
 __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersect_bvh(SceneView sc, BvhView bv, FlatView fl, const uint32_t* __restrict__ q,
                                                                    const unsigned int* __restrict__ count_ptr, unsigned int* __restrict__ cursor,
                                                                    const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                                                                   float4* __restrict__ hit_nt, int* __restrict__ hit_id, int kRefill, int kNodeMin) {
+                                                                   float4* __restrict__ hit_nt, int* __restrict__ hit_id, int kRefill, int kNodeMin,
+                                                                   unsigned long long* __restrict__ counters) {
     extern __shared__ float4 smem[];
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     const float4* __restrict__ nodes = tc.nodes;
@@ -217,6 +205,8 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
     float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
     float best_t = 0.f; int best_id = 0, best_ref = 0; bool have = false;
     bool exhausted = false;
+    TravCount cnt = {0u, 0u, 0u, 0u};                          // COUNT only
+    unsigned int n_queries = 0;
 
     auto pop = [&]() -> int {
         while (sp > 0) {
@@ -234,9 +224,10 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
     };
     auto test_leaf = [&](int link) {
         const unsigned int v = (unsigned int)(~link);
-        const int first = (int)(v & 0xffffffu), cnt = (int)(v >> 24);
-        for (int i = 0; i < cnt; ++i) {
+        const int first = (int)(v & 0xffffffu), n_refs = (int)(v >> 24);
+        for (int i = 0; i < n_refs; ++i) {
             const int r = refs[first + i];
+            if (COUNT) { if (r >= kTriRef) ++cnt.tri; else if (r >= 0) ++cnt.sph; else ++cnt.box; }
             if (r >= kTriRef) {
                 const int k = r - kTriRef;
                 float t; float3 nrm;
@@ -301,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
                         ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
                         best_t = __int_as_float(0x7f800000); best_id = 0x7fffffff; best_ref = 0; have = false;
                         cur = 0; leaf0 = NONE; sp = 0; state = ACTIVE;
+                        if (COUNT) ++n_queries;
                     }
                 }
                 if (base + (unsigned int)__popc(m_idle) >= count) exhausted = true;       // warp-uniform
@@ -311,6 +303,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
         for (;;) {
             const bool in_node = state == ACTIVE && cur >= 0;
             if (in_node) {
+                if (COUNT) ++cnt.nodes;
                 const float4 n0 = nodes[4 * cur], n1 = nodes[4 * cur + 1], n2 = nodes[4 * cur + 2];
                 const int2 ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
                 const float ax0 = fmaf(n0.x, ix, ox), bx0 = fmaf(n0.y, ix, ox), ay0 = fmaf(n0.z, iy, oy), by0 = fmaf(n0.w, iy, oy);
@@ -344,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
             settle();
         }
     }
+    if (COUNT) flush_trav_count(cnt, n_queries, counters);
 }
 
 // The same state machine over the 8-WIDE quantised BVH (bvh_wide.h): a node step tests eight children at once, the
@@ -546,35 +540,37 @@ __global__ void k_wf_commit(int n, const float4* __restrict__ launch_acc, float4
     accum[p] = a;
 }
 
-__global__ void k_wf_count_primaries(int n_inside, unsigned long long* seg_counter) {
-    atomicAdd(seg_counter + 2, (unsigned long long)n_inside); atomicAdd(seg_counter + 3, (unsigned long long)n_inside);
-}
-
 template <typename T>
 cudaError_t grow(T*& p, size_t n) {
     if (p) cudaFree(p);
     p = nullptr;
-    return cudaMalloc((void**)&p, n * sizeof(T));
+    const cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e != cudaSuccess) p = nullptr;
+    return e;
 }
 
 template <typename K>
 cudaError_t optin(K kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStagedBytes); }
 
 cudaError_t ensure_optin() {
-    // the attribute is per DEVICE: a process may hold contexts on several GPUs (tests/multigpu, rt_resolve_fused)
+    // the attribute is per DEVICE: a process may hold contexts on several GPUs (rt_create_multi), used from several host threads
     static bool done_on[64] = {false};
+    static std::mutex mu;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
     bool& done = done_on[dev & 63];
     if (done) return cudaSuccess;
 #define RTB_WF_OPTIN(K) \
     if ((e = optin(K<0>)) != cudaSuccess) return e; if ((e = optin(K<1>)) != cudaSuccess) return e; \
     if ((e = optin(K<2>)) != cudaSuccess) return e; if ((e = optin(K<3>)) != cudaSuccess) return e; \
     if ((e = optin(K<4>)) != cudaSuccess) return e;
-    RTB_WF_OPTIN(k_wf_primary) RTB_WF_OPTIN(k_wf_intersect)
+    RTB_WF_OPTIN(k_wf_intersect)
     if ((e = optin(k_wf_intersect_bvh<2>)) != cudaSuccess) return e;
     if ((e = optin(k_wf_intersect_bvh<3>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_intersect_bvh<2, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_intersect_bvh<3, true>)) != cudaSuccess) return e;
     if ((e = optin(k_wf_intersect_bvh8)) != cudaSuccess) return e;
 #undef RTB_WF_OPTIN
     done = true;
@@ -585,21 +581,57 @@ cudaError_t ensure_optin() {
 
 WavefrontBuffers* wavefront_create() { return new WavefrontBuffers(); }
 
+// frees the path-state arrays (everything that scales with the wave); the small counter block stays
+void wavefront_release(WavefrontBuffers* wb) {
+    if (!wb) return;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(wb->ray_o[k]); cudaFree(wb->ray_d[k]); cudaFree(wb->thr[k]); cudaFree(wb->rad[k]); cudaFree(wb->q[k]);
+        wb->ray_o[k] = wb->ray_d[k] = wb->thr[k] = wb->rad[k] = nullptr; wb->q[k] = nullptr;
+    }
+    cudaFree(wb->hit_nt); cudaFree(wb->hit_id); cudaFree(wb->wave_rad); cudaFree(wb->launch_acc);
+    wb->hit_nt = nullptr; wb->hit_id = nullptr; wb->wave_rad = nullptr; wb->launch_acc = nullptr;
+    wb->cap_paths = wb->cap_px = 0;
+}
+
 void wavefront_destroy(WavefrontBuffers* wb) {
     if (!wb) return;
-    for (int k = 0; k < 2; ++k) { cudaFree(wb->ray_o[k]); cudaFree(wb->ray_d[k]); cudaFree(wb->thr[k]); cudaFree(wb->rad[k]); }
-    cudaFree(wb->hit_nt); cudaFree(wb->hit_id);
-    cudaFree(wb->wave_rad); cudaFree(wb->q[0]); cudaFree(wb->q[1]); cudaFree(wb->counters); cudaFree(wb->launch_acc);
-    cudaFree(wb->prim_nt); cudaFree(wb->prim_id);
+    wavefront_release(wb);
+    cudaFree(wb->counters);
     delete wb;
 }
 
+namespace {
+// all per-path arrays for `n` paths; on failure everything is freed again and the thread's last error is cleared
+cudaError_t alloc_paths(WavefrontBuffers* wb, size_t n) {
+    cudaError_t e;
+    if ((e = grow(wb->ray_o[0], n)) != cudaSuccess || (e = grow(wb->ray_d[0], n)) != cudaSuccess ||
+        (e = grow(wb->thr[0], n)) != cudaSuccess || (e = grow(wb->rad[0], n)) != cudaSuccess ||
+        (e = grow(wb->ray_o[1], n)) != cudaSuccess || (e = grow(wb->ray_d[1], n)) != cudaSuccess ||
+        (e = grow(wb->thr[1], n)) != cudaSuccess || (e = grow(wb->rad[1], n)) != cudaSuccess ||
+        (e = grow(wb->hit_nt, n)) != cudaSuccess || (e = grow(wb->hit_id, n)) != cudaSuccess ||
+        (e = grow(wb->wave_rad, n)) != cudaSuccess || (e = grow(wb->q[0], n)) != cudaSuccess ||
+        (e = grow(wb->q[1], n)) != cudaSuccess) {
+        float4* keep = wb->launch_acc; const size_t keep_px = wb->cap_px;
+        wb->launch_acc = nullptr;
+        wavefront_release(wb);
+        wb->launch_acc = keep; wb->cap_px = keep_px;
+        cudaGetLastError();                                  // a failed cudaMalloc leaves the error set: the next launch check must not see it
+        return e;
+    }
+    wb->cap_paths = n;
+    return cudaSuccess;
+}
+}  // namespace
+
 cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
-                                    float4* accum, uint32_t s_begin, int n_samples, bool reuse, unsigned long long* seg_counter,
-                                    cudaStream_t st, bool bvh_refill, int k_refill, int k_node_min, int wave_mpaths) {
+                                    float4* accum, uint32_t s_begin, int n_samples, const PrimCache* prim_cache, unsigned long long* seg_counter,
+                                    cudaStream_t st, bool bvh_refill, int k_refill, int k_node_min, int wave_mpaths, bool count_traversal) {
     if (k_refill < 1) k_refill = 1; if (k_refill > 32) k_refill = 32;
     if (k_node_min < 1) k_node_min = 1; if (k_node_min > 32) k_node_min = 32;
     if (n_samples <= 0) return cudaSuccess;
+    const bool reuse = prim_cache != nullptr;
+    const float4* prim_nt = reuse ? prim_cache->nt : nullptr;
+    const int* prim_id = reuse ? prim_cache->id : nullptr;
     cudaError_t e = ensure_optin();
     if (e != cudaSuccess) return e;
     const WaveGeom g = wave_geom(fr.width, fr.height);
@@ -607,7 +639,8 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     // Samples per wave. The late bounce rounds of a wave hold a few per cent of its paths, and a persistent intersect kernel
     // needs ~150 k rays just to fill the machine once, so small waves spend most of their rounds in the tail: on the
     // 1 M-triangle mesh at 1080p 8 M / 34 M / 136 M paths per wave give 3.1 / 4.7 / 5.4 G segments/s (profiles/r1A_wave_sweep.log).
-    // Default 128 M paths (172 B each, ~22 GB), at most 64 samples per pixel, never more than a third of the free memory.
+    // Default 128 M paths (172 B each, ~22 GB), at most 64 samples per pixel, never more than a third of the free memory; if
+    // the allocation fails all the same (another context or process took the memory) the wave is halved until it fits.
     size_t wave_paths = (size_t)(wave_mpaths >= 1 && wave_mpaths <= 1024 ? wave_mpaths : 128) << 20;
     if (const char* wp = getenv("RTB200_WAVE_MPATHS")) { const long v = atol(wp); if (v >= 1 && v <= 1024) wave_paths = (size_t)v << 20; }
     {
@@ -621,30 +654,22 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     if (s_cap < 1) s_cap = 1;
     if (s_cap > 64) s_cap = 64;
     if (s_cap > n_samples) s_cap = n_samples;
-    const size_t np_cap = (size_t)g.npad * s_cap;
-    if (np_cap >= (size_t)1 << 32) return cudaErrorInvalidValue;
-    if (wb->cap_paths < np_cap) {
-        cudaStreamSynchronize(st);
-        if ((e = grow(wb->ray_o[0], np_cap)) != cudaSuccess || (e = grow(wb->ray_d[0], np_cap)) != cudaSuccess ||
-            (e = grow(wb->thr[0], np_cap)) != cudaSuccess || (e = grow(wb->rad[0], np_cap)) != cudaSuccess ||
-            (e = grow(wb->ray_o[1], np_cap)) != cudaSuccess || (e = grow(wb->ray_d[1], np_cap)) != cudaSuccess ||
-            (e = grow(wb->thr[1], np_cap)) != cudaSuccess || (e = grow(wb->rad[1], np_cap)) != cudaSuccess ||
-            (e = grow(wb->hit_nt, np_cap)) != cudaSuccess || (e = grow(wb->hit_id, np_cap)) != cudaSuccess ||
-            (e = grow(wb->wave_rad, np_cap)) != cudaSuccess || (e = grow(wb->q[0], np_cap)) != cudaSuccess ||
-            (e = grow(wb->q[1], np_cap)) != cudaSuccess) { wb->cap_paths = 0; return e; }
-        wb->cap_paths = np_cap;
-    }
+    if ((size_t)g.npad * s_cap >= (size_t)1 << 32) return cudaErrorInvalidValue;
     if (wb->cap_px < npix) {
         cudaStreamSynchronize(st);
-        if ((e = grow(wb->launch_acc, npix)) != cudaSuccess) { wb->cap_px = 0; return e; }
+        if ((e = grow(wb->launch_acc, npix)) != cudaSuccess) { wb->cap_px = 0; cudaGetLastError(); return e; }
         wb->cap_px = npix;
     }
-    if (wb->cap_tiles < (size_t)g.npad) {
+    if (wb->cap_paths < (size_t)g.npad * s_cap) {
         cudaStreamSynchronize(st);
-        if ((e = grow(wb->prim_nt, (size_t)g.npad)) != cudaSuccess || (e = grow(wb->prim_id, (size_t)g.npad)) != cudaSuccess) { wb->cap_tiles = 0; return e; }
-        wb->cap_tiles = (size_t)g.npad;
+        for (;;) {
+            e = alloc_paths(wb, (size_t)g.npad * s_cap);
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorMemoryAllocation || s_cap == 1) return e;      // s_cap == 1: not even one sample per pixel fits
+            s_cap = (s_cap + 1) / 2;
+        }
     }
-    if (!wb->counters && (e = cudaMalloc((void**)&wb->counters, 2 * kMaxRounds * sizeof(unsigned int))) != cudaSuccess) return e;
+    if (!wb->counters && (e = cudaMalloc((void**)&wb->counters, 2 * kMaxRounds * sizeof(unsigned int))) != cudaSuccess) { cudaGetLastError(); return e; }
     const int rounds = reuse ? fr.max_bounces : fr.max_bounces + 1;
     if (rounds > kMaxRounds - 1) return cudaErrorInvalidValue;
 
@@ -653,28 +678,18 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     size_t sb; const int mode = pick_mode(sc, ac, sb);
     const int persistent_blocks = sms * 8;
+    const bool count = count_traversal && (mode == 2 || mode == 3) && bvh_refill && !ac.bvh.wnodes;
 
     if ((e = cudaMemsetAsync(wb->launch_acc, 0, npix * sizeof(float4), st)) != cudaSuccess) return e;
-    if (reuse) {
-        const int blocks = (g.npad + kThreads - 1) / kThreads;
-        switch (mode) {
-            case 0: k_wf_primary<0><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
-            case 1: k_wf_primary<1><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
-            case 2: k_wf_primary<2><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
-            case 3: k_wf_primary<3><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
-            default: k_wf_primary<4><<<blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, wb->prim_nt, wb->prim_id); break;
-        }
-        k_wf_count_primaries<<<1, 1, 0, st>>>((int)npix, seg_counter);
-    }
     for (int s0 = 0; s0 < n_samples; s0 += s_cap) {
         const int sw = n_samples - s0 < s_cap ? n_samples - s0 : s_cap;
         const uint32_t s_first = s_begin + (uint32_t)s0;
         const size_t np = (size_t)g.npad * sw;
         if ((e = cudaMemsetAsync(wb->counters, 0, 2 * kMaxRounds * sizeof(unsigned int), st)) != cudaSuccess) return e;
         const int gen_blocks = (int)((np + 255) / 256);
-        if (reuse) k_wf_generate<true><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, wb->prim_nt, wb->prim_id, wb->ray_o[0], wb->ray_d[0],
+        if (reuse) k_wf_generate<true><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, prim_nt, prim_id, wb->ray_o[0], wb->ray_d[0],
                                                                     wb->thr[0], wb->rad[0], wb->wave_rad, wb->q[0], wb->counters, seg_counter);
-        else k_wf_generate<false><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, wb->prim_nt, wb->prim_id, wb->ray_o[0], wb->ray_d[0],
+        else k_wf_generate<false><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, prim_nt, prim_id, wb->ray_o[0], wb->ray_d[0],
                                                                wb->thr[0], wb->rad[0], wb->wave_rad, wb->q[0], wb->counters, seg_counter);
         for (int r = 0; r < rounds; ++r) {
             const int a = r & 1, b = a ^ 1;                  // this round's dense state set, the next round's
@@ -682,18 +697,22 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
             uint32_t* qout = wb->q[b];
             unsigned int* cnt = wb->counters + r;
             unsigned int* cur = wb->counters + kMaxRounds + r;
+#define RTB_WF_ARGS sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id
             switch (mode) {
-                case 0: k_wf_intersect<0><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id); break;
-                case 1: k_wf_intersect<1><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id); break;
-                case 2: if (bvh_refill) k_wf_intersect_bvh<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id, k_refill, k_node_min);
-                        else k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id);
+                case 0: k_wf_intersect<0><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS); break;
+                case 1: k_wf_intersect<1><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS); break;
+                case 2: if (count) k_wf_intersect_bvh<2, true><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS, k_refill, k_node_min, seg_counter);
+                        else if (bvh_refill) k_wf_intersect_bvh<2><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS, k_refill, k_node_min, seg_counter);
+                        else k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS);
                         break;
                 case 3: if (bvh_refill && ac.bvh.wnodes) k_wf_intersect_bvh8<<<sms * RTB_WF_BVH8_MIN_BLOCKS, kThreads, sb, st>>>(sc, ac.bvh, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id, k_refill, k_node_min);
-                        else if (bvh_refill) k_wf_intersect_bvh<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id, k_refill, k_node_min);
-                        else k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id);
+                        else if (count) k_wf_intersect_bvh<3, true><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS, k_refill, k_node_min, seg_counter);
+                        else if (bvh_refill) k_wf_intersect_bvh<3><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS, k_refill, k_node_min, seg_counter);
+                        else k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS);
                         break;
-                default: k_wf_intersect<4><<<persistent_blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id); break;
+                default: k_wf_intersect<4><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS); break;
             }
+#undef RTB_WF_ARGS
             k_wf_shade<<<sms * 8, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, qin, cnt, qout, cnt + 1, wb->ray_o[a], wb->ray_d[a], wb->thr[a], wb->rad[a], wb->ray_o[b], wb->ray_d[b], wb->thr[b], wb->rad[b],
                                                  wb->hit_nt, wb->hit_id, wb->wave_rad, seg_counter);
         }

@@ -19,6 +19,8 @@ RT_OBJ_NONE, RT_OBJ_SPHERE, RT_OBJ_CUBE, RT_OBJ_MESH = 0, 1, 2, 3
 RT_MODE_PATH, RT_MODE_PREVIEW = 0, 1
 RT_OPT_PIPELINE, RT_OPT_ACCEL, RT_OPT_BVH_THRESHOLD, RT_OPT_BVH_SCHED, RT_OPT_BVH_WAIT_K, RT_OPT_BVH_LEAF, RT_OPT_PRIMARY_REUSE = 1, 2, 3, 4, 5, 6, 7
 RT_OPT_WF_REFILL, RT_OPT_WF_NODE_MIN, RT_OPT_POOL_TILES, RT_OPT_FLAT_COOP, RT_OPT_BVH_WIDE, RT_OPT_WF_WAVE_MPATHS = 8, 9, 10, 11, 12, 13
+RT_OPT_TRAVERSAL_STATS = 14
+RT_MAX_PEERS = 16
 RT_PIPELINE_AUTO, RT_PIPELINE_REGEN, RT_PIPELINE_WAVEFRONT = 0, 1, 2
 RT_ACCEL_AUTO, RT_ACCEL_BRUTE, RT_ACCEL_BVH, RT_ACCEL_FLAT = 0, 1, 2, 3
 
@@ -49,6 +51,12 @@ class RtStats(C.Structure):
                 ("traced_segments", C.c_uint64), ("total_traced_segments", C.c_uint64)]
 
 
+class RtTraversalStats(C.Structure):
+    _fields_ = [("queries", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
+                ("sphere_tests", C.c_uint64), ("cube_tests", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("node_bytes", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 OBJECT_DTYPE = np.dtype([("type", "<i4"), ("pos", "<f4", 3), ("radius", "<f4"), ("half", "<f4", 3),
                          ("base", "<f4", 3), ("emissive", "<f4", 3), ("spec_color", "<f4", 3),
                          ("smoothness", "<f4"), ("spec_amount", "<f4")])
@@ -64,6 +72,10 @@ EXPORTS = [
     "rt_write_accum", "rt_selftest", "rt_get_stats", "rt_accum_device_ptr", "rt_set_stream", "rt_sync", "rt_set_sample_count", "rt_resolve_device",
     "rt_host_alloc", "rt_host_free", "rt_set_mesh", "rt_load_mesh_obj", "rt_get_mesh_info", "rt_set_pixel_step", "rt_reference_pixel_step", "rt_reference_strip_columns",
     "rt_argb_device_ptr", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_resolve_fused", "rt_read_surface",
+    "rt_get_traversal_stats", "rt_exchange_setup", "rt_exchange_resolve",
+    "rt_create_multi", "rt_group_destroy", "rt_group_size", "rt_group_ctx", "rt_group_last_error", "rt_group_set_scene", "rt_group_load_scene",
+    "rt_group_set_mesh", "rt_group_set_camera", "rt_group_set_params", "rt_group_set_option", "rt_group_reset_accumulation",
+    "rt_group_render_spp", "rt_group_resolve_rgba8", "rt_group_get_stats",
 ]
 
 
@@ -95,9 +107,16 @@ def load_library(path=None):
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name in ("rt_host_alloc", "rt_host_free", "rt_last_error", "rt_accum_device_ptr", "rt_argb_device_ptr", "rt_create", "rt_default_params", "rt_default_camera",
-                    "rt_rotate_camera", "rt_abi_version", "rt_object_name", "rt_scene_name"):
+                    "rt_rotate_camera", "rt_abi_version", "rt_object_name", "rt_scene_name", "rt_group_ctx", "rt_group_last_error"):
             continue
         fn.restype = C.c_int
+    lib.rt_group_ctx.restype = C.c_void_p
+    lib.rt_group_ctx.argtypes = [C.c_void_p, C.c_int]
+    lib.rt_group_last_error.restype = C.c_char_p
+    lib.rt_group_last_error.argtypes = [C.c_void_p]
+    lib.rt_create_multi.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    for name in ("rt_group_destroy", "rt_group_size", "rt_group_reset_accumulation"):
+        getattr(lib, name).argtypes = [C.c_void_p]
     lib.rt_object_name.restype = C.c_char_p
     lib.rt_object_name.argtypes = [C.c_void_p, C.c_int]
     lib.rt_scene_name.restype = C.c_char_p
@@ -203,19 +222,24 @@ def shard_range(spp, rank, world, next_sample=0):
 class PathTracer:
     """One rt_ctx. Mirrors the call sequence main() makes into the hot path."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _borrowed=None):
         self.lib = load_library()
-        h = C.c_void_p()
-        rc = self.lib.rt_create(device, C.byref(h))
-        if rc != RT_OK:
-            raise RtError(rc, (self.lib.rt_last_error(None) or b"").decode())
-        self.h = h
+        self.owned = _borrowed is None
+        if _borrowed is not None:                  # a member of a TracerGroup: the group owns the handle
+            self.h = C.c_void_p(_borrowed)
+        else:
+            h = C.c_void_p()
+            rc = self.lib.rt_create(device, C.byref(h))
+            if rc != RT_OK:
+                raise RtError(rc, (self.lib.rt_last_error(None) or b"").decode())
+            self.h = h
         self.params = default_params()
         self.camera = default_camera()
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.rt_destroy(self.h)
+            if self.owned:
+                self.lib.rt_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -363,6 +387,20 @@ class PathTracer:
         self._chk(self.lib.rt_get_stats(self.h, C.byref(s)))
         return s
 
+    def traversal_stats(self):
+        s = RtTraversalStats()
+        self._chk(self.lib.rt_get_traversal_stats(self.h, C.byref(s)))
+        return s
+
+    def exchange_setup(self, rank, world, accum_ptrs, flag_ptrs, dst_argb_ptr):
+        """accum_ptrs / flag_ptrs: device pointers in rank order (None for this rank's own)."""
+        a = (C.c_void_p * world)(*accum_ptrs)
+        f = (C.c_void_p * world)(*flag_ptrs)
+        return self._chk(self.lib.rt_exchange_setup(self.h, rank, world, a, f, C.c_void_p(dst_argb_ptr) if dst_argb_ptr else None))
+
+    def exchange_resolve(self, total_samples, flip_y=True):
+        return self._chk(self.lib.rt_exchange_resolve(self.h, total_samples, int(flip_y)))
+
     # interop
     def accum_device_ptr(self):
         return self.lib.rt_accum_device_ptr(self.h)
@@ -406,3 +444,85 @@ class PathTracer:
     def resolve_device(self, dev_accum_ptr, samples, first_pixel, n_pixels, dev_out_ptr, flip_y=True):
         return self._chk(self.lib.rt_resolve_device(self.h, C.c_void_p(dev_accum_ptr), samples, first_pixel, n_pixels,
                                                     C.c_void_p(dev_out_ptr), int(flip_y)))
+
+
+class TracerGroup:
+    """rt_group: library-owned multi-GPU in one process (rt_create_multi). members[i] is a PathTracer view of member i."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devices = list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        g = C.c_void_p()
+        rc = self.lib.rt_create_multi(len(devices), arr, C.byref(g))
+        if rc != RT_OK:
+            raise RtError(rc, (self.lib.rt_group_last_error(None) or b"").decode())
+        self.g = g
+        self.params = default_params()
+        self.members = [PathTracer(_borrowed=self.lib.rt_group_ctx(self.g, i)) for i in range(len(devices))]
+
+    def close(self):
+        if getattr(self, "g", None):
+            for m in self.members:
+                m.close()
+            self.lib.rt_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise RtError(rc, (self.lib.rt_group_last_error(self.g) or b"").decode())
+        return rc
+
+    def size(self):
+        return self.lib.rt_group_size(self.g)
+
+    def set_scene(self, objs):
+        objs = np.ascontiguousarray(objs, OBJECT_DTYPE)
+        return self._chk(self.lib.rt_group_set_scene(self.g, _p(objs), len(objs)))
+
+    def load_scene(self, path):
+        return self._chk(self.lib.rt_group_load_scene(self.g, str(path).encode()))
+
+    def set_mesh(self, object_index, vertices, triangles):
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, np.int32).reshape(-1, 3)
+        return self._chk(self.lib.rt_group_set_mesh(self.g, object_index, _p(v), len(v), _p(t), len(t)))
+
+    def set_camera(self, cam):
+        return self._chk(self.lib.rt_group_set_camera(self.g, C.byref(cam)))
+
+    def set_params(self, params=None, **kw):
+        if params is not None:
+            self.params = params
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        for m in self.members:
+            m.params = self.params
+        return self._chk(self.lib.rt_group_set_params(self.g, C.byref(self.params)))
+
+    def set_option(self, opt, value):
+        return self._chk(self.lib.rt_group_set_option(self.g, opt, value))
+
+    def reset_accumulation(self):
+        return self._chk(self.lib.rt_group_reset_accumulation(self.g))
+
+    def render_spp(self, spp):
+        return self._chk(self.lib.rt_group_render_spp(self.g, spp))
+
+    def resolve_rgba8(self, flip_y=True, out=None):
+        w, h = self.params.width, self.params.height
+        if out is None:
+            out = np.zeros((h, w), np.uint32)
+        self._chk(self.lib.rt_group_resolve_rgba8(self.g, _p(out), out.strides[0], int(flip_y)))
+        return out
+
+    def stats(self):
+        s = RtStats()
+        self._chk(self.lib.rt_group_get_stats(self.g, C.byref(s)))
+        return s
