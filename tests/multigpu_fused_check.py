@@ -1,6 +1,9 @@
 """Run under torchrun with N >= 2 GPUs: spp-sharded render on every rank, then the fused peer-memory
 reduce + resolve kernel (buffers mapped through CUDA IPC) against the oracle's resolve of the host-side
-sum of all ranks' buffers. Prints 'FUSED_OK' on rank 0. Used by tests/test_gpu_parity.py."""
+sum of all ranks' buffers. Prints 'FUSED_OK' on rank 0. Used by tests/test_gpu_parity.py.
+With --exchange: the same through rt_exchange_setup / rt_exchange_resolve, where the ranks order themselves with flags in
+peer-mapped device memory (no barrier, no collective between render and resolve), three frames in a row with a reset in
+between; prints 'EXCHANGE_OK'. Used by tests/test_gpu_round2.py."""
 import os
 import sys
 
@@ -13,6 +16,56 @@ sys.path.insert(0, os.path.join(ROOT, "software-raytracer_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import rtb200  # noqa: E402
 from oracle_py import Oracle  # noqa: E402
+
+
+def exchange_main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, h = 320, 200
+    objs = np.load(os.path.join(ROOT, "tests", "golden", "bundled_scenes.npz"))["Scene3_indirect"]
+    t = rtb200.PathTracer(local)
+    t.set_scene(objs); t.set_camera(rtb200.default_camera())
+    t.set_params(rtb200.default_params(width=w, height=h, mode=0, max_bounces=8, seed_lo=11, seed_hi=22))
+    t.set_shard(rank, world)
+    t.reset_accumulation()
+
+    def gather(which):
+        mine = torch.tensor(list(t.ipc_export(which)), dtype=torch.uint8, device="cuda")
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        return [bytes(x.cpu().tolist()) for x in allh]
+    acc_h, srf_h, flg_h = gather(0), gather(1), gather(2)
+    accum = [None if r == rank else t.ipc_open(acc_h[r]) for r in range(world)]
+    flags = [None if r == rank else t.ipc_open(flg_h[r]) for r in range(world)]
+    dst = None if rank == 0 else t.ipc_open(srf_h[0])
+    t.exchange_setup(rank, world, accum, flags, dst)
+    dist.barrier()                                       # setup only: every rank has mapped every buffer
+    ok = True
+    orc = Oracle()
+    for frame, spp in enumerate((10, 3, 17)):
+        t.reset_accumulation()
+        if rank == world - 1 and frame == 1:
+            torch.cuda._sleep(200_000_000)               # a late rank: the others must wait for it ON THE DEVICE
+        t.render_spp(spp)
+        t.exchange_resolve(spp)                          # no host synchronisation, no collective
+        surf = t.read_surface() if rank == 0 else None   # rank 0: ordered after every rank's slice by the exchange itself
+        t.sync()
+        mine, n = t.read_accum()
+        parts = [torch.empty(h, w, 4, device="cuda") for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(mine).cuda())
+        if rank == 0:
+            total = np.zeros((h, w, 4), np.float32)
+            for p in parts:
+                total = total + p.cpu().numpy()
+            ok = ok and np.array_equal(surf, orc.resolve_argb8(total, spp))
+        dist.barrier()
+    if rank == 0:
+        print("EXCHANGE_OK" if ok else "EXCHANGE_MISMATCH", flush=True)
+    t.close()
+    dist.destroy_process_group()
 
 
 def main():
@@ -65,4 +118,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--exchange" in sys.argv:
+        exchange_main()
+    else:
+        main()
