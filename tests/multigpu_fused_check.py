@@ -6,6 +6,7 @@ peer-mapped device memory (no barrier, no collective between render and resolve)
 between; prints 'EXCHANGE_OK'. Used by tests/test_gpu_round2.py."""
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -48,7 +49,7 @@ def exchange_main():
     for frame, spp in enumerate((10, 3, 17)):
         t.reset_accumulation()
         if rank == world - 1 and frame == 1:
-            torch.cuda._sleep(200_000_000)               # a late rank: the others must wait for it ON THE DEVICE
+            time.sleep(0.25)                             # a late rank: the others wait for its signal ON THE DEVICE
         t.render_spp(spp)
         t.exchange_resolve(spp)                          # no host synchronisation, no collective
         surf = t.read_surface() if rank == 0 else None   # rank 0: ordered after every rank's slice by the exchange itself
