@@ -203,7 +203,8 @@ def make_tracer(args, device, stream_handle, wl, seed_hi=0):
     tr.set_option(rtb200.RT_OPT_ACCEL, {"auto": rtb200.RT_ACCEL_AUTO, "brute": rtb200.RT_ACCEL_BRUTE, "bvh": rtb200.RT_ACCEL_BVH,
                                         "flat": rtb200.RT_ACCEL_FLAT}[args.accel])
     tr.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 0 if args.no_primary_reuse else 1)
-    tr.set_option(rtb200.RT_OPT_PIPELINE, {"auto": rtb200.RT_PIPELINE_AUTO, "regen": rtb200.RT_PIPELINE_REGEN, "wavefront": rtb200.RT_PIPELINE_WAVEFRONT}[args.pipeline])
+    tr.set_option(rtb200.RT_OPT_PIPELINE, {"auto": rtb200.RT_PIPELINE_AUTO, "regen": rtb200.RT_PIPELINE_REGEN, "wavefront": rtb200.RT_PIPELINE_WAVEFRONT,
+                                           "stream": rtb200.RT_PIPELINE_STREAM}[args.pipeline])
     for opt, v in ((rtb200.RT_OPT_BVH_SCHED, args.bvh_sched), (rtb200.RT_OPT_BVH_WIDE, args.bvh_wide), (rtb200.RT_OPT_BVH_WAIT_K, args.wait_k),
                    (rtb200.RT_OPT_FLAT_COOP, args.flat_coop), (rtb200.RT_OPT_WF_REFILL, args.wf_refill), (rtb200.RT_OPT_WF_NODE_MIN, args.wf_node_min),
                    (rtb200.RT_OPT_WF_WAVE_MPATHS, args.wave_mpaths)):
@@ -220,7 +221,8 @@ def make_tracer(args, device, stream_handle, wl, seed_hi=0):
 
 ACCEL_NAMES = {1: "brute-force object loop", 2: "host-built BVH candidates + strict tests",
                3: "flat two-level accelerator (conservative FMA culls, warp-uniform) + strict tests"}
-PIPE_NAMES = {1: "regeneration megakernel", 2: "wavefront (raygen / persistent intersect / shade + ballot compaction)"}
+PIPE_NAMES = {1: "regeneration megakernel", 2: "wavefront (raygen / persistent intersect / shade + ballot compaction)",
+              3: "streaming (one persistent kernel: lanes claim paths, traverse with postponed leaves, shade and continue; no per-bounce state)"}
 
 
 def fp32_roofline(objs, st, delivered_per_step, traced_per_step, kern_s, peaks, peaks_src, w, h):
@@ -261,13 +263,14 @@ def bvh_roofline(tr, wl, spp, traced_per_s, kern_share, peaks, peaks_src, pipeli
     ach = bytes_per_query * traced_per_s / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
     wf = pipeline == rtb200.RT_PIPELINE_WAVEFRONT
+    kname = {rtb200.RT_PIPELINE_WAVEFRONT: "k_wf_intersect_bvh", rtb200.RT_PIPELINE_STREAM: "k_wf_stream"}.get(pipeline, "k_render_regen<3>")
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "basis": "executed closest-hit queries/s x (%d B x %.1f node visits + 20 B x %.2f sphere + 36 B x %.2f cube + 52 B x %.2f triangle tests) per query, device counters of this run"
                      % (ts.node_bytes, nodes, sph, cube, tri),
             "bytes_per_query": bytes_per_query, "node_visits_per_query": nodes, "prim_tests_per_query": sph + cube + tri, "flop_per_query": flop_per_query,
             "achieved_tflops": flop_per_query * traced_per_s / 1e12,
             "traffic": None, "traffic_note": "BVH + primitives are L2-resident (0.9 MB / 75 MB in a 126 MB L2): dram bytes per launch are the path state, see profiles/ ncu summaries",
-            "kernel": "k_wf_intersect_bvh" if wf else "k_render_regen<3>", "kernel_share_of_step": kern_share,
+            "kernel": kname, "kernel_share_of_step": kern_share,
             "peak_source": "%s MEASURED_PEAKS.json hbm_gbs" % peaks_src,
             "note": "node and primitive fetches are served by L1/L2, not HBM: frac is algorithmic bytes against the HBM copy peak as SURVEY.md 8d defines it; the kernel is bound by "
                     "instruction issue under divergence and dependent L2 round trips (ncu: issue slots busy, long-scoreboard stalls, L1 hit rate in profiles/)"}
@@ -311,7 +314,7 @@ def run_leg(args, config, torch, stream, steps=3, warmup=3):
            "accel": ACCEL_NAMES[s1.accel], "pipeline": PIPE_NAMES[s1.pipeline], "clocks": clocks}
     kern_s = statistics.mean(ms) * 1e-3
     if s1.accel == rtb200.RT_ACCEL_BVH:
-        out["roofline"] = bvh_roofline(tr, wl, spp, traced / total_s, 0.8 if s1.pipeline == rtb200.RT_PIPELINE_WAVEFRONT else 1.0, peaks, peaks_src, s1.pipeline)
+        out["roofline"] = bvh_roofline(tr, wl, spp, traced / total_s, 0.8 if s1.pipeline == rtb200.RT_PIPELINE_WAVEFRONT else 0.98, peaks, peaks_src, s1.pipeline)
     else:
         out["roofline"] = fp32_roofline(wl["objs"], s1, segs / steps, traced / steps, kern_s, peaks, peaks_src, w, h)
     tr.close()
@@ -558,6 +561,7 @@ def run_b200(args):
         value = segs_all / (total_ms * 1e-3) / 1e6
         kern_s = statistics.mean(step_ms) * 1e-3     # dominant kernel = one k_render_regen launch per step; its duration = the step (N = 1)
         wf = st.pipeline == rtb200.RT_PIPELINE_WAVEFRONT
+        streamk = st.pipeline == rtb200.RT_PIPELINE_STREAM
         cfg = workload_config(wl["scene"], len(objs), w, h)
         par = "single GPU" if world == 1 else ("spp-sharded x%d (%s scaling), " % (world, args.scaling)) + \
             ("fused reduce+resolve kernel over NVLink peer memory, ranks ordered by device-side flags (rt_exchange_resolve)" if fused else "one NCCL all-reduce per step")
@@ -585,6 +589,9 @@ def run_b200(args):
         if wf:
             line["gpu_launches"] = int(args.steps * (3 + 2 * DEPTH) * 2)
             line["gpu_launches_detail"] = "per rank: the wavefront pipeline launches raygen + 2 kernels per bounce round per wave (about 20 per step) + accumulate/commit, in both timed regions"
+        elif streamk:
+            line["gpu_launches"] = int(args.steps * 3 * 2)
+            line["gpu_launches_detail"] = "per rank and wave: k_wf_stream + k_wf_accumulate, + k_wf_commit per step, in both timed regions"
         else:
             per_step = 1 + (2 if world > 1 else 0)   # k_render_regen (+ k_resolve_fused_sync + k_exchange_wait)
             per_e2e = 2 + (1 if world == 1 else 2)   # k_primary_cache (the scene is re-submitted) + k_render_regen + k_resolve | the two exchange kernels
@@ -592,7 +599,7 @@ def run_b200(args):
             line["gpu_launches_detail"] = ("per rank. timed value region: 1 k_render_regen per step" + (" + k_resolve_fused_sync + k_exchange_wait" if world > 1 else "") +
                                            "; e2e region: k_primary_cache + k_render_regen + " + ("k_resolve" if world == 1 else "k_resolve_fused_sync + k_exchange_wait") + " per step")
         if st.accel == rtb200.RT_ACCEL_BVH:
-            line["roofline"] = bvh_roofline(tr, wl, spp, traced_rank / (sum(step_ms) * 1e-3), 0.8 if wf else 1.0, peaks, peaks_src, st.pipeline)
+            line["roofline"] = bvh_roofline(tr, wl, spp, traced_rank / (sum(step_ms) * 1e-3), 0.8 if wf else 0.98, peaks, peaks_src, st.pipeline)
         else:
             line["roofline"] = fp32_roofline(objs, st, segs_rank / args.steps, traced_rank / args.steps, kern_s, peaks, peaks_src, w, h)
         if world > 1:
@@ -635,7 +642,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short legs of the other configs")
     ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh", "flat"], help="closest-hit back end (results are identical)")
-    ap.add_argument("--pipeline", default="auto", choices=["auto", "regen", "wavefront"],
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "regen", "wavefront", "stream"],
                     help="regen: persistent-lane regeneration megakernel (default); wavefront: raygen/intersect/shade kernels over device queues (bit-identical)")
     ap.add_argument("--no-primary-reuse", action="store_true", help="re-trace the (identical) primary ray for every sample, like the reference")
     ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"], help="N > 1 exchange: fused peer-memory reduce+resolve kernel with device-side ordering, or NCCL all-reduce")

@@ -131,14 +131,17 @@ enum {
     RT_OPT_TRAVERSAL_STATS = 14    /* 1: BVH kernels count inner-node visits and primitive tests (rt_get_traversal_stats); a separate
                                       instantiation of the kernels, ~3 % slower. 0 (default): off */
 };
-enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2 };
+enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_REGEN = 1, RT_PIPELINE_WAVEFRONT = 2, RT_PIPELINE_STREAM = 3 };
 /* BRUTE: the reference's object loop. BVH: host-built BVH2. FLAT: two-level flat accelerator for scenes of up
  * to 255 objects (conservative culls with warp-uniform control flow, then the strict tests). All three give
  * bit-identical hits; AUTO measures them on the first rt_render_spp call of at least 64 samples after a scene or parameter
  * change (shorter calls, and camera moves, keep a heuristic choice: flat up to 255 objects, BVH from `bvh_threshold`).
  * RT_PIPELINE_AUTO is the regeneration megakernel, except that BVH scenes of 2048+ primitives also time the wavefront
- * pipeline (raygen / persistent-thread intersect / shade + ray compaction kernels) on the first call of 8+ samples and keep
- * the faster for calls of 8+ samples; shorter calls always use the megakernel. */
+ * pipeline (raygen / persistent-thread intersect / shade + ray compaction kernels, one pass over device queues per bounce)
+ * and the streaming pipeline (RT_PIPELINE_STREAM: ONE persistent kernel per wave whose lanes claim path ids from a global
+ * cursor, traverse with postponed leaves, shade their own hits and go on with the scattered ray - no per-bounce state in
+ * HBM) on the first call of 8+ samples and keep the fastest for calls of 8+ samples; shorter calls always use the
+ * megakernel. All pipelines give bit-identical accumulation buffers. */
 enum { RT_ACCEL_AUTO = 0, RT_ACCEL_BRUTE = 1, RT_ACCEL_BVH = 2, RT_ACCEL_FLAT = 3 };
 
 /* ---- lifetime: replaces the worker spawn/join (Raytracer.cpp:331-342, 598-607) -------- */

@@ -296,9 +296,8 @@ int autotune_accel(rt_ctx* c, int spp) {
 }
 
 // RT_PIPELINE_AUTO: the regeneration megakernel, except for BVH scenes too large to stage in shared memory
-// (thousands of primitives), where the first path-mode render of 8+ samples times both pipelines with up to 16 samples per
-// pixel and keeps the faster (identical results). With this round's wavefront pipeline (waves of up to 128 M paths, dense
-// path state) it wins on both measured scenes: 10 000 spheres 4.1 vs 2.7, 1 M triangles 7.1 vs 4.1 G segments/s.
+// (thousands of primitives), where the first path-mode render of 8+ samples times the megakernel, the bounce-round wavefront
+// pipeline and the streaming kernel with up to 16 samples per pixel and keeps the fastest (identical results).
 constexpr int kWavefrontMinSpp = 8;    // RT_PIPELINE_AUTO: calls shorter than this cannot fill a wave and stay on the megakernel
 int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     if (c->opt_pipeline != RT_PIPELINE_AUTO) return RT_OK;
@@ -316,26 +315,39 @@ int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     if (c->opt_primary_reuse && (rc = ensure_prim_cache(c, ac)) != RT_OK) return rc;
     const PrimCache* prim = prim_cache_arg(c, pc);
     cudaError_t err = cudaSuccess;
-    // The wavefront pipeline's rate depends on how many samples share a wave (launch_render_wavefront), so it is measured with
-    // up to 16 samples per pixel - what a call of this length will really run.
+    // The wavefront pipelines' rate depends on how many samples share a wave (launch_render_wavefront), so they are measured with
+    // up to 16 samples per pixel - what a call of this length will really run. Candidates: 0 megakernel, 1 bounce-round wavefront,
+    // 2 streaming kernel.
     const int n_tune = spp < 16 ? spp : 16;
+    bool usable[3] = {true, true, true};
     for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 allocates the wavefront buffers and warms up
         cudaEventRecord(e[0], c->stream);
         err = launch_render_regen(c->view, ac, c->frame, c->d_tune, 0u, pass ? n_tune : 1, prim, dummy, c->stream);
         cudaEventRecord(e[1], c->stream);
-        if (err == cudaSuccess) err = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_tune, 0u, n_tune, prim, dummy, c->stream, c->opt_bvh_sched == 0,
-                                                             c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths);
-        cudaEventRecord(e[2], c->stream);
-    }
-    if (err == cudaErrorMemoryAllocation) {                    // no room for even the smallest wave: the megakernel gives the same image
-        cudaStreamSynchronize(c->stream);
-        c->tuned_pipeline = RT_PIPELINE_REGEN;
-        return RT_OK;
+        for (int k = 1; k <= 2 && err == cudaSuccess; ++k) {
+            if (usable[k]) {
+                const cudaError_t we = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_tune, 0u, n_tune, prim, dummy, c->stream, c->opt_bvh_sched == 0,
+                                                               c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths, false, k == 2);
+                if (we == cudaErrorMemoryAllocation) usable[k] = false;      // no room for even the smallest wave: not a candidate
+                else err = we;
+            }
+            cudaEventRecord(e[k + 1], c->stream);
+        }
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
-    if (err == cudaSuccess) { cudaEventElapsedTime(&c->tune_pipe_ms[0], e[0], e[1]); cudaEventElapsedTime(&c->tune_pipe_ms[1], e[1], e[2]); }
+    float ms[3] = {0.f, 0.f, 0.f};
+    if (err == cudaSuccess) for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&ms[k], e[k], e[k + 1]);
     if (err != cudaSuccess) return cuda_fail(c, err, "autotune_pipeline");
-    c->tuned_pipeline = c->tune_pipe_ms[1] < c->tune_pipe_ms[0] ? RT_PIPELINE_WAVEFRONT : RT_PIPELINE_REGEN;
+    c->tune_pipe_ms[0] = ms[0]; c->tune_pipe_ms[1] = ms[1]; c->tune_pipe_ms[2] = ms[2];
+    const int kinds[3] = {RT_PIPELINE_REGEN, RT_PIPELINE_WAVEFRONT, RT_PIPELINE_STREAM};
+    int best = 0;
+    for (int k = 1; k < 3; ++k) if (usable[k] && ms[k] < ms[best]) best = k;
+    if (getenv("RTB200_DEBUG"))
+        fprintf(stderr, "[rtb200] pipeline autotune (%d spp): megakernel %.3f ms, wavefront %.3f ms%s, stream %.3f ms%s -> %d\n", n_tune, ms[0], ms[1],
+                usable[1] ? "" : " (no memory)", ms[2], usable[2] ? "" : " (no memory)", kinds[best]);
+    c->tuned_pipeline = kinds[best];
+    // the bounce-round pipeline's path state (up to tens of GB) is not kept when it lost
+    if (kinds[best] != RT_PIPELINE_WAVEFRONT && c->opt_pipeline == RT_PIPELINE_AUTO) { cudaStreamSynchronize(c->stream); wavefront_release(c->wf); }
     return RT_OK;
 }
 
@@ -673,7 +685,7 @@ int rt_set_option(rt_ctx* c, int option, int value) {
     const int retune = -1;
     switch (option) {
         case RT_OPT_PIPELINE:
-            if (value < RT_PIPELINE_AUTO || value > RT_PIPELINE_WAVEFRONT) return bad("RT_OPT_PIPELINE takes RT_PIPELINE_AUTO / REGEN / WAVEFRONT");
+            if (value < RT_PIPELINE_AUTO || value > RT_PIPELINE_STREAM) return bad("RT_OPT_PIPELINE takes RT_PIPELINE_AUTO / REGEN / WAVEFRONT / STREAM");
             c->opt_pipeline = value; return RT_OK;
         case RT_OPT_ACCEL:
             if (value < RT_ACCEL_AUTO || value > RT_ACCEL_FLAT) return bad("RT_OPT_ACCEL takes RT_ACCEL_AUTO / BRUTE / BVH / FLAT");
@@ -790,9 +802,11 @@ int rt_render_spp(rt_ctx* c, int spp) {
         // this rank's slice of the global sample indices [next, next+spp)
         int mine = 0; uint32_t first = 0;
         rt_shard_range(spp, c->rank, c->world, c->next_sample, &first, &mine);
-        bool wavefront = (c->opt_pipeline == RT_PIPELINE_WAVEFRONT ||
-                          (c->opt_pipeline == RT_PIPELINE_AUTO && c->tuned_pipeline == RT_PIPELINE_WAVEFRONT && mine >= kWavefrontMinSpp)) &&
-                         c->par.max_bounces <= 60;            // deeper paths: the megakernel (identical results)
+        const int pipe = c->opt_pipeline != RT_PIPELINE_AUTO ? c->opt_pipeline : (c->tuned_pipeline > 0 && mine >= kWavefrontMinSpp ? c->tuned_pipeline : RT_PIPELINE_REGEN);
+        // the streaming kernel walks the binary BVH only; for other back ends RT_PIPELINE_STREAM runs the bounce-round kernels
+        const bool streaming = pipe == RT_PIPELINE_STREAM && ac.kind == kAccelBvh && !ac.bvh.wnodes && c->opt_bvh_sched == 0;
+        bool wavefront = (pipe == RT_PIPELINE_WAVEFRONT || pipe == RT_PIPELINE_STREAM) &&
+                         (streaming || c->par.max_bounces <= 60);   // bounce rounds: one queue counter per round; deeper paths use the megakernel
         const bool scheduled = !wavefront && ac.kind == kAccelBvh && c->opt_bvh_sched && c->view.n_tri == 0;   // experimental kernel, re-traces primaries
         PrimCache pc;
         if (c->opt_primary_reuse && !scheduled && mine > 0 && (rc = ensure_prim_cache(c, ac)) != RT_OK) return rc;
@@ -800,7 +814,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
         if (wavefront) {
             if (!c->wf) c->wf = wavefront_create();
             const cudaError_t we = launch_render_wavefront(c->wf, c->view, ac, c->frame, c->d_accum, first, mine, prim, c->d_counters, c->stream, c->opt_bvh_sched == 0,
-                                                           c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths, c->opt_trav_stats != 0);
+                                                           c->opt_wf_refill, c->opt_wf_node_min, c->opt_wf_wave_mpaths, c->opt_trav_stats != 0, streaming);
             if (we == cudaErrorMemoryAllocation) {
                 // not even one sample per pixel of path state fits next to what else lives on the device: the megakernel
                 // needs no state and gives the same image (nothing was launched: allocation precedes the first kernel)
@@ -808,7 +822,7 @@ int rt_render_spp(rt_ctx* c, int spp) {
                 if (c->opt_pipeline == RT_PIPELINE_AUTO) c->tuned_pipeline = RT_PIPELINE_REGEN;
             } else {
                 RT_CUDA(c, we);
-                c->used_pipeline = RT_PIPELINE_WAVEFRONT;
+                c->used_pipeline = streaming ? RT_PIPELINE_STREAM : RT_PIPELINE_WAVEFRONT;
             }
         }
         if (wavefront) {}

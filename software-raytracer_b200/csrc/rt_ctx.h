@@ -101,7 +101,7 @@ struct rt_ctx {
     int tuned_flat_coop = 1;
     int tuned_accel = -1;          // RT_ACCEL_AUTO decision for the current scene/camera/params (-1: not measured yet)
     int tuned_pipeline = -1;       // RT_PIPELINE_AUTO decision for large BVH scenes (-1: not measured yet)
-    float tune_pipe_ms[2] = {0.f, 0.f};
+    float tune_pipe_ms[3] = {0.f, 0.f, 0.f};
     float4* d_tune = nullptr; size_t cap_tune = 0;
     float tune_ms[4] = {0.f, 0.f, 0.f, 0.f};
     int used_pipeline = RT_PIPELINE_REGEN, used_accel = RT_ACCEL_BRUTE;

@@ -87,6 +87,7 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
                                     unsigned long long* seg_counter, cudaStream_t st, bool bvh_refill = true,
                                     int k_refill = 8, int k_node_min = 8,
                                     int wave_mpaths = 0,    // paths per wave in units of 2^20 (0: default 128, capped by free memory)
-                                    bool count_traversal = false);
+                                    bool count_traversal = false,
+                                    bool streaming = false);   // RT_PIPELINE_STREAM: one persistent kernel traces AND shades whole paths (binary-BVH back ends)
 void wavefront_release(WavefrontBuffers* wb);   // frees the device buffers (scene / resolution change); they are reallocated on the next use
 }  // namespace rtb

@@ -28,7 +28,7 @@
 namespace rtb {
 
 struct WavefrontBuffers {
-    size_t cap_paths = 0, cap_px = 0;
+    size_t cap_paths = 0, cap_px = 0, cap_rad = 0;      // per-path state arrays | launch_acc | wave_rad
     // Path state lives in DENSE ping-pong sets: slot i of round r's set is the i-th surviving path, so every kernel reads and
     // writes consecutive records (with one fixed slot per path and a queue of path ids the survivors of the later rounds are
     // scattered and a 32-byte sector carries one useful record: the shade kernel moved 3.8x its useful bytes).
@@ -340,6 +340,225 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
     if (COUNT) flush_trav_count(cnt, n_queries, counters);
 }
 
+// ---- STREAMING variant: the whole path in the persistent kernel (RT_PIPELINE_STREAM) ----------------------------------
+// The bounce-round pipeline above moves every path's state through HBM once per bounce (~170 B per segment), needs two more
+// kernels per round and runs its late rounds - a few per cent of the paths - on an almost empty machine, which is why it wants
+// waves of 128 M paths (22 GB of state). Here the lane that finishes a traversal SHADES its hit on the spot and goes on with
+// the scattered ray; a lane whose path ended stores the path's radiance (16 B) and claims the next path id from one global
+// cursor (ids are sample-major over tile-major pixels, like the wavefront's). The traversal is the state machine of
+// k_wf_intersect_bvh (speculative while-while, postponed leaves, refill at kRefill free lanes); the shading block runs for the
+// DONE lanes of a warp together under the same refill condition. Path state that is only needed at a hit (throughput, radiance
+// so far, depth, pixel, sample) lives in shared memory, 9 words per thread, so the traversal keeps its 64 registers.
+// No queues, no per-bounce state, no rounds: HBM sees the primary-hit cache (20 B per path) and the finished radiance (16 B per
+// path); samples are added per pixel in sample order by k_wf_accumulate afterwards, so the sum is BIT-IDENTICAL to the
+// megakernel's and to the wavefront pipeline's (tests/test_gpu_round2.py).
+constexpr int kStreamStateWords = 9;       // T.xyz, L.xyz, depth, pixel, sample - per thread, [word][thread] in shared memory
+#ifndef RTB_WF_STREAM_MIN_BLOCKS
+#define RTB_WF_STREAM_MIN_BLOCKS 8
+#endif
+template <int MODE, bool REUSE, bool COUNT>
+__global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_stream(SceneView sc, BvhView bv, FlatView fl, FrameView fr, int tiles_x, int npad,
+                                                                                uint32_t s_first, unsigned int n_paths, const float4* __restrict__ prim_nt,
+                                                                                const int* __restrict__ prim_id, float4* __restrict__ wave_rad,
+                                                                                unsigned int* __restrict__ cursor, int kRefill, int kNodeMin,
+                                                                                unsigned long long* __restrict__ seg_counter) {
+    extern __shared__ float4 smem[];
+    float* const ps = reinterpret_cast<float*>(smem) + threadIdx.x;           // this thread's path state, words kThreads apart
+    const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem + (kStreamStateWords * kThreads + 3) / 4);
+    const float4* __restrict__ nodes = tc.nodes;
+    const int* __restrict__ refs = tc.refs;
+    int* const stk = tc.stack;
+    float* const stk_t = tc.stack_t;
+    const int stride = tc.stride;
+    const int lane = threadIdx.x & 31;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NONE = (int)0x80000000;
+    enum { IDLE = 0, ACTIVE = 1, DONE = 2 };
+
+    int state = IDLE, cur = NONE, leaf0 = NONE, sp = 0;
+    uint32_t pid = 0;
+    float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f), bn = f3(0.f, 0.f, 0.f);
+    float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+    float best_t = 0.f; int best_id = 0, best_ref = 0; bool have = false;
+    bool exhausted = false;
+    TravCount cnt = {0u, 0u, 0u, 0u};
+    unsigned int segs = 0, traced = 0;
+
+    auto pop = [&]() -> int {
+        while (sp > 0) {
+            --sp;
+            if (stk_t[sp * stride] > best_t) continue;       // entered after the best hit found since the push
+            return stk[sp * stride];
+        }
+        return NONE;
+    };
+    auto settle = [&]() {
+        if (cur == NONE) cur = pop();
+        if (cur < 0 && cur != NONE && leaf0 == NONE) { leaf0 = cur; cur = pop(); }
+        if (cur == NONE && leaf0 == NONE) state = DONE;
+    };
+    auto test_leaf = [&](int link) {
+        const unsigned int v = (unsigned int)(~link);
+        const int first = (int)(v & 0xffffffu), n_refs = (int)(v >> 24);
+        for (int i = 0; i < n_refs; ++i) {
+            const int r = refs[first + i];
+            if (COUNT) { if (r >= kTriRef) ++cnt.tri; else if (r >= 0) ++cnt.sph; else ++cnt.box; }
+            if (r >= kTriRef) {
+                const int k = r - kTriRef;
+                float t; float3 nrm;
+                if (tri_hit(__ldg(sc.tri + 3 * k), __ldg(sc.tri + 3 * k + 1), __ldg(sc.tri + 3 * k + 2), o, d, t, nrm)) {
+                    const int oid = __ldg(sc.tri_obj + k);
+                    if (t < best_t || (t == best_t && (oid < best_id || (oid == best_id && r < best_ref)))) {
+                        best_t = t; best_id = oid; best_ref = r; bn = nrm; have = true;
+                    }
+                }
+            } else if (r >= 0) {
+                float t;
+                if (sphere_t(tc.sph[r], o, d, t)) {
+                    const int oid = sc.sph_id[r];
+                    if (t < best_t || (t == best_t && oid < best_id)) { best_t = t; best_id = oid; best_ref = r; have = true; }
+                }
+            } else {
+                const int j = ~r;
+                float dist; float3 nrm;
+                if (box_hit(tc.box[2 * j], tc.box[2 * j + 1], o, d, dist, nrm)) {
+                    const int oid = sc.box_id[j];
+                    if (dist < best_t || (dist == best_t && oid < best_id)) { best_t = dist; best_id = oid; best_ref = r; bn = nrm; have = true; }
+                }
+            }
+        }
+    };
+    // start the traversal of the ray (o, d)
+    auto begin_ray = [&]() {
+        const float big = 1e30f;
+        ix = fabsf(d.x) > 1e-30f ? RTB_FAST_RCP(d.x) : copysignf(big, d.x);
+        iy = fabsf(d.y) > 1e-30f ? RTB_FAST_RCP(d.y) : copysignf(big, d.y);
+        iz = fabsf(d.z) > 1e-30f ? RTB_FAST_RCP(d.z) : copysignf(big, d.z);
+        ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
+        best_t = __int_as_float(0x7f800000); best_id = 0x7fffffff; best_ref = 0; have = false;
+        cur = 0; leaf0 = NONE; sp = 0; state = ACTIVE;
+    };
+
+    for (;;) {
+        // ---- shade + refill ---------------------------------------------------------------------------------
+        const unsigned m_free = __ballot_sync(FULL, state != ACTIVE);
+        if (__popc(m_free) >= kRefill || m_free == FULL) {
+            if (state == DONE) {                             // the finished traversals of the warp are shaded together
+                Hit h;
+                h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f); h.p = f3(0.f, 0.f, 0.f);
+                if (have) {
+                    h.id = best_id; h.t = best_t;
+                    h.p = f3(o.x + d.x * best_t, o.y + d.y * best_t, o.z + d.z * best_t);                    // Object.hpp:136 / :229
+                    if (best_ref >= 0 && best_ref < kTriRef) {
+                        const float4 s4 = tc.sph[best_ref];
+                        h.n = normalized3(f3(h.p.x - s4.x, h.p.y - s4.y, h.p.z - s4.z));                   // Object.hpp:137
+                    } else h.n = bn;
+                }
+                ++segs; ++traced;
+                float3 T = f3(ps[0], ps[kThreads], ps[2 * kThreads]), L = f3(ps[3 * kThreads], ps[4 * kThreads], ps[5 * kThreads]);
+                int depth = __float_as_int(ps[6 * kThreads]);
+                float3 c;
+                if (path_ends(sc, fr, h, d, T, L, depth, c)) {
+                    wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f);
+                    state = IDLE;
+                } else {
+                    scatter_segment(sc, fr, h, __float_as_uint(ps[7 * kThreads]), __float_as_uint(ps[8 * kThreads]), o, d, T, L, depth);
+                    ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = L.x; ps[4 * kThreads] = L.y; ps[5 * kThreads] = L.z;
+                    ps[6 * kThreads] = __int_as_float(depth);
+                    begin_ray();
+                }
+            }
+            if (!exhausted) {                                // every idle lane claims the next path id: one atomicAdd per warp
+                const unsigned m_idle = __ballot_sync(FULL, state == IDLE);
+                if (m_idle) {
+                    unsigned int base = 0;
+                    const int leader = __ffs((int)m_idle) - 1;
+                    if (lane == leader) base = atomicAdd(cursor, (unsigned int)__popc(m_idle));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (state == IDLE) {
+                        const unsigned int i = base + (unsigned int)__popc(m_idle & ((1u << lane) - 1u));
+                        int px, py;
+                        if (i < n_paths && tile_to_pixel(fr, tiles_x, (int)(i % (unsigned int)npad), px, py)) {
+                            pid = i;
+                            const uint32_t pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
+                            const uint32_t sample = s_first + i / (unsigned int)npad;
+                            o = fr.cam_pos; d = ray_dir(fr, px, py);
+                            float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
+                            int depth = 0;
+                            bool live = true;
+                            if (REUSE) {                     // start from the pixel's cached primary hit (k_primary_cache)
+                                const float4 nt = __ldg(prim_nt + pixel);
+                                Hit h0;
+                                h0.id = __ldg(prim_id + pixel); h0.t = nt.w; h0.n = f3(nt.x, nt.y, nt.z);
+                                h0.p = f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w);
+                                ++segs;                      // the reused primary segment: delivered, not traced
+                                float3 c;
+                                if (path_ends(sc, fr, h0, d, T, L, 0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
+                                else scatter_segment(sc, fr, h0, pixel, sample, o, d, T, L, depth);
+                            }
+                            if (live) {
+                                ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = L.x; ps[4 * kThreads] = L.y; ps[5 * kThreads] = L.z;
+                                ps[6 * kThreads] = __int_as_float(depth); ps[7 * kThreads] = __uint_as_float(pixel); ps[8 * kThreads] = __uint_as_float(sample);
+                                begin_ray();
+                            }
+                        }
+                    }
+                    if (base + (unsigned int)__popc(m_idle) >= n_paths) exhausted = true;       // warp-uniform
+                }
+            }
+            if (!__any_sync(FULL, state == ACTIVE)) {
+                if (exhausted) break;                        // no traversal in flight, nothing left to claim (DONE lanes were shaded above)
+                continue;                                    // this pass's paths all ended at once (sky pixels): claim more
+            }
+        }
+        // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
+        for (;;) {
+            const bool in_node = state == ACTIVE && cur >= 0;
+            if (in_node) {
+                if (COUNT) ++cnt.nodes;
+                const float4 n0 = nodes[4 * cur], n1 = nodes[4 * cur + 1], n2 = nodes[4 * cur + 2];
+                const int2 ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
+                const float ax0 = fmaf(n0.x, ix, ox), bx0 = fmaf(n0.y, ix, ox), ay0 = fmaf(n0.z, iy, oy), by0 = fmaf(n0.w, iy, oy);
+                const float az0 = fmaf(n1.x, iz, oz), bz0 = fmaf(n1.y, iz, oz);
+                const float ax1 = fmaf(n1.z, ix, ox), bx1 = fmaf(n1.w, ix, ox), ay1 = fmaf(n2.x, iy, oy), by1 = fmaf(n2.y, iy, oy);
+                const float az1 = fmaf(n2.z, iz, oz), bz1 = fmaf(n2.w, iz, oz);
+                const float lo0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fminf(az0, bz0));
+                const float hi0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fmaxf(az0, bz0));
+                const float lo1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fminf(az1, bz1));
+                const float hi1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fmaxf(az1, bz1));
+                const bool h0 = lo0 <= hi0 && hi0 >= 0.f && lo0 <= best_t;
+                const bool h1 = lo1 <= hi1 && hi1 >= 0.f && lo1 <= best_t;
+                if (h0 && h1) {
+                    const bool swap = lo1 < lo0;
+                    stk[sp * stride] = swap ? ch.x : ch.y;
+                    stk_t[sp * stride] = swap ? lo0 : lo1;
+                    ++sp;
+                    cur = swap ? ch.y : ch.x;
+                } else if (h0) cur = ch.x;
+                else if (h1) cur = ch.y;
+                else cur = NONE;
+                settle();
+            }
+            if (__popc(__ballot_sync(FULL, state == ACTIVE && cur >= 0)) < kNodeMin) break;
+        }
+        // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
+        if (state == ACTIVE) {
+            if (leaf0 != NONE) { test_leaf(leaf0); leaf0 = NONE; }
+            if (cur < 0 && cur != NONE) { test_leaf(cur); cur = NONE; }
+            settle();
+        }
+    }
+    // segment counters: delivered [0..1], executed [2..3]; one atomic per warp and counter
+    unsigned int tot = segs, tot_tr = traced;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { tot += __shfl_down_sync(FULL, tot, off); tot_tr += __shfl_down_sync(FULL, tot_tr, off); }
+    if (lane == 0 && tot) {
+        atomicAdd(seg_counter, (unsigned long long)tot); atomicAdd(seg_counter + 1, (unsigned long long)tot);
+        atomicAdd(seg_counter + 2, (unsigned long long)tot_tr); atomicAdd(seg_counter + 3, (unsigned long long)tot_tr);
+    }
+    if (COUNT) flush_trav_count(cnt, traced, seg_counter);
+}
+
 // The same state machine over the 8-WIDE quantised BVH (bvh_wide.h): a node step tests eight children at once, the
 // line's nearest inner child becomes the lane's next node and the other hit children wait on the stack as one group
 // with the smallest of their entry parameters (groups that start behind the best hit are dropped at the pop); the node's
@@ -572,6 +791,10 @@ cudaError_t ensure_optin() {
     if ((e = optin(k_wf_intersect_bvh<2, true>)) != cudaSuccess) return e;
     if ((e = optin(k_wf_intersect_bvh<3, true>)) != cudaSuccess) return e;
     if ((e = optin(k_wf_intersect_bvh8)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_stream<2, true, false>)) != cudaSuccess) return e; if ((e = optin(k_wf_stream<2, false, false>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_stream<3, true, false>)) != cudaSuccess) return e; if ((e = optin(k_wf_stream<3, false, false>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_stream<2, true, true>)) != cudaSuccess) return e; if ((e = optin(k_wf_stream<2, false, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_stream<3, true, true>)) != cudaSuccess) return e; if ((e = optin(k_wf_stream<3, false, true>)) != cudaSuccess) return e;
 #undef RTB_WF_OPTIN
     done = true;
     return cudaSuccess;
@@ -590,7 +813,7 @@ void wavefront_release(WavefrontBuffers* wb) {
     }
     cudaFree(wb->hit_nt); cudaFree(wb->hit_id); cudaFree(wb->wave_rad); cudaFree(wb->launch_acc);
     wb->hit_nt = nullptr; wb->hit_id = nullptr; wb->wave_rad = nullptr; wb->launch_acc = nullptr;
-    wb->cap_paths = wb->cap_px = 0;
+    wb->cap_paths = wb->cap_px = wb->cap_rad = 0;
 }
 
 void wavefront_destroy(WavefrontBuffers* wb) {
@@ -609,7 +832,7 @@ cudaError_t alloc_paths(WavefrontBuffers* wb, size_t n) {
         (e = grow(wb->ray_o[1], n)) != cudaSuccess || (e = grow(wb->ray_d[1], n)) != cudaSuccess ||
         (e = grow(wb->thr[1], n)) != cudaSuccess || (e = grow(wb->rad[1], n)) != cudaSuccess ||
         (e = grow(wb->hit_nt, n)) != cudaSuccess || (e = grow(wb->hit_id, n)) != cudaSuccess ||
-        (e = grow(wb->wave_rad, n)) != cudaSuccess || (e = grow(wb->q[0], n)) != cudaSuccess ||
+        (wb->cap_rad < n && (e = grow(wb->wave_rad, n)) != cudaSuccess) || (e = grow(wb->q[0], n)) != cudaSuccess ||
         (e = grow(wb->q[1], n)) != cudaSuccess) {
         float4* keep = wb->launch_acc; const size_t keep_px = wb->cap_px;
         wb->launch_acc = nullptr;
@@ -619,13 +842,22 @@ cudaError_t alloc_paths(WavefrontBuffers* wb, size_t n) {
         return e;
     }
     wb->cap_paths = n;
+    if (wb->cap_rad < n) wb->cap_rad = n;
+    return cudaSuccess;
+}
+// the streaming kernel needs only the finished radiance per path
+cudaError_t alloc_radiance(WavefrontBuffers* wb, size_t n) {
+    if (wb->cap_rad >= n) return cudaSuccess;
+    const cudaError_t e = grow(wb->wave_rad, n);
+    if (e != cudaSuccess) { wb->cap_rad = 0; cudaGetLastError(); return e; }
+    wb->cap_rad = n;
     return cudaSuccess;
 }
 }  // namespace
 
 cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, const AccelSel& ac, const FrameView& fr,
                                     float4* accum, uint32_t s_begin, int n_samples, const PrimCache* prim_cache, unsigned long long* seg_counter,
-                                    cudaStream_t st, bool bvh_refill, int k_refill, int k_node_min, int wave_mpaths, bool count_traversal) {
+                                    cudaStream_t st, bool bvh_refill, int k_refill, int k_node_min, int wave_mpaths, bool count_traversal, bool streaming) {
     if (k_refill < 1) k_refill = 1; if (k_refill > 32) k_refill = 32;
     if (k_node_min < 1) k_node_min = 1; if (k_node_min > 32) k_node_min = 32;
     if (n_samples <= 0) return cudaSuccess;
@@ -643,10 +875,15 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     // the allocation fails all the same (another context or process took the memory) the wave is halved until it fits.
     size_t wave_paths = (size_t)(wave_mpaths >= 1 && wave_mpaths <= 1024 ? wave_mpaths : 128) << 20;
     if (const char* wp = getenv("RTB200_WAVE_MPATHS")) { const long v = atol(wp); if (v >= 1 && v <= 1024) wave_paths = (size_t)v << 20; }
+    size_t sb; const int mode = pick_mode(sc, ac, sb);
+    // the streaming kernel walks the binary BVH; other back ends fall back to the bounce-round kernels (identical results)
+    streaming = streaming && (mode == 2 || mode == 3) && !ac.bvh.wnodes;
+    const size_t bytes_per_path = streaming ? sizeof(float4) : kBytesPerPath;
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t budget = (free_b + wb->cap_paths * kBytesPerPath) / 3 / kBytesPerPath;
+            const size_t have = streaming ? wb->cap_rad * sizeof(float4) : wb->cap_paths * kBytesPerPath;
+            const size_t budget = (free_b + have) / 3 / bytes_per_path;
             if (wave_paths > budget) wave_paths = budget;
         }
     }
@@ -660,10 +897,10 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
         if ((e = grow(wb->launch_acc, npix)) != cudaSuccess) { wb->cap_px = 0; cudaGetLastError(); return e; }
         wb->cap_px = npix;
     }
-    if (wb->cap_paths < (size_t)g.npad * s_cap) {
+    if (streaming ? wb->cap_rad < (size_t)g.npad * s_cap : wb->cap_paths < (size_t)g.npad * s_cap) {
         cudaStreamSynchronize(st);
         for (;;) {
-            e = alloc_paths(wb, (size_t)g.npad * s_cap);
+            e = streaming ? alloc_radiance(wb, (size_t)g.npad * s_cap) : alloc_paths(wb, (size_t)g.npad * s_cap);
             if (e == cudaSuccess) break;
             if (e != cudaErrorMemoryAllocation || s_cap == 1) return e;      // s_cap == 1: not even one sample per pixel fits
             s_cap = (s_cap + 1) / 2;
@@ -671,12 +908,11 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     }
     if (!wb->counters && (e = cudaMalloc((void**)&wb->counters, 2 * kMaxRounds * sizeof(unsigned int))) != cudaSuccess) { cudaGetLastError(); return e; }
     const int rounds = reuse ? fr.max_bounces : fr.max_bounces + 1;
-    if (rounds > kMaxRounds - 1) return cudaErrorInvalidValue;
+    if (!streaming && rounds > kMaxRounds - 1) return cudaErrorInvalidValue;      // one queue counter per bounce round; the streaming kernel has no rounds
 
     int device = 0, sms = 0;
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    size_t sb; const int mode = pick_mode(sc, ac, sb);
     const int persistent_blocks = sms * 8;
     const bool count = count_traversal && (mode == 2 || mode == 3) && bvh_refill && !ac.bvh.wnodes;
 
@@ -686,6 +922,22 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
         const uint32_t s_first = s_begin + (uint32_t)s0;
         const size_t np = (size_t)g.npad * sw;
         if ((e = cudaMemsetAsync(wb->counters, 0, 2 * kMaxRounds * sizeof(unsigned int), st)) != cudaSuccess) return e;
+        if (streaming) {
+            // one persistent launch per wave: paths are claimed from counters[0], traced and shaded to the end in the kernel
+            const size_t ssb = sb + (size_t)((kStreamStateWords * kThreads + 3) / 4) * sizeof(float4);
+            const int blocks = sms * RTB_WF_STREAM_MIN_BLOCKS;
+#define RTB_STREAM_ARGS sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, s_first, (unsigned int)np, prim_nt, prim_id, wb->wave_rad, wb->counters, k_refill, k_node_min, seg_counter
+#define RTB_STREAM_LAUNCH(M)                                                                                                        \
+            if (reuse) { if (count) k_wf_stream<M, true, true><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS);                     \
+                         else k_wf_stream<M, true, false><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS); }                       \
+            else { if (count) k_wf_stream<M, false, true><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS);                          \
+                   else k_wf_stream<M, false, false><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS); }
+            if (mode == 2) { RTB_STREAM_LAUNCH(2) } else { RTB_STREAM_LAUNCH(3) }
+#undef RTB_STREAM_LAUNCH
+#undef RTB_STREAM_ARGS
+            k_wf_accumulate<<<(g.npad + 255) / 256, 256, 0, st>>>(fr, g.tiles_x, g.npad, sw, wb->wave_rad, wb->launch_acc);
+            continue;
+        }
         const int gen_blocks = (int)((np + 255) / 256);
         if (reuse) k_wf_generate<true><<<gen_blocks, 256, 0, st>>>(sc, fr, g.tiles_x, g.npad, s_first, sw, prim_nt, prim_id, wb->ray_o[0], wb->ray_d[0],
                                                                     wb->thr[0], wb->rad[0], wb->wave_rad, wb->q[0], wb->counters, seg_counter);

@@ -119,11 +119,14 @@ def test_traversal_counters_equal_the_host_emulation(tracer):
 
 # ---- BASELINE configs at production shape ------------------------------------------------------------------------
 def _auto_vs_megakernel(tracer, setup_scene, w, h, spp, small_wave_mpaths):
-    """RT_PIPELINE_AUTO (must pick the wavefront pipeline) vs the megakernel vs the wavefront pipeline forced into many
-    small waves: bit-identical accumulation buffers and identical segment counts; traversal counters sane."""
+    """RT_PIPELINE_AUTO (must pick one of the two persistent-thread pipelines) vs the megakernel vs the bounce-round wavefront
+    pipeline vs the streaming kernel, the last two also forced into many small waves: bit-identical accumulation buffers and
+    identical segment counts; traversal counters sane."""
     out = {}
     try:
         for name, pipe, mp, cnt in (("auto", rtb200.RT_PIPELINE_AUTO, 0, 0), ("regen", rtb200.RT_PIPELINE_REGEN, 0, 0),
+                                    ("wavefront", rtb200.RT_PIPELINE_WAVEFRONT, 0, 0), ("stream", rtb200.RT_PIPELINE_STREAM, 0, 0),
+                                    ("stream_waves", rtb200.RT_PIPELINE_STREAM, small_wave_mpaths, 1),
                                     ("waves", rtb200.RT_PIPELINE_WAVEFRONT, small_wave_mpaths, 1)):
             tracer.set_option(rtb200.RT_OPT_PIPELINE, pipe)
             tracer.set_option(rtb200.RT_OPT_WF_WAVE_MPATHS, mp)
@@ -136,18 +139,22 @@ def _auto_vs_megakernel(tracer, setup_scene, w, h, spp, small_wave_mpaths):
         tracer.set_option(rtb200.RT_OPT_PIPELINE, rtb200.RT_PIPELINE_AUTO)
         tracer.set_option(rtb200.RT_OPT_WF_WAVE_MPATHS, 0)
         tracer.set_option(rtb200.RT_OPT_TRAVERSAL_STATS, 0)
-    assert out["auto"][3] == rtb200.RT_PIPELINE_WAVEFRONT and out["auto"][4] == rtb200.RT_ACCEL_BVH
-    assert out["regen"][3] == rtb200.RT_PIPELINE_REGEN and out["waves"][3] == rtb200.RT_PIPELINE_WAVEFRONT
-    for name in ("regen", "waves"):
+    assert out["auto"][3] in (rtb200.RT_PIPELINE_WAVEFRONT, rtb200.RT_PIPELINE_STREAM) and out["auto"][4] == rtb200.RT_ACCEL_BVH
+    assert out["regen"][3] == rtb200.RT_PIPELINE_REGEN and out["waves"][3] == out["wavefront"][3] == rtb200.RT_PIPELINE_WAVEFRONT
+    assert out["stream"][3] == out["stream_waves"][3] == rtb200.RT_PIPELINE_STREAM
+    for name in ("regen", "wavefront", "stream", "stream_waves", "waves"):
         assert np.array_equal(bits(out["auto"][0]), bits(out[name][0])), name
         assert out["auto"][1:3] == out[name][1:3], name
+    for name in ("stream_waves", "waves"):
+        ts = out[name][6]
+        assert ts.queries == out[name][2] - w * h, name      # every executed query but the cached primaries went through the counting kernel
     a = out["auto"][0]
     assert np.all(np.isfinite(a)) and a[..., :3].max() > 0
     ts = out["waves"][6]
-    assert ts.queries == out["waves"][2] - w * h          # every executed query but the cached primaries went through the counting kernel
     assert 5 < ts.node_visits / ts.queries < 400 and 0.2 < ts.prim_tests / ts.queries < 60
-    print("%dx%d x %d spp: auto(wavefront) %.1f ms, megakernel %.1f ms, small waves %.1f ms; %.1f node visits, %.1f primitive tests per query"
-          % (w, h, spp, out["auto"][5], out["regen"][5], out["waves"][5], ts.node_visits / ts.queries, ts.prim_tests / ts.queries))
+    print("%dx%d x %d spp: auto(pipeline %d) %.1f ms, megakernel %.1f ms, wavefront %.1f ms, stream %.1f ms; small waves: wavefront %.1f ms, stream %.1f ms; %.1f node visits, %.1f primitive tests per query"
+          % (w, h, spp, out["auto"][3], out["auto"][5], out["regen"][5], out["wavefront"][5], out["stream"][5], out["waves"][5], out["stream_waves"][5],
+             ts.node_visits / ts.queries, ts.prim_tests / ts.queries))
     return out
 
 
@@ -362,3 +369,55 @@ def test_headless_cpp_driver_matches_the_c_abi(tracer, tmp_path, scenes):
     # the interactive loop (BASELINE configs[4]) runs and reports latencies
     r = subprocess.run([exe, "--scene", scene_file, "--width", "640", "--height", "360", "--interactive", "50", "--scale", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and '"p50_ms"' in r.stdout, r.stdout + r.stderr
+
+
+def test_headless_cpp_driver_on_several_gpus(tmp_path, scenes):
+    """`rt_headless --gpus N`: the library-owned group from a C++ host - no torch, no IPC (Raytracer.cpp:331-342, 598-607)."""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    exe = os.path.join(ROOT, "software-raytracer_b200", "bin", "rt_headless")
+    scene_file = str(tmp_path / "Scene1.json")
+    assert rtb200.scene_file_write(scene_file, scenes["Scene1"], None, "Scene1") == 0
+    w, h, spp = 320, 180, 16
+    ppm = str(tmp_path / "g.ppm")
+    r = subprocess.run([exe, "--scene", scene_file, "--width", str(w), "--height", str(h), "--spp", str(spp), "--bounces", "8", "--gpus", str(n), "--out", ppm],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and '"gpus": %d' % n in r.stdout, r.stdout + r.stderr
+    g = rtb200.TracerGroup(list(range(n)))
+    try:
+        g.set_scene(scenes["Scene1"]); g.set_camera(rtb200.default_camera())
+        g.set_params(rtb200.default_params(width=w, height=h, mode=rtb200.RT_MODE_PATH, max_bounces=8))
+        g.reset_accumulation(); g.render_spp(spp)
+        argb = g.resolve_rgba8(True)
+    finally:
+        g.close()
+    want = np.stack([(argb >> 16) & 255, (argb >> 8) & 255, argb & 255], -1).astype(np.uint8)
+    assert np.array_equal(_read_ppm(ppm), want)
+
+
+@pytest.mark.parametrize("reuse", [1, 0])
+def test_streaming_pipeline_is_bit_identical_on_small_bvh_scenes(tracer, scenes, reuse):
+    """RT_PIPELINE_STREAM over a BVH staged in shared memory (bundled scenes, sphere + cube mix) and read from global memory
+    (3000 primitives), with and without primary-hit reuse, max_bounces 0 and 8: the megakernel's bits and counts."""
+    cases = [(scenes["Scene1"], 333, 77, 8), (scenes["Scene3_indirect"], 160, 120, 8), (scenes["Scene_indirect"], 160, 120, 0),
+             (synthetic_spheres(3000, cubes_every=9), 256, 144, 8)]
+    try:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_BVH)
+        tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, reuse)
+        for i, (objs, w, h, mb) in enumerate(cases):
+            res = {}
+            for pipe in (rtb200.RT_PIPELINE_REGEN, rtb200.RT_PIPELINE_STREAM):
+                tracer.set_option(rtb200.RT_OPT_PIPELINE, pipe)
+                setup(tracer, objs, w, h, config3_camera(rtb200.default_camera) if i == 3 else None, max_bounces=mb)
+                tracer.render_spp(5); tracer.render_spp(2)
+                st = tracer.stats()
+                assert st.pipeline == pipe
+                res[pipe] = (tracer.read_accum()[0], st.segments, st.traced_segments, st.paths)
+            a, b = res[rtb200.RT_PIPELINE_REGEN], res[rtb200.RT_PIPELINE_STREAM]
+            assert np.array_equal(bits(a[0]), bits(b[0])) and a[1:] == b[1:], (i, reuse)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_PIPELINE, rtb200.RT_PIPELINE_AUTO)
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 1)
