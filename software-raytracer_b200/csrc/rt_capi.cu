@@ -858,10 +858,19 @@ int rt_resolve_rgba8(rt_ctx* c, uint32_t* host_out, int pitch_bytes, int flip_y)
     if (rc != RT_OK) return rc;
     const int w = c->par.width, h = c->par.height;
     if (!host_out || pitch_bytes < w * 4) return fail(c, RT_ERR_INVALID, "rt_resolve_rgba8: bad output buffer");
+    // A page-locked host surface (rt_host_alloc) with a tight pitch is written by the resolve kernel itself, over PCIe (zero-copy):
+    // an interactive frame then has no separate device-to-host copy to set up and wait for. RTB200_ZEROCOPY=0 turns it off.
+    uint32_t* mapped = nullptr;
+    static const bool zero_copy = [] { const char* v = getenv("RTB200_ZEROCOPY"); return !(v && v[0] == '0'); }();
+    if (zero_copy && pitch_bytes == w * 4) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) mapped = (uint32_t*)at.devicePointer;
+        else cudaGetLastError();
+    }
     cudaEventRecord(c->ev2, c->stream);
-    cudaError_t e = launch_resolve(c->d_accum, c->samples, w, h, 0, w * h, flip_y, c->d_argb, 0, c->stream);
+    cudaError_t e = launch_resolve(c->d_accum, c->samples, w, h, 0, w * h, flip_y, c->d_argb, 0, c->stream, mapped);
     cudaEventRecord(c->ev3, c->stream);
-    if (e == cudaSuccess) {
+    if (e == cudaSuccess && !mapped) {
         if (pitch_bytes == w * 4)                              // tightly packed surface: one linear copy
             e = cudaMemcpyAsync(host_out, c->d_argb, (size_t)w * 4 * (size_t)h, cudaMemcpyDeviceToHost, c->stream);
         else

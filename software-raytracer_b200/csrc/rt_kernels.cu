@@ -583,8 +583,10 @@ __device__ __forceinline__ uint32_t resolve_pixel(float4 a, float count) {
 // Generic slice resolve: pixels [first, first+n) of a width x height image; `accum` points at
 // the slice. Output row = flip ? (H-1-y) : y (Raytracer.cpp:64), tightly packed width*4 pitch,
 // `out` points at the start of the WHOLE image when whole_image_out, else at the slice.
+// out2 (optional): a second whole-image destination - the caller's page-locked HOST surface, written straight over PCIe
+// by the kernel's coalesced stores (zero-copy), so that an interactive frame needs no separate device-to-host copy.
 __global__ void k_resolve(const float4* __restrict__ accum, float count, int width, int height, int first, int n,
-                          int flip_y, uint32_t* __restrict__ out, int out_is_slice) {
+                          int flip_y, uint32_t* __restrict__ out, int out_is_slice, uint32_t* __restrict__ out2) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int p = first + i;
@@ -592,6 +594,7 @@ __global__ void k_resolve(const float4* __restrict__ accum, float count, int wid
     const uint32_t v = resolve_pixel(accum[i], count);
     const size_t dst = (size_t)x + (size_t)(flip_y ? height - 1 - y : y) * width;
     out[out_is_slice ? (size_t)i : dst] = v;
+    if (out2) out2[dst] = v;
 }
 
 // ---- fused multi-GPU reduce + resolve over peer memory -----------------------------------------
@@ -889,9 +892,9 @@ cudaError_t launch_render_blocks(const SceneView& sc, const AccelSel& ac, const 
 }
 
 cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int height, int first, int n, int flip_y,
-                           uint32_t* out, int out_is_slice, cudaStream_t st) {
+                           uint32_t* out, int out_is_slice, cudaStream_t st, uint32_t* mapped_host_out) {
     if (n <= 0) return cudaSuccess;
-    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(accum, (float)samples, width, height, first, n, flip_y, out, out_is_slice);
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(accum, (float)samples, width, height, first, n, flip_y, out, out_is_slice, mapped_host_out);
     return cudaGetLastError();
 }
 

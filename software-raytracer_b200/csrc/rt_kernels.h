@@ -53,7 +53,8 @@ cudaError_t launch_render_preview(const SceneView& sc, const AccelSel& ac, const
 cudaError_t launch_render_blocks(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum, uint32_t s_begin,
                                  int n_samples, int steps, int strip_w, unsigned long long* seg_counter, cudaStream_t st);
 cudaError_t launch_resolve(const float4* accum, uint32_t samples, int width, int height, int first, int n, int flip_y,
-                           uint32_t* out, int out_is_slice, cudaStream_t st);
+                           uint32_t* out, int out_is_slice, cudaStream_t st,
+                           uint32_t* mapped_host_out = nullptr);   // device alias of a page-locked host surface (whole image, tight pitch): also written, zero-copy
 
 cudaError_t launch_resolve_fused(const PeerPtrs& peers, int world, uint32_t samples, int width, int height, int first, int n,
                                  int flip_y, uint32_t* out, cudaStream_t st);
