@@ -3,11 +3,13 @@
 #pragma once
 #include "rt_device.cuh"
 #include "rt_kernels.h"
+#include "rt_bvh_lane.cuh"
 
 namespace rtb {
 
 constexpr int kTileW = 16, kTileH = 8;          // CTA tile: 4 warps, each an 8x4 pixel block
 constexpr int kThreads = 128;
+static_assert(kThreads == kLaneThreads, "rt_bvh_lane.cuh lays the traversal stacks out for CTAs of kThreads threads");
 #ifndef RTB_BVH_POP_CULL
 #define RTB_BVH_POP_CULL 1             // big (global-memory) BVHs: keep the far child's entry distance on the stack, skip stale pops
 #endif

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_wf_intersect(SceneView sc, BvhV
     }
 }
 
+
 // BVH scenes: persistent threads with PER-LANE ray replacement and POSTPONED leaves ("speculative while-while").
 // With one ray per lane per batch (k_wf_intersect above) a warp runs until its longest traversal ends: on the
 // 10 000-sphere scene 5 of 32 lanes are active on average (profiles/r1l_summary_c3_bvh.txt). Here every lane is
@@ -190,152 +191,55 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     const float4* __restrict__ nodes = tc.nodes;
     const int* __restrict__ refs = tc.refs;
-    int* const stk = tc.stack;
-    float* const stk_t = tc.stack_t;
-    const int stride = tc.stride;
     const unsigned int count = *count_ptr;
     const int lane = threadIdx.x & 31;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int NONE = (int)0x80000000;                     // "no link": never a real leaf (a leaf's count is <= 127)
-    enum { IDLE = 0, ACTIVE = 1, DONE = 2 };
 
-    int state = IDLE, cur = NONE, leaf0 = NONE, sp = 0;
+    BvhLane L;                                               // rt_bvh_lane.cuh: traversal state + shared-memory stack
+    L.init(tc.stack);
     uint32_t pid = 0;
-    float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f), bn = f3(0.f, 0.f, 0.f);
-    float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
-    float best_t = 0.f; int best_id = 0, best_ref = 0; bool have = false;
+    float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
     bool exhausted = false;
     TravCount cnt = {0u, 0u, 0u, 0u};                          // COUNT only
     unsigned int n_queries = 0;
 
-    auto pop = [&]() -> int {
-        while (sp > 0) {
-            --sp;
-            if (stk_t[sp * stride] > best_t) continue;       // entered after the best hit found since the push
-            return stk[sp * stride];
-        }
-        return NONE;
-    };
-    // keep at most one stashed leaf and, if there is more work, an inner node (or a second leaf) in `cur`
-    auto settle = [&]() {
-        if (cur == NONE) cur = pop();
-        if (cur < 0 && cur != NONE && leaf0 == NONE) { leaf0 = cur; cur = pop(); }
-        if (cur == NONE && leaf0 == NONE) state = DONE;
-    };
-    auto test_leaf = [&](int link) {
-        const unsigned int v = (unsigned int)(~link);
-        const int first = (int)(v & 0xffffffu), n_refs = (int)(v >> 24);
-        for (int i = 0; i < n_refs; ++i) {
-            const int r = refs[first + i];
-            if (COUNT) { if (r >= kTriRef) ++cnt.tri; else if (r >= 0) ++cnt.sph; else ++cnt.box; }
-            if (r >= kTriRef) {
-                const int k = r - kTriRef;
-                float t; float3 nrm;
-                if (tri_hit(__ldg(sc.tri + 3 * k), __ldg(sc.tri + 3 * k + 1), __ldg(sc.tri + 3 * k + 2), o, d, t, nrm)) {
-                    const int oid = __ldg(sc.tri_obj + k);
-                    if (t < best_t || (t == best_t && (oid < best_id || (oid == best_id && r < best_ref)))) {
-                        best_t = t; best_id = oid; best_ref = r; bn = nrm; have = true;
-                    }
-                }
-            } else if (r >= 0) {
-                float t;
-                if (sphere_t(tc.sph[r], o, d, t)) {
-                    const int oid = sc.sph_id[r];
-                    if (t < best_t || (t == best_t && oid < best_id)) { best_t = t; best_id = oid; best_ref = r; have = true; }
-                }
-            } else {
-                const int j = ~r;
-                float dist; float3 nrm;
-                if (box_hit(tc.box[2 * j], tc.box[2 * j + 1], o, d, dist, nrm)) {
-                    const int oid = sc.box_id[j];
-                    if (dist < best_t || (dist == best_t && oid < best_id)) { best_t = dist; best_id = oid; best_ref = r; bn = nrm; have = true; }
-                }
-            }
-        }
-    };
-
     for (;;) {
         // ---- refill ---------------------------------------------------------------------------------------
-        const unsigned m_free = __ballot_sync(FULL, state != ACTIVE);
+        const unsigned m_free = __ballot_sync(FULL, L.state != BvhLane::ACTIVE);
         if (__popc(m_free) >= kRefill || m_free == FULL) {
-            if (state == DONE) {                             // write the pending hits together
-                Hit h;
-                h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f);
-                if (have) {
-                    h.id = best_id; h.t = best_t;
-                    if (best_ref >= 0 && best_ref < kTriRef) {
-                        const float4 s4 = tc.sph[best_ref];
-                        const float3 p = f3(o.x + d.x * best_t, o.y + d.y * best_t, o.z + d.z * best_t);      // Object.hpp:136
-                        h.n = normalized3(f3(p.x - s4.x, p.y - s4.y, p.z - s4.z));                         // Object.hpp:137
-                    } else h.n = bn;
-                }
+            if (L.state == BvhLane::DONE) {                  // write the pending hits together
+                const Hit h = L.finish(tc.sph, o, d);
                 hit_nt[pid] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
                 hit_id[pid] = h.id;
-                state = IDLE;
+                L.state = BvhLane::IDLE;
             }
             if (!exhausted) {
-                const unsigned m_idle = __ballot_sync(FULL, state == IDLE);
+                const unsigned m_idle = __ballot_sync(FULL, L.state == BvhLane::IDLE);
                 unsigned int base = 0;
                 const int leader = __ffs((int)m_idle) - 1;
                 if (lane == leader) base = atomicAdd(cursor, (unsigned int)__popc(m_idle));
                 base = __shfl_sync(FULL, base, leader);
-                if (state == IDLE) {
+                if (L.state == BvhLane::IDLE) {
                     const unsigned int i = base + (unsigned int)__popc(m_idle & ((1u << lane) - 1u));
                     if (i < count) {
                         pid = i;                             // dense state: slot = queue position
                         const float4 o4 = ray_o[pid], d4 = ray_d[pid];
                         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
-                        const float big = 1e30f;
-                        ix = fabsf(d.x) > 1e-30f ? RTB_FAST_RCP(d.x) : copysignf(big, d.x);
-                        iy = fabsf(d.y) > 1e-30f ? RTB_FAST_RCP(d.y) : copysignf(big, d.y);
-                        iz = fabsf(d.z) > 1e-30f ? RTB_FAST_RCP(d.z) : copysignf(big, d.z);
-                        ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
-                        best_t = __int_as_float(0x7f800000); best_id = 0x7fffffff; best_ref = 0; have = false;
-                        cur = 0; leaf0 = NONE; sp = 0; state = ACTIVE;
+                        L.begin(o, d);
                         if (COUNT) ++n_queries;
                     }
                 }
                 if (base + (unsigned int)__popc(m_idle) >= count) exhausted = true;       // warp-uniform
             }
-            if (!__any_sync(FULL, state == ACTIVE)) break;    // nothing left to traverse (DONE lanes were flushed above)
+            if (!__any_sync(FULL, L.state == BvhLane::ACTIVE)) break;    // nothing left to traverse (DONE lanes were flushed above)
         }
         // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
         for (;;) {
-            const bool in_node = state == ACTIVE && cur >= 0;
-            if (in_node) {
-                if (COUNT) ++cnt.nodes;
-                const float4 n0 = nodes[4 * cur], n1 = nodes[4 * cur + 1], n2 = nodes[4 * cur + 2];
-                const int2 ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
-                const float ax0 = fmaf(n0.x, ix, ox), bx0 = fmaf(n0.y, ix, ox), ay0 = fmaf(n0.z, iy, oy), by0 = fmaf(n0.w, iy, oy);
-                const float az0 = fmaf(n1.x, iz, oz), bz0 = fmaf(n1.y, iz, oz);
-                const float ax1 = fmaf(n1.z, ix, ox), bx1 = fmaf(n1.w, ix, ox), ay1 = fmaf(n2.x, iy, oy), by1 = fmaf(n2.y, iy, oy);
-                const float az1 = fmaf(n2.z, iz, oz), bz1 = fmaf(n2.w, iz, oz);
-                const float lo0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fminf(az0, bz0));
-                const float hi0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fmaxf(az0, bz0));
-                const float lo1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fminf(az1, bz1));
-                const float hi1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fmaxf(az1, bz1));
-                const bool h0 = lo0 <= hi0 && hi0 >= 0.f && lo0 <= best_t;
-                const bool h1 = lo1 <= hi1 && hi1 >= 0.f && lo1 <= best_t;
-                if (h0 && h1) {
-                    const bool swap = lo1 < lo0;
-                    const int far_link = swap ? ch.x : ch.y;
-                    stk[sp * stride] = far_link;
-                    stk_t[sp * stride] = swap ? lo0 : lo1;
-                    ++sp;
-                    cur = swap ? ch.y : ch.x;
-                } else if (h0) cur = ch.x;
-                else if (h1) cur = ch.y;
-                else cur = NONE;
-                settle();
-            }
-            if (__popc(__ballot_sync(FULL, state == ACTIVE && cur >= 0)) < kNodeMin) break;
+            if (L.in_node()) L.node_step<COUNT>(nodes, cnt);
+            if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
-        if (state == ACTIVE) {
-            if (leaf0 != NONE) { test_leaf(leaf0); leaf0 = NONE; }
-            if (cur < 0 && cur != NONE) { test_leaf(cur); cur = NONE; }
-            settle();
-        }
+        if (L.state == BvhLane::ACTIVE) L.leaf_step<COUNT>(sc, tc.sph, tc.box, refs, o, d, cnt);
     }
     if (COUNT) flush_trav_count(cnt, n_queries, counters);
 }
@@ -367,115 +271,45 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem + (kStreamStateWords * kThreads + 3) / 4);
     const float4* __restrict__ nodes = tc.nodes;
     const int* __restrict__ refs = tc.refs;
-    int* const stk = tc.stack;
-    float* const stk_t = tc.stack_t;
-    const int stride = tc.stride;
     const int lane = threadIdx.x & 31;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int NONE = (int)0x80000000;
-    enum { IDLE = 0, ACTIVE = 1, DONE = 2 };
 
-    int state = IDLE, cur = NONE, leaf0 = NONE, sp = 0;
+    BvhLane L;                                               // rt_bvh_lane.cuh: traversal state + shared-memory stack
+    L.init(tc.stack);
     uint32_t pid = 0;
-    float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f), bn = f3(0.f, 0.f, 0.f);
-    float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
-    float best_t = 0.f; int best_id = 0, best_ref = 0; bool have = false;
+    float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
     bool exhausted = false;
     TravCount cnt = {0u, 0u, 0u, 0u};
     unsigned int segs = 0, traced = 0;
 
-    auto pop = [&]() -> int {
-        while (sp > 0) {
-            --sp;
-            if (stk_t[sp * stride] > best_t) continue;       // entered after the best hit found since the push
-            return stk[sp * stride];
-        }
-        return NONE;
-    };
-    auto settle = [&]() {
-        if (cur == NONE) cur = pop();
-        if (cur < 0 && cur != NONE && leaf0 == NONE) { leaf0 = cur; cur = pop(); }
-        if (cur == NONE && leaf0 == NONE) state = DONE;
-    };
-    auto test_leaf = [&](int link) {
-        const unsigned int v = (unsigned int)(~link);
-        const int first = (int)(v & 0xffffffu), n_refs = (int)(v >> 24);
-        for (int i = 0; i < n_refs; ++i) {
-            const int r = refs[first + i];
-            if (COUNT) { if (r >= kTriRef) ++cnt.tri; else if (r >= 0) ++cnt.sph; else ++cnt.box; }
-            if (r >= kTriRef) {
-                const int k = r - kTriRef;
-                float t; float3 nrm;
-                if (tri_hit(__ldg(sc.tri + 3 * k), __ldg(sc.tri + 3 * k + 1), __ldg(sc.tri + 3 * k + 2), o, d, t, nrm)) {
-                    const int oid = __ldg(sc.tri_obj + k);
-                    if (t < best_t || (t == best_t && (oid < best_id || (oid == best_id && r < best_ref)))) {
-                        best_t = t; best_id = oid; best_ref = r; bn = nrm; have = true;
-                    }
-                }
-            } else if (r >= 0) {
-                float t;
-                if (sphere_t(tc.sph[r], o, d, t)) {
-                    const int oid = sc.sph_id[r];
-                    if (t < best_t || (t == best_t && oid < best_id)) { best_t = t; best_id = oid; best_ref = r; have = true; }
-                }
-            } else {
-                const int j = ~r;
-                float dist; float3 nrm;
-                if (box_hit(tc.box[2 * j], tc.box[2 * j + 1], o, d, dist, nrm)) {
-                    const int oid = sc.box_id[j];
-                    if (dist < best_t || (dist == best_t && oid < best_id)) { best_t = dist; best_id = oid; best_ref = r; bn = nrm; have = true; }
-                }
-            }
-        }
-    };
-    // start the traversal of the ray (o, d)
-    auto begin_ray = [&]() {
-        const float big = 1e30f;
-        ix = fabsf(d.x) > 1e-30f ? RTB_FAST_RCP(d.x) : copysignf(big, d.x);
-        iy = fabsf(d.y) > 1e-30f ? RTB_FAST_RCP(d.y) : copysignf(big, d.y);
-        iz = fabsf(d.z) > 1e-30f ? RTB_FAST_RCP(d.z) : copysignf(big, d.z);
-        ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
-        best_t = __int_as_float(0x7f800000); best_id = 0x7fffffff; best_ref = 0; have = false;
-        cur = 0; leaf0 = NONE; sp = 0; state = ACTIVE;
-    };
-
     for (;;) {
         // ---- shade + refill ---------------------------------------------------------------------------------
-        const unsigned m_free = __ballot_sync(FULL, state != ACTIVE);
+        const unsigned m_free = __ballot_sync(FULL, L.state != BvhLane::ACTIVE);
         if (__popc(m_free) >= kRefill || m_free == FULL) {
-            if (state == DONE) {                             // the finished traversals of the warp are shaded together
-                Hit h;
-                h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f); h.p = f3(0.f, 0.f, 0.f);
-                if (have) {
-                    h.id = best_id; h.t = best_t;
-                    h.p = f3(o.x + d.x * best_t, o.y + d.y * best_t, o.z + d.z * best_t);                    // Object.hpp:136 / :229
-                    if (best_ref >= 0 && best_ref < kTriRef) {
-                        const float4 s4 = tc.sph[best_ref];
-                        h.n = normalized3(f3(h.p.x - s4.x, h.p.y - s4.y, h.p.z - s4.z));                   // Object.hpp:137
-                    } else h.n = bn;
-                }
+            if (L.state == BvhLane::DONE) {                  // the finished traversals of the warp are shaded together
+                const Hit h = L.finish(tc.sph, o, d);
                 ++segs; ++traced;
-                float3 T = f3(ps[0], ps[kThreads], ps[2 * kThreads]), L = f3(ps[3 * kThreads], ps[4 * kThreads], ps[5 * kThreads]);
+                float3 T = f3(ps[0], ps[kThreads], ps[2 * kThreads]), Lr = f3(ps[3 * kThreads], ps[4 * kThreads], ps[5 * kThreads]);
                 int depth = __float_as_int(ps[6 * kThreads]);
                 float3 c;
-                if (path_ends(sc, fr, h, d, T, L, depth, c)) {
+                if (path_ends(sc, fr, h, d, T, Lr, depth, c)) {
                     wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f);
-                    state = IDLE;
+                    L.state = BvhLane::IDLE;
                 } else {
-                    scatter_segment(sc, fr, h, __float_as_uint(ps[7 * kThreads]), __float_as_uint(ps[8 * kThreads]), o, d, T, L, depth);
-                    ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = L.x; ps[4 * kThreads] = L.y; ps[5 * kThreads] = L.z;
+                    scatter_segment(sc, fr, h, __float_as_uint(ps[7 * kThreads]), __float_as_uint(ps[8 * kThreads]), o, d, T, Lr, depth);
+                    ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = Lr.x; ps[4 * kThreads] = Lr.y; ps[5 * kThreads] = Lr.z;
                     ps[6 * kThreads] = __int_as_float(depth);
-                    begin_ray();
+                    L.begin(o, d);
                 }
             }
             if (!exhausted) {                                // every idle lane claims the next path id: one atomicAdd per warp
-                const unsigned m_idle = __ballot_sync(FULL, state == IDLE);
+                const unsigned m_idle = __ballot_sync(FULL, L.state == BvhLane::IDLE);
                 if (m_idle) {
                     unsigned int base = 0;
                     const int leader = __ffs((int)m_idle) - 1;
                     if (lane == leader) base = atomicAdd(cursor, (unsigned int)__popc(m_idle));
                     base = __shfl_sync(FULL, base, leader);
-                    if (state == IDLE) {
+                    if (L.state == BvhLane::IDLE) {
                         const unsigned int i = base + (unsigned int)__popc(m_idle & ((1u << lane) - 1u));
                         int px, py;
                         if (i < n_paths && tile_to_pixel(fr, tiles_x, (int)(i % (unsigned int)npad), px, py)) {
@@ -483,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
                             const uint32_t pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
                             const uint32_t sample = s_first + i / (unsigned int)npad;
                             o = fr.cam_pos; d = ray_dir(fr, px, py);
-                            float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
+                            float3 T = f3(0.f, 0.f, 0.f), Lr = f3(0.f, 0.f, 0.f);
                             int depth = 0;
                             bool live = true;
                             if (REUSE) {                     // start from the pixel's cached primary hit (k_primary_cache)
@@ -493,60 +327,31 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
                                 h0.p = f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w);
                                 ++segs;                      // the reused primary segment: delivered, not traced
                                 float3 c;
-                                if (path_ends(sc, fr, h0, d, T, L, 0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
-                                else scatter_segment(sc, fr, h0, pixel, sample, o, d, T, L, depth);
+                                if (path_ends(sc, fr, h0, d, T, Lr, 0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
+                                else scatter_segment(sc, fr, h0, pixel, sample, o, d, T, Lr, depth);
                             }
                             if (live) {
-                                ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = L.x; ps[4 * kThreads] = L.y; ps[5 * kThreads] = L.z;
+                                ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = Lr.x; ps[4 * kThreads] = Lr.y; ps[5 * kThreads] = Lr.z;
                                 ps[6 * kThreads] = __int_as_float(depth); ps[7 * kThreads] = __uint_as_float(pixel); ps[8 * kThreads] = __uint_as_float(sample);
-                                begin_ray();
+                                L.begin(o, d);
                             }
                         }
                     }
                     if (base + (unsigned int)__popc(m_idle) >= n_paths) exhausted = true;       // warp-uniform
                 }
             }
-            if (!__any_sync(FULL, state == ACTIVE)) {
+            if (!__any_sync(FULL, L.state == BvhLane::ACTIVE)) {
                 if (exhausted) break;                        // no traversal in flight, nothing left to claim (DONE lanes were shaded above)
                 continue;                                    // this pass's paths all ended at once (sky pixels): claim more
             }
         }
         // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
         for (;;) {
-            const bool in_node = state == ACTIVE && cur >= 0;
-            if (in_node) {
-                if (COUNT) ++cnt.nodes;
-                const float4 n0 = nodes[4 * cur], n1 = nodes[4 * cur + 1], n2 = nodes[4 * cur + 2];
-                const int2 ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
-                const float ax0 = fmaf(n0.x, ix, ox), bx0 = fmaf(n0.y, ix, ox), ay0 = fmaf(n0.z, iy, oy), by0 = fmaf(n0.w, iy, oy);
-                const float az0 = fmaf(n1.x, iz, oz), bz0 = fmaf(n1.y, iz, oz);
-                const float ax1 = fmaf(n1.z, ix, ox), bx1 = fmaf(n1.w, ix, ox), ay1 = fmaf(n2.x, iy, oy), by1 = fmaf(n2.y, iy, oy);
-                const float az1 = fmaf(n2.z, iz, oz), bz1 = fmaf(n2.w, iz, oz);
-                const float lo0 = fmaxf(fmaxf(fminf(ax0, bx0), fminf(ay0, by0)), fminf(az0, bz0));
-                const float hi0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fmaxf(az0, bz0));
-                const float lo1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fminf(az1, bz1));
-                const float hi1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fmaxf(az1, bz1));
-                const bool h0 = lo0 <= hi0 && hi0 >= 0.f && lo0 <= best_t;
-                const bool h1 = lo1 <= hi1 && hi1 >= 0.f && lo1 <= best_t;
-                if (h0 && h1) {
-                    const bool swap = lo1 < lo0;
-                    stk[sp * stride] = swap ? ch.x : ch.y;
-                    stk_t[sp * stride] = swap ? lo0 : lo1;
-                    ++sp;
-                    cur = swap ? ch.y : ch.x;
-                } else if (h0) cur = ch.x;
-                else if (h1) cur = ch.y;
-                else cur = NONE;
-                settle();
-            }
-            if (__popc(__ballot_sync(FULL, state == ACTIVE && cur >= 0)) < kNodeMin) break;
+            if (L.in_node()) L.node_step<COUNT>(nodes, cnt);
+            if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
-        if (state == ACTIVE) {
-            if (leaf0 != NONE) { test_leaf(leaf0); leaf0 = NONE; }
-            if (cur < 0 && cur != NONE) { test_leaf(cur); cur = NONE; }
-            settle();
-        }
+        if (L.state == BvhLane::ACTIVE) L.leaf_step<COUNT>(sc, tc.sph, tc.box, refs, o, d, cnt);
     }
     // segment counters: delivered [0..1], executed [2..3]; one atomic per warp and counter
     unsigned int tot = segs, tot_tr = traced;

@@ -67,7 +67,7 @@ def test_same_camera_resubmitted_keeps_the_cache(tracer, scenes):
     tracer.set_params(tracer.params)                      # same parameters again
     tracer.render_spp(1)
     t3 = tracer.stats().total_traced_segments
-    assert t2 - t1 < 160 * 120 * 1.2 and abs((t3 - t2) - (t2 - t1)) < 0.1 * (t2 - t1)    # no second primary pass
+    assert t2 - t1 < 160 * 120 * 1.6 and abs((t3 - t2) - (t2 - t1)) < 0.1 * (t2 - t1)    # no second primary pass (it would add 160 * 120)
 
 
 # ---- traversal counters (bytes per segment from node visits and primitive tests) -----------------------
