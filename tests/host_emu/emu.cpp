@@ -6,6 +6,7 @@
 #include "cuda_shim.h"
 #define RTB_HOST_EMULATION 1
 #include "../../software-raytracer_b200/csrc/rt_device.cuh"
+#include "../../software-raytracer_b200/csrc/rt_bvh_lane.cuh"
 #include "../../software-raytracer_b200/csrc/rt_host_pack.h"
 #include "../../software-raytracer_b200/csrc/bvh_build.h"
 #include "../../software-raytracer_b200/csrc/bvh_wide.h"
@@ -214,4 +215,59 @@ int emu_tri_records(const float* pos3, const float* verts, int n_verts, const in
     for (size_t i = 0; i < t.bounds.size(); ++i) bounds6[i] = t.bounds[i];
     return t.count();
 }
+}
+
+
+// The per-lane traversal state machine of the persistent kernels (csrc/rt_bvh_lane.cuh: BvhLane + the sentinel stack) driven on
+// the CPU with a RANDOM schedule of node phases and leaf phases - the device ends a node phase by a warp vote - against the plain
+// per-ray loop closest_hit_bvh() on the same rays. Returns the number of rays whose hit differs in any bit (must be 0);
+// *steps receives the node and leaf steps taken.
+extern "C" int emu_lane_schedules(const rt_object* objects, int n_obj, const float* mverts, int n_mverts, const int32_t* mtris, int n_mtris, int mesh_object,
+                                  const float* org, const float* dir, int n_rays, unsigned seed, int leaf_bias, long long* steps) {
+    std::vector<rt_object> objs(objects, objects + n_obj);
+    std::vector<HostMesh> meshes((size_t)n_obj);
+    if (mesh_object >= 0 && mesh_object < n_obj) {
+        meshes[(size_t)mesh_object].vertices.assign(mverts, mverts + (size_t)3 * n_mverts);
+        meshes[(size_t)mesh_object].indices.assign(mtris, mtris + (size_t)3 * n_mtris);
+    }
+    TriRecords tris;
+    build_tri_records(objs, meshes, tris);
+    std::vector<float4> sph, box, mat; std::vector<int> sph_id, box_id;
+    pack_scene(objs, sph, sph_id, box, box_id, mat);
+    SceneView sc;
+    sc.sph = sph.data(); sc.sph_id = sph_id.data(); sc.box = box.data(); sc.box_id = box_id.data(); sc.mat = mat.data();
+    sc.n_sph = (int)sph_id.size(); sc.n_box = (int)box_id.size(); sc.n_obj = n_obj;
+    sc.tri = reinterpret_cast<const float4*>(tris.rec.data()); sc.tri_obj = tris.obj.data(); sc.n_tri = tris.count();
+    float ext = 0.f;
+    for (int i = 0; i < 3 * n_rays; ++i) ext = fmaxf(ext, fabsf(org[i]));
+    HostBvh bvh;
+    build_bvh(objs, ext, bvh, 4, &tris);
+    if (bvh.max_depth + 2 > 62) return -1;
+    const float4* nodes = reinterpret_cast<const float4*>(bvh.nodes.data());
+    std::vector<int> stack((size_t)bvh.max_depth + 8);
+    unsigned rng = seed * 2654435761u + 12345u;
+    int bad = 0;
+    long long n_node = 0, n_leaf = 0;
+    BvhLane L;
+    L.init(nullptr);
+    for (int i = 0; i < n_rays; ++i) {
+        const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        const Hit want = closest_hit_bvh(sc, sc.sph, sc.box, nodes, bvh.refs.data(), stack.data(), 1, o, d);
+        TravCount cnt = {0u, 0u, 0u, 0u};
+        L.begin(o, d);                                       // the stack must be empty again after every traversal
+        while (L.state == BvhLane::ACTIVE) {                 // one warp iteration: a node phase of at least one step, then the leaf phase
+            for (;;) {
+                if (L.in_node()) { L.node_step<true>(nodes, cnt); ++n_node; }
+                rng = rng * 1664525u + 1013904223u;
+                // leaf_bias 0: the node phase runs until the lane has no inner node left; 8: one node step per leaf phase
+                if (!L.in_node() || (int)((rng >> 16) % 8u) < leaf_bias) break;
+            }
+            if (L.state == BvhLane::ACTIVE) { L.leaf_step<true>(sc, sc.sph, sc.box, bvh.refs.data(), o, d, cnt); ++n_leaf; }
+        }
+        if (L.state != BvhLane::DONE || L.ls.sp != LaneStack::kEntry) { ++bad; L.init(nullptr); continue; }
+        const Hit got = L.finish(sc.sph, o, d);
+        if (got.id != want.id || memcmp(&got.t, &want.t, 4) || memcmp(&got.n, &want.n, 12) || memcmp(&got.p, &want.p, 12)) ++bad;
+    }
+    if (steps) { steps[0] = n_node; steps[1] = n_leaf; }
+    return bad;
 }

@@ -17,15 +17,22 @@ EMU_DIR = os.path.join(ROOT, "tests", "host_emu")
 EMU_SO = os.path.join(EMU_DIR, "libemu.so")
 
 
-@pytest.fixture(scope="session")
-def emu():
+def build_emu():
+    """g++ build of the device code for the host (tests/host_emu/emu.cpp + the host builders); returns the library path."""
     srcs = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(ROOT, "software-raytracer_b200", "csrc", "bvh_build.cpp"),
             os.path.join(ROOT, "software-raytracer_b200", "csrc", "bvh_wide.cpp"),
             os.path.join(ROOT, "software-raytracer_b200", "csrc", "flat_build.cpp"),
             os.path.join(ROOT, "software-raytracer_b200", "csrc", "mesh.cpp")]
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + os.path.join(ROOT, "include"),
-                           "-o", EMU_SO] + srcs)
-    lib = C.CDLL(EMU_SO)
+    hdrs = [os.path.join(ROOT, "software-raytracer_b200", "csrc", f) for f in ("rt_device.cuh", "rt_bvh_lane.cuh")]
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(f) > os.path.getmtime(EMU_SO) for f in srcs + hdrs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + os.path.join(ROOT, "include"),
+                               "-o", EMU_SO] + srcs)
+    return EMU_SO
+
+
+@pytest.fixture(scope="session")
+def emu():
+    lib = C.CDLL(build_emu())
     lib.emu_render.restype = C.c_longlong
     lib.emu_render_mesh.restype = C.c_longlong
 
@@ -169,3 +176,35 @@ def test_wide_bvh_makes_about_half_the_node_visits(emu):
     assert sa == sb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert b2_visits > 0 and 0.3 * b2_visits < w_visits < 0.6 * b2_visits, (b2_visits, w_visits)
     assert w_prims < 2.0 * b2_prims, (b2_prims, w_prims)
+
+
+@pytest.mark.parametrize("leaf_bias", [0, 2, 8])
+def test_lane_state_machine_equals_the_per_ray_loop_under_random_schedules(emu, leaf_bias):
+    """csrc/rt_bvh_lane.cuh (the traversal state machine of k_wf_intersect_bvh and k_wf_stream with its sentinel stack), compiled
+    for the host: whatever the interleaving of node steps and postponed leaf steps, the hit is closest_hit_bvh()'s bit for bit
+    and the stack is back at its sentinel. Spheres + cubes + a triangle mesh, origins inside and outside the scene."""
+    from rtb200.scenes import synthetic_spheres, heightfield_mesh, mesh_scene
+    lib = C.CDLL(EMU_SO)
+    lib.emu_lane_schedules.restype = C.c_int
+    rng = np.random.default_rng(31 + leaf_bias)
+    n = 1500
+    cases = []
+    o = synthetic_spheres(700, seed=9, cubes_every=7)
+    org = rng.uniform([-60, -2, -10], [60, 25, 115], (n, 3)).astype(np.float32)
+    cases.append((o, None, org))
+    v, tr = heightfield_mesh(40, 24, seed=6)
+    cases.append((mesh_scene(), (v, tr), rng.uniform([-9, -2.5, -1], [9, 5, 12], (n, 3)).astype(np.float32)))
+    for objs, mesh, org in cases:
+        d = rng.normal(size=(n, 3))
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        d[::50, 0] = 0; d[::50] /= np.linalg.norm(d[::50], axis=1, keepdims=True)       # exactly-zero direction components
+        d = d.astype(np.float32)
+        objs = np.ascontiguousarray(objs, rtb200.OBJECT_DTYPE)
+        steps = (C.c_longlong * 2)()
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        mv = np.ascontiguousarray(mesh[0], np.float32) if mesh else None
+        mt = np.ascontiguousarray(mesh[1], np.int32) if mesh else None
+        bad = lib.emu_lane_schedules(p(objs), len(objs), p(mv), len(mv) if mesh else 0, p(mt), len(mt) if mesh else 0, 0 if mesh else -1,
+                                     p(org), p(d), n, 77 + leaf_bias, leaf_bias, steps)
+        assert bad == 0, (leaf_bias, bad)
+        assert steps[0] > 2 * n and steps[1] > n / 4

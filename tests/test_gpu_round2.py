@@ -74,13 +74,8 @@ def test_same_camera_resubmitted_keeps_the_cache(tracer, scenes):
 def test_traversal_counters_equal_the_host_emulation(tracer):
     """The counting instantiation of the per-ray BVH loop must visit exactly the nodes and test exactly the primitives the
     same code does when compiled for the host (tests/host_emu), where the counters were first defined."""
-    from test_device_logic_cpu import EMU_DIR, EMU_SO
-    srcs = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(ROOT, "software-raytracer_b200", "csrc", f)
-                                                  for f in ("bvh_build.cpp", "bvh_wide.cpp", "flat_build.cpp", "mesh.cpp")]
-    if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-DRTB_HOST_EMULATION", "-I", EMU_DIR,
-                               "-o", EMU_SO] + srcs)
-    lib = C.CDLL(EMU_SO)
+    from test_device_logic_cpu import build_emu
+    lib = C.CDLL(build_emu())
     lib.emu_render.restype = C.c_longlong
     objs = synthetic_spheres(300, seed=4, cubes_every=11)
     w, h, n = 96, 64, 3
