@@ -502,8 +502,8 @@ def test_flat_accel_hit_for_hit_bundled(tracer, scenes, golden, meta, scene):
             assert np.array_equal(bits(v[0]), bits(base[0])), k              # same bits
             assert v[1] == base[1], k                                        # same path segments delivered
             if k[1]:
-                # reuse: one primary query per pixel per launch (2 launches), plus every secondary segment
-                assert v[2] == base[1] - 160 * 120 * 16 + 2 * 160 * 120, k
+                # reuse: one primary query per pixel for BOTH launches (the per-pixel cache persists), plus every secondary segment
+                assert v[2] == base[1] - 160 * 120 * 16 + 160 * 120, k
     finally:
         tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
         tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 1)
