@@ -87,11 +87,29 @@ struct BvhLane {
         if (cur < 0 && cur != NONE && leaf0 == NONE) { leaf0 = cur; cur = ls.pop(best_t); }
         if (cur == NONE && leaf0 == NONE) state = DONE;
     }
-    template <bool COUNT>
+    // GLOBAL_NODES: the node array lives in global memory (not staged into shared memory): the 64-byte node is fetched with TWO
+    // 256-bit loads (LDG.E.ENL2.256, sm_100) instead of three 128-bit and one 64-bit load. The lanes of a warp sit in different
+    // nodes, so every load instruction costs one L1 wavefront PER LANE whatever its width - and ncu shows the L1 data pipe at
+    // 94 % on the 10 000-sphere scene with four loads per visit (profiles/r2c_summary_stream_c3.txt).
+    template <bool COUNT, bool GLOBAL_NODES = false>
     __device__ __forceinline__ void node_step(const float4* __restrict__ nodes, TravCount& cnt) {   // requires in_node()
         if (COUNT) ++cnt.nodes;
-        const float4 n0 = nodes[4 * cur], n1 = nodes[4 * cur + 1], n2 = nodes[4 * cur + 2];
-        const int2 ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
+        float4 n0, n1, n2;
+        int2 ch;
+#ifndef RTB_HOST_EMULATION
+        if (GLOBAL_NODES) {
+            const float4* np = nodes + 4 * cur;
+            float pad0, pad1;
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(np));
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=r"(ch.x), "=r"(ch.y), "=f"(pad0), "=f"(pad1) : "l"(np + 2));
+        } else
+#endif
+        {
+            n0 = nodes[4 * cur]; n1 = nodes[4 * cur + 1]; n2 = nodes[4 * cur + 2];
+            ch = *reinterpret_cast<const int2*>(nodes + 4 * cur + 3);
+        }
         const float ax0 = fmaf(n0.x, ix, ox), bx0 = fmaf(n0.y, ix, ox), ay0 = fmaf(n0.z, iy, oy), by0 = fmaf(n0.w, iy, oy);
         const float az0 = fmaf(n1.x, iz, oz), bz0 = fmaf(n1.y, iz, oz);
         const float ax1 = fmaf(n1.z, ix, ox), bx1 = fmaf(n1.w, ix, ox), ay1 = fmaf(n2.x, iy, oy), by1 = fmaf(n2.y, iy, oy);

@@ -108,7 +108,7 @@ struct rt_ctx {
     float last_render_ms = 0.f, last_resolve_ms = 0.f;
     bool render_timed = false, resolve_timed = false;
 };
-constexpr int kCounters = 16;
+constexpr int kCounters = 32;      // the autotuners use d_counters + 4 as a scratch block of the same layout (rt_kernels.h kTileCursorSlot)
 
 
 // helpers of rt_capi.cu that rt_group.cu uses

@@ -213,25 +213,25 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
 // ---- few samples per pixel: warp-level pixel pool -------------------------------------------------------------
 // With one lane per pixel a launch of n samples keeps a warp busy for the LONGEST of its 32 pixels' work; for large
 // n that averages out (29.8 of 32 lanes alive at 1024 spp), but an interactive 1-spp frame runs ~4.5 warp iterations
-// for 2.1 segments per path. Here a warp owns `pool_tiles` consecutive 8x4 pixel tiles and its lanes pull PIXELS
-// from that pool (one ballot + popcount, no atomics): a lane that finishes a pixel's n samples starts the next
+// for 2.1 segments per path. Here the grid is PERSISTENT (one wave of CTAs): a warp claims chunks of `pool_tiles` consecutive
+// 8x4 pixel tiles from one cursor per launch (one atomicAdd per chunk, requested ahead of time) and its lanes pull PIXELS
+// from the current chunk (one ballot + popcount): a lane that finishes a pixel's n samples starts the next
 // pixel at once. One pixel is still traced by one lane, samples in order, one write: the same bits as k_render_regen.
 template <int MODE, bool REUSE>
 __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
                                                            uint32_t s_begin, int n_samples, int pool_tiles, PrimCache prim,
-                                                           unsigned long long* __restrict__ seg_counter) {
+                                                           unsigned int* __restrict__ tile_cursor, unsigned long long* __restrict__ seg_counter) {
     extern __shared__ float4 smem[];
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int tiles_x = (fr.width + 7) / 8, tiles_y = (fr.height + 3) / 4;
-    const long long warp_id = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const long long tile0 = warp_id * pool_tiles;
-    const long long n_tiles = (long long)tiles_x * tiles_y;
-    long long rem = n_tiles - tile0;
-    const int total = rem <= 0 ? 0 : (int)(rem < pool_tiles ? rem : pool_tiles) * 32;     // pool entries (some outside the image)
-    int next = 0;                                                                           // warp-uniform
-
+    const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    // the warp's current chunk of `pool_tiles` tiles, claimed from the launch's cursor; the NEXT chunk is requested as soon as
+    // the current one is half handed out, so the atomic's round trip overlaps the tracing (its result is first read when needed)
+    unsigned int tile0 = 0, claimed = 0;                                                    // warp-uniform
+    int next = 0, total = 0;
+    bool have_claim = false, drained = false;
     bool busy = false;
     uint32_t pixel = 0;
     float3 d0 = f3(0.f, 0.f, 1.f), acc = f3(0.f, 0.f, 0.f), o = fr.cam_pos, d = d0;
@@ -243,12 +243,23 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
 
     for (;;) {
         const unsigned m_need = __ballot_sync(FULL, !busy);
+        if (!have_claim && !drained && 2 * next >= total) {  // ask for the next chunk early
+            if (lane == 0) claimed = atomicAdd(tile_cursor, (unsigned int)pool_tiles);
+            have_claim = true;
+        }
+        if (m_need != 0u && next >= total && have_claim) {   // the current chunk is handed out: switch to the claimed one
+            tile0 = __shfl_sync(FULL, claimed, 0);
+            have_claim = false;
+            if (tile0 >= n_tiles) { drained = true; total = 0; }
+            else { const unsigned int rem = n_tiles - tile0; total = (int)(rem < (unsigned int)pool_tiles ? rem : (unsigned int)pool_tiles) * 32; }
+            next = 0;
+        }
         if (m_need != 0u && next < total) {
             const int idx = next + __popc(m_need & ((1u << lane) - 1u));
             next += __popc(m_need);
             if (!busy && idx < total) {
-                const long long tile = tile0 + (idx >> 5);
-                const int px = (int)(tile % tiles_x) * 8 + (idx & 7), py = (int)(tile / tiles_x) * 4 + ((idx & 31) >> 3);
+                const unsigned int tile = tile0 + (unsigned int)(idx >> 5);
+                const int px = (int)(tile % (unsigned int)tiles_x) * 8 + (idx & 7), py = (int)(tile / (unsigned int)tiles_x) * 4 + ((idx & 31) >> 3);
                 if (px < fr.width && py < fr.height) {
                     pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
                     d0 = ray_dir(fr, px, py);
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
                 }
             }
         }
-        if (!__any_sync(FULL, busy)) { if (next >= total) break; else continue; }
+        if (!__any_sync(FULL, busy)) { if (drained) break; else continue; }     // not drained: the next pass switches to the claimed chunk
         Hit h = trace_all<MODE>(sc, tc, o, d, busy);
         if (busy) {
             ++segs; ++traced;
@@ -836,10 +847,17 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
     // the pooled flat traversal pays from ~16 spp per launch on; short launches (the pixel pool's) run the per-lane form
     size_t sb; const int mode = pick_mode(sc, ac, sb, kThreads, flat_coop && pool_tiles < 2 && n_samples >= 16);
     if (pool_tiles >= 2) {
+        // persistent grid: at most one resident wave of CTAs; the warps claim tiles until the image is handed out
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long n_tiles = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
-        const long long warps = (n_tiles + pool_tiles - 1) / pool_tiles;
-        const unsigned int blocks = (unsigned int)((warps + kThreads / 32 - 1) / (kThreads / 32));
-        RTB_DISPATCH2(mode, reuse_primary, k_render_pool, blocks, sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, prim, seg_counter)
+        const long long chunks = (n_tiles + pool_tiles - 1) / pool_tiles;
+        long long blocks = (chunks + kThreads / 32 - 1) / (kThreads / 32);
+        if (blocks > (long long)sms * RTB_REGEN_MIN_BLOCKS) blocks = (long long)sms * RTB_REGEN_MIN_BLOCKS;
+        unsigned int* cursor = reinterpret_cast<unsigned int*>(seg_counter + kTileCursorSlot);
+        if ((e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st)) != cudaSuccess) return e;
+        RTB_DISPATCH2(mode, reuse_primary, k_render_pool, (unsigned int)blocks, sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, prim, cursor, seg_counter)
         return cudaGetLastError();
     }
     if (count_traversal && (mode == 2 || mode == 3) && !ac.bvh.wnodes) {

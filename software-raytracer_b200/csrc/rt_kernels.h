@@ -22,6 +22,10 @@ constexpr size_t kMaxStagedBytes = 128 * 1024;
 constexpr size_t kMaxBvhStagedBytes = 48 * 1024;
 
 
+// Layout of the counter block the render launchers get (rt_ctx::d_counters, or an offset into it for the autotuner's scratch):
+// [0..3] segment counters, [8..12] traversal statistics, [kTileCursorSlot] the tile cursor of the pixel-pool kernel.
+constexpr int kTileCursorSlot = 13;
+
 struct PeerPtrs { const float4* p[16]; };      // every rank's accumulation buffer, rank order (RT_MAX_PEERS)
 
 // Per-pixel primary-hit cache of a context (RT_OPT_PRIMARY_REUSE): (normal, t) and object id (-1 = miss) per pixel, y-up row-major.

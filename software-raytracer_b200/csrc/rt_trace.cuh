@@ -101,7 +101,7 @@ template <int MODE, bool COUNT = false>
 __device__ __forceinline__ Hit trace(const SceneView& sc, const TraceCtx& t, float3 o, float3 d, TravCount* tcnt = nullptr) {
     if (MODE == 4 || MODE == 5) return closest_hit_flat(sc, t.fl, t.sph, t.box, t.q, t.stride, o, d);
     if (MODE == 3 && t.wnodes) return closest_hit_bvh8(sc, t.sph, t.box, t.wnodes, t.wrefs, t.stack, t.stride, t.wentries, t.k47, o, d);
-    if (MODE >= 2) return closest_hit_bvh<COUNT>(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr, tcnt);
+    if (MODE >= 2) return closest_hit_bvh<COUNT, MODE == 3>(sc, t.sph, t.box, t.nodes, t.refs, t.stack, t.stride, o, d, (RTB_BVH_POP_CULL && MODE == 3) ? t.stack_t : nullptr, tcnt);
     return closest_hit(sc, t.sph, t.box, o, d);
 }
 

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
         }
         // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
         for (;;) {
-            if (L.in_node()) L.node_step<COUNT>(nodes, cnt);
+            if (L.in_node()) L.node_step<COUNT, MODE == 3>(nodes, cnt);
             if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
         }
         // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
         for (;;) {
-            if (L.in_node()) L.node_step<COUNT>(nodes, cnt);
+            if (L.in_node()) L.node_step<COUNT, MODE == 3>(nodes, cnt);
             if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------

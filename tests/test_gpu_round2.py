@@ -236,7 +236,7 @@ def test_mesh_against_float64_moller_trumbore(tracer):
 
 # ---- option validation ---------------------------------------------------------------------------
 def test_set_option_rejects_out_of_range_values(tracer):
-    bad = [(rtb200.RT_OPT_ACCEL, 7), (rtb200.RT_OPT_ACCEL, -1), (rtb200.RT_OPT_PIPELINE, 3), (rtb200.RT_OPT_BVH_THRESHOLD, 0),
+    bad = [(rtb200.RT_OPT_ACCEL, 7), (rtb200.RT_OPT_ACCEL, -1), (rtb200.RT_OPT_PIPELINE, 4), (rtb200.RT_OPT_BVH_THRESHOLD, 0),
            (rtb200.RT_OPT_BVH_LEAF, 0), (rtb200.RT_OPT_BVH_LEAF, 200), (rtb200.RT_OPT_WF_REFILL, 0), (rtb200.RT_OPT_WF_NODE_MIN, 33),
            (rtb200.RT_OPT_WF_WAVE_MPATHS, -5), (rtb200.RT_OPT_BVH_WIDE, 3), (rtb200.RT_OPT_FLAT_COOP, 9), (rtb200.RT_OPT_POOL_TILES, 99),
            (rtb200.RT_OPT_BVH_SCHED, 2), (99, 0)]
