@@ -261,4 +261,33 @@ void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostB
     out.nodes.swap(t.nodes); out.refs.swap(t.refs); out.max_depth = t.max_depth;
 }
 
+void build_leaf_slots(const HostBvh& bvh, const float* sph4, const int* sph_id, const float* box4, const int* box_id,
+                      const TriRecords* tris, std::vector<float>& slots) {
+    slots.assign(bvh.refs.size() * 16, 0.f);
+    auto put_int = [](float* dst, int32_t v) { memcpy(dst, &v, 4); };
+    for (size_t j = 0; j < bvh.refs.size(); ++j) {
+        float* w = slots.data() + 16 * j;
+        const int32_t r = bvh.refs[j];
+        put_int(w + 4, r);
+        if (r >= kTriRefBase) {
+            const size_t k = (size_t)(r - kTriRefBase);
+            const float* t = tris->rec.data() + 12 * k;
+            w[0] = t[0]; w[1] = t[1]; w[2] = t[2]; w[3] = t[3];
+            put_int(w + 5, tris->obj[k]);
+            w[6] = t[4]; w[7] = t[5];
+            for (int q = 0; q < 6; ++q) w[8 + q] = t[6 + q];
+        } else if (r >= 0) {
+            const float* sp = sph4 + 4 * (size_t)r;
+            w[0] = sp[0]; w[1] = sp[1]; w[2] = sp[2]; w[3] = sp[3];
+            put_int(w + 5, sph_id[r]);
+        } else {
+            const size_t c = (size_t)(~r);
+            const float* bp = box4 + 8 * c;                  // (px, py, pz, 0) (hx, hy, hz, 0)
+            w[0] = bp[0]; w[1] = bp[1]; w[2] = bp[2]; w[3] = bp[4];
+            put_int(w + 5, box_id[c]);
+            w[6] = bp[5]; w[7] = bp[6];
+        }
+    }
+}
+
 }  // namespace rtb

@@ -55,4 +55,17 @@ constexpr int kMaxBvhDepth = 40;     // traversal stack entries per thread
 void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostBvh& out, int max_leaf = 4,
                const TriRecords* tris = nullptr, float origin_offset = 0.f, int threads = 0);   // origin_offset: |rt_params.eps|
 
+// Leaf-ordered primitive SLOTS for BVHs traversed from global memory: one 64-byte record per leaf reference, in `refs` order,
+// so that a leaf test is a load at (first + i) instead of refs[first + i] -> geometry array -> id array (two dependent scattered
+// loads per primitive, three for the id of a hit). 16 words per slot:
+//   w0..w3  sphere (cx, cy, cz, r^2) | cube (px, py, pz, hx) | triangle (n.xyz, dn)
+//   w4      the leaf reference itself (>= 0 sphere slot, < 0 ~cube slot, >= kTriRefBase triangle): type tag + tie-break key
+//   w5      object id
+//   w6, w7  cube (hy, hz) | triangle (m1.x, m1.y)
+//   w8..w13 triangle (m1.z, k1, m2.x, m2.y, m2.z, k2)          (second half: only triangles read it)
+// Spheres and cubes are decided by ONE 256-bit load, triangles by two. The values are the same floats the unordered arrays hold,
+// so hits are bit-identical. sph / box: the packed geometry lists of pack_scene() (rt_host_pack.h), ids likewise.
+void build_leaf_slots(const HostBvh& bvh, const float* sph4, const int* sph_id, const float* box4, const int* box_id,
+                      const TriRecords* tris, std::vector<float>& slots);
+
 }  // namespace rtb

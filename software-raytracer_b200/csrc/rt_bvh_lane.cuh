@@ -129,11 +129,54 @@ struct BvhLane {
         else cur = NONE;
         settle();
     }
+    // 32 bytes of a leaf slot (bvh_build.h build_leaf_slots): one 256-bit load
+    __device__ __forceinline__ static void load_half_slot(const float4* p, float4& a, float4& b) {
+#ifdef RTB_HOST_EMULATION
+        a = p[0]; b = p[1];
+#else
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#endif
+    }
+    // slots != nullptr: the leaf's primitives come from the leaf-ordered 64-byte slots (one 256-bit load decides a sphere or a
+    // cube, two a triangle; the reference key and the object id ride along) instead of refs[] -> geometry array -> id array.
+    // Same floats, same tests, same tie rule.
     template <bool COUNT>
     __device__ __forceinline__ void test_leaf(const SceneView& sc, const float4* __restrict__ sph, const float4* __restrict__ box,
-                                              const int* __restrict__ refs, int link, float3 o, float3 d, TravCount& cnt) {
+                                              const int* __restrict__ refs, const float4* __restrict__ slots, int link, float3 o, float3 d,
+                                              TravCount& cnt) {
         const unsigned int v = (unsigned int)(~link);
         const int first = (int)(v & 0xffffffu), n_refs = (int)(v >> 24);
+        if (slots) {
+            for (int i = 0; i < n_refs; ++i) {
+                const float4* sp = slots + 4 * (size_t)(first + i);
+                float4 a, b;
+                load_half_slot(sp, a, b);
+                const int r = __float_as_int(b.x), oid = __float_as_int(b.y);
+                if (COUNT) { if (r >= kTriRef) ++cnt.tri; else if (r >= 0) ++cnt.sph; else ++cnt.box; }
+                if (r >= kTriRef) {
+                    float4 c2, d2;
+                    load_half_slot(sp + 2, c2, d2);
+                    float t; float3 nrm;
+                    if (tri_hit(a, make_float4(b.z, b.w, c2.x, c2.y), make_float4(c2.z, c2.w, d2.x, d2.y), o, d, t, nrm)) {
+                        if (t < best_t || (t == best_t && (oid < best_id || (oid == best_id && r < best_ref)))) {
+                            best_t = t; best_id = oid; best_ref = r; bn = nrm; have = true;
+                        }
+                    }
+                } else if (r >= 0) {
+                    float t;
+                    if (sphere_t(a, o, d, t)) {
+                        if (t < best_t || (t == best_t && oid < best_id)) { best_t = t; best_id = oid; best_ref = r; have = true; }
+                    }
+                } else {
+                    float dist; float3 nrm;
+                    if (box_hit(make_float4(a.x, a.y, a.z, 0.f), make_float4(a.w, b.z, b.w, 0.f), o, d, dist, nrm)) {
+                        if (dist < best_t || (dist == best_t && oid < best_id)) { best_t = dist; best_id = oid; best_ref = r; bn = nrm; have = true; }
+                    }
+                }
+            }
+            return;
+        }
         for (int i = 0; i < n_refs; ++i) {
             const int r = refs[first + i];
             if (COUNT) { if (r >= kTriRef) ++cnt.tri; else if (r >= 0) ++cnt.sph; else ++cnt.box; }
@@ -164,9 +207,10 @@ struct BvhLane {
     }
     template <bool COUNT>
     __device__ __forceinline__ void leaf_step(const SceneView& sc, const float4* __restrict__ sph, const float4* __restrict__ box,
-                                              const int* __restrict__ refs, float3 o, float3 d, TravCount& cnt) {   // requires state == ACTIVE
-        if (leaf0 != NONE) { test_leaf<COUNT>(sc, sph, box, refs, leaf0, o, d, cnt); leaf0 = NONE; }
-        if (cur < 0 && cur != NONE) { test_leaf<COUNT>(sc, sph, box, refs, cur, o, d, cnt); cur = NONE; }
+                                              const int* __restrict__ refs, const float4* __restrict__ slots, float3 o, float3 d,
+                                              TravCount& cnt) {                                    // requires state == ACTIVE
+        if (leaf0 != NONE) { test_leaf<COUNT>(sc, sph, box, refs, slots, leaf0, o, d, cnt); leaf0 = NONE; }
+        if (cur < 0 && cur != NONE) { test_leaf<COUNT>(sc, sph, box, refs, slots, cur, o, d, cnt); cur = NONE; }
         settle();
     }
     // the closest hit as closest_hit_bvh() reports it

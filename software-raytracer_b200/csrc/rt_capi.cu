@@ -144,6 +144,22 @@ int ensure_bvh(rt_ctx* c, float origin_extent) {
         if (!c->wide.refs.empty())
             RT_CUDA(c, cudaMemcpyAsync(c->d_wide_refs, c->wide.refs.data(), c->wide.refs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     }
+    // leaf-ordered primitive slots for BVHs that are traversed from global memory (rt_trace.cuh pick_mode: MODE 3)
+    c->bview.slots = nullptr;
+    {
+        std::vector<float4> sph, box, mat; std::vector<int> sph_id, box_id;
+        pack_scene(c->scene.objects, sph, sph_id, box, box_id, mat);
+        const size_t staged = ((size_t)2 * (c->bvh.max_depth + 2) * 128 * sizeof(int)) + (sph.size() + box.size()) * sizeof(float4) +
+                              c->bvh.nodes.size() * 64 + c->bvh.refs.size() * 4 + 16;
+        if (staged > kMaxBvhStagedBytes && !c->wide.usable && !c->bvh.refs.empty()) {
+            std::vector<float> slots;
+            build_leaf_slots(c->bvh, reinterpret_cast<const float*>(sph.data()), sph_id.data(), reinterpret_cast<const float*>(box.data()), box_id.data(), &c->tris, slots);
+            RT_CUDA(c, ensure_capacity(c->d_bvh_slots, c->cap_bvh_slots, slots.size() / 4));
+            RT_CUDA(c, cudaMemcpyAsync(c->d_bvh_slots, slots.data(), slots.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            RT_CUDA(c, cudaStreamSynchronize(c->stream));     // the host vector dies here
+            c->bview.slots = c->d_bvh_slots;
+        }
+    }
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->bview.nodes = c->d_bvh_nodes; c->bview.refs = c->d_bvh_refs;
     c->bview.n_nodes = (int)c->bvh.nodes.size(); c->bview.n_refs = (int)c->bvh.refs.size();
@@ -488,7 +504,7 @@ int rt_destroy(rt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
-    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_wide_nodes); cudaFree(c->d_wide_refs); cudaFree(c->d_tune);
+    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_bvh_slots); cudaFree(c->d_wide_nodes); cudaFree(c->d_wide_refs); cudaFree(c->d_tune);
     cudaFree(c->d_tri); cudaFree(c->d_tri_obj); cudaFree(c->d_prim_nt); cudaFree(c->d_prim_id); cudaFree(c->d_flags);
     wavefront_destroy(c->wf);
     cudaFree(c->d_flat_boxes); cudaFree(c->d_flat_cull); cudaFree(c->d_flat_slots); cudaFree(c->d_flat_ids);

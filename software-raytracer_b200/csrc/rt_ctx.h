@@ -58,7 +58,8 @@ struct rt_ctx {
     HostBvh bvh;
     BvhView bview;
     float4* d_bvh_nodes = nullptr; int* d_bvh_refs = nullptr;
-    size_t cap_bvh_nodes = 0, cap_bvh_refs = 0;
+    float4* d_bvh_slots = nullptr;     // leaf-ordered primitive slots (BVHs too large to stage in shared memory)
+    size_t cap_bvh_nodes = 0, cap_bvh_refs = 0, cap_bvh_slots = 0;
     HostWideBvh wide;                  // 8-wide quantised form for BVHs read from global memory (bvh_wide.h)
     uint4* d_wide_nodes = nullptr; int* d_wide_refs = nullptr;
     size_t cap_wide_nodes = 0, cap_wide_refs = 0;

@@ -834,16 +834,15 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
     prim.nt = prim_cache ? prim_cache->nt : nullptr; prim.id = prim_cache ? prim_cache->id : nullptr;
     cudaError_t e = ensure_smem_optin();
     if (e != cudaSuccess) return e;
-    // few samples per launch: lanes pull pixels from a warp-level pool (k_render_pool); many: one pixel per lane.
-    // Measured (scratch/pool_sweep.py, Scene1): pools pay while the grid still has several waves of warps - 2 tiles at
-    // 1 spp (720p 0.205 -> 0.181 ms), 4 tiles at 1080p (0.427 -> 0.329 ms), 2 tiles up to 4 spp at 1080p; larger pools
-    // lose to the imbalance between warps, and from 16 spp on one pixel per lane is as good.
+    // few samples per launch: lanes pull pixels from chunks of tiles claimed by their warp (k_render_pool); many: one pixel per lane.
+    // Measured on B200 (scratch/pool_sweep.py, Scene1, persistent grid + primary-hit cache): 1 spp 720p 0.174 (one pixel per lane) ->
+    // 0.158 ms with chunks of 2 tiles, 1080p 0.364 -> 0.257 ms; 2 spp pays at 1080p only (0.549 -> 0.514 ms); from 4 spp on one pixel
+    // per lane wins, and larger chunks lose to the imbalance between warps at the end of the launch (8 tiles: 0.295 ms at 720p).
     const long long n_tiles_all = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
     int pool_tiles = 1;
     if (count_traversal) pool_override = 1;                   // the counting instantiations exist for the one-pixel-per-lane kernel only
     if (pool_override > 0) pool_tiles = pool_override > 32 ? 32 : pool_override;
-    else if (n_samples == 1) pool_tiles = n_tiles_all >= 50000 ? 4 : 2;
-    else if (n_samples <= 4 && n_tiles_all >= 50000) pool_tiles = 2;
+    else if (n_samples == 1 || (n_samples == 2 && n_tiles_all >= 50000)) pool_tiles = 2;
     // the pooled flat traversal pays from ~16 spp per launch on; short launches (the pixel pool's) run the per-lane form
     size_t sb; const int mode = pick_mode(sc, ac, sb, kThreads, flat_coop && pool_tiles < 2 && n_samples >= 16);
     if (pool_tiles >= 2) {

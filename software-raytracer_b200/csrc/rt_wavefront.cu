@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
             if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
-        if (L.state == BvhLane::ACTIVE) L.leaf_step<COUNT>(sc, tc.sph, tc.box, refs, o, d, cnt);
+        if (L.state == BvhLane::ACTIVE) L.leaf_step<COUNT>(sc, tc.sph, tc.box, refs, MODE == 3 ? bv.slots : nullptr, o, d, cnt);
     }
     if (COUNT) flush_trav_count(cnt, n_queries, counters);
 }
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
             if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
-        if (L.state == BvhLane::ACTIVE) L.leaf_step<COUNT>(sc, tc.sph, tc.box, refs, o, d, cnt);
+        if (L.state == BvhLane::ACTIVE) L.leaf_step<COUNT>(sc, tc.sph, tc.box, refs, MODE == 3 ? bv.slots : nullptr, o, d, cnt);
     }
     // segment counters: delivered [0..1], executed [2..3]; one atomic per warp and counter
     unsigned int tot = segs, tot_tr = traced;

@@ -25,6 +25,7 @@ static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 // PRMT: nibble k of s selects result byte k from the 8 bytes of (y:x); bit 3 of the nibble replicates the byte's sign bit
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
     const uint64_t src = ((uint64_t)y << 32) | x;

@@ -223,7 +223,7 @@ int emu_tri_records(const float* pos3, const float* verts, int n_verts, const in
 // per-ray loop closest_hit_bvh() on the same rays. Returns the number of rays whose hit differs in any bit (must be 0);
 // *steps receives the node and leaf steps taken.
 extern "C" int emu_lane_schedules(const rt_object* objects, int n_obj, const float* mverts, int n_mverts, const int32_t* mtris, int n_mtris, int mesh_object,
-                                  const float* org, const float* dir, int n_rays, unsigned seed, int leaf_bias, long long* steps) {
+                                  const float* org, const float* dir, int n_rays, unsigned seed, int leaf_bias, int use_slots, long long* steps) {
     std::vector<rt_object> objs(objects, objects + n_obj);
     std::vector<HostMesh> meshes((size_t)n_obj);
     if (mesh_object >= 0 && mesh_object < n_obj) {
@@ -245,6 +245,9 @@ extern "C" int emu_lane_schedules(const rt_object* objects, int n_obj, const flo
     if (bvh.max_depth + 2 > 62) return -1;
     const float4* nodes = reinterpret_cast<const float4*>(bvh.nodes.data());
     std::vector<int> stack((size_t)bvh.max_depth + 8);
+    std::vector<float> slots;                                // leaf-ordered primitive slots (bvh_build.h), what MODE 3 kernels read
+    if (use_slots) build_leaf_slots(bvh, reinterpret_cast<const float*>(sph.data()), sph_id.data(), reinterpret_cast<const float*>(box.data()), box_id.data(), &tris, slots);
+    const float4* slot4 = use_slots ? reinterpret_cast<const float4*>(slots.data()) : nullptr;
     unsigned rng = seed * 2654435761u + 12345u;
     int bad = 0;
     long long n_node = 0, n_leaf = 0;
@@ -262,7 +265,7 @@ extern "C" int emu_lane_schedules(const rt_object* objects, int n_obj, const flo
                 // leaf_bias 0: the node phase runs until the lane has no inner node left; 8: one node step per leaf phase
                 if (!L.in_node() || (int)((rng >> 16) % 8u) < leaf_bias) break;
             }
-            if (L.state == BvhLane::ACTIVE) { L.leaf_step<true>(sc, sc.sph, sc.box, bvh.refs.data(), o, d, cnt); ++n_leaf; }
+            if (L.state == BvhLane::ACTIVE) { L.leaf_step<true>(sc, sc.sph, sc.box, bvh.refs.data(), slot4, o, d, cnt); ++n_leaf; }
         }
         if (L.state != BvhLane::DONE || L.ls.sp != LaneStack::kEntry) { ++bad; L.init(nullptr); continue; }
         const Hit got = L.finish(sc.sph, o, d);
