@@ -317,7 +317,7 @@ int rt_read_surface(rt_ctx* ctx, uint32_t* host_out, int pitch_bytes);
  *   3. the last CTA signals "my slice is written and I have finished reading your buffers" to every peer;
  *   4. a one-warp kernel waits until every rank has sent that, so whatever is enqueued next on the stream - rank 0's
  *      rt_read_surface, any rank's next rt_reset_accumulation - is ordered after the whole exchange.
- * Epochs only grow, nothing is reset. A wait gives up after ~4 s (a peer died) and the next rt_sync / rt_read_surface
+ * Epochs only grow, nothing is reset. Every rank needs its OWN device (the ranks wait for each other inside kernels). A wait gives up after ~4 s (a peer died) and the next rt_sync / rt_read_surface
  * reports RT_ERR_CUDA. total_samples: samples per pixel summed over all ranks (the resolve's divisor). */
 int rt_exchange_setup(rt_ctx* ctx, int rank, int world, void* const* accum_ptrs, void* const* flag_ptrs, void* dst_argb_whole_image);
 int rt_exchange_resolve(rt_ctx* ctx, uint32_t total_samples, int flip_y);

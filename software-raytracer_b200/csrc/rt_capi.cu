@@ -1150,22 +1150,18 @@ int rt_exchange_setup(rt_ctx* c, int rank, int world, void* const* accum_ptrs, v
         return fail(c, RT_ERR_INVALID, "rt_exchange_setup: bad arguments");
     ExchangeState& x = c->exch;
     x.ready = false;
-    int devices[RT_MAX_PEERS];
+    // NOTE: every rank must run on its OWN device - the ranks wait for each other inside kernels, and kernels of two ranks on one
+    // GPU are not guaranteed to run concurrently. This cannot be checked here: for a CUDA-IPC mapping cudaPointerGetAttributes
+    // reports the importing context's device, not the exporter's. (Ranks sharing a device: rt_resolve_fused + host-side ordering.)
     for (int r = 0; r < world; ++r) {
         const void* a = r == rank && !accum_ptrs[r] ? (const void*)c->d_accum : accum_ptrs[r];
         void* f = r == rank && !flag_ptrs[r] ? (void*)c->d_flags : flag_ptrs[r];
         if (!a || !f) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: NULL peer pointer");
         if ((rc = enable_peer_access_to(c, a, "rt_exchange_setup: accumulation buffer")) != RT_OK) return rc;
         if ((rc = enable_peer_access_to(c, f, "rt_exchange_setup: exchange flags")) != RT_OK) return rc;
-        cudaPointerAttributes at;
-        RT_CUDA(c, cudaPointerGetAttributes(&at, a));
-        devices[r] = at.device;
-        // ranks that share a GPU would wait for each other inside kernels that cannot be relied on to run concurrently
-        for (int q = 0; q < r; ++q)
-            if (devices[q] == devices[r]) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: two ranks on one device (every rank needs its own GPU; use rt_resolve_fused with host-side ordering instead)");
         x.accum[r] = (const float4*)a; x.flags[r] = (ExchFlags*)f;
     }
-    if (devices[rank] != c->device) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: entry `rank` is not this context's buffer");
+    if (x.accum[rank] != c->d_accum || x.flags[rank] != c->d_flags) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: entry `rank` is not this context's own buffer");
     if (!dst) dst = rank == 0 ? (void*)c->d_argb : nullptr;
     if (!dst) return fail(c, RT_ERR_INVALID, "rt_exchange_setup: NULL destination surface");
     if ((rc = enable_peer_access_to(c, dst, "rt_exchange_setup: destination surface")) != RT_OK) return rc;
