@@ -128,6 +128,9 @@ enum {
                                       scene, the resolution or the secondary-origin offset changes (identical ray: the reference has
                                       no pixel jitter, Raytracer.cpp:106-122); 0: re-trace it for every sample like the reference.
                                       Results are bit-identical. */
+    RT_OPT_BVH_QUANT = 15,         /* 1 (default): BVHs traversed from global memory by the persistent kernels also get 32-byte nodes with 16-bit
+                                      child planes on one grid per tree (conservative, identical results; falls back to the float nodes
+                                      when the grid would be coarser than 1/8 of the median primitive extent); 0: float nodes only */
     RT_OPT_TRAVERSAL_STATS = 14    /* 1: BVH kernels count inner-node visits and primitive tests (rt_get_traversal_stats); a separate
                                       instantiation of the kernels, ~3 % slower. 0 (default): off */
 };

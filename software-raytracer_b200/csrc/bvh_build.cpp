@@ -290,4 +290,68 @@ void build_leaf_slots(const HostBvh& bvh, const float* sph4, const int* sph_id, 
     }
 }
 
+// Error budget of the device's decode (rt_bvh_lane.cuh node_step, Q16 branch), per axis, in units of step / |d| (the parameter
+// distance of one grid step): a = step * inv with inv = rcp(d) (2 ulp) and one rounding: relative 3.6e-7, times q + 2^23 <= 8.5e6
+// would be 3 units - but the same a enters b2 = fma(-2^23, a, b) with the opposite sign, so what remains is the error on q * a
+// (q <= 65535: 0.024 units) plus the rounding of b2 itself, |b2| <= 2^23 |a| + |b|: half an ulp = 0.5 |a| + 6e-8 |b| (|b| <= 2 extent
+// |inv|, i.e. 1.2e-7 extent / step = 0.008 units for a 65530-step grid) plus the final rounding of t (|t| <= 65536 |a| + ...: 0.004
+// units) plus the rounding of b = (org - o) * inv (two roundings and the reciprocal: 4.8e-7 x 2 extent = 0.06 units). Sum < 0.6 units:
+// ONE extra unit on each side is enough.
+void build_qnodes(const HostBvh& bvh, HostQNodes& out) {
+    out = HostQNodes();
+    const size_t n = bvh.nodes.size();
+    if (n == 0) return;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (const BvhNode& nd : bvh.nodes)
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < 3; ++k) {
+                const double a = nd.f[6 * c + 2 * k], b = nd.f[6 * c + 2 * k + 1];
+                if (!(a <= b)) continue;                       // empty child box (inverted): encoded as an empty slab below
+                lo[k] = std::min(lo[k], a); hi[k] = std::max(hi[k], b);
+            }
+    std::vector<float> ext[3];
+    for (int k = 0; k < 3; ++k) {
+        if (!(lo[k] <= hi[k]) || !std::isfinite(lo[k]) || !std::isfinite(hi[k])) return;
+        const double range = std::max(hi[k] - lo[k], 1e-30);
+        out.step[k] = (float)(range / 65528.0);
+        if (!(out.step[k] > 0.f) || !std::isfinite(out.step[k])) return;
+        out.org[k] = (float)(lo[k] - 3.0 * (double)out.step[k]);
+        // the float org / step must still cover the range with the margins: q in [2, 65533] before the extra unit
+        if ((hi[k] - (double)out.org[k]) / (double)out.step[k] > 65533.0 || (lo[k] - (double)out.org[k]) / (double)out.step[k] < 2.0) return;
+    }
+    // coarseness check against the leaf-level boxes (children that are leaves): median extent per axis
+    for (const BvhNode& nd : bvh.nodes)
+        for (int c = 0; c < 2; ++c)
+            if (nd.c[c] < 0)
+                for (int k = 0; k < 3; ++k) { const float e = nd.f[6 * c + 2 * k + 1] - nd.f[6 * c + 2 * k]; if (e >= 0.f) ext[k].push_back(e); }
+    for (int k = 0; k < 3; ++k) {
+        if (ext[k].empty()) continue;
+        std::nth_element(ext[k].begin(), ext[k].begin() + ext[k].size() / 2, ext[k].end());
+        const float med = ext[k][ext[k].size() / 2];
+        if (out.step[k] > 0.125f * med) return;               // too coarse: the quantised boxes would be visibly larger than the float ones
+    }
+    out.words.assign(n * 8, 0u);
+    for (size_t i = 0; i < n; ++i) {
+        const BvhNode& nd = bvh.nodes[i];
+        uint32_t* w = out.words.data() + 8 * i;
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < 3; ++k) {
+                const double a = nd.f[6 * c + 2 * k], b = nd.f[6 * c + 2 * k + 1];
+                uint32_t qlo, qhi;
+                if (!(a <= b)) { qlo = 65535u; qhi = 0u; }     // empty: lo > hi on every axis -> the slab test fails
+                else {
+                    const double fl = std::floor((a - (double)out.org[k]) / (double)out.step[k]) - 1.0;
+                    const double ce = std::ceil((b - (double)out.org[k]) / (double)out.step[k]) + 1.0;
+                    qlo = (uint32_t)std::min(65535.0, std::max(0.0, fl));
+                    qhi = (uint32_t)std::min(65535.0, std::max(0.0, ce));
+                    // containment with the budget of the decode: a full unit of slack on both sides, checked in double
+                    if ((double)out.org[k] + ((double)qlo + 0.7) * (double)out.step[k] > a || (double)out.org[k] + ((double)qhi - 0.7) * (double)out.step[k] < b) { out.words.clear(); return; }
+                }
+                w[3 * c + k] = qlo | (qhi << 16);
+            }
+        w[6] = (uint32_t)nd.c[0]; w[7] = (uint32_t)nd.c[1];
+    }
+    out.usable = true;
+}
+
 }  // namespace rtb

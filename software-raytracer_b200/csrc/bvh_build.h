@@ -68,4 +68,23 @@ void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostB
 void build_leaf_slots(const HostBvh& bvh, const float* sph4, const int* sph_id, const float* box4, const int* box_id,
                       const TriRecords* tris, std::vector<float>& slots);
 
+// 32-byte nodes with 16-bit child planes on ONE grid per tree: the form the persistent kernels traverse when the tree lives in
+// global memory. Why: the lanes of a warp sit in different nodes, so every load instruction of a node fetch costs one L1 wavefront
+// PER LANE whatever its width, and the L1 data pipe is what bounds those kernels - a 64-byte node is two
+// 256-bit loads, a 32-byte node one.
+//   word k (k = 0..2)   child 0, axis k:  lo | hi << 16          word 3 + k   child 1, axis k
+//   word 6, 7           the two child links (as in BvhNode)
+// plane = org[axis] + q * step[axis]. Encoding (double arithmetic on the float org / step the device gets): lo is rounded DOWN and
+// hi UP to the grid and both are moved one more unit outwards, which covers the decode's own rounding: the device evaluates
+// t = fma(float(2^23 + q), step/d, (org - o)/d - 2^23 step/d), whose error is below 0.6 step/d (derivation in bvh_build.cpp), i.e.
+// the decoded slab always CONTAINS the slab of the float box, which itself is conservative (kInflate). Still only a candidate
+// filter: hits are decided by the strict tests. usable = false when the grid would be too coarse for the scene's primitives
+// (step above 1/8 of the median primitive box extent on some axis): the float nodes are traversed then.
+struct HostQNodes {
+    std::vector<uint32_t> words;       // 8 per node, same node indices as HostBvh::nodes
+    float org[3] = {0.f, 0.f, 0.f}, step[3] = {1.f, 1.f, 1.f};
+    bool usable = false;
+};
+void build_qnodes(const HostBvh& bvh, HostQNodes& out);
+
 }  // namespace rtb

@@ -70,13 +70,21 @@ struct BvhLane {
         state = IDLE; cur = NONE; leaf0 = NONE;
         ix = iy = iz = ox = oy = oz = 0.f; best_t = 0.f; best_id = 0; best_ref = 0; have = false; bn = f3(0.f, 0.f, 0.f);
     }
-    // start at the root; the stack is empty (the previous traversal ended by popping the sentinel)
-    __device__ __forceinline__ void begin(float3 o, float3 d) {
+    // start at the root; the stack is empty (the previous traversal ended by popping the sentinel).
+    // Plane parameters are t = fma(P, ix, ox). Float nodes: P = the plane's coordinate, ix = 1/d, ox = -o/d. Quantised nodes (q16,
+    // bvh_build.h HostQNodes): P = the float 2^23 + q built from the 16-bit plane by one PRMT, ix = step/d, ox = (org - o)/d - 2^23 step/d.
+    __device__ __forceinline__ void begin(float3 o, float3 d, bool q16 = false, float3 q_org = f3(0.f, 0.f, 0.f), float3 q_step = f3(1.f, 1.f, 1.f)) {
         const float big = 1e30f;
         ix = fabsf(d.x) > 1e-30f ? RTB_FAST_RCP(d.x) : copysignf(big, d.x);
         iy = fabsf(d.y) > 1e-30f ? RTB_FAST_RCP(d.y) : copysignf(big, d.y);
         iz = fabsf(d.z) > 1e-30f ? RTB_FAST_RCP(d.z) : copysignf(big, d.z);
-        ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
+        if (q16) {
+            ox = (q_org.x - o.x) * ix; oy = (q_org.y - o.y) * iy; oz = (q_org.z - o.z) * iz;
+            ix *= q_step.x; iy *= q_step.y; iz *= q_step.z;
+            ox = fmaf(-8388608.f, ix, ox); oy = fmaf(-8388608.f, iy, oy); oz = fmaf(-8388608.f, iz, oz);
+        } else {
+            ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
+        }
         best_t = __int_as_float(0x7f800000); best_id = 0x7fffffff; best_ref = 0; have = false;
         cur = 0; leaf0 = NONE; state = ACTIVE;
     }
@@ -91,11 +99,31 @@ struct BvhLane {
     // 256-bit loads (LDG.E.ENL2.256, sm_100) instead of three 128-bit and one 64-bit load. The lanes of a warp sit in different
     // nodes, so every load instruction costs one L1 wavefront PER LANE whatever its width - and ncu shows the L1 data pipe at
     // 94 % on the 10 000-sphere scene with four loads per visit (profiles/r2c_summary_stream_c3.txt).
+    // qnodes != nullptr (warp-uniform): the 32-byte quantised node - ONE 256-bit load, twelve PRMTs - instead of the 64-byte float node.
     template <bool COUNT, bool GLOBAL_NODES = false>
-    __device__ __forceinline__ void node_step(const float4* __restrict__ nodes, TravCount& cnt) {   // requires in_node()
+    __device__ __forceinline__ void node_step(const float4* __restrict__ nodes, TravCount& cnt, const uint4* __restrict__ qnodes = nullptr,
+                                              uint32_t q2f16 = 0x4B00u) {   // requires in_node()
         if (COUNT) ++cnt.nodes;
         float4 n0, n1, n2;
         int2 ch;
+        if (GLOBAL_NODES && qnodes) {
+            uint4 q0, q1;
+#ifdef RTB_HOST_EMULATION
+            q0 = qnodes[2 * cur]; q1 = qnodes[2 * cur + 1];
+#else
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(qnodes + 2 * cur));
+#endif
+            // float 2^23 + q: bits 0x4B00 : q (low half of a word: selector 0x5410, high half: 0x5432)
+#define RTB_QLO(w) __uint_as_float(__byte_perm((w), q2f16, 0x5410u))
+#define RTB_QHI(w) __uint_as_float(__byte_perm((w), q2f16, 0x5432u))
+            n0 = make_float4(RTB_QLO(q0.x), RTB_QHI(q0.x), RTB_QLO(q0.y), RTB_QHI(q0.y));       // child 0: x lo hi, y lo hi
+            n1 = make_float4(RTB_QLO(q0.z), RTB_QHI(q0.z), RTB_QLO(q0.w), RTB_QHI(q0.w));       // child 0: z lo hi; child 1: x lo hi
+            n2 = make_float4(RTB_QLO(q1.x), RTB_QHI(q1.x), RTB_QLO(q1.y), RTB_QHI(q1.y));       // child 1: y lo hi, z lo hi
+#undef RTB_QLO
+#undef RTB_QHI
+            ch.x = (int)q1.z; ch.y = (int)q1.w;
+        } else
 #ifndef RTB_HOST_EMULATION
         if (GLOBAL_NODES) {
             const float4* np = nodes + 4 * cur;

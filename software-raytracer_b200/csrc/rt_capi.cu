@@ -160,6 +160,20 @@ int ensure_bvh(rt_ctx* c, float origin_extent) {
             c->bview.slots = c->d_bvh_slots;
         }
     }
+    // ... and the 32-byte quantised form of the nodes for the persistent kernels (one 256-bit load per node visit)
+    c->bview.qnodes = nullptr; c->bview.q2f16 = 0x4B00u;
+    if (c->bview.slots && c->opt_bvh_quant) {
+        HostQNodes qn;
+        build_qnodes(c->bvh, qn);
+        if (qn.usable) {
+            RT_CUDA(c, ensure_capacity(c->d_bvh_qnodes, c->cap_bvh_qnodes, qn.words.size() / 4));
+            RT_CUDA(c, cudaMemcpyAsync(c->d_bvh_qnodes, qn.words.data(), qn.words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+            RT_CUDA(c, cudaStreamSynchronize(c->stream));
+            c->bview.qnodes = c->d_bvh_qnodes;
+            c->bview.q_org = make_float3(qn.org[0], qn.org[1], qn.org[2]);
+            c->bview.q_step = make_float3(qn.step[0], qn.step[1], qn.step[2]);
+        }
+    }
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->bview.nodes = c->d_bvh_nodes; c->bview.refs = c->d_bvh_refs;
     c->bview.n_nodes = (int)c->bvh.nodes.size(); c->bview.n_refs = (int)c->bvh.refs.size();
@@ -471,6 +485,7 @@ int rt_create(int cuda_device, rt_ctx** out) {
     if (!c) return fail(nullptr, RT_ERR_NOMEM, "rt_create: out of host memory");
     c->device = cuda_device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* q = getenv("RTB200_BVH_QUANT")) c->opt_bvh_quant = q[0] != '0';      // A/B runs of the quantised nodes (RT_OPT_BVH_QUANT)
     rt_default_params(&c->par);
     rt_default_camera(&c->cam);
     memset(&c->view, 0, sizeof c->view);
@@ -504,7 +519,7 @@ int rt_destroy(rt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sph); cudaFree(c->d_sph_id); cudaFree(c->d_box); cudaFree(c->d_box_id); cudaFree(c->d_mat);
     cudaFree(c->d_accum); cudaFree(c->d_argb); cudaFree(c->d_counters); cudaFree(c->d_scratch);
-    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_bvh_slots); cudaFree(c->d_wide_nodes); cudaFree(c->d_wide_refs); cudaFree(c->d_tune);
+    cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_refs); cudaFree(c->d_bvh_slots); cudaFree(c->d_bvh_qnodes); cudaFree(c->d_wide_nodes); cudaFree(c->d_wide_refs); cudaFree(c->d_tune);
     cudaFree(c->d_tri); cudaFree(c->d_tri_obj); cudaFree(c->d_prim_nt); cudaFree(c->d_prim_id); cudaFree(c->d_flags);
     wavefront_destroy(c->wf);
     cudaFree(c->d_flat_boxes); cudaFree(c->d_flat_cull); cudaFree(c->d_flat_slots); cudaFree(c->d_flat_ids);
@@ -738,6 +753,7 @@ int rt_set_option(rt_ctx* c, int option, int value) {
             if (value < 1 || value > 32) return bad("RT_OPT_BVH_WAIT_K takes 1 .. 32 lanes");
             c->opt_bvh_wait_k = value; return RT_OK;
         case RT_OPT_TRAVERSAL_STATS: c->opt_trav_stats = value != 0; return RT_OK;
+        case RT_OPT_BVH_QUANT: c->opt_bvh_quant = value != 0; c->bvh_valid = false; c->tuned_pipeline = retune; return RT_OK;
     }
     return fail(c, RT_ERR_INVALID, "rt_set_option: unknown option");
 }

@@ -59,7 +59,9 @@ struct rt_ctx {
     BvhView bview;
     float4* d_bvh_nodes = nullptr; int* d_bvh_refs = nullptr;
     float4* d_bvh_slots = nullptr;     // leaf-ordered primitive slots (BVHs too large to stage in shared memory)
-    size_t cap_bvh_nodes = 0, cap_bvh_refs = 0, cap_bvh_slots = 0;
+    uint4* d_bvh_qnodes = nullptr;     // 32-byte quantised nodes of the same tree (bvh_build.h HostQNodes)
+    size_t cap_bvh_nodes = 0, cap_bvh_refs = 0, cap_bvh_slots = 0, cap_bvh_qnodes = 0;
+    int opt_bvh_quant = 1;             // RT_OPT_BVH_QUANT
     HostWideBvh wide;                  // 8-wide quantised form for BVHs read from global memory (bvh_wide.h)
     uint4* d_wide_nodes = nullptr; int* d_wide_refs = nullptr;
     size_t cap_wide_nodes = 0, cap_wide_refs = 0;

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     const float4* __restrict__ nodes = tc.nodes;
     const int* __restrict__ refs = tc.refs;
+    const uint4* __restrict__ qnodes = MODE == 3 ? bv.qnodes : nullptr;     // 32-byte quantised nodes when the host built them
     const unsigned int count = *count_ptr;
     const int lane = threadIdx.x & 31;
     constexpr unsigned FULL = 0xffffffffu;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
                         pid = i;                             // dense state: slot = queue position
                         const float4 o4 = ray_o[pid], d4 = ray_d[pid];
                         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
-                        L.begin(o, d);
+                        L.begin(o, d, qnodes != nullptr, bv.q_org, bv.q_step);
                         if (COUNT) ++n_queries;
                     }
                 }
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
         }
         // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
         for (;;) {
-            if (L.in_node()) L.node_step<COUNT, MODE == 3>(nodes, cnt);
+            if (L.in_node()) L.node_step<COUNT, MODE == 3>(nodes, cnt, qnodes, bv.q2f16);
             if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem + (kStreamStateWords * kThreads + 3) / 4);
     const float4* __restrict__ nodes = tc.nodes;
     const int* __restrict__ refs = tc.refs;
+    const uint4* __restrict__ qnodes = MODE == 3 ? bv.qnodes : nullptr;     // 32-byte quantised nodes when the host built them
     const int lane = threadIdx.x & 31;
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
                     scatter_segment(sc, fr, h, __float_as_uint(ps[7 * kThreads]), __float_as_uint(ps[8 * kThreads]), o, d, T, Lr, depth);
                     ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = Lr.x; ps[4 * kThreads] = Lr.y; ps[5 * kThreads] = Lr.z;
                     ps[6 * kThreads] = __int_as_float(depth);
-                    L.begin(o, d);
+                    L.begin(o, d, qnodes != nullptr, bv.q_org, bv.q_step);
                 }
             }
             if (!exhausted) {                                // every idle lane claims the next path id: one atomicAdd per warp
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
                             if (live) {
                                 ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = Lr.x; ps[4 * kThreads] = Lr.y; ps[5 * kThreads] = Lr.z;
                                 ps[6 * kThreads] = __int_as_float(depth); ps[7 * kThreads] = __uint_as_float(pixel); ps[8 * kThreads] = __uint_as_float(sample);
-                                L.begin(o, d);
+                                L.begin(o, d, qnodes != nullptr, bv.q_org, bv.q_step);
                             }
                         }
                     }
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
         }
         // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
         for (;;) {
-            if (L.in_node()) L.node_step<COUNT, MODE == 3>(nodes, cnt);
+            if (L.in_node()) L.node_step<COUNT, MODE == 3>(nodes, cnt, qnodes, bv.q2f16);
             if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------

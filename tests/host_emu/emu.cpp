@@ -248,6 +248,11 @@ extern "C" int emu_lane_schedules(const rt_object* objects, int n_obj, const flo
     std::vector<float> slots;                                // leaf-ordered primitive slots (bvh_build.h), what MODE 3 kernels read
     if (use_slots) build_leaf_slots(bvh, reinterpret_cast<const float*>(sph.data()), sph_id.data(), reinterpret_cast<const float*>(box.data()), box_id.data(), &tris, slots);
     const float4* slot4 = use_slots ? reinterpret_cast<const float4*>(slots.data()) : nullptr;
+    // use_slots == 2: also the 32-byte quantised nodes (bvh_build.h HostQNodes) - the conservative encoding AND the device's decode
+    HostQNodes qn;
+    if (use_slots == 2) { build_qnodes(bvh, qn); if (!qn.usable) return -2; }
+    const uint4* qnodes = use_slots == 2 ? reinterpret_cast<const uint4*>(qn.words.data()) : nullptr;
+    const float3 q_org = f3(qn.org[0], qn.org[1], qn.org[2]), q_step = f3(qn.step[0], qn.step[1], qn.step[2]);
     unsigned rng = seed * 2654435761u + 12345u;
     int bad = 0;
     long long n_node = 0, n_leaf = 0;
@@ -257,10 +262,10 @@ extern "C" int emu_lane_schedules(const rt_object* objects, int n_obj, const flo
         const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
         const Hit want = closest_hit_bvh(sc, sc.sph, sc.box, nodes, bvh.refs.data(), stack.data(), 1, o, d);
         TravCount cnt = {0u, 0u, 0u, 0u};
-        L.begin(o, d);                                       // the stack must be empty again after every traversal
+        L.begin(o, d, qnodes != nullptr, q_org, q_step);       // the stack must be empty again after every traversal
         while (L.state == BvhLane::ACTIVE) {                 // one warp iteration: a node phase of at least one step, then the leaf phase
             for (;;) {
-                if (L.in_node()) { L.node_step<true>(nodes, cnt); ++n_node; }
+                if (L.in_node()) { L.node_step<true, true>(nodes, cnt, qnodes, 0x4B00u); ++n_node; }
                 rng = rng * 1664525u + 1013904223u;
                 // leaf_bias 0: the node phase runs until the lane has no inner node left; 8: one node step per leaf phase
                 if (!L.in_node() || (int)((rng >> 16) % 8u) < leaf_bias) break;
@@ -273,4 +278,46 @@ extern "C" int emu_lane_schedules(const rt_object* objects, int n_obj, const flo
     }
     if (steps) { steps[0] = n_node; steps[1] = n_leaf; }
     return bad;
+}
+
+
+// Quantised nodes of a scene's BVH (bvh_build.h HostQNodes), checked independently of the builder's own assert: out[0] = usable,
+// out[1] = smallest slack (in grid units) between a decoded plane and the float plane it must enclose (>= 1 by construction),
+// out[2] = mean ratio decoded / float box surface area over all child boxes, out[3] = nodes.
+extern "C" void emu_qnodes_check(const rt_object* objects, int n_obj, const float* mverts, int n_mverts, const int32_t* mtris, int n_mtris, int mesh_object,
+                                 float origin_extent, double* out) {
+    std::vector<rt_object> objs(objects, objects + n_obj);
+    std::vector<HostMesh> meshes((size_t)n_obj);
+    if (mesh_object >= 0 && mesh_object < n_obj) {
+        meshes[(size_t)mesh_object].vertices.assign(mverts, mverts + (size_t)3 * n_mverts);
+        meshes[(size_t)mesh_object].indices.assign(mtris, mtris + (size_t)3 * n_mtris);
+    }
+    TriRecords tris;
+    build_tri_records(objs, meshes, tris);
+    HostBvh bvh;
+    build_bvh(objs, origin_extent, bvh, 4, &tris);
+    HostQNodes qn;
+    build_qnodes(bvh, qn);
+    out[0] = qn.usable ? 1 : 0; out[1] = 1e300; out[2] = 0; out[3] = (double)bvh.nodes.size();
+    if (!qn.usable) return;
+    double ratio = 0; long long boxes = 0;
+    for (size_t i = 0; i < bvh.nodes.size(); ++i) {
+        const BvhNode& nd = bvh.nodes[i];
+        for (int c = 0; c < 2; ++c) {
+            double e[3], q[3]; bool empty = false;
+            for (int k = 0; k < 3; ++k) {
+                const double a = nd.f[6 * c + 2 * k], b = nd.f[6 * c + 2 * k + 1];
+                if (!(a <= b)) { empty = true; break; }
+                const uint32_t w = qn.words[8 * i + 3 * c + k];
+                const double lo = (double)qn.org[k] + (double)(w & 0xffffu) * (double)qn.step[k], hi = (double)qn.org[k] + (double)(w >> 16) * (double)qn.step[k];
+                out[1] = std::min(out[1], std::min((a - lo) / (double)qn.step[k], (hi - b) / (double)qn.step[k]));
+                e[k] = b - a; q[k] = hi - lo;
+            }
+            if (empty) continue;
+            const double sa = e[0] * e[1] + e[1] * e[2] + e[2] * e[0], sq = q[0] * q[1] + q[1] * q[2] + q[2] * q[0];
+            if (sa > 0) { ratio += sq / sa; ++boxes; }
+        }
+        if ((int32_t)qn.words[8 * i + 6] != nd.c[0] || (int32_t)qn.words[8 * i + 7] != nd.c[1]) out[1] = -1;     // links must be copied verbatim
+    }
+    out[2] = boxes ? ratio / (double)boxes : 0;
 }

@@ -178,13 +178,15 @@ def test_wide_bvh_makes_about_half_the_node_visits(emu):
     assert w_prims < 2.0 * b2_prims, (b2_prims, w_prims)
 
 
-@pytest.mark.parametrize("use_slots", [0, 1])
+@pytest.mark.parametrize("use_slots", [0, 1, 2])
 @pytest.mark.parametrize("leaf_bias", [0, 2, 8])
 def test_lane_state_machine_equals_the_per_ray_loop_under_random_schedules(emu, leaf_bias, use_slots):
     """csrc/rt_bvh_lane.cuh (the traversal state machine of k_wf_intersect_bvh and k_wf_stream with its sentinel stack), compiled
     for the host: whatever the interleaving of node steps and postponed leaf steps, the hit is closest_hit_bvh()'s bit for bit
     and the stack is back at its sentinel. Spheres + cubes + a triangle mesh, origins inside and outside the scene; with the leaf
-    primitives read through refs[] and through the leaf-ordered 64-byte slots (bvh_build.h build_leaf_slots)."""
+    primitives read through refs[] (0), through the leaf-ordered 64-byte slots (1, bvh_build.h build_leaf_slots), and with the
+    32-byte nodes whose child planes are quantised to 16 bits (2, HostQNodes): the decoded boxes must contain the float ones for
+    every ray, or a hit would be lost."""
     from rtb200.scenes import synthetic_spheres, heightfield_mesh, mesh_scene
     lib = C.CDLL(EMU_SO)
     lib.emu_lane_schedules.restype = C.c_int
@@ -208,5 +210,5 @@ def test_lane_state_machine_equals_the_per_ray_loop_under_random_schedules(emu, 
         mt = np.ascontiguousarray(mesh[1], np.int32) if mesh else None
         bad = lib.emu_lane_schedules(p(objs), len(objs), p(mv), len(mv) if mesh else 0, p(mt), len(mt) if mesh else 0, 0 if mesh else -1,
                                      p(org), p(d), n, 77 + leaf_bias, leaf_bias, use_slots, steps)
-        assert bad == 0, (leaf_bias, bad)
+        assert bad == 0, (leaf_bias, use_slots, bad)
         assert steps[0] > 2 * n and steps[1] > n / 4

@@ -187,3 +187,28 @@ def test_bvh_parallel_build_is_byte_identical(lib):
         assert bvh_digest(lib, mesh_scene(), threads, (v, tr)) == want, threads
     small = synthetic_spheres(300)                                     # below the threshold: the sequential path whatever the count
     assert bvh_digest(lib, small, 8) == bvh_digest(lib, small, 1)
+
+
+def test_quantised_nodes_enclose_the_float_boxes(lib):
+    """bvh_build.h HostQNodes: every decoded 16-bit plane lies at least one grid unit outside the float plane it replaces (the
+    decode's own rounding is below 0.6 units), the links are copied verbatim, and the boxes grow little on the benchmark
+    scenes; a scene whose extent dwarfs its primitives is refused (the float nodes are traversed then)."""
+    from rtb200.scenes import synthetic_spheres, heightfield_mesh, mesh_scene
+    lib.emu_qnodes_check.restype = None
+    p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+    def check(objs, mesh=None, extent=30.0):
+        objs = np.ascontiguousarray(objs, rtb200.OBJECT_DTYPE)
+        out = (C.c_double * 4)()
+        mv = np.ascontiguousarray(mesh[0], np.float32) if mesh else None
+        mt = np.ascontiguousarray(mesh[1], np.int32) if mesh else None
+        lib.emu_qnodes_check(p(objs), len(objs), p(mv), len(mv) if mesh else 0, p(mt), len(mt) if mesh else 0, 0 if mesh else -1, C.c_float(extent), out)
+        return list(out)
+    usable, slack, growth, n = check(synthetic_spheres(10000))            # BASELINE config 3 (ground sphere r = 1000: a 2000-unit grid)
+    assert usable == 1 and 1.0 <= slack < 2.01 and 1.0 < growth < 1.35 and n > 2000, (usable, slack, growth, n)
+    v, tr = heightfield_mesh(256, 128)
+    usable, slack, growth, n = check(mesh_scene(), (v, tr))
+    assert usable == 1 and 1.0 <= slack < 2.01 and 1.0 < growth < 1.25, (usable, slack, growth)
+    tiny = synthetic_spheres(3000)
+    tiny["radius"][:3000] *= 0.002                                         # 3000 specks in a 2000-unit scene: the grid is far too coarse
+    assert check(tiny)[0] == 0
