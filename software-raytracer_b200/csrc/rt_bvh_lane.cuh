@@ -62,6 +62,7 @@ struct BvhLane {
     LaneStack ls;
     int state, cur, leaf0;
     float ix, iy, iz, ox, oy, oz;
+    uint32_t snx, sny, snz, sfx, sfy, sfz;                   // quantised nodes: PRMT selectors of the NEAR / FAR plane per axis (by the direction's sign)
     float best_t; int best_id, best_ref; bool have;
     float3 bn;
 
@@ -69,6 +70,7 @@ struct BvhLane {
         ls.init(stack_slot);
         state = IDLE; cur = NONE; leaf0 = NONE;
         ix = iy = iz = ox = oy = oz = 0.f; best_t = 0.f; best_id = 0; best_ref = 0; have = false; bn = f3(0.f, 0.f, 0.f);
+        snx = sny = snz = 0x5410u; sfx = sfy = sfz = 0x5432u;
     }
     // start at the root; the stack is empty (the previous traversal ended by popping the sentinel).
     // Plane parameters are t = fma(P, ix, ox). Float nodes: P = the plane's coordinate, ix = 1/d, ox = -o/d. Quantised nodes (q16,
@@ -82,6 +84,11 @@ struct BvhLane {
             ox = (q_org.x - o.x) * ix; oy = (q_org.y - o.y) * iy; oz = (q_org.z - o.z) * iz;
             ix *= q_step.x; iy *= q_step.y; iz *= q_step.z;
             ox = fmaf(-8388608.f, ix, ox); oy = fmaf(-8388608.f, iy, oy); oz = fmaf(-8388608.f, iz, oz);
+            // a word holds lo | hi << 16: the line enters a slab through lo when it runs in +axis direction, through hi otherwise. The
+            // PRMT that builds the float picks the half, so the per-axis min / max of the float-node test disappear.
+            snx = ix < 0.f ? 0x5432u : 0x5410u; sfx = snx ^ 0x0022u;
+            sny = iy < 0.f ? 0x5432u : 0x5410u; sfy = sny ^ 0x0022u;
+            snz = iz < 0.f ? 0x5432u : 0x5410u; sfz = snz ^ 0x0022u;
         } else {
             ox = -o.x * ix; oy = -o.y * iy; oz = -o.z * iz;
         }
@@ -114,15 +121,15 @@ struct BvhLane {
             asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(qnodes + 2 * cur));
 #endif
-            // float 2^23 + q: bits 0x4B00 : q (low half of a word: selector 0x5410, high half: 0x5432)
-#define RTB_QLO(w) __uint_as_float(__byte_perm((w), q2f16, 0x5410u))
-#define RTB_QHI(w) __uint_as_float(__byte_perm((w), q2f16, 0x5432u))
-            n0 = make_float4(RTB_QLO(q0.x), RTB_QHI(q0.x), RTB_QLO(q0.y), RTB_QHI(q0.y));       // child 0: x lo hi, y lo hi
-            n1 = make_float4(RTB_QLO(q0.z), RTB_QHI(q0.z), RTB_QLO(q0.w), RTB_QHI(q0.w));       // child 0: z lo hi; child 1: x lo hi
-            n2 = make_float4(RTB_QLO(q1.x), RTB_QHI(q1.x), RTB_QLO(q1.y), RTB_QHI(q1.y));       // child 1: y lo hi, z lo hi
-#undef RTB_QLO
-#undef RTB_QHI
-            ch.x = (int)q1.z; ch.y = (int)q1.w;
+            // float 2^23 + q: bits 0x4B00 : q, the half chosen by the ray's near / far selector of that axis (begin())
+#define RTB_QP(w, sel) __uint_as_float(__byte_perm((w), q2f16, (sel)))
+            const float lo0 = fmaxf(fmaxf(fmaf(RTB_QP(q0.x, snx), ix, ox), fmaf(RTB_QP(q0.y, sny), iy, oy)), fmaf(RTB_QP(q0.z, snz), iz, oz));
+            const float hi0 = fminf(fminf(fmaf(RTB_QP(q0.x, sfx), ix, ox), fmaf(RTB_QP(q0.y, sfy), iy, oy)), fmaf(RTB_QP(q0.z, sfz), iz, oz));
+            const float lo1 = fmaxf(fmaxf(fmaf(RTB_QP(q0.w, snx), ix, ox), fmaf(RTB_QP(q1.x, sny), iy, oy)), fmaf(RTB_QP(q1.y, snz), iz, oz));
+            const float hi1 = fminf(fminf(fmaf(RTB_QP(q0.w, sfx), ix, ox), fmaf(RTB_QP(q1.x, sfy), iy, oy)), fmaf(RTB_QP(q1.y, sfz), iz, oz));
+#undef RTB_QP
+            descend(lo0, hi0, lo1, hi1, (int)q1.z, (int)q1.w);
+            return;
         } else
 #ifndef RTB_HOST_EMULATION
         if (GLOBAL_NODES) {
@@ -146,14 +153,18 @@ struct BvhLane {
         const float hi0 = fminf(fminf(fmaxf(ax0, bx0), fmaxf(ay0, by0)), fmaxf(az0, bz0));
         const float lo1 = fmaxf(fmaxf(fminf(ax1, bx1), fminf(ay1, by1)), fminf(az1, bz1));
         const float hi1 = fminf(fminf(fmaxf(ax1, bx1), fmaxf(ay1, by1)), fmaxf(az1, bz1));
+        descend(lo0, hi0, lo1, hi1, ch.x, ch.y);
+    }
+    // the children's parameter intervals [lo, hi] decide where the lane goes: nearer child first, the other one waits on the stack
+    __device__ __forceinline__ void descend(float lo0, float hi0, float lo1, float hi1, int c0, int c1) {
         const bool h0 = lo0 <= hi0 && hi0 >= 0.f && lo0 <= best_t;
         const bool h1 = lo1 <= hi1 && hi1 >= 0.f && lo1 <= best_t;
         if (h0 && h1) {
             const bool swap = lo1 < lo0;
-            ls.push(swap ? ch.x : ch.y, swap ? lo0 : lo1);   // the far child waits with its entry distance
-            cur = swap ? ch.y : ch.x;
-        } else if (h0) cur = ch.x;
-        else if (h1) cur = ch.y;
+            ls.push(swap ? c0 : c1, swap ? lo0 : lo1);       // the far child waits with its entry distance
+            cur = swap ? c1 : c0;
+        } else if (h0) cur = c0;
+        else if (h1) cur = c1;
         else cur = NONE;
         settle();
     }
