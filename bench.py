@@ -607,10 +607,6 @@ def run_b200(args):
             line["exchange_ms"] = exchange_ms
             if strong_obj:
                 line["strong"] = strong_obj
-        if world == 1 and not args.no_cpu and args.config in ("c1", "c2"):
-            rate, info = cpu_reference_run(objs, args.cpu_frames, w, h)
-            line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
-                                    "sample": info["sample"], "threads": info["threads"]}
     tr.close()
     del accum, flush
     if rank == 0:
@@ -622,6 +618,12 @@ def run_b200(args):
                 except Exception as e:                # a leg must not take the headline down with it
                     legs.append({"config": c, "error": "%s: %s" % (type(e).__name__, e)})
             line["configs"] = legs
+        # the CPU baseline comes LAST: measured on the same box, the BVH legs (about 40 small launches per step) ran 11-19 % slower
+        # when they followed the reference's 16-thread CPU run (profiles/r2l_bench_n1.json vs the --no-cpu run of the same call)
+        if world == 1 and not args.no_cpu and args.config in ("c1", "c2"):
+            rate, info = cpu_reference_run(objs, args.cpu_frames, w, h)
+            line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                                    "sample": info["sample"], "threads": info["threads"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -694,6 +694,9 @@ int rt_set_params(rt_ctx* c, const rt_params* p) {
     bool resized = p->width != c->par.width || p->height != c->par.height;
     if (!(fabsf(p->eps) <= fabsf(c->par.eps))) { c->bvh_valid = false; c->flat_valid = false; }   // margins were derived for the old offset
     if (resized || p->max_bounces != c->par.max_bounces || p->mode != c->par.mode) c->tuned_accel = c->tuned_pipeline = -1;
+    // the primary-hit cache keeps the environment colour of the pixels whose primary ray misses
+    if (memcmp(p->sun_dir, c->par.sun_dir, sizeof p->sun_dir) || memcmp(p->sky, c->par.sky, sizeof p->sky) || memcmp(p->horizon, c->par.horizon, sizeof p->horizon) ||
+        memcmp(p->ground, c->par.ground, sizeof p->ground) || memcmp(p->sun, c->par.sun, sizeof p->sun)) c->prim_valid = false;
     c->par = *p;
     if (c->par.max_bounces < 0) c->par.max_bounces = 0;        // MAXBOUNCES = max(MAXBOUNCES, 0) Raytracer.cpp:475
     c->frame_dirty = true;

@@ -5,6 +5,7 @@
 // Compiled with -fmad=false (see rt_device.cuh for the parity rules).
 #include "rt_kernels.h"
 
+#include <cstdlib>
 #include <mutex>
 
 #include "rt_device.cuh"
@@ -69,8 +70,9 @@ __global__ void __launch_bounds__(kThreads) k_trace_rays(SceneView sc, BvhView b
 // ---- the per-pixel primary-hit cache (RT_OPT_PRIMARY_REUSE) ------------------------------------------------------
 // GetRayDirection shoots every sample of a pixel through the pixel CORNER (no jitter, Raytracer.cpp:106-122), so the primary
 // closest-hit query of a pixel has the same inputs - and the same result - for every sample of every frame until the camera,
-// the scene or the resolution changes. It is traced ONCE, here, into (normal, t) + object id per pixel (20 B, y-up row-major
-// like the accumulation buffer); the render kernels start every sample from it. counters[2..3] (queries executed) += pixels.
+// the scene, the resolution or the environment colours change. It is traced ONCE, here, into (normal, t) + object id per pixel
+// (20 B, y-up row-major like the accumulation buffer; a miss keeps GetEnvironmentColor(d) instead of the normal); the render
+// kernels start every sample from it. counters[2..3] (queries executed) += pixels.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) k_primary_cache(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ prim_nt,
                                                              int* __restrict__ prim_id, unsigned long long* __restrict__ counters) {
@@ -79,8 +81,12 @@ __global__ void __launch_bounds__(kThreads) k_primary_cache(SceneView sc, BvhVie
     int px, py;
     if (tile_pixel(fr, px, py)) {
         const size_t p = (size_t)px + (size_t)py * fr.width;
-        const Hit h = trace<MODE>(sc, tc, fr.cam_pos, ray_dir(fr, px, py));
-        prim_nt[p] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
+        const float3 d = ray_dir(fr, px, py);
+        const Hit h = trace<MODE>(sc, tc, fr.cam_pos, d);
+        // a pixel whose primary ray misses has ONE radiance for every sample of every frame: the environment colour of its ray is
+        // kept in place of the normal (rt_device.cuh primary_ends), so that a sky pixel costs a load, not two SFU powers, per call
+        const float3 v = h.id >= 0 ? h.n : env_color(fr, d);
+        prim_nt[p] = make_float4(v.x, v.y, v.z, h.t);
         prim_id[p] = h.id;
     }
     if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
         if (n_samples > 0) {
             h0 = cached_primary(prim, pixel, o, d);
             float3 c;
-            if (path_ends(sc, fr, h0, d, T, L, 0, c)) {
+            if (primary_ends(sc, fr, h0, c)) {
                 for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
                 segs = (unsigned int)n_samples;
             } else {
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
                     if (REUSE) {
                         h0 = cached_primary(prim, pixel, o, d);
                         float3 c;
-                        if (path_ends(sc, fr, h0, d, T, L, 0, c)) {
+                        if (primary_ends(sc, fr, h0, c)) {
                             // the primary ray misses (or max_bounces == 0): every sample of the pixel has the value c
                             for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
                             segs += (unsigned int)n_samples;
@@ -844,7 +850,8 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
     if (pool_override > 0) pool_tiles = pool_override > 32 ? 32 : pool_override;
     else if (n_samples == 1 || (n_samples == 2 && n_tiles_all >= 50000)) pool_tiles = 2;
     // the pooled flat traversal pays from ~16 spp per launch on; short launches (the pixel pool's) run the per-lane form
-    size_t sb; const int mode = pick_mode(sc, ac, sb, kThreads, flat_coop && pool_tiles < 2 && n_samples >= 16);
+    static const bool pool_coop = [] { const char* v = getenv("RTB200_POOL_COOP"); return v && v[0] == '1'; }();   // A/B: pooled levels 2/3 in the pixel-pool kernel too
+    size_t sb; const int mode = pick_mode(sc, ac, sb, kThreads, flat_coop && (pool_tiles < 2 ? n_samples >= 16 : pool_coop));
     if (pool_tiles >= 2) {
         // persistent grid: at most one resident wave of CTAs; the warps claim tiles until the image is handed out
         int dev = 0, sms = 0;

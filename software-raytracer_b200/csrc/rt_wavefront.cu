@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(SceneView sc, FrameView fr,
                 h0.p = f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w);
                 delivered = 1;                                               // the reused primary segment
                 float3 c;
-                if (path_ends(sc, fr, h0, d, T, L, 0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
+                if (primary_ends(sc, fr, h0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
                 else scatter_segment(sc, fr, h0, pixel, s, o, d, T, L, depth);
             }
             if (live) { so = make_float4(o.x, o.y, o.z, 0.f); sd = make_float4(d.x, d.y, d.z, __int_as_float(depth)); sT = make_float4(T.x, T.y, T.z, 0.f); sL = make_float4(L.x, L.y, L.z, 0.f); }
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
                                 h0.p = f3(o.x + d.x * nt.w, o.y + d.y * nt.w, o.z + d.z * nt.w);
                                 ++segs;                      // the reused primary segment: delivered, not traced
                                 float3 c;
-                                if (path_ends(sc, fr, h0, d, T, Lr, 0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
+                                if (primary_ends(sc, fr, h0, c)) { wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f); live = false; }
                                 else scatter_segment(sc, fr, h0, pixel, sample, o, d, T, Lr, depth);
                             }
                             if (live) {
@@ -698,6 +698,8 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
     if (s_cap < 1) s_cap = 1;
     if (s_cap > 64) s_cap = 64;
     if (s_cap > n_samples) s_cap = n_samples;
+    // equal waves: 16 samples with room for 15 are two waves of 8, not 15 + a single-sample wave that runs mostly in its tail
+    { const int n_waves = (n_samples + s_cap - 1) / s_cap; s_cap = (n_samples + n_waves - 1) / n_waves; }
     if ((size_t)g.npad * s_cap >= (size_t)1 << 32) return cudaErrorInvalidValue;
     if (wb->cap_px < npix) {
         cudaStreamSynchronize(st);
