@@ -247,7 +247,27 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
     Hit h0;
     h0.id = -1; h0.t = 0.f; h0.n = f3(0.f, 0.f, 0.f); h0.p = f3(0.f, 0.f, 0.f);
 
+    // One iteration: closest hit for the lanes that hold a ray -> end-of-path handling -> idle lanes (also those that finished a pixel
+    // just now) take the next pixels of the chunk -> ONE scatter block for continuing paths, restarted samples and fresh pixels.
+    // (The first version scattered fresh pixels inside the pick-up: a second copy of the scatter code that ran in almost every
+    // iteration for the handful of lanes that had just taken a pixel.)
     for (;;) {
+        Hit h = trace_all<MODE>(sc, tc, o, d, busy);
+        bool scat = false;
+        if (busy) {
+            ++segs; ++traced;
+            float3 c;
+            if (path_ends(sc, fr, h, d, T, L, depth, c)) {
+                acc.x += c.x; acc.y += c.y; acc.z += c.z;
+                ++s; depth = 0; o = fr.cam_pos; d = d0;     // no reuse: the next iteration traces the primary ray again
+                if (s >= n_samples) {
+                    float4 a = accum[pixel];
+                    a.x += acc.x; a.y += acc.y; a.z += acc.z;
+                    accum[pixel] = a;
+                    busy = false;
+                } else if (REUSE) { h = h0; ++segs; scat = true; }     // next sample from the cached primary hit
+            } else scat = true;
+        }
         const unsigned m_need = __ballot_sync(FULL, !busy);
         if (!have_claim && !drained && 2 * next >= total) {  // ask for the next chunk early
             if (lane == 0) claimed = atomicAdd(tile_cursor, (unsigned int)pool_tiles);
@@ -282,33 +302,13 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
                             a.x += acc.x; a.y += acc.y; a.z += acc.z;
                             accum[pixel] = a;
                             busy = false;                    // takes another pixel in the next pass
-                        } else {
-                            scatter_segment(sc, fr, h0, pixel, s_begin, o, d, T, L, depth);
-                            ++segs;
-                        }
+                        } else { h = h0; ++segs; scat = true; }
                     }
                 }
             }
         }
-        if (!__any_sync(FULL, busy)) { if (drained) break; else continue; }     // not drained: the next pass switches to the claimed chunk
-        Hit h = trace_all<MODE>(sc, tc, o, d, busy);
-        if (busy) {
-            ++segs; ++traced;
-            bool scatter = true;
-            float3 c;
-            if (path_ends(sc, fr, h, d, T, L, depth, c)) {
-                scatter = false;
-                acc.x += c.x; acc.y += c.y; acc.z += c.z;
-                ++s; depth = 0; o = fr.cam_pos; d = d0;
-                if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }     // next sample from the cached primary hit
-            }
-            if (s >= n_samples) {
-                float4 a = accum[pixel];
-                a.x += acc.x; a.y += acc.y; a.z += acc.z;
-                accum[pixel] = a;
-                busy = false;
-            } else if (scatter) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
-        }
+        if (scat) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
+        if (!__any_sync(FULL, busy) && drained) break;      // not drained: the next pass switches to the claimed chunk
     }
 
     unsigned int total_s = segs, total_tr = traced;
