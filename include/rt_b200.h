@@ -115,7 +115,8 @@ enum {
     RT_OPT_BVH_LEAF = 6,           /* BVH builder: maximum primitives per leaf (default 4) */
     RT_OPT_WF_REFILL = 8,          /* wavefront BVH intersect: free lanes that trigger a ray refill (default 8) */
     RT_OPT_WF_NODE_MIN = 9,        /* wavefront BVH intersect: lanes with inner-node work below which pending leaves are tested (default 8) */
-    RT_OPT_POOL_TILES = 10,        /* megakernel, few samples per call: 8x4 pixel tiles per warp-level pixel pool; 0 (default) automatic, 1 one pixel per lane */
+    RT_OPT_POOL_TILES = 10,        /* megakernel, few samples per call: 8x4 pixel tiles per chunk a warp of the persistent pixel-pool kernel claims at a time;
+                                      0 (default) automatic (2 for 1-spp calls), 1 one pixel per lane (no pool) */
     RT_OPT_FLAT_COOP = 11,         /* flat accelerator in the megakernel: 1 the warp pools the cluster culls and strict tests of its 32 rays, 0 every lane for itself,
                                       2 (default) pooled for scenes without cubes (open sphere scenes gain ~8 %, cube rooms lose ~10 %) */
     RT_OPT_WF_WAVE_MPATHS = 13,    /* wavefront pipeline: paths per wave in units of 2^20 (0 = default 128, i.e. ~15 GB of path state; at most 64 samples
