@@ -45,9 +45,10 @@ struct Builder {
     std::vector<Prim> prims;
     float eps;
 
-    static constexpr int kBins = 16;
+    static constexpr int kBins = 32;           // upper bound; `bins` is what split() uses
+    int bins = 16;
     int kMaxLeaf = 4;
-    static constexpr float kTravCost = 1.0f, kPrimCost = 0.7f;
+    float kTravCost = 1.0f, kPrimCost = 0.7f;
 
     int32_t make_leaf(int first, int count, Subtree& out) const {
         int start = (int)out.refs.size();
@@ -95,17 +96,17 @@ struct Builder {
             float lo = cb.lo[axis], ext = cb.hi[axis] - cb.lo[axis];
             if (!(ext > 0)) continue;
             Box3 bb[kBins]; int bc[kBins] = {0};
-            float scale = kBins / ext;
+            float scale = bins / ext;
             for (int i = 0; i < count; ++i) {
                 const Prim& p = prims[(size_t)first + i];
-                int b = std::min(kBins - 1, std::max(0, (int)((p.centroid[axis] - lo) * scale)));
+                int b = std::min(bins - 1, std::max(0, (int)((p.centroid[axis] - lo) * scale)));
                 bb[b].grow(p.box); bc[b]++;
             }
             float right_area[kBins]; int right_cnt[kBins];
             Box3 acc; int cnt = 0;
-            for (int b = kBins - 1; b > 0; --b) { acc.grow(bb[b]); cnt += bc[b]; right_area[b] = acc.area(); right_cnt[b] = cnt; }
+            for (int b = bins - 1; b > 0; --b) { acc.grow(bb[b]); cnt += bc[b]; right_area[b] = acc.area(); right_cnt[b] = cnt; }
             acc = Box3(); cnt = 0;
-            for (int b = 0; b < kBins - 1; ++b) {
+            for (int b = 0; b < bins - 1; ++b) {
                 acc.grow(bb[b]); cnt += bc[b];
                 if (cnt == 0 || right_cnt[b + 1] == 0) continue;
                 float cost = acc.area() * cnt + right_area[b + 1] * right_cnt[b + 1];
@@ -118,9 +119,9 @@ struct Builder {
         float leaf_cost = kPrimCost * count;
         float split_cost = kTravCost + kPrimCost * best_cost / std::max(nb.area(), 1e-30f);
         if (!force && count <= kMaxLeaf && leaf_cost <= split_cost) return -1;
-        float lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+        float lo = cb.lo[best_axis], scale = bins / (cb.hi[best_axis] - cb.lo[best_axis]);
         auto mid_it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim& p) {
-            int b = std::min(kBins - 1, std::max(0, (int)((p.centroid[best_axis] - lo) * scale)));
+            int b = std::min(bins - 1, std::max(0, (int)((p.centroid[best_axis] - lo) * scale)));
             return b <= best_bin;
         });
         int mid = (int)(mid_it - prims.begin());
@@ -183,6 +184,8 @@ void build_bvh(const std::vector<rt_object>& objects, float origin_extent, HostB
     out = HostBvh();
     Builder b;
     b.kMaxLeaf = max_leaf < 1 ? 1 : (max_leaf > 64 ? 64 : max_leaf);
+    if (const char* v = getenv("RTB200_BVH_BINS")) { const int n = atoi(v); if (n >= 4 && n <= Builder::kBins) b.bins = n; }          // experiments
+    if (const char* v = getenv("RTB200_BVH_PRIMCOST")) { const float c = (float)atof(v); if (c > 0.f && c < 100.f) b.kPrimCost = c; }
     int sph_slot = 0, box_slot = 0;
     Box3 scene;
     for (const rt_object& o : objects) {
