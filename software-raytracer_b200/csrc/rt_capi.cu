@@ -412,6 +412,17 @@ int enable_peer_access_to(rt_ctx* c, const void* ptr, const char* what) {
     if (e != cudaSuccess) return cuda_fail(c, e, "cudaDeviceEnablePeerAccess");
     return RT_OK;
 }
+// rt_resolve_fused without the per-pointer look-ups: for callers that have established peer access themselves (rt_group.cu)
+int resolve_fused_unchecked(rt_ctx* c, const void* const* accum_ptrs, int world, uint32_t total_samples, int first_pixel, int n_pixels,
+                            void* dst, int flip_y) {
+    RT_CUDA(c, cudaSetDevice(c->device));
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof pp);
+    for (int r = 0; r < world; ++r) pp.p[r] = (const float4*)accum_ptrs[r];
+    RT_CUDA(c, launch_resolve_fused(pp, world, total_samples, c->par.width, c->par.height, first_pixel, n_pixels, flip_y,
+                                    (uint32_t*)dst, c->stream));
+    return RT_OK;
+}
 }  // namespace rtb_capi
 using rtb_capi::prepare;
 using rtb_capi::enable_peer_access_to;
@@ -1149,17 +1160,12 @@ int rt_resolve_fused(rt_ctx* c, const void* const* accum_ptrs, int world, uint32
     if (!accum_ptrs || !dst || world < 1 || world > RT_MAX_PEERS || first_pixel < 0 || n_pixels < 0 ||
         (long long)first_pixel + n_pixels > (long long)c->par.width * c->par.height)
         return fail(c, RT_ERR_INVALID, "rt_resolve_fused: bad arguments");
-    PeerPtrs pp;
-    memset(&pp, 0, sizeof pp);
     for (int r = 0; r < world; ++r) {
         if (!accum_ptrs[r]) return fail(c, RT_ERR_INVALID, "rt_resolve_fused: NULL peer buffer");
         if ((rc = enable_peer_access_to(c, accum_ptrs[r], "rt_resolve_fused: accumulation buffer")) != RT_OK) return rc;
-        pp.p[r] = (const float4*)accum_ptrs[r];
     }
     if ((rc = enable_peer_access_to(c, dst, "rt_resolve_fused: destination surface")) != RT_OK) return rc;
-    RT_CUDA(c, launch_resolve_fused(pp, world, total_samples, c->par.width, c->par.height, first_pixel, n_pixels, flip_y,
-                                    (uint32_t*)dst, c->stream));
-    return RT_OK;
+    return rtb_capi::resolve_fused_unchecked(c, accum_ptrs, world, total_samples, first_pixel, n_pixels, dst, flip_y);
 }
 
 int rt_exchange_setup(rt_ctx* c, int rank, int world, void* const* accum_ptrs, void* const* flag_ptrs, void* dst) {

@@ -119,4 +119,6 @@ namespace rtb_capi {
 int fail(rt_ctx* c, int code, const std::string& msg);
 int prepare(rt_ctx* c);
 int enable_peer_access_to(rt_ctx* c, const void* ptr, const char* what);   // no-op for the context's own device
+int resolve_fused_unchecked(rt_ctx* c, const void* const* accum_ptrs, int world, uint32_t total_samples, int first_pixel, int n_pixels,
+                            void* dst, int flip_y);
 }

@@ -200,7 +200,7 @@ int rt_group_resolve_rgba8(rt_group* g, uint32_t* host_out, int pitch_bytes, int
         RTG_CUDA(g, cudaSetDevice(c->device));
         for (int j = 0; j < n; ++j) if (j != i) RTG_CUDA(g, cudaStreamWaitEvent(c->stream, g->ev_rendered[(size_t)j], 0));
         const int first = (int)(n_px * i / n), count = (int)(n_px * (i + 1) / n) - first;
-        const int rc = rt_resolve_fused(c, accum, n, total, first, count, c0->d_argb, flip_y);
+        const int rc = rtb_capi::resolve_fused_unchecked(c, accum, n, total, first, count, c0->d_argb, flip_y);   // peer access was enabled at creation
         if (rc != RT_OK) return member_fail(g, i, rc);
         RTG_CUDA(g, cudaSetDevice(c->device));
         RTG_CUDA(g, cudaEventRecord(g->ev_resolved[(size_t)i], c->stream));          // "my slice is written, I have read your buffers"

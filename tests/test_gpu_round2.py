@@ -70,6 +70,26 @@ def test_same_camera_resubmitted_keeps_the_cache(tracer, scenes):
     assert t2 - t1 < 160 * 120 * 1.6 and abs((t3 - t2) - (t2 - t1)) < 0.1 * (t2 - t1)    # no second primary pass (it would add 160 * 120)
 
 
+def test_environment_change_drops_the_cached_sky_colours(tracer, scenes):
+    """The cache keeps GetEnvironmentColor(d) for pixels whose primary ray misses: new sky / sun parameters must invalidate it."""
+    out = {}
+    try:
+        for reuse in (1, 0):
+            tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, reuse)
+            setup(tracer, scenes["Scene1"], 160, 120)
+            tracer.render_spp(2)
+            a = tracer.read_accum()[0]
+            tracer.params.sky[0], tracer.params.sky[1], tracer.params.sky[2] = 9.0, 1.0, 0.5
+            tracer.params.sun_dir[0], tracer.params.sun_dir[1], tracer.params.sun_dir[2] = 0.0, -0.6, -0.8
+            tracer.set_params(tracer.params)
+            tracer.reset_accumulation(); tracer.render_spp(2)
+            out[reuse] = (a, tracer.read_accum()[0])
+    finally:
+        tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 1)
+    assert np.array_equal(bits(out[1][0]), bits(out[0][0])) and np.array_equal(bits(out[1][1]), bits(out[0][1]))
+    assert not np.array_equal(out[1][0], out[1][1])
+
+
 # ---- traversal counters (SURVEY.md 8d: bytes per segment from node visits and primitive tests) -----------------------
 def test_traversal_counters_equal_the_host_emulation(tracer):
     """The counting instantiation of the per-ray BVH loop must visit exactly the nodes and test exactly the primitives the
