@@ -33,6 +33,7 @@ inline void fill_frame_view(const rt_camera& cam, const rt_params& p, FrameView&
     f.dissipation = p.dissipation; f.eps = p.eps;
     f.width = p.width; f.height = p.height; f.max_bounces = p.max_bounces; f.mode = p.mode; f.selected_id = p.selected_id;
     f.seed_lo = p.seed_lo; f.seed_hi = p.seed_hi;
+    for (uint32_t r = 0; r < 10; ++r) { f.key_sched[2 * r] = p.seed_lo + r * 0x9E3779B9u; f.key_sched[2 * r + 1] = p.seed_hi + r * 0xBB67AE85u; }
 }
 
 // Scene object list -> dense per-type geometry lists + per-object material records.

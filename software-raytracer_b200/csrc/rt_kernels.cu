@@ -122,6 +122,35 @@ __global__ void k_selftest_uniform(int* failures) {
     if (__float_as_uint(unit_from_word(w)) != __float_as_uint(unit_from_word_div(w))) atomicAdd(failures, 1);
 }
 
+// normalized3() (shared reciprocal) against normalized3_div() (three IEEE divisions) on 64 vectors per thread: components uniform in
+// [-1, 1] like the sampler's, products of those with random powers of two across and beyond the fast path's range (2^-56 .. 2^56),
+// mantissas of all ones / all zeros / one bit, exact zeros. Bits must be equal, NaN patterns included.
+__global__ void k_selftest_normalize(int* failures, uint32_t seed) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    for (uint32_t it = 0; it < 64u; ++it) {
+        const uint4 w = philox4x32_10(tid, it, 0u, 0u, seed, 0x5e1f7e57u);
+        float v[3];
+        const uint32_t ws[3] = {w.x, w.y, w.z};
+        const uint32_t kind = w.w & 7u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t u = ws[k];
+            float f = (unit_from_word(u) - 0.5f) * 2.f;                              // the sampler's own values
+            if (kind >= 2u) f = __uint_as_float((u & 0x807fffffu) | ((127u - 56u + ((u >> 23) % 113u)) << 23));   // random sign, mantissa, exponent
+            if (kind == 5u) f = __uint_as_float((__float_as_uint(f) & 0xff800000u) | ((u & 0x00800000u) ? 0x007fffffu : 0u));
+            if (kind == 6u) f = __uint_as_float((__float_as_uint(f) & 0xff800000u) | (1u << (u % 23u)));
+            if (kind == 7u && (w.w >> 3) % 3u == (uint32_t)k) f = (u & 1u) ? 0.f : -0.f;
+            v[k] = f;
+        }
+        if (kind == 3u) { v[1] = v[0] * 0x1p-20f; v[2] = v[0] * 0x1p-38f; }          // very different magnitudes
+        if (kind == 4u) { const float sc = __uint_as_float((127u - 30u + (w.w >> 8) % 61u) << 23); v[0] *= sc; v[1] *= sc; v[2] *= sc; }
+        const float3 a = normalized3(f3(v[0], v[1], v[2])), b = normalized3_div(f3(v[0], v[1], v[2]));
+        if (__float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y) || __float_as_uint(a.z) != __float_as_uint(b.z)) ++bad;
+    }
+    if (bad) atomicAdd(failures, bad);
+}
+
 __global__ void k_philox(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32_10(ctr.x, ctr.y, ctr.z, ctr.w, key.x, key.y); }
 
 // ---- the render kernel -----------------------------------------------------------------------
@@ -820,6 +849,13 @@ cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(dev_failures, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     k_selftest_uniform<<<32768 / 256, 256, 0, st>>>(dev_failures);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_selftest_normalize(int* dev_failures, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(dev_failures, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_selftest_normalize<<<16384, 256, 0, st>>>(dev_failures, 0x2b200u);            // 2^28 vectors
     return cudaGetLastError();
 }
 

@@ -43,6 +43,7 @@ cudaError_t launch_primary_cache(const SceneView& sc, const AccelSel& ac, const 
 cudaError_t launch_env_color(const FrameView& fr, const float* dir, int n, float* out, cudaStream_t st);
 cudaError_t launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t* dev_out4, cudaStream_t st);
 cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st);
+cudaError_t launch_selftest_normalize(int* dev_failures, cudaStream_t st);
 cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st);
 // prim_cache != NULL: primary-hit reuse (every sample starts from the cached primary hit); NULL: every sample re-traces it.
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,

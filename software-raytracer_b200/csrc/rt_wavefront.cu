@@ -261,8 +261,37 @@ constexpr int kStreamStateWords = 9;       // T.xyz, L.xyz, depth, pixel, sample
 #ifndef RTB_WF_STREAM_MIN_BLOCKS
 #define RTB_WF_STREAM_MIN_BLOCKS 8
 #endif
+#ifndef RTB_STREAM_SHADE_NOINLINE
+#define RTB_STREAM_SHADE_NOINLINE 0    // measured (profiles/r2t_ab.txt): as a call the kernel is 6 % SLOWER on both BVH scenes
+#endif
+#if RTB_STREAM_SHADE_NOINLINE
+#define RTB_STREAM_SHADE_ATTR __noinline__
+#else
+#define RTB_STREAM_SHADE_ATTR __forceinline__
+#endif
+// The shading of one finished traversal of the streaming kernel. Inlined, its ~40 live values (Philox block, normalisations, the sky's
+// powers) set the register count of the whole kernel and the traversal loop spills a little at 64 registers; as a CALL
+// (RTB_STREAM_SHADE_NOINLINE=1) the loop keeps its registers, but the call's argument traffic and the parameter structs read through
+// generic pointers cost more than the spills: C3 101.0 -> 107.3 ms, C4 28.9 -> 30.7 ms per step. Returns true when the path goes on
+// with the scattered ray (o, d); false when it ended (radiance stored).
+static __device__ RTB_STREAM_SHADE_ATTR bool stream_shade(const SceneView& sc, const FrameView& fr, const Hit& h, float* __restrict__ ps, float3& o, float3& d,
+                                                          float4* __restrict__ wave_rad, uint32_t pid) {
+    float3 T = f3(ps[0], ps[kThreads], ps[2 * kThreads]), Lr = f3(ps[3 * kThreads], ps[4 * kThreads], ps[5 * kThreads]);
+    int depth = __float_as_int(ps[6 * kThreads]);
+    float3 c;
+    if (path_ends(sc, fr, h, d, T, Lr, depth, c)) {
+        wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f);
+        return false;
+    }
+    scatter_segment(sc, fr, h, __float_as_uint(ps[7 * kThreads]), __float_as_uint(ps[8 * kThreads]), o, d, T, Lr, depth);
+    ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = Lr.x; ps[4 * kThreads] = Lr.y; ps[5 * kThreads] = Lr.z;
+    ps[6 * kThreads] = __int_as_float(depth);
+    return true;
+}
+
 template <int MODE, bool REUSE, bool COUNT>
-__global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_stream(SceneView sc, BvhView bv, FlatView fl, FrameView fr, int tiles_x, int npad,
+__global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_stream(const __grid_constant__ SceneView sc, const __grid_constant__ BvhView bv, const __grid_constant__ FlatView fl,
+                                                                                const __grid_constant__ FrameView fr, int tiles_x, int npad,
                                                                                 uint32_t s_first, unsigned int n_paths, const float4* __restrict__ prim_nt,
                                                                                 const int* __restrict__ prim_id, float4* __restrict__ wave_rad,
                                                                                 unsigned int* __restrict__ cursor, int kRefill, int kNodeMin,
@@ -291,18 +320,8 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
             if (L.state == BvhLane::DONE) {                  // the finished traversals of the warp are shaded together
                 const Hit h = L.finish(tc.sph, o, d);
                 ++segs; ++traced;
-                float3 T = f3(ps[0], ps[kThreads], ps[2 * kThreads]), Lr = f3(ps[3 * kThreads], ps[4 * kThreads], ps[5 * kThreads]);
-                int depth = __float_as_int(ps[6 * kThreads]);
-                float3 c;
-                if (path_ends(sc, fr, h, d, T, Lr, depth, c)) {
-                    wave_rad[pid] = make_float4(c.x, c.y, c.z, 0.f);
-                    L.state = BvhLane::IDLE;
-                } else {
-                    scatter_segment(sc, fr, h, __float_as_uint(ps[7 * kThreads]), __float_as_uint(ps[8 * kThreads]), o, d, T, Lr, depth);
-                    ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = Lr.x; ps[4 * kThreads] = Lr.y; ps[5 * kThreads] = Lr.z;
-                    ps[6 * kThreads] = __int_as_float(depth);
-                    L.begin(o, d, qnodes != nullptr, bv.q_org, bv.q_step);
-                }
+                if (stream_shade(sc, fr, h, ps, o, d, wave_rad, pid)) L.begin(o, d, qnodes != nullptr, bv.q_org, bv.q_step);
+                else L.state = BvhLane::IDLE;
             }
             if (!exhausted) {                                // every idle lane claims the next path id: one atomicAdd per warp
                 const unsigned m_idle = __ballot_sync(FULL, L.state == BvhLane::IDLE);
