@@ -50,6 +50,12 @@ def test_uniform_shortcut_is_exact_on_device(tracer):
     assert tracer.selftest(0) == 0
 
 
+def test_shared_reciprocal_normalize_is_exact_on_device(tracer):
+    """normalize (Common.hpp:159-162): one refined reciprocal + the IEEE correction per component == three IEEE divisions,
+    bit for bit on 2^28 vectors (sampler values, random exponents across the fast path's range limits, edge mantissas, zeros)."""
+    assert tracer.selftest(1) == 0
+
+
 def test_philox_device_matches_known_answers(tracer, oracle):
     assert tracer.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert tracer.philox([0xffffffff] * 4, [0xffffffff] * 2).tolist() == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
