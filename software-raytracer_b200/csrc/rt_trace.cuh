@@ -23,7 +23,7 @@ static_assert(kThreads == kLaneThreads, "rt_bvh_lane.cuh lays the traversal stac
 //                                                                    form exists (bvh_wide.h) MODE 3 traverses that one
 // MODE 4: flat two-level accelerator (flat_build.h), everything staged in shared memory
 // Shared memory layout: [BVH stack: stack_entries x blockDim ints][spheres][cubes][nodes][refs]
-//                       MODE 4: [candidate queues: kFlatQueue x blockDim bytes][spheres][cubes][level-1 boxes][cull records][prim ids][cull slots]
+//                       MODE 4: [cluster boxes per octant: 16 x n_clusters float4][candidate queues: kFlatQueue x blockDim bytes][spheres][cubes][level-1 boxes][cull records][prim ids][cull slots]
 struct TraceCtx {
     const float4* sph; const float4* box; const float4* nodes; const int* refs;
     int* stack; float* stack_t; int stride;
@@ -48,6 +48,12 @@ __device__ __forceinline__ TraceCtx setup_trace(const SceneView& sc, const BvhVi
     float4* p = smem;
     t.coop = nullptr;
     if (MODE == 4 || MODE == 5) {
+#ifndef RTB_FLAT_NO_OCT
+        // the per-octant cluster boxes FIRST: every query addresses them per lane (base + octant), and at offset 0 of the dynamic
+        // shared memory that address is one add instead of the whole layout computation re-done in vector registers
+        for (int i = threadIdx.x; i < 8 * fl.n_clusters; i += blockDim.x) flat_fill_oct(fl.boxes, i >> 3, i & 7, p);
+        t.fl.oct = p; p += 16 * fl.n_clusters;
+#endif
         t.q = reinterpret_cast<unsigned char*>(p) + threadIdx.x;
         p += (kFlatQueue * blockDim.x + 15) / 16;
         if (MODE == 5) {
@@ -254,7 +260,7 @@ __device__ __forceinline__ Hit trace_all(const SceneView& sc, const TraceCtx& t,
 inline size_t staged_bytes(const SceneView& sc) { return (size_t)(sc.n_sph + 2 * sc.n_box) * sizeof(float4); }
 inline size_t flat_staged_bytes(const SceneView& sc, const FlatView& fl, int threads) {
     const size_t ncull = (size_t)kClusterStride * fl.n_clusters + fl.n_singles;
-    return (size_t)kFlatQueue * threads + staged_bytes(sc) + (size_t)2 * (fl.n_clusters + fl.n_cubes) * 16 + ncull * 16 + (size_t)(sc.n_sph + sc.n_box) * 4 + ncull + 16;
+    return (size_t)kFlatQueue * threads + staged_bytes(sc) + (size_t)2 * (fl.n_clusters + fl.n_cubes) * 16 + (size_t)16 * fl.n_clusters * 16 + ncull * 16 + (size_t)(sc.n_sph + sc.n_box) * 4 + ncull + 16;
 }
 inline int pick_mode(const SceneView& sc, const AccelSel& ac, size_t& smem, int threads = kThreads, bool coop = false) {
     const size_t geo = staged_bytes(sc);

@@ -62,6 +62,9 @@ long long emu_render_mesh(const rt_object* objects, int n_obj, const rt_camera* 
     fv.boxes = reinterpret_cast<const float4*>(flat.boxes.data()); fv.cull = reinterpret_cast<const float4*>(flat.cull.data());
     fv.cull_slot = flat.cull_slot.data(); fv.prim_id = flat.prim_id.data();
     fv.n_clusters = flat.n_clusters; fv.n_cubes = flat.n_cubes; fv.n_singles = flat.n_singles; fv.kappa = flat.kappa;
+    std::vector<float4> oct((size_t)16 * flat.n_clusters + 1);                   // the per-octant cluster boxes, as setup_trace() stages them
+    for (int i = 0; i < 8 * flat.n_clusters; ++i) flat_fill_oct(fv.boxes, i >> 3, i & 7, oct.data());
+    fv.oct = oct.data();
     long long segs = 0;
     for (int py = 0; py < fr.height; ++py)
         for (int px = 0; px < fr.width; ++px) {
