@@ -323,22 +323,28 @@ def run_leg(args, config, torch, stream, steps=3, warmup=3):
 
 
 def interactive_line(tr, wl, frames):
-    """BASELINE.json configs[4]: progressive 1 spp frames at 1280x720, each frame = rt_render_spp(1) + rt_resolve_rgba8 into a
-    HOST surface (D2H 3.7 MB), what a viewer's frame loop does (Raytracer.cpp:572-595). Frame latency p50/p99 (host clock around
-    the two calls; rt_resolve_rgba8 synchronises) and the device time of the render kernel alone."""
+    """BASELINE.json configs[4]: progressive 1 spp frames at 1280x720, each frame = rt_render_frame(1) into a HOST surface
+    (3.7 MB per frame over PCIe), what a viewer's frame loop does (Raytracer.cpp:572-595). Frame latency p50/p99 (host clock around
+    the call, which synchronises), the same frame as rt_render_spp + rt_resolve_rgba8, and the device time of the render kernel alone."""
     import rtb200
     w, h = wl["w"], wl["h"]
     out, _owner = rtb200.host_surface(w, h)              # page-locked surface (rt_host_alloc): one DMA per frame
     for _ in range(20):
-        tr.render_spp(1); tr.resolve_rgba8(True, out)
+        tr.render_frame(1, True, out)
+    lat2 = []
+    for _ in range(frames // 4):                         # the two-call form of the same frame, for comparison
+        t0 = time.perf_counter()
+        tr.render_spp(1)
+        tr.resolve_rgba8(True, out)
+        lat2.append((time.perf_counter() - t0) * 1e3)
+    lat2.sort()
     tr.reset_accumulation(); tr.sync()
     st0 = tr.stats()
     lat, dev = [], []
     t_all = time.perf_counter()
     for _ in range(frames):
         t0 = time.perf_counter()
-        tr.render_spp(1)
-        tr.resolve_rgba8(True, out)                      # synchronises: the frame is on the host
+        tr.render_frame(1, True, out)                    # rt_render_frame: synchronises, the frame is on the host
         lat.append((time.perf_counter() - t0) * 1e3)
     total = time.perf_counter() - t_all
     for _ in range(50):                                  # device time of the render kernel (rt_get_stats synchronises: outside the latency loop)
@@ -353,8 +359,8 @@ def interactive_line(tr, wl, frames):
     peaks, peaks_src = measured_peaks()
     line = {"config": "c5", "metric": "frame latency, progressive 1 spp/frame (BASELINE.json configs[4])", "value": lat[len(lat) // 2], "unit": "ms (p50)",
             "p99_ms": lat[int(len(lat) * 0.99) - 1], "mean_ms": 1e3 * total / frames, "frames": frames, "fps": frames / total,
-            "render_kernel_ms_p50": dev[len(dev) // 2], "higher_is_better": False,
-            "workload": "Scene1 %dx%d, 1 spp per frame, depth %d, render + resolve + D2H of %d bytes per frame into a page-locked host surface; static camera: primary hits come from the per-pixel cache"
+            "render_kernel_ms_p50": dev[len(dev) // 2], "two_call_frame_ms_p50": lat2[len(lat2) // 2], "higher_is_better": False,
+            "workload": "Scene1 %dx%d, 1 spp per frame, depth %d, one rt_render_frame per frame: the render kernel resolves the pixels it finishes and streams them (%d bytes per frame) into a page-locked host surface while it traces; two_call_frame = rt_render_spp + rt_resolve_rgba8 (render, resolve, copy one after the other); static camera: primary hits come from the per-pixel cache"
                         % (w, h, DEPTH, w * h * 4),
             "data": wl["data"], "Msegments_per_s": segs / n_all / (total / frames) / 1e6, "segments_per_path": segs / (w * h * n_all), "traced_segments_per_path": traced / (w * h * n_all),
             "accel": ACCEL_NAMES[st1.accel], "pipeline": PIPE_NAMES[st1.pipeline],

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 3
+#define RT_B200_ABI_VERSION 4
 
 typedef struct rt_ctx rt_ctx;
 
@@ -231,6 +231,14 @@ int rt_render_spp(rt_ctx* ctx, int spp);
  * the resolve half of SetScreenPixel (Raytracer.cpp:73-75, Common.hpp:189-206).
  * host_out: height rows of pitch_bytes. Synchronises. */
 int rt_resolve_rgba8(rt_ctx* ctx, uint32_t* host_out, int pitch_bytes, int flip_y);
+
+/* One progressive frame = rt_render_spp(ctx, spp) followed by rt_resolve_rgba8(ctx, host_out, pitch_bytes, flip_y), same
+ * accumulation buffer, same surface bits, as ONE call: the reference's frame resolves every pixel the moment it is traced
+ * (renderArea -> SetScreenPixel, Raytracer.cpp:63-76,223-257), and for 1-2 samples per pixel so does the render kernel here - pixels
+ * are resolved as they finish and streamed to a page-locked surface (rt_host_alloc, tight pitch) while the rest of the frame is
+ * still being traced, so the frame costs the render alone instead of render + resolve + copy. Other cases (more samples, block-
+ * filled frames, preview, shards of a multi-GPU render) run the two steps back to back. Synchronises. */
+int rt_render_frame(rt_ctx* ctx, int spp, uint32_t* host_out, int pitch_bytes, int flip_y);
 
 /* Page-locked host memory for the surface handed to rt_resolve_rgba8 / rt_read_surface: the device-to-host copy
  * then runs as one DMA instead of being staged by the driver (1280x720 frame loop: 0.30 ms instead of 0.44 ms per

@@ -22,8 +22,8 @@ def child(case):
     w, h, spp, pipe, reps = 1920, 1080, 1024, rtb200.RT_PIPELINE_AUTO, 5
     if case == "c1":
         w, h, spp, reps = 640, 480, 64, 20
-    elif case in ("c5", "c5_1080"):
-        w, h, spp, reps = (1280, 720, 1, 400) if case == "c5" else (1920, 1080, 1, 400)
+    elif case in ("c5", "c5_1080", "c5f", "c5f_1080"):           # c5f: one rt_render_frame per frame
+        w, h, spp, reps = (1280, 720, 1, 400) if case in ("c5", "c5f") else (1920, 1080, 1, 400)
     elif case.startswith("c3"):
         objs, cam, w, h, spp = synthetic_spheres(10000), config3_camera(rtb200.default_camera), 3840, 2160, 16
     elif case.startswith("c4"):
@@ -42,13 +42,17 @@ def child(case):
     out = {"case": case}
     if case.startswith("c5"):
         surf, _owner = rtb200.host_surface(w, h)
+        fused = case.startswith("c5f")
         for _ in range(50):
-            t.render_spp(1); t.resolve_rgba8(True, surf)
+            if fused: t.render_frame(1, True, surf)
+            else: t.render_spp(1); t.resolve_rgba8(True, surf)
         ms, wall = [], []
         for _ in range(reps):
             t0 = time.perf_counter()
-            t.render_spp(1); t.resolve_rgba8(True, surf)
+            if fused: t.render_frame(1, True, surf)
+            else: t.render_spp(1); t.resolve_rgba8(True, surf)
             wall.append((time.perf_counter() - t0) * 1e3)
+        out["surface_sum"] = int(surf.astype(np.uint64).sum())
         for _ in range(100):
             t.render_spp(1); ms.append(t.stats().last_render_ms)
         ms.sort(); wall.sort()

@@ -812,7 +812,8 @@ int rt_reset_accumulation(rt_ctx* c) {
     return RT_OK;
 }
 
-int rt_render_spp(rt_ctx* c, int spp) {
+// rt_render_spp; `frame` != nullptr (rt_render_frame): the launch may resolve the frame itself (FrameTarget::fused)
+static int render_samples(rt_ctx* c, int spp, FrameTarget* frame) {
     int rc = prepare(c);
     if (rc != RT_OK) return rc;
     if (spp < 0) return fail(c, RT_ERR_INVALID, "rt_render_spp: negative spp");
@@ -874,10 +875,12 @@ int rt_render_spp(rt_ctx* c, int spp) {
         if (wavefront) {}
         else if (scheduled)
             RT_CUDA(c, launch_render_bvh(c->view, ac, c->frame, c->d_accum, first, mine, c->d_counters, c->opt_bvh_wait_k, c->stream));
-        else
+        else {
+            if (frame) frame->samples_after = c->samples + (uint32_t)mine;
             RT_CUDA(c, launch_render_regen(c->view, ac, c->frame, c->d_accum, first, mine, prim, c->d_counters, c->stream, c->opt_pool_tiles,
                                            c->opt_flat_coop == 2 ? (c->opt_accel == RT_ACCEL_AUTO ? c->tuned_flat_coop != 0 : c->view.n_box == 0) : c->opt_flat_coop != 0,
-                                           c->opt_trav_stats != 0));
+                                           c->opt_trav_stats != 0, c->world == 1 && mine > 0 ? frame : nullptr));
+        }
         if (!wavefront) c->used_pipeline = RT_PIPELINE_REGEN;
         c->next_sample += (uint32_t)spp;
         c->samples += (uint32_t)mine;      // what THIS buffer holds; rt_set_sample_count after an external reduce
@@ -885,6 +888,44 @@ int rt_render_spp(rt_ctx* c, int spp) {
     }
     RT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->render_timed = true;
+    return RT_OK;
+}
+
+int rt_render_spp(rt_ctx* c, int spp) { return render_samples(c, spp, nullptr); }
+
+// device pointer of a page-locked host surface with a tight pitch (what the kernels can store to directly), else nullptr
+static uint32_t* mapped_surface(uint32_t* host_out, int pitch_bytes, int w) {
+    static const bool zero_copy = [] { const char* v = getenv("RTB200_ZEROCOPY"); return !(v && v[0] == '0'); }();
+    if (!zero_copy || pitch_bytes != w * 4) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return (uint32_t*)at.devicePointer;
+    cudaGetLastError();
+    return nullptr;
+}
+
+// One progressive frame: rt_render_spp(spp) + rt_resolve_rgba8(host_out) with the same result, as ONE call - which is what the
+// reference's frame is (renderArea resolves every pixel as it is traced, Raytracer.cpp:63-76,223-257). For 1-2 samples per pixel the
+// render kernel resolves the pixels it finishes and streams them to a page-locked surface while it is still tracing (FrameOut,
+// rt_kernels.cu); every other case runs the two steps one after the other.
+int rt_render_frame(rt_ctx* c, int spp, uint32_t* host_out, int pitch_bytes, int flip_y) {
+    int rc = prepare(c);
+    if (rc != RT_OK) return rc;
+    const int w = c->par.width, h = c->par.height;
+    if (!host_out || pitch_bytes < w * 4) return fail(c, RT_ERR_INVALID, "rt_render_frame: bad output buffer");
+    static const bool fuse_on = [] { const char* v = getenv("RTB200_FRAME_FUSE"); return !(v && v[0] == '0'); }();
+    FrameTarget ft;
+    ft.surface = c->d_argb; ft.mapped_host = mapped_surface(host_out, pitch_bytes, w); ft.flip_y = flip_y ? 1 : 0;
+    const bool candidate = fuse_on && c->par.mode == RT_MODE_PATH && c->pixel_step <= 1 && c->world == 1;
+    if ((rc = render_samples(c, spp, candidate ? &ft : nullptr)) != RT_OK) return rc;
+    if (!ft.fused) return rt_resolve_rgba8(c, host_out, pitch_bytes, flip_y);
+    cudaError_t e = cudaSuccess;
+    if (!ft.mapped_host) {
+        if (pitch_bytes == w * 4) e = cudaMemcpyAsync(host_out, c->d_argb, (size_t)w * 4 * (size_t)h, cudaMemcpyDeviceToHost, c->stream);
+        else e = cudaMemcpy2DAsync(host_out, (size_t)pitch_bytes, c->d_argb, (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(c, e, "rt_render_frame");
+    c->last_resolve_ms = 0.f;                                 // no separate resolve ran
     return RT_OK;
 }
 
@@ -906,13 +947,7 @@ int rt_resolve_rgba8(rt_ctx* c, uint32_t* host_out, int pitch_bytes, int flip_y)
     if (!host_out || pitch_bytes < w * 4) return fail(c, RT_ERR_INVALID, "rt_resolve_rgba8: bad output buffer");
     // A page-locked host surface (rt_host_alloc) with a tight pitch is written by the resolve kernel itself, over PCIe (zero-copy):
     // an interactive frame then has no separate device-to-host copy to set up and wait for. RTB200_ZEROCOPY=0 turns it off.
-    uint32_t* mapped = nullptr;
-    static const bool zero_copy = [] { const char* v = getenv("RTB200_ZEROCOPY"); return !(v && v[0] == '0'); }();
-    if (zero_copy && pitch_bytes == w * 4) {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, host_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) mapped = (uint32_t*)at.devicePointer;
-        else cudaGetLastError();
-    }
+    uint32_t* mapped = mapped_surface(host_out, pitch_bytes, w);
     cudaEventRecord(c->ev2, c->stream);
     cudaError_t e = launch_resolve(c->d_accum, c->samples, w, h, 0, w * h, flip_y, c->d_argb, 0, c->stream, mapped);
     cudaEventRecord(c->ev3, c->stream);

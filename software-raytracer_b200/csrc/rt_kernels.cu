@@ -245,6 +245,42 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     if (COUNT) flush_trav_count(cnt, traced, seg_counter);
 }
 
+// ---- resolve: sum/count -> Reinhard -> truncating ARGB8 pack (Raytracer.cpp:73-75) -----------
+__device__ __forceinline__ uint32_t pack_lane(float v) {
+    const float s = v * 255.f;                              // Common.hpp:190-193 (int)(c*255)
+    int i;
+    // out-of-range and NaN conversions give INT_MIN on the reference's x86 targets (cvttss2si)
+    if (!(s > -2147483904.0f && s < 2147483648.0f)) i = (int)0x80000000;
+    else i = __float2int_rz(s);
+    if (i > 255) i = 255;                                   // :195-198
+    return (uint32_t)(i & 0xff);                            // (Uint8) :200-203
+}
+__device__ __forceinline__ uint32_t resolve_pixel(float4 a, float count) {
+    float r = a.x, g = a.y, b = a.z;
+    if (count > 0.f) { r = r / count; g = g / count; b = b / count; }      // sum -> mean; count 0: already a mean
+    const float R = c0(r / c0(1.f + r)), G = c0(g / c0(1.f + g)), B = c0(b / c0(1.f + b));   // :74
+    return (pack_lane(R) << 16) | (pack_lane(G) << 8) | pack_lane(B);                        // alpha byte 0
+}
+// ---- frame fused into the render (rt_render_frame) --------------------------------------------------------------------
+// An interactive frame is rt_render_spp(1) + rt_resolve_rgba8: render kernel, resolve kernel, 3.7 MB (720p) over PCIe, one after the
+// other - the copy alone is a third of the frame. The reference resolves every pixel the moment it is traced (SetScreenPixel inside
+// renderArea, Raytracer.cpp:63-76,250). With a FrameOut the pixel-pool kernel does the same: the lane that finishes a pixel resolves it
+// into the device surface, and when the last pixel of a warp's CHUNK (two 8x4 tiles, all traced by that warp) is done the warp copies
+// the chunk's rows to the caller's page-locked surface (64-byte row segments over PCIe, spread over the whole render). Chunk
+// bookkeeping is warp-uniform: pixels left per in-flight chunk as the four bytes of one register, the chunks' first tiles in shared
+// memory (4 words per warp behind the trace layout).
+struct FrameOut {
+    uint32_t* out;         // device surface (whole image), nullptr: not fused
+    uint32_t* out2;        // mapped page-locked host surface or nullptr
+    float count;           // samples in the accumulation buffer after this launch
+    int flip_y;
+    int smem_off;          // byte offset of the 4 x (threads / 32) chunk words in dynamic shared memory
+};
+__device__ __forceinline__ void frame_store(const FrameOut& fo, const FrameView& fr, uint32_t pixel, float4 a) {
+    const uint32_t y = pixel / (uint32_t)fr.width, x = pixel - y * (uint32_t)fr.width;
+    fo.out[(size_t)x + (size_t)(fo.flip_y ? (uint32_t)fr.height - 1u - y : y) * (uint32_t)fr.width] = resolve_pixel(a, fo.count);
+}
+
 // ---- few samples per pixel: warp-level pixel pool -------------------------------------------------------------
 // With one lane per pixel a launch of n samples keeps a warp busy for the LONGEST of its 32 pixels' work; for large
 // n that averages out (29.8 of 32 lanes alive at 1024 spp), but an interactive 1-spp frame runs ~4.5 warp iterations
@@ -252,16 +288,53 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
 // 8x4 pixel tiles from one cursor per launch (one atomicAdd per chunk, requested ahead of time) and its lanes pull PIXELS
 // from the current chunk (one ballot + popcount): a lane that finishes a pixel's n samples starts the next
 // pixel at once. One pixel is still traced by one lane, samples in order, one write: the same bits as k_render_regen.
-template <int MODE, bool REUSE>
+template <int MODE, bool REUSE, bool FRAME>
 __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
                                                            uint32_t s_begin, int n_samples, int pool_tiles, PrimCache prim,
-                                                           unsigned int* __restrict__ tile_cursor, unsigned long long* __restrict__ seg_counter) {
+                                                           unsigned int* __restrict__ tile_cursor, unsigned long long* __restrict__ seg_counter, FrameOut fo) {
     extern __shared__ float4 smem[];
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int tiles_x = (fr.width + 7) / 8, tiles_y = (fr.height + 3) / 4;
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    // frame output (FRAME: its own instantiation, the bookkeeping costs registers; requires pool_tiles <= 2): see FrameOut
+    constexpr bool fuse = FRAME;
+    unsigned int* const chunk_tile = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(smem) + fo.smem_off) + (threadIdx.x >> 5) * 4;
+    unsigned int left4 = 0u;                                  // pixels not yet finished of the chunks in flight, byte (seq & 3)
+    int seq_cur = -1, my_seq = 0, fin_seq = 0;                // chunks are numbered per warp in claim order
+    bool fin = false;
+    // a chunk whose last pixel finished: the warp copies its rows from the device surface to the host surface
+    auto chunk_done = [&](int sq) {
+        if (fo.out2 == nullptr) return;
+        __syncwarp();                                        // the pixels were stored by lanes of this warp
+        const unsigned int t0 = chunk_tile[sq & 3];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int row = 2 * p + (lane >> 4), xx = lane & 15;
+            const unsigned int tile = t0 + (unsigned int)(xx >> 3);
+            if ((xx >> 3) < pool_tiles && tile < n_tiles) {
+                const int x = (int)(tile % (unsigned int)tiles_x) * 8 + (xx & 7), y = (int)(tile / (unsigned int)tiles_x) * 4 + row;
+                if (x < fr.width && y < fr.height) {
+                    const size_t dst = (size_t)x + (size_t)(fo.flip_y ? fr.height - 1 - y : y) * fr.width;
+                    fo.out2[dst] = __ldcg(fo.out + dst);
+                }
+            }
+        }
+    };
+    // the lanes flagged `fin` finished a pixel of chunk fin_seq in this pass
+    auto retire = [&]() {
+        unsigned m_fin = __ballot_sync(FULL, fin);
+        while (m_fin) {
+            const int sq = __shfl_sync(FULL, fin_seq, __ffs((int)m_fin) - 1);
+            const unsigned same = __ballot_sync(FULL, fin && fin_seq == sq);
+            m_fin &= ~same;
+            const int sh = 8 * (sq & 3);
+            left4 -= (unsigned int)__popc(same) << sh;
+            if (((left4 >> sh) & 0xffu) == 0u) chunk_done(sq);
+        }
+        fin = false;
+    };
     // the warp's current chunk of `pool_tiles` tiles, claimed from the launch's cursor; the NEXT chunk is requested as soon as
     // the current one is half handed out, so the atomic's round trip overlaps the tracing (its result is first read when needed)
     unsigned int tile0 = 0, claimed = 0;                                                    // warp-uniform
@@ -293,21 +366,29 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
                     float4 a = accum[pixel];
                     a.x += acc.x; a.y += acc.y; a.z += acc.z;
                     accum[pixel] = a;
+                    if (fuse) { frame_store(fo, fr, pixel, a); fin = true; fin_seq = my_seq; }
                     busy = false;
                 } else if (REUSE) { h = h0; ++segs; scat = true; }     // next sample from the cached primary hit
             } else scat = true;
         }
         const unsigned m_need = __ballot_sync(FULL, !busy);
+        if (fuse) retire();
         if (!have_claim && !drained && 2 * next >= total) {  // ask for the next chunk early
             if (lane == 0) claimed = atomicAdd(tile_cursor, (unsigned int)pool_tiles);
             have_claim = true;
         }
-        if (m_need != 0u && next >= total && have_claim) {   // the current chunk is handed out: switch to the claimed one
+        // (frame output: the chunk four claims back must be complete before its bookkeeping slot is used again - else wait a pass)
+        if (m_need != 0u && next >= total && have_claim && !(fuse && ((left4 >> (8 * ((seq_cur + 1) & 3))) & 0xffu) != 0u)) {   // the current chunk is handed out: switch to the claimed one
             tile0 = __shfl_sync(FULL, claimed, 0);
             have_claim = false;
             if (tile0 >= n_tiles) { drained = true; total = 0; }
             else { const unsigned int rem = n_tiles - tile0; total = (int)(rem < (unsigned int)pool_tiles ? rem : (unsigned int)pool_tiles) * 32; }
             next = 0;
+            if (fuse && total > 0) {
+                ++seq_cur;
+                left4 += (unsigned int)total << (8 * (seq_cur & 3));
+                if (lane == 0) chunk_tile[seq_cur & 3] = tile0;
+            }
         }
         if (m_need != 0u && next < total) {
             const int idx = next + __popc(m_need & ((1u << lane) - 1u));
@@ -315,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
             if (!busy && idx < total) {
                 const unsigned int tile = tile0 + (unsigned int)(idx >> 5);
                 const int px = (int)(tile % (unsigned int)tiles_x) * 8 + (idx & 7), py = (int)(tile / (unsigned int)tiles_x) * 4 + ((idx & 31) >> 3);
+                if (fuse) { my_seq = seq_cur; if (!(px < fr.width && py < fr.height)) { fin = true; fin_seq = my_seq; } }   // nothing to trace for this slot of the chunk
                 if (px < fr.width && py < fr.height) {
                     pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
                     d0 = ray_dir(fr, px, py);
@@ -330,12 +412,14 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
                             float4 a = accum[pixel];
                             a.x += acc.x; a.y += acc.y; a.z += acc.z;
                             accum[pixel] = a;
+                            if (fuse) { frame_store(fo, fr, pixel, a); fin = true; fin_seq = my_seq; }
                             busy = false;                    // takes another pixel in the next pass
                         } else { h = h0; ++segs; scat = true; }
                     }
                 }
             }
         }
+        if (fuse) retire();                                  // fresh pixels whose primary ray misses are finished at once
         if (scat) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
         if (!__any_sync(FULL, busy) && drained) break;      // not drained: the next pass switches to the claimed chunk
     }
@@ -610,22 +694,7 @@ __global__ void __launch_bounds__(kThreads) k_render_blocks(SceneView sc, BvhVie
     if (segs) for (int k = 0; k < 4; ++k) atomicAdd(seg_counter + k, (unsigned long long)segs);
 }
 
-// ---- resolve: sum/count -> Reinhard -> truncating ARGB8 pack (Raytracer.cpp:73-75) -----------
-__device__ __forceinline__ uint32_t pack_lane(float v) {
-    const float s = v * 255.f;                              // Common.hpp:190-193 (int)(c*255)
-    int i;
-    // out-of-range and NaN conversions give INT_MIN on the reference's x86 targets (cvttss2si)
-    if (!(s > -2147483904.0f && s < 2147483648.0f)) i = (int)0x80000000;
-    else i = __float2int_rz(s);
-    if (i > 255) i = 255;                                   // :195-198
-    return (uint32_t)(i & 0xff);                            // (Uint8) :200-203
-}
-__device__ __forceinline__ uint32_t resolve_pixel(float4 a, float count) {
-    float r = a.x, g = a.y, b = a.z;
-    if (count > 0.f) { r = r / count; g = g / count; b = b / count; }      // sum -> mean; count 0: already a mean
-    const float R = c0(r / c0(1.f + r)), G = c0(g / c0(1.f + g)), B = c0(b / c0(1.f + b));   // :74
-    return (pack_lane(R) << 16) | (pack_lane(G) << 8) | pack_lane(B);                        // alpha byte 0
-}
+// ---- resolve kernels (resolve_pixel(): above k_render_pool, which resolves finished pixels itself) -----------
 // Generic slice resolve: pixels [first, first+n) of a width x height image; `accum` points at
 // the slice. Output row = flip ? (H-1-y) : y (Raytracer.cpp:64), tightly packed width*4 pitch,
 // `out` points at the start of the WHOLE image when whole_image_out, else at the slice.
@@ -760,7 +829,14 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(K<3, false>)) != cudaSuccess) return e; if ((e = optin(K<3, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<4, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true>)) != cudaSuccess) return e; \
     if ((e = optin(K<5, false>)) != cudaSuccess) return e; if ((e = optin(K<5, true>)) != cudaSuccess) return e;
-    RTB_OPTIN2(k_render_regen) RTB_OPTIN2(k_render_pool) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick) RTB_OPTIN(k_render_blocks)
+#define RTB_OPTIN3(K) \
+    if ((e = optin(K<0, false, false>)) != cudaSuccess) return e; if ((e = optin(K<0, true, false>)) != cudaSuccess) return e; if ((e = optin(K<0, false, true>)) != cudaSuccess) return e; if ((e = optin(K<0, true, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<1, false, false>)) != cudaSuccess) return e; if ((e = optin(K<1, true, false>)) != cudaSuccess) return e; if ((e = optin(K<1, false, true>)) != cudaSuccess) return e; if ((e = optin(K<1, true, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<2, false, false>)) != cudaSuccess) return e; if ((e = optin(K<2, true, false>)) != cudaSuccess) return e; if ((e = optin(K<2, false, true>)) != cudaSuccess) return e; if ((e = optin(K<2, true, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<3, false, false>)) != cudaSuccess) return e; if ((e = optin(K<3, true, false>)) != cudaSuccess) return e; if ((e = optin(K<3, false, true>)) != cudaSuccess) return e; if ((e = optin(K<3, true, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<4, false, false>)) != cudaSuccess) return e; if ((e = optin(K<4, true, false>)) != cudaSuccess) return e; if ((e = optin(K<4, false, true>)) != cudaSuccess) return e; if ((e = optin(K<4, true, true>)) != cudaSuccess) return e; \
+    if ((e = optin(K<5, false, false>)) != cudaSuccess) return e; if ((e = optin(K<5, true, false>)) != cudaSuccess) return e; if ((e = optin(K<5, false, true>)) != cudaSuccess) return e; if ((e = optin(K<5, true, true>)) != cudaSuccess) return e;
+    RTB_OPTIN2(k_render_regen) RTB_OPTIN3(k_render_pool) RTB_OPTIN(k_render_preview) RTB_OPTIN(k_primary_aov) RTB_OPTIN(k_trace_rays) RTB_OPTIN(k_pick) RTB_OPTIN(k_render_blocks)
     RTB_OPTIN(k_primary_cache)
     if ((e = optin(k_render_bvh<2>)) != cudaSuccess) return e;
     if ((e = optin(k_render_bvh<3>)) != cudaSuccess) return e;
@@ -773,6 +849,7 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(k_render_regen<3, false, true>)) != cudaSuccess) return e;
 #undef RTB_OPTIN
 #undef RTB_OPTIN2
+#undef RTB_OPTIN3
     done = true;
     return cudaSuccess;
 }
@@ -869,7 +946,7 @@ cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView
 
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                 uint32_t s_begin, int n_samples, const PrimCache* prim_cache, unsigned long long* seg_counter, cudaStream_t st, int pool_override, bool flat_coop,
-                                bool count_traversal) {
+                                bool count_traversal, FrameTarget* frame) {
     if (n_samples <= 0) return cudaSuccess;
     const bool reuse_primary = prim_cache != nullptr;
     PrimCache prim;
@@ -899,7 +976,22 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
         if (blocks > (long long)sms * RTB_REGEN_MIN_BLOCKS) blocks = (long long)sms * RTB_REGEN_MIN_BLOCKS;
         unsigned int* cursor = reinterpret_cast<unsigned int*>(seg_counter + kTileCursorSlot);
         if ((e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st)) != cudaSuccess) return e;
-        RTB_DISPATCH2(mode, reuse_primary, k_render_pool, (unsigned int)blocks, sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, prim, cursor, seg_counter)
+        FrameOut fo;
+        fo.out = nullptr; fo.out2 = nullptr; fo.count = 0.f; fo.flip_y = 0; fo.smem_off = 0;
+        if (frame && frame->surface && pool_tiles == 2) {     // resolve + host copy inside the render (FrameOut)
+            fo.out = frame->surface; fo.out2 = frame->mapped_host; fo.count = (float)frame->samples_after; fo.flip_y = frame->flip_y;
+            fo.smem_off = (int)((sb + 15) / 16 * 16);
+            sb = (size_t)fo.smem_off + (size_t)(kThreads / 32) * 4 * sizeof(unsigned int);
+            frame->fused = true;
+        }
+#define RTB_POOL_CASE(M) case M: \
+            if (fo.out) { if (reuse_primary) k_render_pool<M, true, true><<<(unsigned int)blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, prim, cursor, seg_counter, fo); \
+                          else k_render_pool<M, false, true><<<(unsigned int)blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, prim, cursor, seg_counter, fo); } \
+            else { if (reuse_primary) k_render_pool<M, true, false><<<(unsigned int)blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, prim, cursor, seg_counter, fo); \
+                   else k_render_pool<M, false, false><<<(unsigned int)blocks, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, pool_tiles, prim, cursor, seg_counter, fo); } \
+            break;
+        switch (mode) { RTB_POOL_CASE(0) RTB_POOL_CASE(1) RTB_POOL_CASE(2) RTB_POOL_CASE(3) RTB_POOL_CASE(4) default: RTB_POOL_CASE(5) }
+#undef RTB_POOL_CASE
         return cudaGetLastError();
     }
     if (count_traversal && (mode == 2 || mode == 3) && !ac.bvh.wnodes) {

@@ -45,12 +45,23 @@ cudaError_t launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 cudaError_t launch_selftest_uniform(int* dev_failures, cudaStream_t st);
 cudaError_t launch_selftest_normalize(int* dev_failures, cudaStream_t st);
 cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView& fr, int px, int py, int* dev_id, cudaStream_t st);
+// A frame rendered INTO a surface (rt_render_frame): when the launch is the pixel-pool kernel's (1-2 samples), finished pixels are
+// resolved into `surface` by the render kernel itself and - with `mapped_host` - copied to the caller's page-locked surface chunk by
+// chunk while the render goes on; `fused` tells the caller whether that happened (else it resolves as usual).
+struct FrameTarget {
+    uint32_t* surface = nullptr;       // device surface, whole image
+    uint32_t* mapped_host = nullptr;   // device pointer of the page-locked host surface, or nullptr
+    uint32_t samples_after = 0;        // samples in the accumulation buffer once this launch is done
+    int flip_y = 1;
+    bool fused = false;                // out
+};
 // prim_cache != NULL: primary-hit reuse (every sample starts from the cached primary hit); NULL: every sample re-traces it.
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                 uint32_t s_begin, int n_samples, const PrimCache* prim_cache, unsigned long long* seg_counter, cudaStream_t st,
                                 int pool_override = 0,    // 0: automatic; 1: always one pixel per lane; n >= 2: pool of n tiles per warp
                                 bool flat_coop = true,    // flat accelerator: warp-cooperative levels 2/3 (rt_trace.cuh)
-                                bool count_traversal = false);   // binary-BVH back ends: count node visits / primitive tests into seg_counter[8..12]
+                                bool count_traversal = false,    // binary-BVH back ends: count node visits / primitive tests into seg_counter[8..12]
+                                FrameTarget* frame = nullptr);
 cudaError_t launch_render_bvh(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum, uint32_t s_begin,
                               int n_samples, unsigned long long* seg_counter, int wait_k, cudaStream_t st);
 cudaError_t launch_render_preview(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,

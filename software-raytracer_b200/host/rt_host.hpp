@@ -170,6 +170,28 @@ public:
     // One deviation, on purpose: the reference's running mean counts that second frame twice (ACCUMULATIONFRAMES is
     // already 2 when it overwrites); here every accumulated frame has the same weight.
     bool RenderFrame() {
+        if (!BeginFrame()) return false;
+        check(rt_render_spp(ctx, 1), ctx);
+        return true;
+    }
+    // The same frame traced AND presented in one call (rt_render_frame): the reference's workers write the surface pixel by
+    // pixel while they trace (SetScreenPixel inside renderArea, :63-76,250), and so does the render kernel for full-resolution
+    // accumulation frames - with a page-locked surface the frame then costs the render alone.
+    bool RenderFrame(uint32_t* pixels, int pitch_bytes) {
+        if (!BeginFrame()) return false;
+        check(rt_render_frame(ctx, 1, pixels, pitch_bytes, 1), ctx);
+        return true;
+    }
+    // SDL surface update (the resolve half of SetScreenPixel, Raytracer.cpp:73-75): ARGB8, rows y-down.
+    void Present(uint32_t* pixels, int pitch_bytes) { check(rt_resolve_rgba8(ctx, pixels, pitch_bytes, 1), ctx); }
+    // Mouse picking (Raytracer.cpp:530-541), window coordinates.
+    int Pick(int x, int y) { int id = -1; check(rt_pick(ctx, x, y, &id), ctx); return id; }
+    int Width() const { return par.width; }
+    int Height() const { return par.height; }
+
+private:
+    // the frame state machine up to (not including) the trace: false when nothing is to be rendered
+    bool BeginFrame() {
         if (pause || (!doSetFrame && ACCUMULATIONFRAMES == TARGETFRAMES)) return false;     // :572
         par.max_bounces = MAXBOUNCES; par.mode = SIMPLEDRAW ? RT_MODE_PREVIEW : RT_MODE_PATH; par.selected_id = selectedObject;
         check(rt_set_params(ctx, &par), ctx);
@@ -184,15 +206,8 @@ public:
         }
         if (setFrame) check(rt_reset_accumulation(ctx), ctx);
         check(rt_set_pixel_step(ctx, rt_reference_pixel_step(SCREEN_SCALE, progressiveResolutionScaler), rt_reference_strip_columns(par.width)), ctx);
-        check(rt_render_spp(ctx, 1), ctx);
         return true;
     }
-    // SDL surface update (the resolve half of SetScreenPixel, Raytracer.cpp:73-75): ARGB8, rows y-down.
-    void Present(uint32_t* pixels, int pitch_bytes) { check(rt_resolve_rgba8(ctx, pixels, pitch_bytes, 1), ctx); }
-    // Mouse picking (Raytracer.cpp:530-541), window coordinates.
-    int Pick(int x, int y) { int id = -1; check(rt_pick(ctx, x, y, &id), ctx); return id; }
-    int Width() const { return par.width; }
-    int Height() const { return par.height; }
 };
 
 }  // namespace rtb200

@@ -65,7 +65,7 @@ assert OBJECT_DTYPE.itemsize == C.sizeof(RtObject) == 76
 
 # every symbol include/rt_b200.h declares
 EXPORTS = [
-    "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_load_scene", "rt_save_scene", "rt_set_scene",
+    "rt_create", "rt_destroy", "rt_render_frame", "rt_last_error", "rt_abi_version", "rt_load_scene", "rt_save_scene", "rt_set_scene",
     "rt_get_scene", "rt_default_params", "rt_default_camera", "rt_rotate_camera", "rt_set_camera", "rt_set_params",
     "rt_set_option", "rt_set_shard", "rt_shard_range", "rt_reset_accumulation", "rt_render_spp", "rt_resolve_rgba8", "rt_pick",
     "rt_read_accum", "rt_read_aov", "rt_read_ray_dirs", "rt_trace_rays", "rt_env_color", "rt_philox_block",
@@ -318,6 +318,14 @@ class PathTracer:
         if out is None:
             out = np.zeros((h, w), np.uint32)
         self._chk(self.lib.rt_resolve_rgba8(self.h, _p(out), out.strides[0], int(flip_y)))
+        return out
+
+    def render_frame(self, spp=1, flip_y=True, out=None):
+        """rt_render_frame: spp more samples per pixel and the resolved frame in `out` (a host_surface() makes it one fused pass)."""
+        w, h = self.params.width, self.params.height
+        if out is None:
+            out = np.zeros((h, w), np.uint32)
+        self._chk(self.lib.rt_render_frame(self.h, int(spp), _p(out), out.strides[0], int(flip_y)))
         return out
 
     def pick(self, x, y_window):

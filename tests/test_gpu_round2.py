@@ -436,3 +436,50 @@ def test_streaming_pipeline_is_bit_identical_on_small_bvh_scenes(tracer, scenes,
         tracer.set_option(rtb200.RT_OPT_PIPELINE, rtb200.RT_PIPELINE_AUTO)
         tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
         tracer.set_option(rtb200.RT_OPT_PRIMARY_REUSE, 1)
+
+
+# ---- rt_render_frame: the frame resolved (and streamed to the host surface) by the render kernel itself ----------------------------
+@pytest.mark.parametrize("scene,w,h", [("Scene1", 333, 77), ("Scene3_indirect", 640, 360), ("Scene1", 1283, 721)])
+def test_render_frame_equals_render_then_resolve(tracer, scenes, scene, w, h):
+    """One call per progressive frame (Raytracer.cpp:223-257: renderArea resolves every pixel as it traces it) == rt_render_spp +
+    rt_resolve_rgba8, bit for bit: surface AND accumulation buffer, frame after frame, page-locked and pageable surfaces, both row
+    orders, widths that cut tiles (partial 8x4 tiles and a last chunk of one tile), 1 spp (fused) and 4 spp (two steps inside)."""
+    pinned, _owner = rtb200.host_surface(w, h)
+    for flip in (True, False):
+        setup(tracer, scenes[scene], w, h)
+        want = []
+        for n in (1, 1, 1, 4, 1, 2):
+            tracer.render_spp(n)
+            want.append(tracer.resolve_rgba8(flip).copy())
+        acc_want, n_want = tracer.read_accum()
+        setup(tracer, scenes[scene], w, h)
+        for i, n in enumerate((1, 1, 1, 4, 1, 2)):
+            pinned[:] = 0xdeadbeef
+            got = tracer.render_frame(n, flip, pinned)
+            assert np.array_equal(got, want[i]), (flip, i, int((got != want[i]).sum()))
+        acc, n_got = tracer.read_accum()
+        assert n_got == n_want and np.array_equal(bits(acc), bits(acc_want))
+        setup(tracer, scenes[scene], w, h)               # pageable destination: fused resolve + one copy
+        for i, n in enumerate((1, 1, 1)):
+            got = tracer.render_frame(n, flip)
+            assert np.array_equal(got, want[i]), (flip, i)
+
+
+def test_render_frame_sky_only_and_other_modes(tracer, scenes):
+    """Every pixel a miss (finished the moment it is picked up), preview mode and block-filled frames (not fused: same result)."""
+    w, h = 200, 50
+    pinned, _owner = rtb200.host_surface(w, h)
+    setup(tracer, scenes["Scene1"][:0], w, h)
+    tracer.render_spp(1)
+    want = tracer.resolve_rgba8().copy()
+    setup(tracer, scenes["Scene1"][:0], w, h)
+    assert np.array_equal(tracer.render_frame(1, True, pinned), want)
+    setup(tracer, scenes["Scene1"], w, h)
+    tracer.set_pixel_step(4, 16)
+    try:
+        tracer.render_spp(1)
+        want = tracer.resolve_rgba8().copy()
+        tracer.reset_accumulation()
+        assert np.array_equal(tracer.render_frame(1, True, pinned), want)
+    finally:
+        tracer.set_pixel_step(1, 0)
