@@ -237,7 +237,7 @@ def fp32_roofline(objs, st, delivered_per_step, traced_per_step, kern_s, peaks, 
     return {"bound": "fp32", "achieved": ach_exec, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_exec / peak_tf,
             "basis": "executed closest-hit queries x the reference's brute-force op count per segment (23/sphere + 30/cube + 110)",
             "achieved_delivered": ach_deliv, "frac_delivered": ach_deliv / peak_tf,
-            "traffic": 33.3e6 * (w * h) / (1920 * 1080), "traffic_note": "dram read+write per launch, ncu --set full at 1080p (profiles/r1y_summary_final_1024spp.txt) scaled by pixel count: the float4 accumulation buffer once; independent of spp",
+            "traffic": 86.2e6 * (w * h) / (1920 * 1080), "traffic_note": "dram read+write per launch, ncu --set full at 1080p (profiles/r2v_summary_regen_c2_1024spp.txt: 75.4 MB read + 10.8 MB written) scaled by pixel count: the primary-hit cache (20 B per pixel) and the float4 accumulation buffer once, the write mostly still in L2 when the launch ends; independent of spp",
             "kernel": "k_render_regen", "kernel_ms": kern_s * 1e3, "flop_per_segment": fps,
             "peak_source": "%d SMs x 128 lanes x 2 (FMA) x %.0f MHz (%s MEASURED_PEAKS.json sm_max_mhz)" % (st.sm_count, sm_mhz, peaks_src),
             "note": "path is FP32-CUDA-core issue bound, not HBM or tensor (SURVEY.md 8d). The strict-IEEE build (-fmad=false) issues multiply and add separately, "
