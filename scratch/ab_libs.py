@@ -22,8 +22,8 @@ def child(case):
     w, h, spp, pipe, reps = 1920, 1080, 1024, rtb200.RT_PIPELINE_AUTO, 5
     if case == "c1":
         w, h, spp, reps = 640, 480, 64, 20
-    elif case in ("c5", "c5_1080", "c5f", "c5f_1080"):           # c5f: one rt_render_frame per frame
-        w, h, spp, reps = (1280, 720, 1, 400) if case in ("c5", "c5f") else (1920, 1080, 1, 400)
+    elif case in ("c5", "c5_1080", "c5f", "c5f_1080", "c5p"):    # c5f: one rt_render_frame per frame; c5p: the same into pageable memory
+        w, h, spp, reps = (1280, 720, 1, 400) if case in ("c5", "c5f", "c5p") else (1920, 1080, 1, 400)
     elif case.startswith("c3"):
         objs, cam, w, h, spp = synthetic_spheres(10000), config3_camera(rtb200.default_camera), 3840, 2160, 16
     elif case.startswith("c4"):
@@ -42,7 +42,8 @@ def child(case):
     out = {"case": case}
     if case.startswith("c5"):
         surf, _owner = rtb200.host_surface(w, h)
-        fused = case.startswith("c5f")
+        if case == "c5p": surf = np.zeros((h, w), np.uint32)
+        fused = case.startswith("c5f") or case == "c5p"
         for _ in range(50):
             if fused: t.render_frame(1, True, surf)
             else: t.render_spp(1); t.resolve_rgba8(True, surf)
@@ -55,6 +56,11 @@ def child(case):
         out["surface_sum"] = int(surf.astype(np.uint64).sum())
         for _ in range(100):
             t.render_spp(1); ms.append(t.stats().last_render_ms)
+        if fused:
+            fk = []
+            for _ in range(100):
+                t.render_frame(1, True, surf); fk.append(t.stats().last_render_ms)
+            fk.sort(); out["frame_kernel_ms_p50"] = round(fk[len(fk) // 2], 4)
         ms.sort(); wall.sort()
         out.update(render_ms_p50=round(ms[len(ms) // 2], 4), frame_ms_p50=round(wall[len(wall) // 2], 4), frame_ms_p99=round(wall[int(len(wall) * 0.99)], 4))
     else:

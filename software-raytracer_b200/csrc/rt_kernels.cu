@@ -265,22 +265,18 @@ __device__ __forceinline__ uint32_t resolve_pixel(float4 a, float count) {
 // ---- frame fused into the render (rt_render_frame) --------------------------------------------------------------------
 // An interactive frame is rt_render_spp(1) + rt_resolve_rgba8: render kernel, resolve kernel, 3.7 MB (720p) over PCIe, one after the
 // other - the copy alone is a third of the frame. The reference resolves every pixel the moment it is traced (SetScreenPixel inside
-// renderArea, Raytracer.cpp:63-76,250). With a FrameOut the pixel-pool kernel does the same: the lane that finishes a pixel resolves it
-// into the device surface, and when the last pixel of a warp's CHUNK (two 8x4 tiles, all traced by that warp) is done the warp copies
-// the chunk's rows to the caller's page-locked surface (64-byte row segments over PCIe, spread over the whole render). Chunk
-// bookkeeping is warp-uniform: pixels left per in-flight chunk as the four bytes of one register, the chunks' first tiles in shared
-// memory (4 words per warp behind the trace layout).
+// renderArea, Raytracer.cpp:63-76,250). With a FrameOut the pixel-pool kernel does the same at the granularity of a warp's CHUNK (two
+// tiles of 32 pixels, all traced by that warp): when the chunk's last pixel is done the warp resolves the chunk and stores its rows
+// to the device surface and to the caller's page-locked surface (whole 128-byte lines over PCIe, spread over the whole render). Chunk
+// bookkeeping is warp-uniform: pixels left per in-flight chunk as the eight bytes of one 64-bit register, the chunks' first tiles in
+// shared memory (8 words per warp behind the trace layout).
 struct FrameOut {
     uint32_t* out;         // device surface (whole image), nullptr: not fused
     uint32_t* out2;        // mapped page-locked host surface or nullptr
     float count;           // samples in the accumulation buffer after this launch
     int flip_y;
-    int smem_off;          // byte offset of the 4 x (threads / 32) chunk words in dynamic shared memory
+    int smem_off;          // byte offset of the kPoolSlots x (threads / 32) chunk words in dynamic shared memory
 };
-__device__ __forceinline__ void frame_store(const FrameOut& fo, const FrameView& fr, uint32_t pixel, float4 a) {
-    const uint32_t y = pixel / (uint32_t)fr.width, x = pixel - y * (uint32_t)fr.width;
-    fo.out[(size_t)x + (size_t)(fo.flip_y ? (uint32_t)fr.height - 1u - y : y) * (uint32_t)fr.width] = resolve_pixel(a, fo.count);
-}
 
 // ---- few samples per pixel: warp-level pixel pool -------------------------------------------------------------
 // With one lane per pixel a launch of n samples keeps a warp busy for the LONGEST of its 32 pixels' work; for large
@@ -289,6 +285,35 @@ __device__ __forceinline__ void frame_store(const FrameOut& fo, const FrameView&
 // 8x4 pixel tiles from one cursor per launch (one atomicAdd per chunk, requested ahead of time) and its lanes pull PIXELS
 // from the current chunk (one ballot + popcount): a lane that finishes a pixel's n samples starts the next
 // pixel at once. One pixel is still traced by one lane, samples in order, one write: the same bits as k_render_regen.
+// Tile shape of the pixel pool: 32 pixels, kPoolTW wide. A chunk is two tiles side by side, and its rows are what chunk_done() sends
+// over PCIe in one piece: 8x4 tiles give 64-byte rows, 16x2 tiles 128-byte rows (one full line per store instruction and row).
+#ifndef RTB_POOL_TILE_W
+#define RTB_POOL_TILE_W 32             // measured (profiles/r2y_ab_pool_tile_shape.txt, 720p 1 spp): render alone 0.145 (8x4) / 0.142 (16x2) / 0.138 ms (32x1)
+#endif
+constexpr int kPoolTW = RTB_POOL_TILE_W, kPoolTH = 32 / kPoolTW;
+constexpr int kPoolSlots = 8;          // chunks of one warp that may be in flight with frame output (one byte of a 64-bit register each)
+static_assert(kPoolTW == 8 || kPoolTW == 16 || kPoolTW == 32, "pool tiles are 8x4, 16x2 or 32x1");
+// A chunk whose last pixel finished: the warp resolves its 64 sums (L2 loads: they were written by lanes of this warp) and stores the
+// rows to the device surface and to the host surface - 32 lanes at once, once per chunk. OUT of line: inlined at both retire points
+// its four copies of the resolve (six IEEE divisions with their slow paths each) made the render loop 1000 instructions longer.
+// (Resolving each pixel where its sum is written - for the one or two lanes that finish in a pass, in almost every pass - was worse still.)
+static __device__ __noinline__ void pool_chunk_out(const float4* accum, uint32_t* out, uint32_t* out2, float count, int flip_y, int width, int height,
+                                                   int tiles_x, unsigned int n_tiles, int pool_tiles, unsigned int t0, int lane) {
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {                            // the chunk row-major, 2 * kPoolTW pixels per row: 32 consecutive positions per pass
+        const int q = 32 * p + lane, row = q / (2 * kPoolTW), xx = q % (2 * kPoolTW);
+        const unsigned int tile = t0 + (unsigned int)(xx / kPoolTW);
+        if ((xx / kPoolTW) < pool_tiles && tile < n_tiles) {
+            const int x = (int)(tile % (unsigned int)tiles_x) * kPoolTW + (xx % kPoolTW), y = (int)(tile / (unsigned int)tiles_x) * kPoolTH + row;
+            if (x < width && y < height) {
+                const uint32_t v = resolve_pixel(__ldcg(accum + ((size_t)x + (size_t)y * width)), count);
+                const size_t dst = (size_t)x + (size_t)(flip_y ? height - 1 - y : y) * width;
+                out[dst] = v;
+                if (out2) out2[dst] = v;
+            }
+        }
+    }
+}
 template <int MODE, bool REUSE, bool FRAME>
 __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
                                                            uint32_t s_begin, int n_samples, int pool_tiles, PrimCache prim,
@@ -297,44 +322,36 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int tiles_x = (fr.width + 7) / 8, tiles_y = (fr.height + 3) / 4;
+    const int tiles_x = (fr.width + kPoolTW - 1) / kPoolTW, tiles_y = (fr.height + kPoolTH - 1) / kPoolTH;
     const unsigned int n_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     // frame output (FRAME: its own instantiation, the bookkeeping costs registers; requires pool_tiles <= 2): see FrameOut
     constexpr bool fuse = FRAME;
-    unsigned int* const chunk_tile = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(smem) + fo.smem_off) + (threadIdx.x >> 5) * 4;
-    unsigned int left4 = 0u;                                  // pixels not yet finished of the chunks in flight, byte (seq & 3)
-    int seq_cur = -1, my_seq = 0, fin_seq = 0;                // chunks are numbered per warp in claim order
-    bool fin = false;
-    // a chunk whose last pixel finished: the warp copies its rows from the device surface to the host surface
-    auto chunk_done = [&](int sq) {
-        if (fo.out2 == nullptr) return;
-        __syncwarp();                                        // the pixels were stored by lanes of this warp
-        const unsigned int t0 = chunk_tile[sq & 3];
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const int row = 2 * p + (lane >> 4), xx = lane & 15;
-            const unsigned int tile = t0 + (unsigned int)(xx >> 3);
-            if ((xx >> 3) < pool_tiles && tile < n_tiles) {
-                const int x = (int)(tile % (unsigned int)tiles_x) * 8 + (xx & 7), y = (int)(tile / (unsigned int)tiles_x) * 4 + row;
-                if (x < fr.width && y < fr.height) {
-                    const size_t dst = (size_t)x + (size_t)(fo.flip_y ? fr.height - 1 - y : y) * fr.width;
-                    fo.out2[dst] = __ldcg(fo.out + dst);
+    unsigned int* const chunk_tile = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(smem) + fo.smem_off) + (threadIdx.x >> 5) * kPoolSlots;
+    unsigned long long left8 = 0ull;                          // pixels not yet finished of the chunks in flight, byte (seq % kPoolSlots)
+    int seq_cur = -1, my_seq = 0;                             // chunks are numbered per warp in claim order
+    // a lane can finish two pixels in one pass: the one it was tracing, and a fresh one whose primary ray misses (or a chunk slot
+    // outside the image): the chunk numbers of both, -1 = none
+    int fin_a = -1, fin_b = -1;
+    uint32_t pixel = 0;                                       // the lane's current pixel
+    // end of a pass: the finished pixels leave their chunks' counts; a chunk that reaches zero is resolved and sent (ONE call site)
+    auto retire = [&]() {
+#pragma unroll 1
+        for (int e = 0; e < 2; ++e) {
+            const int mine = e ? fin_b : fin_a;
+            unsigned m_fin = __ballot_sync(FULL, mine >= 0);
+            while (m_fin) {
+                const int sq = __shfl_sync(FULL, mine, __ffs((int)m_fin) - 1);
+                const unsigned same = __ballot_sync(FULL, mine == sq);
+                m_fin &= ~same;
+                const int sh = 8 * (sq & (kPoolSlots - 1));
+                left8 -= (unsigned long long)__popc(same) << sh;
+                if (((left8 >> sh) & 0xffull) == 0ull) {
+                    __syncwarp();                            // the chunk's sums were written by lanes of this warp
+                    pool_chunk_out(accum, fo.out, fo.out2, fo.count, fo.flip_y, fr.width, fr.height, tiles_x, n_tiles, pool_tiles, chunk_tile[sq & (kPoolSlots - 1)], lane);
                 }
             }
         }
-    };
-    // the lanes flagged `fin` finished a pixel of chunk fin_seq in this pass
-    auto retire = [&]() {
-        unsigned m_fin = __ballot_sync(FULL, fin);
-        while (m_fin) {
-            const int sq = __shfl_sync(FULL, fin_seq, __ffs((int)m_fin) - 1);
-            const unsigned same = __ballot_sync(FULL, fin && fin_seq == sq);
-            m_fin &= ~same;
-            const int sh = 8 * (sq & 3);
-            left4 -= (unsigned int)__popc(same) << sh;
-            if (((left4 >> sh) & 0xffu) == 0u) chunk_done(sq);
-        }
-        fin = false;
+        fin_a = -1; fin_b = -1;
     };
     // the warp's current chunk of `pool_tiles` tiles, claimed from the launch's cursor; the NEXT chunk is requested as soon as
     // the current one is half handed out, so the atomic's round trip overlaps the tracing (its result is first read when needed)
@@ -342,7 +359,6 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
     int next = 0, total = 0;
     bool have_claim = false, drained = false;
     bool busy = false;
-    uint32_t pixel = 0;
     float3 d0 = f3(0.f, 0.f, 1.f), acc = f3(0.f, 0.f, 0.f), o = fr.cam_pos, d = d0;
     float3 T = f3(0.f, 0.f, 0.f), L = f3(0.f, 0.f, 0.f);
     int s = 0, depth = 0;
@@ -367,19 +383,19 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
                     float4 a = accum[pixel];
                     a.x += acc.x; a.y += acc.y; a.z += acc.z;
                     accum[pixel] = a;
-                    if (fuse) { frame_store(fo, fr, pixel, a); fin = true; fin_seq = my_seq; }
+                    if (fuse) fin_a = my_seq;
                     busy = false;
                 } else if (REUSE) { h = h0; ++segs; scat = true; }     // next sample from the cached primary hit
             } else scat = true;
         }
         const unsigned m_need = __ballot_sync(FULL, !busy);
-        if (fuse) retire();
         if (!have_claim && !drained && 2 * next >= total) {  // ask for the next chunk early
             if (lane == 0) claimed = atomicAdd(tile_cursor, (unsigned int)pool_tiles);
             have_claim = true;
         }
-        // (frame output: the chunk four claims back must be complete before its bookkeeping slot is used again - else wait a pass)
-        if (m_need != 0u && next >= total && have_claim && !(fuse && ((left4 >> (8 * ((seq_cur + 1) & 3))) & 0xffu) != 0u)) {   // the current chunk is handed out: switch to the claimed one
+        // (frame output: the chunk kPoolSlots claims back must be complete before its bookkeeping slot is used again - else wait a pass.
+        // With 4 slots that happened often enough - one deep path under 31 lanes racing through sky chunks - to cost 15 % of the kernel.)
+        if (m_need != 0u && next >= total && have_claim && !(fuse && ((left8 >> (8 * ((seq_cur + 1) & (kPoolSlots - 1)))) & 0xffull) != 0ull)) {   // the current chunk is handed out: switch to the claimed one
             tile0 = __shfl_sync(FULL, claimed, 0);
             have_claim = false;
             if (tile0 >= n_tiles) { drained = true; total = 0; }
@@ -387,8 +403,8 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
             next = 0;
             if (fuse && total > 0) {
                 ++seq_cur;
-                left4 += (unsigned int)total << (8 * (seq_cur & 3));
-                if (lane == 0) chunk_tile[seq_cur & 3] = tile0;
+                left8 += (unsigned long long)total << (8 * (seq_cur & (kPoolSlots - 1)));
+                if (lane == 0) chunk_tile[seq_cur & (kPoolSlots - 1)] = tile0;
             }
         }
         if (m_need != 0u && next < total) {
@@ -396,8 +412,8 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
             next += __popc(m_need);
             if (!busy && idx < total) {
                 const unsigned int tile = tile0 + (unsigned int)(idx >> 5);
-                const int px = (int)(tile % (unsigned int)tiles_x) * 8 + (idx & 7), py = (int)(tile / (unsigned int)tiles_x) * 4 + ((idx & 31) >> 3);
-                if (fuse) { my_seq = seq_cur; if (!(px < fr.width && py < fr.height)) { fin = true; fin_seq = my_seq; } }   // nothing to trace for this slot of the chunk
+                const int px = (int)(tile % (unsigned int)tiles_x) * kPoolTW + (idx % kPoolTW), py = (int)(tile / (unsigned int)tiles_x) * kPoolTH + ((idx & 31) / kPoolTW);
+                if (fuse) { my_seq = seq_cur; if (!(px < fr.width && py < fr.height)) fin_b = my_seq; }   // nothing to trace for this slot of the chunk
                 if (px < fr.width && py < fr.height) {
                     pixel = (uint32_t)px + (uint32_t)py * (uint32_t)fr.width;
                     d0 = ray_dir(fr, px, py);
@@ -413,14 +429,14 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_pool(
                             float4 a = accum[pixel];
                             a.x += acc.x; a.y += acc.y; a.z += acc.z;
                             accum[pixel] = a;
-                            if (fuse) { frame_store(fo, fr, pixel, a); fin = true; fin_seq = my_seq; }
+                            if (fuse) fin_b = my_seq;
                             busy = false;                    // takes another pixel in the next pass
                         } else { h = h0; ++segs; scat = true; }
                     }
                 }
             }
         }
-        if (fuse) retire();                                  // fresh pixels whose primary ray misses are finished at once
+        if (fuse) retire();
         if (scat) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
         if (!__any_sync(FULL, busy) && drained) break;      // not drained: the next pass switches to the claimed chunk
     }
@@ -958,7 +974,7 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
     // Measured on B200 (scratch/pool_sweep.py, Scene1, persistent grid + primary-hit cache): 1 spp 720p 0.174 (one pixel per lane) ->
     // 0.158 ms with chunks of 2 tiles, 1080p 0.364 -> 0.257 ms; 2 spp pays at 1080p only (0.549 -> 0.514 ms); from 4 spp on one pixel
     // per lane wins, and larger chunks lose to the imbalance between warps at the end of the launch (8 tiles: 0.295 ms at 720p).
-    const long long n_tiles_all = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
+    const long long n_tiles_all = (long long)((fr.width + kPoolTW - 1) / kPoolTW) * ((fr.height + kPoolTH - 1) / kPoolTH);
     int pool_tiles = 1;
     if (count_traversal) pool_override = 1;                   // the counting instantiations exist for the one-pixel-per-lane kernel only
     if (pool_override > 0) pool_tiles = pool_override > 32 ? 32 : pool_override;
@@ -973,7 +989,7 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
         static std::atomic<int> sms_of[64];                  // per device; the attribute query costs microseconds of every frame
         int sms = sms_of[dev & 63].load(std::memory_order_relaxed);
         if (sms == 0) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); sms_of[dev & 63].store(sms, std::memory_order_relaxed); }
-        const long long n_tiles = (long long)((fr.width + 7) / 8) * ((fr.height + 3) / 4);
+        const long long n_tiles = n_tiles_all;
         const long long chunks = (n_tiles + pool_tiles - 1) / pool_tiles;
         long long blocks = (chunks + kThreads / 32 - 1) / (kThreads / 32);
         if (blocks > (long long)sms * RTB_REGEN_MIN_BLOCKS) blocks = (long long)sms * RTB_REGEN_MIN_BLOCKS;
@@ -985,7 +1001,7 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
         if (frame && frame->surface && pool_tiles == 2) {     // resolve + host copy inside the render (FrameOut)
             fo.out = frame->surface; fo.out2 = frame->mapped_host; fo.count = (float)frame->samples_after; fo.flip_y = frame->flip_y;
             fo.smem_off = (int)((sb + 15) / 16 * 16);
-            sb = (size_t)fo.smem_off + (size_t)(kThreads / 32) * 4 * sizeof(unsigned int);
+            sb = (size_t)fo.smem_off + (size_t)(kThreads / 32) * kPoolSlots * sizeof(unsigned int);
             frame->fused = true;
         }
 #define RTB_POOL_CASE(M) case M: \
