@@ -107,13 +107,15 @@ struct BvhLane {
     // nodes, so every load instruction costs one L1 wavefront PER LANE whatever its width - and ncu shows the L1 data pipe at
     // 94 % on the 10 000-sphere scene with four loads per visit (profiles/r2c_summary_stream_c3.txt).
     // qnodes != nullptr (warp-uniform): the 32-byte quantised node - ONE 256-bit load, twelve PRMTs - instead of the 64-byte float node.
-    template <bool COUNT, bool GLOBAL_NODES = false>
+    // QMODE: -1 the node form is decided at run time (qnodes != nullptr), 0 float nodes, 1 quantised nodes - the persistent kernels
+    // are instantiated per form, which takes the pointer test (four uniform instructions) and the dead form's code out of every step.
+    template <bool COUNT, bool GLOBAL_NODES = false, int QMODE = -1>
     __device__ __forceinline__ void node_step(const float4* __restrict__ nodes, TravCount& cnt, const uint4* __restrict__ qnodes = nullptr,
                                               uint32_t q2f16 = 0x4B00u) {   // requires in_node()
         if (COUNT) ++cnt.nodes;
         float4 n0, n1, n2;
         int2 ch;
-        if (GLOBAL_NODES && qnodes) {
+        if (GLOBAL_NODES && (QMODE == 1 || (QMODE == -1 && qnodes))) {
             uint4 q0, q1;
 #ifdef RTB_HOST_EMULATION
             q0 = qnodes[2 * cur]; q1 = qnodes[2 * cur + 1];

@@ -181,7 +181,12 @@ __global__ void __launch_bounds__(kThreads, 6) k_wf_intersect(SceneView sc, BvhV
 #ifndef RTB_WF_BVH_MIN_BLOCKS
 #define RTB_WF_BVH_MIN_BLOCKS 8      // 63 registers, no spills: the kernel waits on node fetches (issue slots 52 % busy at 6), +8 % at 8
 #endif
-template <int MODE, bool COUNT = false>
+#ifndef RTB_WF_NODE_UNROLL
+#define RTB_WF_NODE_UNROLL 2           // node steps per warp vote in the node phase: the vote, its count and the branch are ~10 of a step's ~90
+                                       // instructions. Measured (profiles/r2ad_ab_node_unroll.txt): C3 92.9 / 88.3 / 89.3 / 88.4 ms and C4 23.2 / 22.1 /
+                                       // 22.2 / 22.1 ms per step with 1 / 2 / 3 / 4 (streaming kernel: 2 best, 3 and 4 lose)
+#endif
+template <int MODE, bool COUNT = false, bool QUANT = false>
 __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersect_bvh(SceneView sc, BvhView bv, FlatView fl, const uint32_t* __restrict__ q,
                                                                    const unsigned int* __restrict__ count_ptr, unsigned int* __restrict__ cursor,
                                                                    const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem);
     const float4* __restrict__ nodes = tc.nodes;
     const int* __restrict__ refs = tc.refs;
-    const uint4* __restrict__ qnodes = MODE == 3 ? bv.qnodes : nullptr;     // 32-byte quantised nodes when the host built them
+    const uint4* __restrict__ qnodes = (MODE == 3 && QUANT) ? bv.qnodes : nullptr;     // 32-byte quantised nodes (the host built them: QUANT)
     const unsigned int count = *count_ptr;
     const int lane = threadIdx.x & 31;
     constexpr unsigned FULL = 0xffffffffu;
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
                         pid = i;                             // dense state: slot = queue position
                         const float4 o4 = ray_o[pid], d4 = ray_d[pid];
                         o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
-                        L.begin(o, d, qnodes != nullptr, bv.q_org, bv.q_step);
+                        L.begin(o, d, QUANT, bv.q_org, bv.q_step);
                         if (COUNT) ++n_queries;
                     }
                 }
@@ -236,7 +241,9 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_BVH_MIN_BLOCKS) k_wf_intersec
         }
         // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
         for (;;) {
-            if (L.in_node()) L.node_step<COUNT, MODE == 3>(nodes, cnt, qnodes, bv.q2f16);
+#pragma unroll
+            for (int u = 0; u < RTB_WF_NODE_UNROLL; ++u)
+                if (L.in_node()) L.node_step<COUNT, MODE == 3, QUANT ? 1 : 0>(nodes, cnt, qnodes, bv.q2f16);
             if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
@@ -289,7 +296,7 @@ static __device__ RTB_STREAM_SHADE_ATTR bool stream_shade(const SceneView& sc, c
     return true;
 }
 
-template <int MODE, bool REUSE, bool COUNT>
+template <int MODE, bool REUSE, bool COUNT, bool QUANT = false>
 __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_stream(const __grid_constant__ SceneView sc, const __grid_constant__ BvhView bv, const __grid_constant__ FlatView fl,
                                                                                 const __grid_constant__ FrameView fr, int tiles_x, int npad,
                                                                                 uint32_t s_first, unsigned int n_paths, const float4* __restrict__ prim_nt,
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
     const TraceCtx tc = setup_trace<MODE>(sc, bv, fl, smem + (kStreamStateWords * kThreads + 3) / 4);
     const float4* __restrict__ nodes = tc.nodes;
     const int* __restrict__ refs = tc.refs;
-    const uint4* __restrict__ qnodes = MODE == 3 ? bv.qnodes : nullptr;     // 32-byte quantised nodes when the host built them
+    const uint4* __restrict__ qnodes = (MODE == 3 && QUANT) ? bv.qnodes : nullptr;     // 32-byte quantised nodes (the host built them: QUANT)
     const int lane = threadIdx.x & 31;
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
             if (L.state == BvhLane::DONE) {                  // the finished traversals of the warp are shaded together
                 const Hit h = L.finish(tc.sph, o, d);
                 ++segs; ++traced;
-                if (stream_shade(sc, fr, h, ps, o, d, wave_rad, pid)) L.begin(o, d, qnodes != nullptr, bv.q_org, bv.q_step);
+                if (stream_shade(sc, fr, h, ps, o, d, wave_rad, pid)) L.begin(o, d, QUANT, bv.q_org, bv.q_step);
                 else L.state = BvhLane::IDLE;
             }
             if (!exhausted) {                                // every idle lane claims the next path id: one atomicAdd per warp
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
                             if (live) {
                                 ps[0] = T.x; ps[kThreads] = T.y; ps[2 * kThreads] = T.z; ps[3 * kThreads] = Lr.x; ps[4 * kThreads] = Lr.y; ps[5 * kThreads] = Lr.z;
                                 ps[6 * kThreads] = __int_as_float(depth); ps[7 * kThreads] = __uint_as_float(pixel); ps[8 * kThreads] = __uint_as_float(sample);
-                                L.begin(o, d, qnodes != nullptr, bv.q_org, bv.q_step);
+                                L.begin(o, d, QUANT, bv.q_org, bv.q_step);
                             }
                         }
                     }
@@ -368,7 +375,9 @@ __global__ void __launch_bounds__(kThreads, RTB_WF_STREAM_MIN_BLOCKS) k_wf_strea
         }
         // ---- node phase: at least one step, then for as long as enough lanes hold an inner node ----------------
         for (;;) {
-            if (L.in_node()) L.node_step<COUNT, MODE == 3>(nodes, cnt, qnodes, bv.q2f16);
+#pragma unroll
+            for (int u = 0; u < RTB_WF_NODE_UNROLL; ++u)
+                if (L.in_node()) L.node_step<COUNT, MODE == 3, QUANT ? 1 : 0>(nodes, cnt, qnodes, bv.q2f16);
             if (__popc(__ballot_sync(FULL, L.in_node())) < kNodeMin) break;
         }
         // ---- leaf phase: the stashed leaves (and a second one waiting in `cur`), strict tests ---------------------
@@ -616,6 +625,10 @@ cudaError_t ensure_optin() {
     if ((e = optin(k_wf_intersect_bvh<3>)) != cudaSuccess) return e;
     if ((e = optin(k_wf_intersect_bvh<2, true>)) != cudaSuccess) return e;
     if ((e = optin(k_wf_intersect_bvh<3, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_intersect_bvh<3, false, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_intersect_bvh<3, true, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_stream<3, true, false, true>)) != cudaSuccess) return e; if ((e = optin(k_wf_stream<3, false, false, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_wf_stream<3, true, true, true>)) != cudaSuccess) return e; if ((e = optin(k_wf_stream<3, false, true, true>)) != cudaSuccess) return e;
     if ((e = optin(k_wf_intersect_bvh8)) != cudaSuccess) return e;
     if ((e = optin(k_wf_stream<2, true, false>)) != cudaSuccess) return e; if ((e = optin(k_wf_stream<2, false, false>)) != cudaSuccess) return e;
     if ((e = optin(k_wf_stream<3, true, false>)) != cudaSuccess) return e; if ((e = optin(k_wf_stream<3, false, false>)) != cudaSuccess) return e;
@@ -755,12 +768,12 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
             const size_t ssb = sb + (size_t)((kStreamStateWords * kThreads + 3) / 4) * sizeof(float4);
             const int blocks = sms * RTB_WF_STREAM_MIN_BLOCKS;
 #define RTB_STREAM_ARGS sc, ac.bvh, ac.flat, fr, g.tiles_x, g.npad, s_first, (unsigned int)np, prim_nt, prim_id, wb->wave_rad, wb->counters, k_refill, k_node_min, seg_counter
-#define RTB_STREAM_LAUNCH(M)                                                                                                        \
-            if (reuse) { if (count) k_wf_stream<M, true, true><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS);                     \
-                         else k_wf_stream<M, true, false><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS); }                       \
-            else { if (count) k_wf_stream<M, false, true><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS);                          \
-                   else k_wf_stream<M, false, false><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS); }
-            if (mode == 2) { RTB_STREAM_LAUNCH(2) } else { RTB_STREAM_LAUNCH(3) }
+#define RTB_STREAM_LAUNCH(M, Q)                                                                                                     \
+            if (reuse) { if (count) k_wf_stream<M, true, true, Q><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS);                  \
+                         else k_wf_stream<M, true, false, Q><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS); }                    \
+            else { if (count) k_wf_stream<M, false, true, Q><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS);                       \
+                   else k_wf_stream<M, false, false, Q><<<blocks, kThreads, ssb, st>>>(RTB_STREAM_ARGS); }
+            if (mode == 2) { RTB_STREAM_LAUNCH(2, false) } else if (ac.bvh.qnodes) { RTB_STREAM_LAUNCH(3, true) } else { RTB_STREAM_LAUNCH(3, false) }
 #undef RTB_STREAM_LAUNCH
 #undef RTB_STREAM_ARGS
             k_wf_accumulate<<<(g.npad + 255) / 256, 256, 0, st>>>(fr, g.tiles_x, g.npad, sw, wb->wave_rad, wb->launch_acc);
@@ -786,7 +799,9 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
                         else k_wf_intersect<2><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS);
                         break;
                 case 3: if (bvh_refill && ac.bvh.wnodes) k_wf_intersect_bvh8<<<sms * RTB_WF_BVH8_MIN_BLOCKS, kThreads, sb, st>>>(sc, ac.bvh, qin, cnt, cur, wb->ray_o[a], wb->ray_d[a], wb->hit_nt, wb->hit_id, k_refill, k_node_min);
+                        else if (count && ac.bvh.qnodes) k_wf_intersect_bvh<3, true, true><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS, k_refill, k_node_min, seg_counter);
                         else if (count) k_wf_intersect_bvh<3, true><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS, k_refill, k_node_min, seg_counter);
+                        else if (bvh_refill && ac.bvh.qnodes) k_wf_intersect_bvh<3, false, true><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS, k_refill, k_node_min, seg_counter);
                         else if (bvh_refill) k_wf_intersect_bvh<3><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS, k_refill, k_node_min, seg_counter);
                         else k_wf_intersect<3><<<persistent_blocks, kThreads, sb, st>>>(RTB_WF_ARGS);
                         break;
