@@ -87,6 +87,18 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.1)
 
+    def sample_once(self):
+        """One blocking query (the short legs sample before and after their steps instead of during them: a leg of 3 x 22 ms lies
+        entirely inside the start-up of the first concurrent nvidia-smi, whose device queries were seen to double the step time of
+        the 40-launch wavefront pipeline - profiles/r3a_bench_n1.json c4: 44 ms; the same leg alone or sampled outside: 22 ms)."""
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            if out:
+                self.rows.append([c.strip() for c in out.split(",")])
+        except Exception:
+            pass
+
     def summary(self):
         self.stop_flag = True
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -293,7 +305,8 @@ def run_leg(args, config, torch, stream, steps=3, warmup=3):
             tr.reset_accumulation(); tr.render_spp(spp)
         torch.cuda.synchronize()
         s0 = tr.stats()
-        sampler = ClockSampler(0); sampler.start()
+        sampler = ClockSampler(0)
+        sampler.sample_once()                            # before and after, not during: see sample_once()
         evs = []
         tr.reset_accumulation()
         for _ in range(steps):
@@ -302,7 +315,9 @@ def run_leg(args, config, torch, stream, steps=3, warmup=3):
             e0.record(stream); tr.render_spp(spp); e1.record(stream)
             evs.append((e0, e1))
         torch.cuda.synchronize()
+        sampler.sample_once()
         clocks = sampler.summary()
+        clocks["sampling"] = "one query right before and one right after the leg's timed steps"
         ms = [a.elapsed_time(b) for a, b in evs]
         s1 = tr.stats()
     total_s = sum(ms) * 1e-3

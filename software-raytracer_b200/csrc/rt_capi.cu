@@ -345,14 +345,17 @@ int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     if (c->opt_primary_reuse && (rc = ensure_prim_cache(c, ac)) != RT_OK) return rc;
     const PrimCache* prim = prim_cache_arg(c, pc);
     cudaError_t err = cudaSuccess;
-    // The wavefront pipelines' rate depends on how many samples share a wave (launch_render_wavefront), so they are measured with
-    // up to 16 samples per pixel - what a call of this length will really run. Candidates: 0 megakernel, 1 bounce-round wavefront,
-    // 2 streaming kernel.
-    const int n_tune = spp < 16 ? spp : 16;
+    // The wavefront pipelines' rate depends on how many samples share a wave (launch_render_wavefront: up to 64 per wave), so they
+    // are measured with what a call of this length will really run, up to 64 samples per pixel - with 16 a 64-sample call on the
+    // 1 M-triangle scene was given to the streaming kernel (26.7 ms) although the bounce rounds take 22-23 ms at that length. The
+    // megakernel's time is linear in the sample count: it is timed with up to 16 and scaled. Candidates: 0 megakernel, 1 bounce-round
+    // wavefront, 2 streaming kernel.
+    const int n_tune = spp < 64 ? spp : 64;
+    const int n_regen = n_tune < 16 ? n_tune : 16;
     bool usable[3] = {true, true, true};
     for (int pass = 0; pass < 2 && err == cudaSuccess; ++pass) {   // pass 0 allocates the wavefront buffers and warms up
         cudaEventRecord(e[0], c->stream);
-        err = launch_render_regen(c->view, ac, c->frame, c->d_tune, 0u, pass ? n_tune : 1, prim, dummy, c->stream);
+        err = launch_render_regen(c->view, ac, c->frame, c->d_tune, 0u, pass ? n_regen : 1, prim, dummy, c->stream);
         cudaEventRecord(e[1], c->stream);
         for (int k = 1; k <= 2 && err == cudaSuccess; ++k) {
             if (usable[k]) {
@@ -368,6 +371,7 @@ int autotune_pipeline(rt_ctx* c, const AccelSel& ac, int spp) {
     float ms[3] = {0.f, 0.f, 0.f};
     if (err == cudaSuccess) for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&ms[k], e[k], e[k + 1]);
     if (err != cudaSuccess) return cuda_fail(c, err, "autotune_pipeline");
+    ms[0] *= (float)n_tune / (float)n_regen;
     c->tune_pipe_ms[0] = ms[0]; c->tune_pipe_ms[1] = ms[1]; c->tune_pipe_ms[2] = ms[2];
     const int kinds[3] = {RT_PIPELINE_REGEN, RT_PIPELINE_WAVEFRONT, RT_PIPELINE_STREAM};
     int best = 0;

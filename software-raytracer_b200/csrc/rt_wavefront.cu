@@ -20,6 +20,7 @@
 // k_render_regen (asserted by tests/test_gpu_parity.py), whichever order the queues end up in.
 #include "rt_kernels.h"
 
+#include <cstdio>
 #include <mutex>
 
 #include "rt_device.cuh"
@@ -746,6 +747,12 @@ cudaError_t launch_render_wavefront(WavefrontBuffers* wb, const SceneView& sc, c
             if (e != cudaErrorMemoryAllocation || s_cap == 1) return e;      // s_cap == 1: not even one sample per pixel fits
             s_cap = (s_cap + 1) / 2;
         }
+    }
+    if (getenv("RTB200_DEBUG")) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        fprintf(stderr, "[rtb200] wavefront launch: %d samples, %d per wave (%zu M paths, %s), free %.1f of %.1f GB\n", n_samples, s_cap, ((size_t)g.npad * s_cap) >> 20,
+                streaming ? "streaming" : "bounce rounds", free_b / 1e9, total_b / 1e9);
     }
     if (!wb->counters && (e = cudaMalloc((void**)&wb->counters, 2 * kMaxRounds * sizeof(unsigned int))) != cudaSuccess) { cudaGetLastError(); return e; }
     const int rounds = reuse ? fr.max_bounces : fr.max_bounces + 1;

@@ -16,6 +16,18 @@
 
 #include "rt_host.hpp"
 
+// A page-locked ARGB8 surface (rt_host_alloc): downloads are one DMA, and rt_render_frame writes it from the render kernel.
+struct Pinned {
+    uint32_t* p; size_t n;
+    explicit Pinned(size_t count) : p(static_cast<uint32_t*>(rt_host_alloc(count * 4))), n(count) { if (!p) throw std::runtime_error("rt_host_alloc failed"); }
+    ~Pinned() { rt_host_free(p); }
+    Pinned(const Pinned&) = delete;
+    Pinned& operator=(const Pinned&) = delete;
+    uint32_t* data() { return p; }
+    uint32_t* begin() { return p; }
+    uint32_t* end() { return p + n; }
+};
+
 int main(int argc, char** argv) {
     std::string scene_path, out_path;
     int w = 1280, h = 720, spp = 64, bounces = 8, interactive = 0, gpus = 1;
@@ -47,7 +59,7 @@ int main(int argc, char** argv) {
         par.width = w; par.height = h; par.max_bounces = bounces; par.mode = RT_MODE_PATH;
         rt_camera cam; rt_default_camera(&cam);
         if (rt_group_set_params(g, &par) != RT_OK || rt_group_set_camera(g, &cam) != RT_OK || rt_group_reset_accumulation(g) != RT_OK) return die("setup");
-        std::vector<uint32_t> surface((size_t)w * h);
+        Pinned surface((size_t)w * h);
         using clk = std::chrono::steady_clock;
         if (rt_group_render_spp(g, spp) != RT_OK || rt_group_resolve_rgba8(g, surface.data(), w * 4, 1) != RT_OK) return die("warm-up frame");   // builds, tunes
         if (rt_group_reset_accumulation(g) != RT_OK) return die("reset");
@@ -75,14 +87,13 @@ int main(int argc, char** argv) {
         rtb200::Raytracer rt(w, h);
         rt.SetObjectsToRender(scene1.GetObjects());
         rt.SIMPLEDRAW = preview; rt.MAXBOUNCES = bounces; rt.TARGETFRAMES = 1 << 30; rt.SCREEN_SCALE = scale;
-        std::vector<uint32_t> surface((size_t)w * h);
+        Pinned surface((size_t)w * h);                          // interactive frames are streamed into it by the render kernel itself (rt_render_frame)
         using clk = std::chrono::steady_clock;
         if (interactive > 0) {
             std::vector<double> ms;
             for (int f = 0; f < interactive + 10; ++f) {
                 auto t0 = clk::now();
-                rt.RenderFrame();
-                rt.Present(surface.data(), w * 4);
+                rt.RenderFrame(surface.data(), w * 4);
                 double d = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
                 if (f >= 10) ms.push_back(d);
             }

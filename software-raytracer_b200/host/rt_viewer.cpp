@@ -220,8 +220,7 @@ int main(int argc, char** argv) {
             rt.selectedObject = selected;
 
             // the render step of the loop (:568-590) + the surface update, then present
-            rt.RenderFrame();
-            rt.Present(surface, width * 4);
+            rt.RenderFrame(surface, width * 4);               // traced and presented in one call (rt_render_frame)
             SDL_UpdateTexture(renderTexture, nullptr, surface, width * 4);
             ImGui::Render();
             SDL_RenderSetScale(renderer, io.DisplayFramebufferScale.x, io.DisplayFramebufferScale.y);
