@@ -258,6 +258,10 @@ def fp32_roofline(objs, st, delivered_per_step, traced_per_step, kern_s, peaks, 
             "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_algorithmic_gbs": (w * h * 32 / kern_s) / 1e9}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, from the committed ncu captures (profiles/r3a_summary_wavefront_*.txt)
+NCU_BVH_TRAFFIC = {("synthetic10k", 2): 5.545e9, ("mesh1M", 2): 4.951e9}
+
+
 def bvh_roofline(tr, wl, spp, traced_per_s, kern_share, peaks, peaks_src, pipeline):
     """SURVEY.md 8d for BVH scenes: bytes per segment = node bytes x <nodes visited> + primitive bytes x <primitives tested>,
     from the device's own traversal counters (one extra untimed step with RT_OPT_TRAVERSAL_STATS), times the executed query
@@ -281,7 +285,9 @@ def bvh_roofline(tr, wl, spp, traced_per_s, kern_share, peaks, peaks_src, pipeli
                      % (ts.node_bytes, nodes, sph, cube, tri),
             "bytes_per_query": bytes_per_query, "node_visits_per_query": nodes, "prim_tests_per_query": sph + cube + tri, "flop_per_query": flop_per_query,
             "achieved_tflops": flop_per_query * traced_per_s / 1e12,
-            "traffic": None, "traffic_note": "BVH + primitives are L2-resident (0.9 MB / 75 MB in a 126 MB L2): dram bytes per launch are the path state, see profiles/ ncu summaries",
+            "traffic": NCU_BVH_TRAFFIC.get((wl["scene"], pipeline)),
+            "traffic_note": "dram read+write of the dominant launch (first bounce round of a full wave: c3 133 M rays, c4 69 M rays), ncu --set full, profiles/r3a_summary_wavefront_c3.txt / "
+                            "_c4.txt (3.43 + 2.11 GB and 3.87 + 1.08 GB): the rays read and the hits written; BVH + primitives are L2-resident (0.9 MB / 75 MB in a 126 MB L2). null = no capture of this pipeline",
             "kernel": kname, "kernel_share_of_step": kern_share,
             "peak_source": "%s MEASURED_PEAKS.json hbm_gbs" % peaks_src,
             "note": "node and primitive fetches are served by L1/L2, not HBM: frac is algorithmic bytes against the HBM copy peak as SURVEY.md 8d defines it; the kernel is bound by "
@@ -639,6 +645,18 @@ def run_b200(args):
                 except Exception as e:                # a leg must not take the headline down with it
                     legs.append({"config": c, "error": "%s: %s" % (type(e).__name__, e)})
             line["configs"] = legs
+            # the metric's "ms/frame at 1080p", measured (ms_per_1spp_frame above is the 1024-spp step divided by its samples): one
+            # rt_render_frame(1) per frame at 1920x1080 into a page-locked host surface, static camera, as the c5 leg does at 720p
+            try:
+                wl_f = make_workload("c2", "Scene1", 1)
+                tr_f = make_tracer(args, 0, stream.cuda_stream, wl_f)
+                with torch.cuda.stream(stream):
+                    fl = interactive_line(tr_f, wl_f, frames=200)
+                tr_f.close()
+                line["frame_1080p_1spp"] = {"p50_ms": fl["value"], "p99_ms": fl["p99_ms"], "render_kernel_ms_p50": fl["render_kernel_ms_p50"], "frames": fl["frames"],
+                                            "what": "host clock around rt_render_frame(1) at 1920x1080: render + resolve + 8.3 MB to the host per frame"}
+            except Exception as e:
+                line["frame_1080p_1spp"] = {"error": "%s: %s" % (type(e).__name__, e)}
         # the CPU baseline comes LAST: measured on the same box, the BVH legs (about 40 small launches per step) ran 11-19 % slower
         # when they followed the reference's 16-thread CPU run (profiles/r2l_bench_n1.json vs the --no-cpu run of the same call)
         if world == 1 and not args.no_cpu and args.config in ("c1", "c2"):
