@@ -200,3 +200,19 @@ def test_viewer_source_compiles_against_declaration_stubs():
     # the gated make target reports why it does nothing in this image instead of failing
     r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "software-raytracer_b200"), "viewer"], capture_output=True, text=True)
     assert r.returncode == 0 and "skipped" in r.stdout, r.stdout + r.stderr
+
+
+def test_viewer_links_with_the_scripted_double_and_needs_a_gpu(tmp_path):
+    """The viewer's real source linked with the scripted SDL / ImGui double (tests/viewer_stubs/scripted_sdl_imgui.cpp; the GPU suite
+    runs its main loop, tests/test_gpu_round2.py). Without a CUDA device it must stop with the library's error, not draw anything."""
+    import subprocess
+    pkg = os.path.join(ROOT, "software-raytracer_b200")
+    exe = str(tmp_path / "rt_viewer_scripted")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "viewer_stubs"), "-I", os.path.join(pkg, "host"),
+                        "-I", os.path.join(ROOT, "include"), "-o", exe, os.path.join(pkg, "host", "rt_viewer.cpp"),
+                        os.path.join(ROOT, "tests", "viewer_stubs", "scripted_sdl_imgui.cpp"), "-L", os.path.join(pkg, "lib"), "-lrt_b200",
+                        "-Wl,-rpath," + os.path.join(pkg, "lib")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "--scene", str(tmp_path / "missing.json"), "--width", "64", "--height", "48"], capture_output=True, text=True, timeout=120)
+    if r.returncode != 0:                                   # no GPU here: rt_create refuses, there is no CPU path to fall back to
+        assert "no CPU fallback" in r.stderr, r.stderr

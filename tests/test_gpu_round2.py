@@ -386,6 +386,96 @@ def test_headless_cpp_driver_matches_the_c_abi(tracer, tmp_path, scenes):
     assert r.returncode == 0 and '"p50_ms"' in r.stdout, r.stdout + r.stderr
 
 
+def _build_scripted_viewer(tmp_path):
+    """host/rt_viewer.cpp (the SDL2 / Dear ImGui front end) linked with the scripted headless double of the
+    SDL / ImGui entry points it uses (tests/viewer_stubs/scripted_sdl_imgui.cpp) and the real librt_b200."""
+    pkg = os.path.join(ROOT, "software-raytracer_b200")
+    exe = str(tmp_path / "rt_viewer_scripted")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "viewer_stubs"), "-I", os.path.join(pkg, "host"),
+                        "-I", os.path.join(ROOT, "include"), "-o", exe, os.path.join(pkg, "host", "rt_viewer.cpp"),
+                        os.path.join(ROOT, "tests", "viewer_stubs", "scripted_sdl_imgui.cpp"), "-L", os.path.join(pkg, "lib"), "-lrt_b200",
+                        "-Wl,-rpath," + os.path.join(pkg, "lib")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def _run_scripted_viewer(exe, tmp_path, scene_file, w, h, script):
+    sp, lp = str(tmp_path / "script.txt"), str(tmp_path / "viewer.log")
+    with open(sp, "w") as f:
+        f.write(script)
+    env = dict(os.environ, RT_VIEWER_SCRIPT=sp, RT_VIEWER_LOG=lp)
+    r = subprocess.run([exe, "--scene", scene_file, "--width", str(w), "--height", str(h)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    log = {"title": {}, "name": {}, "surface": {}}
+    for line in open(lp):
+        _, fr, kind, *rest = line.rstrip("\n").split(" ", 3)
+        log[kind][int(fr)] = rest[0] if rest else ""
+    frames = {f: int(t.split("ACCUMULATIONFRAMES: ")[1].split(" ")[0]) for f, t in log["title"].items()}
+    return log, frames
+
+
+def test_viewer_main_loop_scripted_on_the_gpu(tracer, tmp_path, scenes):
+    """The viewer's REAL main loop (host/rt_viewer.cpp: events, fly camera, inspector, picking, the frame state machine of
+    Raytracer.cpp:568-590, rt_render_frame into the streamed surface) on this GPU, with a scripted double in place of SDL2 /
+    Dear ImGui (neither is in the image). Static path-mode frames must equal the same call sequence through ctypes bit for bit;
+    an interactive script must restart, accumulate, pick, delete, create and save as the reference's loop does."""
+    exe = _build_scripted_viewer(tmp_path)
+    objs = scenes["Scene1"]
+    names = ["object %d" % i for i in range(len(objs))]
+    scene_file = str(tmp_path / "Scene1.json")
+    assert rtb200.scene_file_write(scene_file, objs, names, "Scene1") == 0
+    w, h = 640, 360
+
+    # (1) static camera: switch to path mode in frame 0, six frames, dump the last one
+    ppm = str(tmp_path / "static.ppm")
+    log, acc = _run_scripted_viewer(exe, tmp_path, scene_file, w, h, "0 button Switch Render Mode\n5 dump %s\n5 quit\n" % ppm)
+    assert [acc[f] for f in range(6)] == [1, 2, 3, 4, 5, 6]
+    # frame 0 is traced at a quarter of the render scale and overwritten by frame 1 (:576-587); frames 1..5 = 5 samples at render scale 0.5
+    tracer.set_scene(objs); tracer.set_camera(rtb200.default_camera())
+    tracer.set_params(rtb200.default_params(width=w, height=h, mode=rtb200.RT_MODE_PATH, max_bounces=2))     # MAXBOUNCES = 2 (Raytracer.cpp:33)
+    tracer.reset_accumulation()
+    tracer.set_pixel_step(rtb200.reference_pixel_step(0.5, 1.0), rtb200.reference_strip_columns(w))
+    for _ in range(5):
+        tracer.render_spp(1)
+    argb = tracer.resolve_rgba8(True)
+    tracer.set_pixel_step(1, 0)
+    want = np.stack([(argb >> 16) & 255, (argb >> 8) & 255, argb & 255], -1).astype(np.uint8)
+    assert np.array_equal(_read_ppm(ppm), want)
+    assert len(set(log["surface"][f] for f in range(6))) == 6            # every frame shows a different image (noise averages out)
+
+    # (2) interaction
+    tracer.set_params(rtb200.default_params(width=w, height=h, mode=rtb200.RT_MODE_PREVIEW, max_bounces=2))
+    centre = tracer.pick(w // 2, h // 2)
+    assert centre >= 0
+    saved = str(tmp_path / "saved.json")
+    script = "\n".join([
+        "3 button Switch Render Mode",                       # preview -> path mode: restart
+        "8 click %d %d" % (w // 2, h // 2),                  # select what the centre pixel sees
+        "12 rmb down", "13 motion 50 0", "14 rmb up",        # look around: restart while the button is held
+        "18 key DELETE",                                     # remove the selected object: restart
+        "21 menu Sphere", "22 setfloat Sphere Radius=0.75",  # create a sphere 5 units ahead, edit it in the inspector
+        "24 hold W on", "25 hold W off",                     # fly forward for one frame
+        "27 key P", "29 key P",                              # pause / resume
+        "30 settext Save path=%s" % saved, "30 menu Save",
+        "31 quit"]) + "\n"
+    log, acc = _run_scripted_viewer(exe, tmp_path, scene_file, w, h, script)
+    assert [acc[f] for f in range(0, 3)] == [1, 1, 1]                    # preview mode never accumulates (:589)
+    assert [acc[f] for f in range(3, 12)] == list(range(1, 10))          # path mode: restart, then one more frame each
+    assert log["name"].get(8) is None and all(log["name"][f] == names[centre] for f in range(9, 18))   # the inspector shows the picked object from the next frame on
+    assert acc[12] == 1 and acc[13] == 1 and acc[14] == 2                # right button held: every frame restarts (:390-394)
+    assert log["surface"][11] != log["surface"][14]                      # the camera turned
+    assert acc[18] == 1 and 19 not in log["name"]                        # delete: scene re-submitted, nothing selected
+    assert acc[21] == 1 and log["name"][21] == "" and log["name"][22] == ""     # create: selected at once, no name yet (as in the reference)
+    assert acc[22] == 1                                                  # the radius edit re-submits the scene
+    assert acc[24] == 1 and acc[25] == 2                                 # camera moved for one frame
+    assert acc[27] == acc[26] and acc[28] == acc[26] and acc[29] == acc[26] + 1    # paused frames render nothing
+    rc, objs2, err = rtb200.scene_file_read(saved)
+    assert rc == 0, err
+    assert len(objs2) == len(objs) and objs2[-1]["radius"] == np.float32(0.75)
+    kept = [i for i in range(len(objs)) if i != centre]
+    assert np.array_equal(objs2[:-1], np.ascontiguousarray(objs, rtb200.OBJECT_DTYPE)[kept])
+
+
 def test_headless_cpp_driver_on_several_gpus(tmp_path, scenes):
     """`rt_headless --gpus N`: the library-owned group from a C++ host - no torch, no IPC (Raytracer.cpp:331-342, 598-607)."""
     import torch
