@@ -146,8 +146,13 @@ def cpu_reference_run(objs, frames, w=W, h=H, want_ref=True):
         assert ref.load_scene(tmp_scene) == len(objs)
         ref.setup(w, h, 55, DEPTH, False, None)
         sec, segs = ref.render_frames(frames, rng_mode=0, count_segments=True)
-        return segs / sec, {"kind": "reference", "cores": cores, "threads": 16, "seconds": sec, "segments": int(segs),
-                            "sample": "%d frames of 1 spp at %dx%d, depth %d, Scene1; reference's own renderArea loop, 16 threads, per-thread MSVC rand()" % (frames, w, h, DEPTH)}
+        info = {"kind": "reference", "cores": cores, "threads": 16, "seconds": sec, "segments": int(segs),
+                "sample": "%d frames of 1 spp at %dx%d, depth %d, Scene1; reference's own renderArea loop, 16 threads, per-thread MSVC rand()" % (frames, w, h, DEPTH)}
+        if frames >= 8:      # both rand() variants. glibc's rand() is ONE locked global state: the 16 workers serialise on it
+            n2 = max(2, frames // 12)
+            sec2, segs2 = ref.render_frames(n2, rng_mode=2, count_segments=True)
+            info["glibc_rand_variant"] = {"value": segs2 / sec2 / 1e6, "unit": UNIT, "sample": "%d frames, rand() = glibc's global locked generator" % n2}
+        return segs / sec, info
     orc = Oracle()
     cam = OrcCamera(); cam.right[0] = 1; cam.up[1] = 1; cam.forward[2] = 1; cam.fov_deg = 55
     p = orc.default_params(width=w, height=h, max_bounces=DEPTH, mode=0)
@@ -304,7 +309,7 @@ def run_leg(args, config, torch, stream, steps=3, warmup=3):
     peaks, peaks_src = measured_peaks()
     with torch.cuda.stream(stream):
         if config == "c5":
-            line = interactive_line(tr, wl, frames=400)
+            line = interactive_line(tr, wl, frames=1000)     # p50 / p99 over 1000 frames
             tr.close()
             return line
         for _ in range(warmup):
@@ -663,6 +668,8 @@ def run_b200(args):
             rate, info = cpu_reference_run(objs, args.cpu_frames, w, h)
             line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"], "threads": info["threads"]}
+            if "glibc_rand_variant" in info:
+                line["cpu_baseline"]["glibc_rand_variant"] = info["glibc_rand_variant"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
