@@ -668,6 +668,8 @@ def run_b200(args):
             rate, info = cpu_reference_run(objs, args.cpu_frames, w, h)
             line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"], "threads": info["threads"]}
+            line["cpu_baseline"]["paths_per_s_M"] = args.cpu_frames * w * h / info["seconds"] / 1e6
+            line["cpu_baseline"]["ms_per_1spp_frame"] = 1e3 * info["seconds"] / args.cpu_frames
             if "glibc_rand_variant" in info:
                 line["cpu_baseline"]["glibc_rand_variant"] = info["glibc_rand_variant"]
         print(json.dumps(line), flush=True)
