@@ -132,7 +132,7 @@ def write_scene_json(path, objs):
         json.dump({"SceneName": "bench", "SceneObjects": out}, f)
 
 
-def cpu_reference_run(objs, frames, w=W, h=H, want_ref=True):
+def cpu_reference_run(objs, frames, w=W, h=H, want_ref=True, cam=None, fov=55, label="Scene1"):
     """Time the reference's CPU implementation of the path on all host cores: `frames` 1-spp frames at w x h.
     Returns (segments/s, info). oracle/_ref (the reference's own code, 16 strip threads, per-thread MSVC rand) when its .so
     is present, else the bit-for-bit validated C port."""
@@ -144,10 +144,10 @@ def cpu_reference_run(objs, frames, w=W, h=H, want_ref=True):
         write_scene_json(tmp_scene, objs)
         ref = Reference()
         assert ref.load_scene(tmp_scene) == len(objs)
-        ref.setup(w, h, 55, DEPTH, False, None)
+        ref.setup(w, h, fov, DEPTH, False, cam)
         sec, segs = ref.render_frames(frames, rng_mode=0, count_segments=True)
         info = {"kind": "reference", "cores": cores, "threads": 16, "seconds": sec, "segments": int(segs),
-                "sample": "%d frames of 1 spp at %dx%d, depth %d, Scene1; reference's own renderArea loop, 16 threads, per-thread MSVC rand()" % (frames, w, h, DEPTH)}
+                "sample": "%d frames of 1 spp at %dx%d, depth %d, %s; reference's own renderArea loop, 16 threads, per-thread MSVC rand()" % (frames, w, h, DEPTH, label)}
         if frames >= 8:      # both rand() variants. glibc's rand() is ONE locked global state: the 16 workers serialise on it
             n2 = max(2, frames // 12)
             sec2, segs2 = ref.render_frames(n2, rng_mode=2, count_segments=True)
@@ -668,6 +668,16 @@ def run_b200(args):
             rate, info = cpu_reference_run(objs, args.cpu_frames, w, h)
             line["cpu_baseline"] = {"value": rate / 1e6, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"], "threads": info["threads"]}
+            # config 3 on the CPU: the reference has no accelerator, its loop tests all 10 009 objects per segment - a small frame of the
+            # same scene and camera is all it can do in seconds (a rate, resolution-independent up to the sky / object mix)
+            for leg in line.get("configs", []):
+                if leg.get("config") == "c3" and "error" not in leg:
+                    try:
+                        wl3 = make_workload("c3", "Scene1", 0)
+                        r3, i3 = cpu_reference_run(wl3["objs"], 1, 256, 144, cam=wl3["cam"], fov=int(wl3["cam"].fov_deg), label="the config-3 scene and camera")
+                        leg["cpu_baseline"] = {"value": r3 / 1e6, "unit": UNIT, "cores": i3["cores"], "kind": i3["kind"], "threads": i3["threads"], "sample": i3["sample"]}
+                    except Exception as e:
+                        leg["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
             line["cpu_baseline"]["paths_per_s_M"] = args.cpu_frames * w * h / info["seconds"] / 1e6
             line["cpu_baseline"]["ms_per_1spp_frame"] = 1e3 * info["seconds"] / args.cpu_frames
             if "glibc_rand_variant" in info:
