@@ -130,8 +130,8 @@ __device__ __forceinline__ void flush_trav_count(const TravCount& tc, unsigned i
 // active; profiles/r1q_summary_flat_reuse_1024spp.txt). Here the warp pools the work: every lane publishes its ray,
 // the (lane, cluster) pairs of all lanes are enumerated with a prefix sum into one list and each lane culls ONE pair
 // (whoever's it is); the surviving (lane, primitive) candidates are appended to a second list the same way and each
-// lane runs ONE strict test per pass, returning the result to the owning lane with a 64-bit atomicMin on
-// (order-preserving bits of t, object id) - exactly the reference's "closest, lowest id on ties". Lanes without work
+// lane runs ONE strict test per pass, returning the result to the owning lane as the minimum of
+// (order-preserving bits of t, object id) in shared memory - exactly the reference's "closest, lowest id on ties". Lanes without work
 // of their own (sky pixels, finished pixels) serve the others. Must be called by all 32 lanes; `active` = has a ray.
 __device__ __forceinline__ unsigned int warp_incl_scan(unsigned int v, int lane) {
 #pragma unroll
@@ -153,7 +153,6 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
                                                      const float4* __restrict__ box, unsigned char* __restrict__ q, int qstride,
                                                      unsigned char* __restrict__ coop, float3 o, float3 d, bool active) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr unsigned long long kNoHit = 0xffffffffffffffffull;
     const int lane = threadIdx.x & 31;
     float* const ray_s = reinterpret_cast<float*>(coop);
     unsigned short* const pairs = reinterpret_cast<unsigned short*>(coop + 6 * 32 * 4);
@@ -175,7 +174,7 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
     }
     ray_s[lane] = o.x; ray_s[32 + lane] = o.y; ray_s[64 + lane] = o.z;
     ray_s[96 + lane] = d.x; ray_s[128 + lane] = d.y; ray_s[160 + lane] = d.z;
-    key[lane] = kNoHit;
+    reinterpret_cast<unsigned int*>(key)[lane] = 0xffffffffu; reinterpret_cast<unsigned int*>(key)[32 + lane] = 0xffffffffu;
     {
         unsigned int m = cm, j = incl - cnt;
         while (m) { const int k = __ffs((int)m) - 1; m &= m - 1u; pairs[j++] = (unsigned short)((lane << 8) | k); }
@@ -218,29 +217,44 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
     }
     __syncwarp();
     // ---- level 3, spheres: one strict test per lane per pass; the owner gets the minimum of (t, object id) ----
+    // Two native 32-bit shared-memory minima per pass - first the distance, then, among the candidates that have the owner's smallest
+    // distance so far, the object id - instead of one 64-bit atomicMin on (distance, id), which is a compare-and-swap loop in shared
+    // memory (4 % of the kernel's instructions at 10-12 active threads; C2 110.2 -> 108.9 ms, C1 2.05 -> 1.96 ms, same bits:
+    // profiles/r4q_ab_key32.txt). Passes are ordered by __syncwarp; a pass that lowers the distance resets the id word before it
+    // competes for it. Lexicographic minimum of (t, id): the reference's "closest, lowest index on ties" (Raytracer.cpp:127-137).
+    unsigned int* const key_t = reinterpret_cast<unsigned int*>(key);      // [0..31] order-preserving bits of t, [32..63] (object id << 8) | code
     for (base = 0u; base < n_cand; base += 32u) {
         const unsigned int i = base + (unsigned int)lane;
+        unsigned int ob = 0xffffffffu, idc = 0xffffffffu;
+        int ow = 0;
         if (i < n_cand) {
             const unsigned int e = cand[i];
-            const int ow = (int)(e >> 8), code = (int)(e & 255u);
+            ow = (int)(e >> 8);
+            const int code = (int)(e & 255u);
             float t = 0.f;
             if (sphere_t(sph[code], f3(ray_s[ow], ray_s[32 + ow], ray_s[64 + ow]), f3(ray_s[96 + ow], ray_s[128 + ow], ray_s[160 + ow]), t) && t == t) {
-                unsigned int ob = __float_as_uint(t);         // NaN distances never win (`<` is false), as in the per-lane loop
-                ob ^= (unsigned int)((int)ob >> 31) | 0x80000000u;                        // order-preserving bits
-                const unsigned long long kb = ((unsigned long long)ob << 32) | (unsigned long long)(((unsigned int)fv.prim_id[code] << 8) | (unsigned int)code);
-                if (kb < *reinterpret_cast<volatile unsigned long long*>(key + ow)) atomicMin(key + ow, kb);
+                ob = __float_as_uint(t);
+                ob ^= (unsigned int)((int)ob >> 31) | 0x80000000u;
+                idc = ((unsigned int)fv.prim_id[code] << 8) | (unsigned int)code;
             }
         }
+        const unsigned int before = idc != 0xffffffffu ? key_t[ow] : 0u;
+        if (idc != 0xffffffffu && ob < before) atomicMin(key_t + ow, ob);
+        __syncwarp();
+        const unsigned int now = idc != 0xffffffffu ? key_t[ow] : 0u;
+        if (idc != 0xffffffffu && now < before && ob == now) key_t[32 + ow] = 0xffffffffu;     // a new smallest distance: its ids start afresh (same value from every writer)
+        __syncwarp();
+        if (idc != 0xffffffffu && ob == now) atomicMin(key_t + 32 + ow, idc);
+        __syncwarp();
     }
-    __syncwarp();
-    const unsigned long long kb = key[lane];
+    const unsigned int kid = key_t[32 + lane];               // 0xffffffff: no sphere was hit
     float best_t = cube_t; int best_id = cube_id, best_code = cube_code;
-    if (active && kb != kNoHit) {
-        unsigned int ob = (unsigned int)(kb >> 32);
+    if (active && kid != 0xffffffffu) {
+        unsigned int ob = key_t[lane];
         ob ^= (unsigned int)((int)~ob >> 31) | 0x80000000u;
         const float st = __uint_as_float(ob);
-        const int sid = (int)(((unsigned int)kb) >> 8);
-        if (st < best_t || (st == best_t && sid < best_id)) { best_t = st; best_id = sid; best_code = (int)(kb & 255ull); }
+        const int sid = (int)(kid >> 8);
+        if (st < best_t || (st == best_t && sid < best_id)) { best_t = st; best_id = sid; best_code = (int)(kid & 255u); }
     }
     __syncwarp();                                             // everyone is done with the scratch before the next call
     return flat_finish(sc, sph, o, d, best_t, best_id, best_code, bn);
