@@ -90,6 +90,34 @@ def test_primary_visibility_1080p(tracer, scenes, meta, oracle):
     assert abs(float(t[ids >= 0].astype(np.float64).sum()) - 7437034.016766) < 1e-4
 
 
+# SURVEY.md 8c, the table of known answers produced by the reference's own code: hit pixels (of which on a box), sum of t over the hits
+SURVEY_TABLE = [("Scene1", 640, 480, 180409, 0, 1087731.602708), ("Scene3", 640, 480, 306604, 306081, 97006.644109),
+                ("Scene_indirect", 640, 480, 306604, 184709, 1458323.056087), ("Scene1", 1920, 1080, 1158304, 0, 7437034.016766)]
+
+
+@pytest.mark.parametrize("scene,w,h,hits,box_hits,sum_t", SURVEY_TABLE)
+def test_survey_known_answer_table_on_the_device(tracer, scenes, scene, w, h, hits, box_hits, sum_t):
+    setup(tracer, scenes[scene], w, h)
+    ids, t, _, _ = tracer.read_aov()
+    hit = ids >= 0
+    assert int(hit.sum()) == hits
+    is_box = np.ascontiguousarray(scenes[scene], rtb200.OBJECT_DTYPE)["type"] == rtb200.RT_OBJ_CUBE
+    assert int(is_box[ids[hit]].sum()) == box_hits
+    assert abs(float(t[hit].astype(np.float64).sum()) - sum_t) < 1e-5 * max(1.0, sum_t / 1e6)
+
+
+def test_survey_direct_intersector_checks_on_the_device(tracer):
+    from test_oracle_golden import _survey_intersector_cases, _check_survey_intersector_answers
+    objs, org, dirs = _survey_intersector_cases()
+    for accel in (rtb200.RT_ACCEL_BRUTE, rtb200.RT_ACCEL_BVH):
+        try:
+            tracer.set_option(rtb200.RT_OPT_ACCEL, accel)
+            setup(tracer, objs, 64, 48)
+            _check_survey_intersector_answers(*tracer.trace_rays(org, dirs))
+        finally:
+            tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+
+
 @pytest.mark.parametrize("scene", ["Scene1", "Scene2", "Scene3", "Scene_indirect"])
 def test_arbitrary_rays_bit_exact(tracer, scenes, golden, scene):
     z = golden("trace_rays")
