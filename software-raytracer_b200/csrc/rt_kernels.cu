@@ -171,8 +171,12 @@ __global__ void k_philox(uint4 ctr, uint2 key, uint4* out) { *out = philox4x32_1
 // max_bounces == 0) has the same value for every sample: the value is added n times, in order.
 // seg_counter[0..1] count path segments DELIVERED (what the reference traces), seg_counter[2..3] the
 // closest-hit queries actually EXECUTED (with REUSE: the secondary and later segments; the cache pass adds its own).
-template <int MODE, bool REUSE, bool COUNT = false>
-__global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
+// STASH (REUSE only): the pixel's cached primary hit and direction wait in shared memory for the next sample instead of in ten registers
+// across the closest-hit query, which brings the kernel to 72 registers = 7 CTAs per SM. The stash costs 1.5 % at equal occupancy and
+// the seventh CTA gives 4 %: Scene1 1080p 1024 spp 108.2 -> 105.5 ms; a 640x480 launch (2400 CTAs: 2.3 instead of 2.7 waves, the last
+// as long and emptier) loses 4 %, so the launcher takes this form for large grids only (profiles/r4u_ab_stash.txt). Same bits.
+template <int MODE, bool REUSE, bool COUNT = false, bool STASH = false>
+__global__ void __launch_bounds__(kThreads, STASH ? RTB_REGEN_STASH_BLOCKS : RTB_REGEN_MIN_BLOCKS) k_render_regen(SceneView sc, BvhView bv, FlatView fl, FrameView fr, float4* __restrict__ accum,
                                                             uint32_t s_begin, int n_samples, PrimCache prim,
                                                             unsigned long long* __restrict__ seg_counter) {
     extern __shared__ float4 smem[];
@@ -194,9 +198,16 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
     Hit h0;
     h0.id = -1; h0.t = 0.f; h0.n = f3(0.f, 0.f, 0.f); h0.p = f3(0.f, 0.f, 0.f);
     TravCount cnt = {0u, 0u, 0u, 0u};
+    static_assert(!STASH || REUSE, "the stash holds the cached primary hit");
+    __shared__ float stash[STASH ? 10 * kThreads : 1];
+    float* const st = stash + (STASH ? threadIdx.x : 0);
     if (REUSE) {
         if (n_samples > 0) {
             h0 = cached_primary(prim, pixel, o, d);
+            if (STASH) {
+                st[0] = h0.p.x; st[kThreads] = h0.p.y; st[2 * kThreads] = h0.p.z; st[3 * kThreads] = h0.n.x; st[4 * kThreads] = h0.n.y; st[5 * kThreads] = h0.n.z;
+                st[6 * kThreads] = __int_as_float(h0.id); st[7 * kThreads] = d0.x; st[8 * kThreads] = d0.y; st[9 * kThreads] = d0.z;
+            }
             float3 c;
             if (primary_ends(sc, fr, h0, c)) {
                 for (; s < n_samples; ++s) { acc.x += c.x; acc.y += c.y; acc.z += c.z; }
@@ -218,9 +229,19 @@ __global__ void __launch_bounds__(kThreads, RTB_REGEN_MIN_BLOCKS) k_render_regen
             float3 c;
             if (path_ends(sc, fr, h, d, T, L, depth, c)) {
                 acc.x += c.x; acc.y += c.y; acc.z += c.z;
-                ++s; depth = 0; o = fr.cam_pos; d = d0;
+                ++s; depth = 0; o = fr.cam_pos;
                 scatter = false;                             // no reuse: trace the primary ray again
-                if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }   // next sample starts from the cached primary hit
+                if (STASH) {
+                    d = f3(st[7 * kThreads], st[8 * kThreads], st[9 * kThreads]);
+                    if (s < n_samples) {                     // next sample starts from the cached primary hit (scatter_segment reads id, n, p)
+                        h.p = f3(st[0], st[kThreads], st[2 * kThreads]); h.n = f3(st[3 * kThreads], st[4 * kThreads], st[5 * kThreads]);
+                        h.id = __float_as_int(st[6 * kThreads]); h.t = 0.f;
+                        ++segs; scatter = true;
+                    }
+                } else {
+                    d = d0;
+                    if (REUSE && s < n_samples) { h = h0; ++segs; scatter = true; }   // next sample starts from the cached primary hit
+                }
             }
             if (scatter) scatter_segment(sc, fr, h, pixel, s_begin + (uint32_t)s, o, d, T, L, depth);
         }
@@ -864,6 +885,7 @@ static cudaError_t ensure_smem_optin() {
     if ((e = optin(k_render_regen<3, true, true>)) != cudaSuccess) return e;
     if ((e = optin(k_render_regen<2, false, true>)) != cudaSuccess) return e;
     if ((e = optin(k_render_regen<3, false, true>)) != cudaSuccess) return e;
+    if ((e = optin(k_render_regen<5, true, false, true>)) != cudaSuccess) return e;      // the 7-CTA form (STASH)
 #undef RTB_OPTIN
 #undef RTB_OPTIN2
 #undef RTB_OPTIN3
@@ -961,6 +983,8 @@ cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView
     return cudaGetLastError();
 }
 
+constexpr long long kStashMinWarpTiles = 40000;     // 32-pixel tiles = 10 000 CTAs: about ten waves of 148 x 7 (1080p has 64 800 tiles, 720p 28 800, 640x480 9600)
+
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                 uint32_t s_begin, int n_samples, const PrimCache* prim_cache, unsigned long long* seg_counter, cudaStream_t st, int pool_override, bool flat_coop,
                                 bool count_traversal, FrameTarget* frame) {
@@ -1020,6 +1044,12 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
         else if (mode == 2) k_render_regen<2, false, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
         else if (reuse_primary) k_render_regen<3, true, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
         else k_render_regen<3, false, true><<<grid, kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
+        return cudaGetLastError();
+    }
+    // large grids of the pooled flat traversal with the primary-hit cache (the headline configuration): the 7-CTA form (k_render_regen STASH)
+    static const bool no_stash = [] { const char* v = getenv("RTB200_REGEN_STASH"); return v && v[0] == '0'; }();    // A/B
+    if (mode == 5 && reuse_primary && !no_stash && n_tiles_all >= kStashMinWarpTiles) {
+        k_render_regen<5, true, false, true><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
         return cudaGetLastError();
     }
     RTB_DISPATCH2(mode, reuse_primary, k_render_regen, tile_grid(fr.width, fr.height), sb, st, sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter)

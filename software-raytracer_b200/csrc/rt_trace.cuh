@@ -16,6 +16,9 @@ static_assert(kThreads == kLaneThreads, "rt_bvh_lane.cuh lays the traversal stac
 #ifndef RTB_REGEN_MIN_BLOCKS
 #define RTB_REGEN_MIN_BLOCKS 6      // register budget of the render kernel: 65536 / (128 * 6) -> 80 registers
 #endif
+#ifndef RTB_REGEN_STASH_BLOCKS
+#define RTB_REGEN_STASH_BLOCKS 7    // k_render_regen<.., STASH>: 72 registers
+#endif
 
 // ---- closest-hit back ends -------------------------------------------------------------------
 // MODE 0: brute force, geometry staged in shared memory      MODE 1: brute force from global (L1)
@@ -36,7 +39,11 @@ struct TraceCtx {
 // MODE 5 = MODE 4 with warp-cooperative levels 2 and 3 (closest_hit_flat_coop below); per-warp scratch layout:
 // [ray: 6 x 32 floats (o, d)][pairs: kCoopPairs x u16][sphere candidates: kCoopCands x u16][best key: 32 x u64]
 constexpr int kCoopPairs = 64;                  // (owner lane, cluster) pairs per call; more -> per-lane fallback
-constexpr int kCoopCands = 64 * 8 + 32 * 56;    // every pair full + every lane's level-1 queue full: cannot overflow
+#ifndef RTB_COOP_CANDS
+#define RTB_COOP_CANDS 768
+#endif
+constexpr int kCoopCands = RTB_COOP_CANDS;      // sphere candidates per call (every pair full + every lane's level-1 queue full would be 64 * 8 + 32 * 56 = 2304:
+                                                // 4.6 KB per warp, which held the kernel at 6 CTAs per SM); a call whose upper bound is larger takes the per-lane fallback
 constexpr int kCoopBytesPerWarp = 6 * 32 * 4 + kCoopPairs * 2 + kCoopCands * 2 + 32 * 8;
 
 template <int MODE>
@@ -166,7 +173,8 @@ __device__ __forceinline__ Hit closest_hit_flat_coop(const SceneView& sc, const 
     const unsigned int cnt = (unsigned int)__popc(cm);
     const unsigned int incl = warp_incl_scan(cnt, lane);
     const unsigned int n_pairs = __shfl_sync(FULL, incl, 31);
-    if (n_pairs > (unsigned int)kCoopPairs) {                 // rare: every lane works for itself
+    const unsigned int own_all = __reduce_add_sync(FULL, (unsigned int)(nq - nq_cubes));
+    if (n_pairs > (unsigned int)kCoopPairs || own_all + 8u * n_pairs > (unsigned int)kCoopCands) {   // rare: every lane works for itself
         Hit h;
         h.id = -1; h.t = 0.f; h.n = f3(0.f, 0.f, 0.f); h.p = f3(0.f, 0.f, 0.f);
         if (active) h = flat_levels23_outlined(sc, fv, sph, box, q, qstride, o, d, cm, nq);

@@ -937,6 +937,29 @@ def _dense_scene(n, spread, seed):
     return o
 
 
+@pytest.mark.parametrize("scene", ["Scene1", "Scene2"])
+def test_large_grid_form_of_the_megakernel_is_bit_identical(tracer, scenes, scene):
+    """Grids of 40 000+ warp tiles take k_render_regen<5, true, false, STASH> (7 CTAs per SM: the cached primary hit and direction wait
+    in shared memory between samples): 1920x1080 against the per-lane traversal, which never takes that form, and against a launch
+    split into calls - same bits, same segment counts."""
+    out = {}
+    try:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_FLAT)
+        for key, coop, calls in (("coop", 1, (16, 5)), ("lane", 0, (16, 5)), ("coop_one_call", 1, (21,))):
+            tracer.set_option(rtb200.RT_OPT_FLAT_COOP, coop)
+            setup(tracer, scenes[scene], 1920, 1080, None, max_bounces=8)
+            for n in calls:
+                tracer.render_spp(n)
+            st = tracer.stats()
+            out[key] = (tracer.read_accum()[0], st.segments, st.traced_segments)
+    finally:
+        tracer.set_option(rtb200.RT_OPT_ACCEL, rtb200.RT_ACCEL_AUTO)
+        tracer.set_option(rtb200.RT_OPT_FLAT_COOP, 2)
+    assert np.array_equal(bits(out["coop"][0]), bits(out["lane"][0])) and out["coop"][1:] == out["lane"][1:]
+    # 16 + 5 samples in two calls and 21 in one: the per-pixel sums differ only by where the partial sum is rounded into the buffer
+    assert np.allclose(out["coop_one_call"][0], out["coop"][0], rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("case", SCENES + ["dense250", "dense120", "dense40"])
 def test_pooled_flat_traversal_is_bit_identical(tracer, scenes, case):
     """closest_hit_flat_coop (the warp pools its cluster culls and strict tests; launches of >= 16 spp) vs the per-lane
