@@ -212,3 +212,40 @@ def test_lane_state_machine_equals_the_per_ray_loop_under_random_schedules(emu, 
                                      p(org), p(d), n, 77 + leaf_bias, leaf_bias, use_slots, steps)
         assert bad == 0, (leaf_bias, use_slots, bad)
         assert steps[0] > 2 * n and steps[1] > n / 4
+
+
+def test_two_word_minimum_protocol_of_the_pooled_traversal():
+    """closest_hit_flat_coop (csrc/rt_trace.cuh) returns a warp's strict test results to the owning lanes as the minimum of (distance
+    bits, object id) kept in TWO 32-bit shared-memory words per owner: per pass, atomicMin on the distance word; a candidate that LOWERED
+    it resets the id word; candidates that hold the owner's smallest distance atomicMin their id. A model of that protocol with the
+    atomics applied in random order must give the lexicographic minimum for any stream of passes (ties on distance included)."""
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        n_owner = int(rng.integers(1, 6))
+        key_t = [0xffffffff] * n_owner
+        key_id = [0xffffffff] * n_owner
+        seen = [[] for _ in range(n_owner)]
+        for _ in range(int(rng.integers(1, 6))):                      # passes, separated by __syncwarp
+            lanes = []
+            for _ in range(int(rng.integers(0, 33))):
+                lanes.append((int(rng.integers(0, n_owner)), int(rng.integers(0, 4)) * 1000 + 5, int(rng.integers(0, 200))))   # few distinct distances: many ties
+            for ow, ob, idc in lanes:
+                seen[ow].append((ob, idc))
+            before = {}
+            for k in rng.permutation(len(lanes)):                     # phase 1: read, then atomicMin - interleaved in any order
+                ow, ob, idc = lanes[k]
+                before[k] = key_t[ow]
+                if ob < before[k]:
+                    key_t[ow] = min(key_t[ow], ob)
+            now = {k: key_t[lanes[k][0]] for k in range(len(lanes))}   # after the first __syncwarp
+            for k in rng.permutation(len(lanes)):                     # a new smallest distance: its ids start afresh
+                ow, ob, idc = lanes[k]
+                if now[k] < before[k] and ob == now[k]:
+                    key_id[ow] = 0xffffffff
+            for k in rng.permutation(len(lanes)):                     # after the second __syncwarp
+                ow, ob, idc = lanes[k]
+                if ob == now[k]:
+                    key_id[ow] = min(key_id[ow], idc)
+        for ow in range(n_owner):
+            want = min(seen[ow]) if seen[ow] else (0xffffffff, 0xffffffff)
+            assert (key_t[ow], key_id[ow]) == want, (trial, ow)
