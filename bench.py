@@ -21,6 +21,9 @@ checks that the fused surface equals the resolve of the sum of all ranks' buffer
 `configs`: (N = 1, default config only) short legs of the other BASELINE.json configs - c1 640x480x64 spp, c3 10 000
            spheres at 3840x2160 through the BVH / wavefront pipeline, c4 1 M-triangle mesh at 1080p, c5 interactive 1 spp
            frames at 720p - each with its own roofline object, so that every config is observed by whoever runs this file.
+`frame_1080p_1spp`: the metric's "ms/frame at 1080p", measured: p50 / p99 of one rt_render_frame(1) per frame into a host surface.
+`cpu_baseline`: the reference's own renderArea loop on the box's host cores (24 frames of 1 spp; also as Mpaths/s, ms per 1-spp
+           frame, and with glibc's locked rand() instead of MSVC's per-thread one); the c3 leg carries the same for ITS scene.
 `--impl reference`: the reference's own CPU code (oracle/_ref, else the validated C port) on the host cores, same
            metric, bounded sample per step.
 """
