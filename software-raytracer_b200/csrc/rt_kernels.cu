@@ -983,7 +983,10 @@ cudaError_t launch_pick(const SceneView& sc, const AccelSel& ac, const FrameView
     return cudaGetLastError();
 }
 
-constexpr long long kStashMinWarpTiles = 40000;     // 32-pixel tiles = 10 000 CTAs: about ten waves of 148 x 7 (1080p has 64 800 tiles, 720p 28 800, 640x480 9600)
+// 32-pixel tiles = 10 000 CTAs: about ten waves of 148 x 7 (1080p has 64 800 tiles, 720p 28 800, 640x480 9600). Below it the two forms are
+// within the run-to-run noise of each other (profiles/r4z_ab_stash_threshold.txt: 720p 64 spp 3.71 vs 3.77 ms, 960x540 and 640x480 equal;
+// 2560x1440 12.68 vs 13.07 ms), so small grids stay on the form they were tuned and profiled with.
+constexpr long long kStashMinWarpTiles = 40000;
 
 cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const FrameView& fr, float4* accum,
                                 uint32_t s_begin, int n_samples, const PrimCache* prim_cache, unsigned long long* seg_counter, cudaStream_t st, int pool_override, bool flat_coop,
@@ -1048,7 +1051,8 @@ cudaError_t launch_render_regen(const SceneView& sc, const AccelSel& ac, const F
     }
     // large grids of the pooled flat traversal with the primary-hit cache (the headline configuration): the 7-CTA form (k_render_regen STASH)
     static const bool no_stash = [] { const char* v = getenv("RTB200_REGEN_STASH"); return v && v[0] == '0'; }();    // A/B
-    if (mode == 5 && reuse_primary && !no_stash && n_tiles_all >= kStashMinWarpTiles) {
+    static const long long stash_min = [] { const char* v = getenv("RTB200_STASH_MIN_TILES"); return v ? atoll(v) : kStashMinWarpTiles; }();   // A/B
+    if (mode == 5 && reuse_primary && !no_stash && n_tiles_all >= stash_min) {
         k_render_regen<5, true, false, true><<<tile_grid(fr.width, fr.height), kThreads, sb, st>>>(sc, ac.bvh, ac.flat, fr, accum, s_begin, n_samples, prim, seg_counter);
         return cudaGetLastError();
     }
